@@ -1,0 +1,900 @@
+// fitsne_capi.cu -- context, per-iteration launch sequence, CUDA-graph cache and the C ABI
+// (include/fitsne_b200.h) of libfitsne_b200.so.  Kernels live in fitsne_kernels.cuh; cuFFT R2C/C2R is the one
+// library call on the path; NCCL (loaded with dlopen, only for sharded runs) carries the grid all-reduce and
+// the Y all-gather.  There is no CPU fallback anywhere in this file.
+#include "../../include/fitsne_b200.h"
+#include "fitsne_kernels.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace fk;
+
+// ------------------------------------------------------------------------------------------ NCCL (dlopen) --
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err) {
+        if (handle) return true;
+        const char *env = getenv("FITSNE_NCCL_LIB");
+        const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            if (!n) continue;
+            handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (handle) break;
+        }
+        if (!handle) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define LOADSYM(field, name) \
+        *(void **) (&field) = dlsym(handle, name); \
+        if (!field) { err = std::string("libnccl lacks ") + name; return false; }
+        LOADSYM(GetUniqueId, "ncclGetUniqueId");
+        LOADSYM(CommInitRank, "ncclCommInitRank");
+        LOADSYM(CommDestroy, "ncclCommDestroy");
+        LOADSYM(AllReduce, "ncclAllReduce");
+        LOADSYM(AllGather, "ncclAllGather");
+        LOADSYM(GetErrorString, "ncclGetErrorString");
+#undef LOADSYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::string g_create_error;
+
+struct Plans {
+    cufftHandle fwd = 0, inv = 0;
+};
+
+// The launch sequence depends on the FFT length M only (n_boxes and all grid geometry are read from the
+// device-resident GridParams), so one captured graph serves every iteration whose 2G maps to the same M.
+struct GraphKey {
+    int M, kind;   // kind 0: gradient only, 1: full step
+    bool operator<(const GraphKey &o) const {
+        if (M != o.M) return M < o.M;
+        return kind < o.kind;
+    }
+};
+}  // namespace
+
+struct fitsne_ctx {
+    fitsne_config cfg{};
+    int N = 0, D = 0;
+    int rank = 0, world = 1, per = 0, row_begin = 0, row_end = 0, nloc = 0;
+    int device = 0;
+    bool df_is_one = true;
+    int n_fwd = 0, n_kern = 0, n_inv = 0;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+
+    // state (fp32)
+    float *Y = nullptr, *Yb = nullptr, *uY = nullptr, *gains = nullptr, *frep = nullptr, *dC = nullptr;
+    size_t y_elems = 0;   // allocated elements per Y buffer (padded to per*world*D)
+    // CSR
+    uint32_t *row_P = nullptr, *col_P = nullptr;
+    float *val_P = nullptr;
+    uint32_t edge_base = 0;
+    size_t E = 0;
+    int lpr = 32;
+    // sort / bins
+    uint32_t *keys[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
+    float *sorted_u = nullptr;
+    uint32_t *box_start = nullptr, *chunk_off = nullptr, *hist = nullptr;
+    size_t box_cap = 0, hist_cap = 0;
+    float4 *partial = nullptr;
+    size_t partial_cap = 0;
+    // grids
+    float *fft_in = nullptr, *fft_out = nullptr, *compact = nullptr;
+    float2 *spec = nullptr;
+    size_t plane_cap = 0, compact_cap = 0;   // capacity in real elements per plane
+    // small stuff
+    double *colsum_partial = nullptr, *zpartial = nullptr, *kl_partial = nullptr;
+    float2 *bounds_partial = nullptr;
+    GridParams *gp = nullptr;
+    StepParams *sp = nullptr;
+    Scalars *sc = nullptr;
+    int *mismatch = nullptr;
+    float *host_bounds = nullptr, *host_bounds_dev = nullptr;   // mapped pinned
+    int *host_B = nullptr, *host_B_dev = nullptr;               // mapped pinned: the host's n_boxes for this iteration
+    Scalars *host_sc = nullptr;                                 // pinned staging for scalar read-back
+    StepParams sp_host{};
+    bool sp_valid = false;
+    double *staging = nullptr;   // device fp64 staging for Y / dC transfers
+    size_t staging_elems = 0;
+
+    std::map<int, Plans> plans;
+    struct GraphEntry { cudaGraphExec_t exec; uint64_t launches; };
+    std::map<GraphKey, GraphEntry> graphs;
+    int cur_B = -1, cur_M = -1;
+    bool bounds_valid = false, have_grad = false;
+    double last_run_ms = 0;
+    fitsne_stats stats{};
+    cudaEvent_t ev[FITSNE_PHASE_COUNT + 1] = {};
+    bool timing_this_iter = false;
+    std::string err;
+};
+
+// ------------------------------------------------------------------------------------------------ errors --
+static int fail(fitsne_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(c, e_ == cudaErrorMemoryAllocation ? FITSNE_ENOMEM : FITSNE_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CKFFT(call) do { cufftResult r_ = (call); if (r_ != CUFFT_SUCCESS) \
+    return fail(c, FITSNE_ECUDA, "%s failed: cufft error %d (%s:%d)", #call, (int) r_, __FILE__, __LINE__); } while (0)
+#define CKNCCL(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) \
+    return fail(c, FITSNE_ENCCL, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); } while (0)
+#define CKRC(call) do { int rc_ = (call); if (rc_ != 0) return rc_; } while (0)
+#define LAUNCH_CHECK() CK(cudaGetLastError())
+
+static const bool g_trace = getenv("FITSNE_TRACE") != nullptr;
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#define TRACE(...) do { if (g_trace) { fprintf(stderr, "[fitsne %.3f] ", now_ms()); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); } } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int) ((a + b - 1) / b); }
+
+// FFT length for a grid of side G.  Any M >= 2G-1 gives the same linear convolution (the reference uses 2G,
+// nbodyfft.cpp:155-156), so M is taken from a coarse ladder of cuFFT-friendly lengths -- 2^a 3^b 5^c 7^d that
+// are multiples of 32 (16 below 512) -- to keep the number of distinct plans / graphs over a run small:
+// plan creation costs from milliseconds to seconds per new length (cuFFT JIT-compiles kernels on sm_100).
+static int nice_fft_size(int n) {
+    const int q = n <= 512 ? 16 : 32;
+    n = (n + q - 1) / q * q;
+    for (;; n += q) {
+        int m = n;
+        for (int f : {2, 3, 5, 7}) while (m % f == 0) m /= f;
+        if (m == 1) return n;
+    }
+}
+
+template <typename T>
+static int dev_alloc(fitsne_ctx *c, T **p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    CK(cudaMalloc((void **) p, count * sizeof(T) + 256));
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------- capacity / plans --
+// Largest grid a graph for FFT length M may be asked to handle: G <= M/2, hence B <= M/(2p).
+static inline size_t max_boxes_for(const fitsne_ctx *c, int M) {
+    const size_t Bmax = (size_t) std::max(1, M / (2 * c->cfg.nterms));
+    return c->D == 2 ? Bmax * Bmax : Bmax;
+}
+static inline size_t max_chunks_for(const fitsne_ctx *c, int M) {
+    return (size_t) c->nloc / CHUNK + std::min(max_boxes_for(c, M), (size_t) c->nloc) + 2;
+}
+
+static void drop_graphs(fitsne_ctx *c) {
+    for (auto &g : c->graphs) cudaGraphExecDestroy(g.second.exec);
+    c->graphs.clear();
+}
+
+static int ensure_grid_capacity(fitsne_ctx *c, int M) {
+    const int D = c->D, p = c->cfg.nterms;
+    const size_t nb = max_boxes_for(c, M);
+    bool moved = false;
+    if (nb + 2 > c->box_cap) {
+        const size_t cap = nb + nb / 2 + 1024;
+        CKRC(dev_alloc(c, &c->box_start, cap));
+        CKRC(dev_alloc(c, &c->chunk_off, cap));
+        c->box_cap = cap;
+        moved = true;
+    }
+    const size_t nodes = D == 2 ? (size_t) p * p : (size_t) p;
+    const size_t maxchunks = max_chunks_for(c, M);
+    if (maxchunks * nodes > c->partial_cap) {
+        const size_t cap = maxchunks * nodes + maxchunks * nodes / 2;
+        CKRC(dev_alloc(c, &c->partial, cap));
+        c->partial_cap = cap;
+        moved = true;
+    }
+    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
+    if (plane > c->plane_cap) {
+        const size_t cap = plane + plane / 2;
+        const size_t cplane = D == 2 ? (size_t) M * (M / 2 + 1) : (size_t) (M / 2 + 1);
+        const size_t ccap = cplane + cplane / 2 + 64;
+        CKRC(dev_alloc(c, &c->fft_in, cap * (c->n_fwd + c->n_kern)));
+        CKRC(dev_alloc(c, &c->spec, ccap * (c->n_fwd + c->n_kern)));
+        CKRC(dev_alloc(c, &c->fft_out, cap * c->n_inv));
+        if (c->world > 1) CKRC(dev_alloc(c, &c->compact, cap * c->n_fwd / 4 + 1024));
+        c->plane_cap = cap;
+        moved = true;
+    }
+    if (moved) drop_graphs(c);   // captured graphs point at the old buffers
+    return 0;
+}
+
+static int get_plans(fitsne_ctx *c, int M, Plans **out) {
+    auto it = c->plans.find(M);
+    if (it != c->plans.end()) { *out = &it->second; return 0; }
+    Plans pl;
+    const int D = c->D;
+    int n[2] = {M, M};
+    const int rank = D;
+    const int rdist = D == 2 ? M * M : M, cdist = D == 2 ? M * (M / 2 + 1) : (M / 2 + 1);
+    CKFFT(cufftPlanMany(&pl.fwd, rank, n, nullptr, 1, rdist, nullptr, 1, cdist, CUFFT_R2C, c->n_fwd + c->n_kern));
+    CKFFT(cufftPlanMany(&pl.inv, rank, n, nullptr, 1, cdist, nullptr, 1, rdist, CUFFT_C2R, c->n_inv));
+    CKFFT(cufftSetStream(pl.fwd, c->stream));
+    CKFFT(cufftSetStream(pl.inv, c->stream));
+    c->plans[M] = pl;
+    *out = &c->plans[M];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- launch sequences --
+static inline void phase_mark(fitsne_ctx *c, int phase) {
+    if (c->timing_this_iter) cudaEventRecord(c->ev[phase], c->stream);
+}
+
+template <int D>
+static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int do_center) {
+    k_center_bounds<D><<<RED_BLOCKS, 256, 0, c->stream>>>(Yin, Yout, c->N, c->colsum_partial, RED_BLOCKS, do_center,
+                                                          c->bounds_partial, c->sc);
+    k_reduce_bounds<<<1, 256, 0, c->stream>>>(c->bounds_partial, RED_BLOCKS, c->sc, c->host_bounds_dev);
+    LAUNCH_CHECK();
+    c->stats.kernel_launches += 2;
+    return 0;
+}
+
+template <int D, int P>
+static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, int M, const uint32_t *skeys, const uint32_t *sperm) {
+    const int p = c->cfg.nterms;
+    const int nodes = D == 2 ? p * p : p;
+    if (!gather) {
+        const int cpb = std::max(1, 256 / nodes);
+        const size_t maxchunks = max_chunks_for(c, M);
+        k_spread_chunks<D, P><<<cdiv(maxchunks, cpb), cpb * nodes, 0, c->stream>>>(c->sorted_u, c->box_start, c->chunk_off,
+                                                                                    c->gp, cpb, c->partial);
+    } else {
+        k_gather<D, P><<<cdiv(c->nloc, 256), 256, 0, c->stream>>>(c->sorted_u, skeys, sperm, c->nloc, c->gp, c->sc,
+                                                                   c->fft_out, c->frep);
+    }
+    LAUNCH_CHECK();
+    c->stats.kernel_launches += 1;
+    return 0;
+}
+
+template <int D>
+static int launch_spread_gather(fitsne_ctx *c, bool gather, int M, const uint32_t *skeys, const uint32_t *sperm) {
+    switch (c->cfg.nterms) {
+        case 2: return launch_spread_gather_variant<D, 2>(c, gather, M, skeys, sperm);
+        case 3: return launch_spread_gather_variant<D, 3>(c, gather, M, skeys, sperm);
+        case 4: return launch_spread_gather_variant<D, 4>(c, gather, M, skeys, sperm);
+        case 5: return launch_spread_gather_variant<D, 5>(c, gather, M, skeys, sperm);
+        default: return launch_spread_gather_variant<D, 0>(c, gather, M, skeys, sperm);
+    }
+}
+
+template <int D, bool UPDATE>
+static int launch_attract(fitsne_ctx *c) {
+    const int rows = c->row_end - c->row_begin;
+#define ATT(L) k_attract_update<D, L, UPDATE><<<cdiv((long long) rows * L, 256), 256, 0, c->stream>>>( \
+        c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC, c->uY, c->gains, c->Yb)
+    switch (c->lpr) {
+        case 4: ATT(4); break;
+        case 8: ATT(8); break;
+        case 16: ATT(16); break;
+        default: ATT(32); break;
+    }
+#undef ATT
+    LAUNCH_CHECK();
+    c->stats.kernel_launches += 1;
+    return 0;
+}
+
+// Everything from "bounds are known" to either dC (update=false) or the centred new Y and its bounds
+// (update=true).  B is only passed to k_setup_grid (which verifies it against the device's own bounds); every
+// launch shape below depends on M, the shard size and nterms only.  Pure stream work: capturable.
+template <int D>
+static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool update) {
+    const int p = c->cfg.nterms, nloc = c->nloc;
+    cudaStream_t st = c->stream;
+    Plans *pl;
+    CKRC(get_plans(c, M, &pl));
+    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
+
+    phase_mark(c, FITSNE_PHASE_BOUNDS);
+    k_setup_grid<<<1, 32, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals, c->mismatch);
+    c->stats.kernel_launches += 1;
+
+    // ---- bin + stable two-pass LSD radix sort by box
+    phase_mark(c, FITSNE_PHASE_SORT);
+    k_bin<D><<<cdiv(nloc, 256), 256, 0, st>>>(c->Y, c->row_begin, nloc, c->gp, c->keys[0]);
+    const int tiles = cdiv(nloc, SORT_TILE);
+    const size_t scatter_smem = (size_t) (1 << SORT_MAX_BITS) * 4 + (size_t) (SORT_THREADS / 32) * (1 << SORT_MAX_BITS) * 2;
+    int src = 0;
+    for (int ps = 0; ps < 2; ps++) {
+        k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[src], nloc, ps, c->hist, tiles, c->gp);
+        k_scan_u32<ScanIdentity, false><<<1, 1024, 0, st>>>(c->hist, c->hist, tiles, 0, c->gp, ScanIdentity());
+        k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[src], ps == 0 ? nullptr : c->perm[src], c->keys[src ^ 1],
+                                                                  c->perm[src ^ 1], nloc, ps, c->hist, tiles,
+                                                                  (uint32_t) c->row_begin, c->gp);
+        src ^= 1;
+        c->stats.kernel_launches += 3;
+    }
+    const uint32_t *skeys = c->keys[src], *sperm = c->perm[src];
+    k_post_sort<D><<<cdiv(nloc, 256), 256, 0, st>>>(skeys, sperm, c->Y, nloc, c->gp, c->box_start, c->sorted_u);
+    k_scan_u32<ScanChunks, true><<<1, 1024, 0, st>>>(c->box_start, c->chunk_off, 0, 1, c->gp, ScanChunks());
+    c->stats.kernel_launches += 3;
+    LAUNCH_CHECK();
+
+    // ---- spread
+    phase_mark(c, FITSNE_PHASE_SPREAD);
+    CKRC(launch_spread_gather<D>(c, false, M, skeys, sperm));
+    if (c->world == 1) {
+        k_spread_combine<D><<<cdiv(plane, 256), 256, 0, st>>>(c->partial, c->chunk_off, c->gp, c->n_fwd, c->fft_in, nullptr);
+        c->stats.kernel_launches += 1;
+    } else {
+        const int Gc = M / 2;
+        const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
+        k_spread_combine<D><<<cdiv(cplane, 256), 256, 0, st>>>(c->partial, c->chunk_off, c->gp, c->n_fwd, c->fft_in, c->compact);
+        phase_mark(c, FITSNE_PHASE_COLLECTIVES);
+        CKNCCL(g_nccl.AllReduce(c->compact, c->compact, cplane * c->n_fwd, ncclFloat, ncclSum, c->comm, st));
+        k_pad_grids<D><<<cdiv(plane, 256), 256, 0, st>>>(c->compact, c->gp, c->n_fwd, c->fft_in);
+        c->stats.kernel_launches += 3;
+    }
+
+    // ---- kernel samples + one batched R2C over (grids, kernels)
+    phase_mark(c, FITSNE_PHASE_KERNEL_SPECTRUM);
+    k_gen_kernels<D><<<cdiv(plane, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->n_fwd, c->fft_in);
+    LAUNCH_CHECK();
+    phase_mark(c, FITSNE_PHASE_FFT);
+    CKFFT(cufftExecR2C(pl->fwd, c->fft_in, reinterpret_cast<cufftComplex *>(c->spec)));
+    k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->spec, c->gp, c->n_fwd, c->n_fwd, c->df_is_one ? 1 : 0, c->zpartial);
+    k_finalize_z<<<1, 256, 0, st>>>(c->zpartial, Z_BLOCKS, c->N, c->gp, c->sc);
+    CKFFT(cufftExecC2R(pl->inv, reinterpret_cast<cufftComplex *>(c->spec), c->fft_out));
+    c->stats.kernel_launches += 5;
+    LAUNCH_CHECK();
+
+    // ---- gather (+ 1/Z)
+    phase_mark(c, FITSNE_PHASE_GATHER);
+    CKRC(launch_spread_gather<D>(c, true, M, skeys, sperm));
+
+    // ---- attractive term (+ optimiser step)
+    phase_mark(c, FITSNE_PHASE_ATTRACT_UPDATE);
+    if (!update) {
+        CKRC((launch_attract<D, false>(c)));
+        phase_mark(c, FITSNE_PHASE_CENTER);
+    } else {
+        CKRC((launch_attract<D, true>(c)));
+        if (c->world > 1) {
+            CKNCCL(g_nccl.AllGather(c->Yb + (size_t) c->rank * c->per * D, c->Yb, (size_t) c->per * D, ncclFloat, c->comm, st));
+            c->stats.kernel_launches += 1;
+        }
+        phase_mark(c, FITSNE_PHASE_CENTER);
+        k_colsum<D><<<RED_BLOCKS, 256, 0, st>>>(c->Yb, c->N, c->colsum_partial);
+        c->stats.kernel_launches += 1;
+        CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1));
+    }
+    phase_mark(c, FITSNE_PHASE_COUNT);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int enqueue_iteration_d(fitsne_ctx *c, int M, bool update) {
+    // the host's n_boxes choice travels through a mapped pinned word so the captured graph stays valid
+    return c->D == 2 ? enqueue_iteration<2>(c, c->host_B_dev, M, update) : enqueue_iteration<1>(c, c->host_B_dev, M, update);
+}
+
+static int refresh_bounds(fitsne_ctx *c) {
+    if (c->bounds_valid) return 0;
+    if (c->D == 2) CKRC(launch_bounds_only<2>(c, c->Y, c->Y, 0)); else CKRC(launch_bounds_only<1>(c, c->Y, c->Y, 0));
+    c->bounds_valid = true;
+    return 0;
+}
+
+static int push_step_params(fitsne_ctx *c, const StepParams &sp) {
+    if (c->sp_valid && memcmp(&sp, &c->sp_host, sizeof sp) == 0) return 0;
+    c->sp_host = sp;
+    CK(cudaMemcpyAsync(c->sp, &c->sp_host, sizeof sp, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));   // sp_host is reused; rare (only when the schedule changes)
+    c->sp_valid = true;
+    return 0;
+}
+
+// Decide the grid from the (host-visible) bounds and run one iteration, through a cached CUDA graph unless
+// disabled.  The one host<->device handshake per iteration is the 8-byte bounds read.
+static int run_iteration(fitsne_ctx *c, bool update) {
+    CKRC(refresh_bounds(c));
+    TRACE("iteration: waiting for bounds");
+    CK(cudaStreamSynchronize(c->stream));
+    const double mn = (double) c->host_bounds[0], mx = (double) c->host_bounds[1];
+    if (!(mx > mn)) return fail(c, FITSNE_EINVAL, "degenerate embedding: max_coord (%g) <= min_coord (%g)", mx, mn);
+    const int B = choose_n_boxes(mn, mx, c->cfg.intervals_per_integer, c->cfg.min_num_intervals, c->D);
+    const int G = B * c->cfg.nterms;
+    if (sort_bits_for(B, c->D) > SORT_MAX_BITS || (long long) G * 2 > 65536)
+        return fail(c, FITSNE_EINVAL, "grid too large: n_boxes=%d", B);
+    const int M = nice_fft_size(2 * G);
+    TRACE("bounds [%g, %g] -> B=%d G=%d M=%d", mn, mx, B, G, M);
+    CKRC(ensure_grid_capacity(c, M));
+    if (B != c->cur_B || M != c->cur_M) {
+        c->cur_B = B; c->cur_M = M;
+        c->stats.regrids++;
+    }
+    *c->host_B = B;
+    c->stats.n_boxes = B; c->stats.grid_side = G; c->stats.fft_side = M;
+    c->stats.min_coord = mn; c->stats.max_coord = mx;
+
+    const bool timers = (c->cfg.flags & FITSNE_FLAG_TIMERS) != 0;
+    const bool use_graph = !(c->cfg.flags & FITSNE_FLAG_NO_GRAPH) && !timers;
+    c->timing_this_iter = timers;
+    if (!use_graph) {
+        CKRC(enqueue_iteration_d(c, M, update));
+    } else {
+        const GraphKey key{M, update ? 1 : 0};
+        auto it = c->graphs.find(key);
+        if (it == c->graphs.end()) {
+            Plans *pl;
+            TRACE("new graph for M=%d kind=%d: plans", M, update ? 1 : 0);
+            CKRC(get_plans(c, M, &pl));   // plan creation is not capturable
+            TRACE("capture");
+            cudaGraph_t graph;
+            const uint64_t launches_before = c->stats.kernel_launches;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_iteration_d(c, M, update);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc != 0) return rc;
+            if (e != cudaSuccess) return fail(c, FITSNE_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            cudaGraphExec_t exec;
+            TRACE("instantiate");
+            CK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            TRACE("graph ready");
+            c->graphs[key] = fitsne_ctx::GraphEntry{exec, c->stats.kernel_launches - launches_before};
+            it = c->graphs.find(key);
+            c->stats.kernel_launches = launches_before;
+        }
+        c->stats.kernel_launches += it->second.launches;
+        CK(cudaGraphLaunch(it->second.exec, c->stream));
+        c->stats.graph_launches++;
+    }
+    if (timers) {
+        CK(cudaStreamSynchronize(c->stream));
+        int order[] = {FITSNE_PHASE_BOUNDS, FITSNE_PHASE_SORT, FITSNE_PHASE_SPREAD, FITSNE_PHASE_COLLECTIVES,
+                       FITSNE_PHASE_KERNEL_SPECTRUM, FITSNE_PHASE_FFT, FITSNE_PHASE_GATHER, FITSNE_PHASE_ATTRACT_UPDATE,
+                       FITSNE_PHASE_CENTER, FITSNE_PHASE_COUNT};
+        std::vector<int> seq;
+        for (int ph : order) {
+            if (ph == FITSNE_PHASE_COLLECTIVES && c->world == 1) continue;
+            seq.push_back(ph);
+        }
+        for (size_t i = 0; i + 1 < seq.size(); i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, c->ev[seq[i]], c->ev[seq[i + 1]]) == cudaSuccess) c->stats.phase_ms[seq[i]] += ms;
+        }
+        c->timing_this_iter = false;
+    }
+    c->have_grad = true;
+    if (update) { c->stats.iterations++; c->bounds_valid = true; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ transfers --
+static int upload_as_float(fitsne_ctx *c, const double *host, float *dev, size_t n) {
+    if (n > c->staging_elems) { CKRC(dev_alloc(c, &c->staging, n)); c->staging_elems = n; }
+    CK(cudaMemcpyAsync(c->staging, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_d2f<<<cdiv(n, 256), 256, 0, c->stream>>>(c->staging, dev, n);
+    LAUNCH_CHECK();
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+static int download_as_double(fitsne_ctx *c, const float *dev, double *host, size_t n) {
+    if (n > c->staging_elems) { CKRC(dev_alloc(c, &c->staging, n)); c->staging_elems = n; }
+    k_f2d<<<cdiv(n, 256), 256, 0, c->stream>>>(dev, c->staging, n);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(host, c->staging, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int read_scalars(fitsne_ctx *c) {
+    CK(cudaMemcpyAsync(c->host_sc, c->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- lifetime --
+static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_dims, const unsigned int *row_P,
+                       const unsigned int *col_P, const double *val_P, const double *Y0, int rank, int world,
+                       int row_begin, int row_end, const void *nccl_id) {
+    if (!cfg || !row_P || N < 2) return fail(c, FITSNE_EINVAL, "bad arguments");
+    if (no_dims != 1 && no_dims != 2)
+        return fail(c, FITSNE_EINVAL, "FFT interpolation scheme supports only 1 or 2 output dimensions, not %d", no_dims);
+    if (cfg->nterms < 1 || cfg->nterms > PMAX) return fail(c, FITSNE_EINVAL, "nterms must be in 1..%d", PMAX);
+    if (!(cfg->df > 0) || !(cfg->intervals_per_integer > 0) || cfg->min_num_intervals < 1)
+        return fail(c, FITSNE_EINVAL, "df, intervals_per_integer and min_num_intervals must be positive");
+    c->cfg = *cfg;
+    c->N = N; c->D = no_dims;
+    c->rank = rank; c->world = world;
+    c->per = cdiv(N, world);
+    if (row_begin != rank * c->per || row_end != std::min(N, (rank + 1) * c->per) || row_end <= row_begin)
+        return fail(c, FITSNE_EINVAL, "rank %d must own rows [%d,%d) (contiguous ceil(N/world) slices)", rank,
+                    rank * c->per, std::min(N, (rank + 1) * c->per));
+    c->row_begin = row_begin; c->row_end = row_end; c->nloc = row_end - row_begin;
+    c->df_is_one = cfg->df == 1.0;
+    c->n_fwd = 1 + no_dims + (c->df_is_one ? 1 : 0);
+    c->n_kern = no_dims + 2;
+    c->n_inv = 1 + no_dims;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(c, FITSNE_ENODEV, "no CUDA device: libfitsne_b200 has no CPU fallback");
+    }
+    if (cfg->device >= 0) { CK(cudaSetDevice(cfg->device)); }
+    CK(cudaGetDevice(&c->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10) return fail(c, FITSNE_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200)", c->device, prop.major, prop.minor);
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CK(cudaEventCreate(&e));
+
+    const size_t yel = (size_t) c->per * world * no_dims;
+    c->y_elems = yel;
+    CKRC(dev_alloc(c, &c->Y, yel)); CKRC(dev_alloc(c, &c->Yb, yel));
+    CKRC(dev_alloc(c, &c->uY, yel)); CKRC(dev_alloc(c, &c->gains, yel));
+    CKRC(dev_alloc(c, &c->frep, yel)); CKRC(dev_alloc(c, &c->dC, yel));
+    CK(cudaMemsetAsync(c->Y, 0, yel * 4, c->stream)); CK(cudaMemsetAsync(c->Yb, 0, yel * 4, c->stream));
+    CK(cudaMemsetAsync(c->uY, 0, yel * 4, c->stream)); CK(cudaMemsetAsync(c->frep, 0, yel * 4, c->stream));
+    CK(cudaMemsetAsync(c->dC, 0, yel * 4, c->stream));
+    k_fill<<<cdiv(yel, 256), 256, 0, c->stream>>>(c->gains, 1.0f, yel);
+    LAUNCH_CHECK();
+
+    // CSR: full row offsets, this rank's edge slice
+    c->edge_base = row_P[row_begin];
+    c->E = (size_t) row_P[row_end] - (size_t) row_P[row_begin];
+    CKRC(dev_alloc(c, &c->row_P, (size_t) N + 1));
+    CK(cudaMemcpyAsync(c->row_P, row_P, ((size_t) N + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CKRC(dev_alloc(c, &c->col_P, c->E + 1)); CKRC(dev_alloc(c, &c->val_P, c->E + 1));
+    if (c->E) {
+        if (!col_P || !val_P) return fail(c, FITSNE_EINVAL, "col_P/val_P are NULL but the graph has edges");
+        CK(cudaMemcpyAsync(c->col_P, col_P, c->E * 4, cudaMemcpyHostToDevice, c->stream));
+        // val_P: double -> float in bounded chunks
+        const size_t chunk = 1u << 24;
+        CKRC(dev_alloc(c, &c->staging, chunk)); c->staging_elems = chunk;
+        for (size_t off = 0; off < c->E; off += chunk) {
+            const size_t n = std::min(chunk, c->E - off);
+            CK(cudaMemcpyAsync(c->staging, val_P + off, n * 8, cudaMemcpyHostToDevice, c->stream));
+            k_d2f<<<cdiv(n, 256), 256, 0, c->stream>>>(c->staging, c->val_P + off, n);
+            CK(cudaStreamSynchronize(c->stream));
+        }
+    }
+    const double avg = (double) c->E / (double) std::max(1, c->nloc);
+    c->lpr = avg > 48 ? 32 : avg > 20 ? 16 : avg > 8 ? 8 : 4;
+
+    CKRC(dev_alloc(c, &c->keys[0], (size_t) c->nloc)); CKRC(dev_alloc(c, &c->keys[1], (size_t) c->nloc));
+    CKRC(dev_alloc(c, &c->perm[0], (size_t) c->nloc)); CKRC(dev_alloc(c, &c->perm[1], (size_t) c->nloc));
+    CKRC(dev_alloc(c, &c->sorted_u, (size_t) c->nloc * no_dims));
+    c->hist_cap = (size_t) cdiv(c->nloc, SORT_TILE) * (1 << SORT_MAX_BITS);
+    CKRC(dev_alloc(c, &c->hist, c->hist_cap));
+    CKRC(dev_alloc(c, &c->colsum_partial, (size_t) RED_BLOCKS * 2));
+    CKRC(dev_alloc(c, &c->bounds_partial, (size_t) RED_BLOCKS));
+    CKRC(dev_alloc(c, &c->zpartial, (size_t) Z_BLOCKS));
+    CKRC(dev_alloc(c, &c->kl_partial, (size_t) 4096));
+    CKRC(dev_alloc(c, &c->gp, (size_t) 1)); CKRC(dev_alloc(c, &c->sp, (size_t) 1)); CKRC(dev_alloc(c, &c->sc, (size_t) 1));
+    CKRC(dev_alloc(c, &c->mismatch, (size_t) 1));
+    CK(cudaMemsetAsync(c->gp, 0, sizeof(GridParams), c->stream));
+    CK(cudaMemsetAsync(c->sc, 0, sizeof(Scalars), c->stream));
+    CK(cudaMemsetAsync(c->mismatch, 0, sizeof(int), c->stream));
+    CK(cudaHostAlloc((void **) &c->host_bounds, 64, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **) &c->host_bounds_dev, c->host_bounds, 0));
+    c->host_B = reinterpret_cast<int *>(c->host_bounds + 8);
+    c->host_B_dev = reinterpret_cast<int *>(c->host_bounds_dev + 8);
+    CK(cudaHostAlloc((void **) &c->host_sc, sizeof(Scalars), cudaHostAllocDefault));
+    if (Y0) CKRC(upload_as_float(c, Y0, c->Y, (size_t) N * no_dims));
+
+    if (world > 1) {
+        if (!nccl_id) return fail(c, FITSNE_EINVAL, "sharded context needs an ncclUniqueId");
+        if (!g_nccl.load(c->err)) return FITSNE_ENCCL;
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof id);
+        CKNCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" {
+
+const char *fitsne_version(void) { return "fitsne_b200 0.1 (sm_100a; protocol-compatible with FIt-SNE 1.2.1)"; }
+
+int fitsne_nccl_unique_id(void *out) {
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_error = err; return FITSNE_ENCCL; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return FITSNE_ENCCL; }
+    memcpy(out, &id, sizeof id);
+    return 0;
+}
+
+int fitsne_destroy(fitsne_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graphs(c);
+    for (auto &p : c->plans) { cufftDestroy(p.second.fwd); cufftDestroy(p.second.inv); }
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->col_P, c->val_P, c->keys[0], c->keys[1],
+                    c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->chunk_off, c->hist, c->partial, c->fft_in,
+                    c->fft_out, c->compact, c->spec, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
+                    c->gp, c->sp, c->sc, c->mismatch, c->staging};
+    for (void *b : bufs) if (b) cudaFree(b);
+    if (c->host_bounds) cudaFreeHost(c->host_bounds);
+    if (c->host_sc) cudaFreeHost(c->host_sc);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int fitsne_create_sharded(const fitsne_config *cfg, int N, int no_dims, const unsigned int *row_P,
+                          const unsigned int *col_P_local, const double *val_P_local, const double *Y0, int rank,
+                          int world_size, int row_begin, int row_end, const void *nccl_unique_id, fitsne_ctx **out) {
+    if (!out) return FITSNE_EINVAL;
+    *out = nullptr;
+    fitsne_ctx *c = new fitsne_ctx();
+    int rc = create_impl(c, cfg, N, no_dims, row_P, col_P_local, val_P_local, Y0, rank, world_size, row_begin, row_end,
+                         nccl_unique_id);
+    if (rc != 0) {
+        g_create_error = c->err;
+        fitsne_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+int fitsne_create(const fitsne_config *cfg, int N, int no_dims, const unsigned int *row_P, const unsigned int *col_P,
+                  const double *val_P, const double *Y0, fitsne_ctx **out) {
+    return fitsne_create_sharded(cfg, N, no_dims, row_P, col_P, val_P, Y0, 0, 1, 0, N, nullptr, out);
+}
+
+const char *fitsne_last_error(const fitsne_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int fitsne_synchronize(fitsne_ctx *c) {
+    if (!c) return FITSNE_EINVAL;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fitsne_set_Y(fitsne_ctx *c, const double *Y) {
+    if (!c || !Y) return FITSNE_EINVAL;
+    CK(cudaSetDevice(c->device));
+    c->bounds_valid = false;
+    return upload_as_float(c, Y, c->Y, (size_t) c->N * c->D);
+}
+
+int fitsne_get_Y(fitsne_ctx *c, double *Y) {
+    if (!c || !Y) return FITSNE_EINVAL;
+    CK(cudaSetDevice(c->device));
+    return download_as_double(c, c->Y, Y, (size_t) c->N * c->D);
+}
+
+int fitsne_set_optimizer_state(fitsne_ctx *c, const double *uY, const double *gains) {
+    if (!c) return FITSNE_EINVAL;
+    CK(cudaSetDevice(c->device));
+    if (uY) CKRC(upload_as_float(c, uY, c->uY, (size_t) c->N * c->D));
+    if (gains) CKRC(upload_as_float(c, gains, c->gains, (size_t) c->N * c->D));
+    return 0;
+}
+
+int fitsne_get_optimizer_state(fitsne_ctx *c, double *uY, double *gains) {
+    if (!c) return FITSNE_EINVAL;
+    CK(cudaSetDevice(c->device));
+    // in a sharded run each rank only maintains its own rows of uY / gains
+    if (uY) CKRC(download_as_double(c, c->uY, uY, (size_t) c->N * c->D));
+    if (gains) CKRC(download_as_double(c, c->gains, gains, (size_t) c->N * c->D));
+    return 0;
+}
+
+static StepParams make_sp(const fitsne_ctx *c, double alpha, double momentum, double lr, double msn, int mode) {
+    StepParams sp;
+    sp.alpha = (float) alpha; sp.momentum = (float) momentum; sp.lr = (float) lr; sp.max_step_norm = (float) msn;
+    sp.mode = mode; sp.inv_df = (float) (1.0 / c->cfg.df);
+    return sp;
+}
+
+int fitsne_gradient(fitsne_ctx *c, double exaggeration, double *dC_out, double *sum_Q_out) {
+    if (!c) return FITSNE_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CKRC(push_step_params(c, make_sp(c, exaggeration, 0, 0, 0, 0)));
+    CKRC(run_iteration(c, false));
+    if (dC_out) {
+        // each rank computed its own rows; rows outside the shard read back as zero
+        CKRC(download_as_double(c, c->dC, dC_out, (size_t) c->N * c->D));
+    }
+    if (sum_Q_out) {
+        CKRC(read_scalars(c));
+        *sum_Q_out = c->host_sc->Z;
+    }
+    return 0;
+}
+
+int fitsne_step(fitsne_ctx *c, const fitsne_step_params *p) {
+    if (!c || !p) return FITSNE_EINVAL;
+    if (p->mode < 0 || p->mode > 2) return fail(c, FITSNE_EINVAL, "bad step mode %d", p->mode);
+    CK(cudaSetDevice(c->device));
+    CKRC(push_step_params(c, make_sp(c, p->exaggeration, p->momentum, p->learning_rate, p->max_step_norm, p->mode)));
+    return run_iteration(c, true);
+}
+
+static int kl_impl(fitsne_ctx *c, double exaggeration, double *C_out) {
+    if (!c->have_grad) return fail(c, FITSNE_ESTATE, "fitsne_kl needs the sum_Q of a previous gradient/step");
+    const int blocks = std::min(4096, std::max(1, cdiv((long long) (c->row_end - c->row_begin) * 32, 256)));
+    if (c->D == 2)
+        k_kl<2><<<blocks, 256, 0, c->stream>>>(c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->row_begin, c->row_end,
+                                              exaggeration, c->cfg.df, c->sc, c->kl_partial);
+    else
+        k_kl<1><<<blocks, 256, 0, c->stream>>>(c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->row_begin, c->row_end,
+                                              exaggeration, c->cfg.df, c->sc, c->kl_partial);
+    k_finalize_kl<<<1, 256, 0, c->stream>>>(c->kl_partial, blocks, c->sc);
+    LAUNCH_CHECK();
+    c->stats.kernel_launches += 2;
+    if (c->world > 1) {
+        double *klp = &c->sc->kl;
+        CKNCCL(g_nccl.AllReduce(klp, klp, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    }
+    CKRC(read_scalars(c));
+    *C_out = c->host_sc->kl;
+    return 0;
+}
+
+int fitsne_kl(fitsne_ctx *c, double exaggeration, double *C_out) {
+    if (!c || !C_out) return FITSNE_EINVAL;
+    CK(cudaSetDevice(c->device));
+    return kl_impl(c, exaggeration, C_out);
+}
+
+static int auto_exaggeration(fitsne_ctx *c, double learning_rate, double *coeff) {
+    const int blocks = 1024;
+    k_row_sum_max<<<blocks, 256, 0, c->stream>>>(c->row_P, c->val_P, c->edge_base, c->row_begin, c->row_end, c->kl_partial);
+    LAUNCH_CHECK();
+    std::vector<double> h(blocks);
+    CK(cudaMemcpyAsync(h.data(), c->kl_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    double mx = 0;
+    for (double v : h) mx = std::max(mx, v);
+    if (c->world > 1) {
+        double *d = &c->sc->kl;
+        CK(cudaMemcpyAsync(d, &mx, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CKNCCL(g_nccl.AllReduce(d, d, 1, ncclDouble, ncclMax, c->comm, c->stream));
+        CK(cudaMemcpyAsync(&mx, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    *coeff = 1.0 / (learning_rate * mx);
+    return 0;
+}
+
+int fitsne_run(fitsne_ctx *c, const fitsne_schedule *s, double *costs, double *Y_out) {
+    if (!c || !s) return FITSNE_EINVAL;
+    CK(cudaSetDevice(c->device));
+    double early = s->early_exag_coeff;
+    if (early == 0) {   // tsne.cpp:392-402
+        CKRC(auto_exaggeration(c, s->learning_rate, &early));
+        if (s->verbose) printf("Max of the val_Ps is: %lf\n", 1.0 / (early * s->learning_rate));
+    }
+    if (s->verbose) printf("Exaggerating Ps by %f\n", early);
+    double alpha = early, momentum = s->momentum;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, c->stream));
+    auto t0 = std::chrono::steady_clock::now();
+    for (int iter = 0; iter < s->max_iter; iter++) {
+        fitsne_step_params sp;
+        sp.exaggeration = alpha; sp.momentum = momentum; sp.learning_rate = s->learning_rate;
+        sp.max_step_norm = s->max_step_norm;
+        sp.mode = FITSNE_STEP_MOMENTUM_CLIP;
+        if (s->no_momentum_during_exag) sp.mode = iter > s->stop_lying_iter ? FITSNE_STEP_MOMENTUM : FITSNE_STEP_PLAIN_GD;
+        CKRC(push_step_params(c, make_sp(c, sp.exaggeration, sp.momentum, sp.learning_rate, sp.max_step_norm, sp.mode)));
+        CKRC(run_iteration(c, true));
+        // schedule changes take effect after the step of that iteration (tsne.cpp:534-544).  The reference
+        // un-exaggerates by dividing and late-exaggerates by multiplying the stored P.
+        if (iter == s->stop_lying_iter) {
+            if (s->verbose) printf("Unexaggerating Ps by %f\n", early);
+            alpha /= early;
+        }
+        if (iter == s->start_late_exag_iter) {
+            if (s->verbose) printf("Exaggerating Ps by %f\n", s->late_exag_coeff);
+            alpha *= s->late_exag_coeff;
+        }
+        if (iter == s->mom_switch_iter) momentum = s->final_momentum;
+        if ((iter + 1) % 50 == 0 || iter == s->max_iter - 1) {
+            double C = 0;
+            CKRC(kl_impl(c, alpha, &C));
+            if (iter < s->stop_lying_iter && s->stop_lying_iter != -1) C = C / early - log(early);
+            if (iter >= s->start_late_exag_iter && s->start_late_exag_iter != -1) C = C / s->late_exag_coeff - log(s->late_exag_coeff);
+            if (costs) costs[iter] = C;
+            if (s->verbose) {
+                auto t1 = std::chrono::steady_clock::now();
+                printf("Iteration %d (50 iterations in %.2f seconds), cost %f\n", iter + 1,
+                       std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count() / (float) 1000.0, C);
+                t0 = std::chrono::steady_clock::now();
+            }
+        }
+    }
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    c->last_run_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (Y_out) CKRC(download_as_double(c, c->Y, Y_out, (size_t) c->N * c->D));
+    return 0;
+}
+
+int fitsne_run_host(const fitsne_config *cfg, const fitsne_schedule *s, int N, int no_dims, const unsigned int *row_P,
+                    const unsigned int *col_P, const double *val_P, double *Y, double *costs) {
+    fitsne_ctx *c = nullptr;
+    int rc = fitsne_create(cfg, N, no_dims, row_P, col_P, val_P, Y, &c);
+    if (rc != 0) return rc;
+    rc = fitsne_run(c, s, costs, Y);
+    if (rc != 0) g_create_error = c->err;
+    fitsne_destroy(c);
+    return rc;
+}
+
+int fitsne_last_run_ms(fitsne_ctx *c, double *ms) {
+    if (!c || !ms) return FITSNE_EINVAL;
+    *ms = c->last_run_ms;
+    return 0;
+}
+
+int fitsne_get_stats(fitsne_ctx *c, fitsne_stats *out) {
+    if (!c || !out) return FITSNE_EINVAL;
+    CK(cudaStreamSynchronize(c->stream));
+    *out = c->stats;
+    return 0;
+}
+
+int fitsne_reset_stats(fitsne_ctx *c) {
+    if (!c) return FITSNE_EINVAL;
+    const fitsne_stats old = c->stats;
+    c->stats = fitsne_stats{};
+    c->stats.n_boxes = old.n_boxes; c->stats.grid_side = old.grid_side; c->stats.fft_side = old.fft_side;
+    c->stats.min_coord = old.min_coord; c->stats.max_coord = old.max_coord;
+    return 0;
+}
+
+int fitsne_debug_copy(fitsne_ctx *c, const char *what, void *dst, size_t dst_bytes, size_t *needed) {
+    if (!c || !what) return FITSNE_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const void *src = nullptr;
+    size_t bytes = 0;
+    const int sorted_buf = 0;   // two LSD passes: sorted data ends up back in buffer 0
+    if (!strcmp(what, "frep")) { src = c->frep; bytes = (size_t) c->N * c->D * 4; }
+    else if (!strcmp(what, "perm")) { src = c->perm[sorted_buf]; bytes = (size_t) c->nloc * 4; }
+    else if (!strcmp(what, "keys")) { src = c->keys[sorted_buf]; bytes = (size_t) c->nloc * 4; }
+    else if (!strcmp(what, "box_start")) { src = c->box_start; bytes = ((c->D == 2 ? (size_t) c->cur_B * c->cur_B : (size_t) c->cur_B) + 1) * 4; }
+    else if (!strcmp(what, "fft_out")) { src = c->fft_out; bytes = (c->D == 2 ? (size_t) c->cur_M * c->cur_M : (size_t) c->cur_M) * c->n_inv * 4; }
+    else return fail(c, FITSNE_EINVAL, "unknown debug array '%s'", what);
+    if (needed) *needed = bytes;
+    if (!dst) return 0;
+    if (dst_bytes < bytes) return fail(c, FITSNE_EINVAL, "buffer too small for '%s': need %zu", what, bytes);
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,998 @@
+// fitsne_kernels.cuh -- hand-written sm_100a kernels for FIt-SNE's per-iteration gradient loop.
+//
+// Everything the reference does per iteration (reference = /root/reference/src/...) in fp32 on the device:
+//   bounds + zero-mean        tsne.cpp:1039-1049, :1851-1876        k_colsum, k_center_bounds, k_setup_grid
+//   point -> box, sort        nbodyfft.cpp:85-114                    k_bin, k_radix_hist/scan/scatter, k_post_sort
+//   Lagrange spread           nbodyfft.cpp:123-147, :310-336         k_spread_chunks, k_spread_combine
+//   kernel samples            nbodyfft.cpp:52-61, tsne.cpp:69-94     k_gen_kernels        (+ cuFFT R2C)
+//   Hadamard + sum_Q          nbodyfft.cpp:184-191, tsne.cpp:1101-1110  k_hadamard, k_finalize_z  (+ cuFFT C2R)
+//   gather + normalise        nbodyfft.cpp:222-239, tsne.cpp:1149-1151  k_gather
+//   attractive + optimiser    tsne.cpp:1121-1137, :479-513           k_attract_update
+//   KL                        tsne.cpp:1329-1355                      k_kl
+//
+// The repulsive part uses the "local offset" formulation documented in tests/device_model.py (identical
+// algebra to the reference's {1,x,y,x^2+y^2} charges, but fp32-safe); binning and in-box coordinates are
+// evaluated in fp64 with the reference's exact operation order.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace fk {
+
+constexpr int PMAX = 16;          // max interpolation points per box and axis
+constexpr int CHUNK = 32;         // points per spread work item
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_IPT = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
+constexpr int SORT_MAX_BITS = 11;
+constexpr int RED_BLOCKS = 592;   // 4 x 148 SMs: partial-reduction width for bounds / column sums
+constexpr int Z_BLOCKS = 592;
+
+// Device-resident description of this iteration's interpolation grid.  Rewritten every iteration by
+// k_setup_grid from the bounds; all kernels read it from memory so that one captured CUDA graph serves every
+// iteration that has the same n_boxes.
+struct GridParams {
+    double mn, mx;        // min_coord / max_coord as the reference computes them (tsne.cpp:1042-1049)
+    double bw;            // (mx-mn)/B                       nbodyfft.cpp:16
+    double bw2;           // (1*bw+mn) - (0*bw+mn)            nbodyfft.cpp:79-80
+    double h;             // node spacing bw/p               nbodyfft.cpp:40
+    double inv_norm;      // 1/M^dims, folded into the kernel spectra (nbodyfft.cpp:202-203)
+    float bwf;
+    int B, G, M, p, xbits, nb, ok;
+    int sort_bits;        // radix digit width: the key (dims*xbits bits) is sorted in exactly two LSD passes
+    int pad_;
+    float s[PMAX];        // in-box node positions (k+1/2)/p, accumulated like nbodyfft.cpp:30-34
+    float inv_den[PMAX];  // 1/prod_{j!=i}(s_i-s_j)          nbodyfft.cpp:313-321
+};
+
+struct StepParams {
+    float alpha;          // exaggeration on P
+    float momentum, lr, max_step_norm;
+    int mode;             // FITSNE_STEP_*
+    float inv_df;
+};
+
+struct Scalars {          // small device-resident results
+    double Z;             // sum_Q (tsne.cpp:1112)
+    float inv_Z;
+    float pad;
+    double mean[2];
+    float bmin, bmax;     // bounds of the current Y (with the 2-D scan quirk)
+    double kl;
+};
+
+// ------------------------------------------------------------------------------------------ helpers --
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum (fixed tree).  sm must hold 32 values.  Result valid in thread 0.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *sm) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    T r = 0;
+    if (w == 0) {
+        r = lane < nw ? sm[lane] : T(0);
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// box index and in-box coordinate of one coordinate, fp64, reference operation order
+// (nbodyfft.cpp:86-113 / :350-363); __d*_rn keeps nvcc from contracting into FMAs the CPU does not use.
+template <bool CLAMP_LOW>
+__device__ __forceinline__ int box_of(float y, const GridParams &gp, float &u) {
+    const double yd = (double) y;
+    int idx = (int) __ddiv_rn(__dsub_rn(yd, gp.mn), gp.bw2);
+    if (idx >= gp.B) idx = gp.B - 1;
+    else if (CLAMP_LOW && idx < 0) idx = 0;
+    if (!CLAMP_LOW && idx < 0) idx = 0;   // 1-D reference has no lower clamp (would index out of bounds); y>=min there
+    const double lower = __dadd_rn(__dmul_rn((double) idx, gp.bw), gp.mn);
+    u = (float) __ddiv_rn(__dsub_rn(yd, lower), gp.bw2);
+    return idx;
+}
+
+// ------------------------------------------------------------------------- column sums, centring, bounds --
+
+// partial[b*D+d] = sum of Y[:,d] over block b's contiguous slice (fixed order -> deterministic)
+template <int D>
+__global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ Y, int N, double *__restrict__ partial) {
+    __shared__ double sm[32];
+    const int per = (N + gridDim.x - 1) / gridDim.x;
+    const int b = blockIdx.x * per, e = min(N, b + per);
+    double s0 = 0, s1 = 0;
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+        if (D == 2) {
+            float2 v = reinterpret_cast<const float2 *>(Y)[i];
+            s0 += v.x; s1 += v.y;
+        } else s0 += Y[i];
+    }
+    double r0 = block_sum(s0, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x * D] = r0;
+    if (D == 2) {
+        double r1 = block_sum(s1, sm);
+        if (threadIdx.x == 0) partial[blockIdx.x * D + 1] = r1;
+    }
+}
+
+// Yout = Yin - mean (tsne.cpp:1851-1876) and per-block (min,max) of the centred values.
+// 2-D min follows the reference's `if (>max) .. else if (<min)` scan (tsne.cpp:1045-1048): values in the
+// strictly ascending prefix of the interleaved sequence x0,y0,x1,y1,... only ever update max, so the min is
+// taken over flat indices >= t, t = length of that prefix.  1-D uses plain min/max (tsne.cpp:769-772).
+template <int D>
+__global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__ Yin, float *__restrict__ Yout, int N,
+                                                       const double *__restrict__ colsum_partial, int nparts,
+                                                       int do_center, float2 *__restrict__ bounds_partial,
+                                                       Scalars *__restrict__ sc) {
+    __shared__ double smd[32];
+    __shared__ float smf[64];
+    __shared__ double mean_s[2];
+    __shared__ int t_s;
+    double mean[2] = {0, 0};
+    if (do_center) {
+        // every block re-reduces the (few hundred) partials in the same fixed order
+        for (int d = 0; d < D; d++) {
+            double s = 0;
+            for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += colsum_partial[i * D + d];
+            double r = block_sum(s, smd);
+            if (threadIdx.x == 0) mean_s[d] = r / (double) N;
+        }
+        __syncthreads();
+        for (int d = 0; d < D; d++) mean[d] = mean_s[d];
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sc->mean[0] = mean[0]; sc->mean[1] = mean[1]; }
+    }
+    const int nflat = N * D;
+    if (threadIdx.x == 0) {
+        int t = 0;
+        if (D == 2) {
+            float run = -INFINITY;
+            while (t < nflat) {
+                float v = (float) ((double) Yin[t] - mean[t & 1]);
+                if (v > run) { run = v; t++; } else break;
+            }
+        }
+        t_s = t;
+    }
+    __syncthreads();
+    const int t0 = t_s;
+    float mn = INFINITY, mx = -INFINITY;
+    const int per = (N + gridDim.x - 1) / gridDim.x;
+    const int b = blockIdx.x * per, e = min(N, b + per);
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+        if (D == 2) {
+            float2 v = reinterpret_cast<const float2 *>(Yin)[i];
+            v.x = (float) ((double) v.x - mean[0]);
+            v.y = (float) ((double) v.y - mean[1]);
+            if (do_center) reinterpret_cast<float2 *>(Yout)[i] = v;
+            mx = fmaxf(mx, fmaxf(v.x, v.y));
+            if (2 * i >= t0) mn = fminf(mn, v.x);
+            if (2 * i + 1 >= t0) mn = fminf(mn, v.y);
+        } else {
+            float v = (float) ((double) Yin[i] - mean[0]);
+            if (do_center) Yout[i] = v;
+            mx = fmaxf(mx, v);
+            mn = fminf(mn, v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { smf[w] = mn; smf[32 + w] = mx; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        mn = lane < nw ? smf[lane] : INFINITY;
+        mx = lane < nw ? smf[32 + lane] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) bounds_partial[blockIdx.x] = make_float2(mn, mx);
+    }
+}
+
+// Reduce the per-block bounds; publish them to the device scalars and to a host-mapped word pair.
+__global__ void __launch_bounds__(256) k_reduce_bounds(const float2 *__restrict__ bounds_partial, int nparts,
+                                                       Scalars *__restrict__ sc, volatile float *host_bounds) {
+    __shared__ float smf[64];
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+        float2 v = bounds_partial[i];
+        mn = fminf(mn, v.x); mx = fmaxf(mx, v.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { smf[w] = mn; smf[32 + w] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int) (blockDim.x >> 5); i++) { mn = fminf(mn, smf[i]); mx = fmaxf(mx, smf[32 + i]); }
+        sc->bmin = mn; sc->bmax = mx;
+        if (host_bounds) { host_bounds[0] = mn; host_bounds[1] = mx; }
+    }
+}
+
+// n_boxes exactly as the reference picks it (tsne.cpp:1065-1077 in 2-D, :774 in 1-D)
+__host__ __device__ inline int choose_n_boxes(double mn, double mx, double ipi, int min_int, int dims) {
+    const int allowed[20] = {25, 36, 50, 55, 60, 65, 70, 75, 80, 85, 90, 96, 100, 110, 120, 130, 140, 150, 175, 200};
+    double v = (mx - mn) / ipi;
+    double m = (double) min_int > v ? (double) min_int : v;   // fmax(min_num_intervals, span/ipi)
+    if (v != v) m = (double) min_int;
+    int n = (int) m;
+    if (dims == 2 && n < allowed[19]) {
+        int c = 0;
+        while (allowed[c] < n) c++;
+        n = allowed[c];
+    }
+    return n;
+}
+
+// Two LSD passes always (so the launch sequence does not depend on B): digit width = ceil(key bits / 2).
+__host__ __device__ inline int sort_bits_for(int B, int dims) {
+    int xb = 0;
+    while ((1 << xb) < B) xb++;
+    const int kb = dims * xb > 1 ? dims * xb : 1;
+    return (kb + 1) / 2;
+}
+
+// Fill GridParams for a grid of B boxes/dim (the host's choice; verified against the device's own bounds).
+__global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restrict__ sc, const int *__restrict__ B_host, int M, int p, int dims,
+                             double ipi, int min_int, int *__restrict__ mismatch) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int B = *reinterpret_cast<const volatile int *>(B_host);
+    const double mn = (double) sc->bmin, mx = (double) sc->bmax;
+    const int want = choose_n_boxes(mn, mx, ipi, min_int, dims);
+    gp->ok = (want == B) && (2 * B * p <= M);
+    if (!gp->ok) *mismatch = want;
+    gp->mn = mn; gp->mx = mx;
+    gp->B = B; gp->p = p; gp->G = B * p; gp->M = M;
+    const double bw = __ddiv_rn(__dsub_rn(mx, mn), (double) B);
+    gp->bw = bw;
+    const double lo0 = __dadd_rn(__dmul_rn(0.0, bw), mn);
+    gp->bw2 = __dsub_rn(__dadd_rn(__dmul_rn(1.0, bw), mn), lo0);
+    gp->bwf = (float) bw;
+    gp->h = __dmul_rn(__ddiv_rn(1.0, (double) p), bw);
+    gp->inv_norm = dims == 2 ? 1.0 / ((double) M * (double) M) : 1.0 / (double) M;
+    int xb = 0;
+    while ((1 << xb) < B) xb++;
+    gp->xbits = xb;
+    gp->sort_bits = sort_bits_for(B, dims);
+    gp->pad_ = 0;
+    gp->nb = dims == 2 ? B * B : B;
+    double s[PMAX];
+    const double hh = 1.0 / (double) p;
+    s[0] = hh / 2;
+    for (int i = 1; i < p; i++) s[i] = s[i - 1] + hh;
+    for (int i = 0; i < p; i++) {
+        double den = 1;
+        for (int j = 0; j < p; j++) if (i != j) den *= s[i] - s[j];
+        gp->s[i] = (float) s[i];
+        gp->inv_den[i] = (float) (1.0 / den);
+    }
+}
+
+// -------------------------------------------------------------------------------------------- binning --
+
+// key = (by << xbits) | bx : least-significant digit is the x box, most-significant the y box
+template <int D>
+__global__ void __launch_bounds__(256) k_bin(const float *__restrict__ Y, int first, int n,
+                                             const GridParams *__restrict__ gpp, uint32_t *__restrict__ keys) {
+    const GridParams &gp = *gpp;
+    if (!gp.ok) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float u;
+    if (D == 2) {
+        const float2 y = reinterpret_cast<const float2 *>(Y)[first + k];
+        const int bx = box_of<true>(y.x, gp, u);
+        const int by = box_of<true>(y.y, gp, u);
+        keys[k] = ((uint32_t) by << gp.xbits) | (uint32_t) bx;
+    } else {
+        keys[k] = (uint32_t) box_of<false>(Y[first + k], gp, u);
+    }
+}
+
+// ----------------------------------------------------------------------------------------- radix sort --
+// Stable LSD radix sort of (key, point index) pairs, one digit of `bits` (<= 11) bits per pass:
+// per-tile digit histogram -> exclusive scan in digit-major order -> stable scatter.  Stability (ties keep
+// point-index order) makes the box-sorted order, hence the spread's summation order, bitwise repeatable.
+
+__global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint32_t *__restrict__ keys, int n, int pass,
+                                                             uint32_t *__restrict__ hist, int tiles,
+                                                             const GridParams *__restrict__ gpp) {
+    if (!gpp->ok) return;
+    __shared__ uint32_t cnt[1 << SORT_MAX_BITS];
+    const int bits = gpp->sort_bits, shift = pass * bits;
+    const int nb = 1 << bits;
+    for (int i = threadIdx.x; i < nb; i += SORT_THREADS) cnt[i] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * SORT_TILE;
+    const uint32_t mask = (uint32_t) nb - 1;
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; r++) {
+        const int i = base + r * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += SORT_THREADS) hist[(size_t) i * tiles + blockIdx.x] = cnt[i];
+}
+
+// Single-CTA exclusive scan of n u32 values, in place.  F transforms the loaded value (identity for the sort,
+// points->chunks for the spread work list).  out[n] receives the total when write_total != 0.
+struct ScanIdentity { __device__ uint32_t operator()(uint32_t v, uint32_t) const { return v; } };
+struct ScanChunks {   // input is box_start[]: element i -> ceil((start[i+1]-start[i]) / CHUNK)
+    __device__ uint32_t operator()(uint32_t v, uint32_t next) const { return (next - v + CHUNK - 1) / CHUNK; }
+};
+template <typename F, bool NEEDS_NEXT>
+__global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int tiles,
+                                                   int write_total, const GridParams *__restrict__ gpp, F f) {
+    if (!gpp->ok) return;
+    // length comes from the device-resident grid description: tiles>0 -> radix histogram (bins x tiles), else boxes
+    const int n = tiles > 0 ? (1 << gpp->sort_bits) * tiles : gpp->nb;
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s, total_s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    // rounds of 1024 threads x 4 consecutive elements, warp-shuffle scans, running carry
+    for (int base = 0; base < n; base += 4096) {
+        uint32_t v[4];
+        uint32_t tsum = 0;
+        const int i0 = base + threadIdx.x * 4;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = i0 + j;
+            uint32_t x = 0;
+            if (i < n) x = f(in[i], NEEDS_NEXT ? in[i + 1] : 0u);
+            v[j] = tsum;
+            tsum += x;
+        }
+        uint32_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t ws = wsum[lane];
+            uint32_t winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            wsum[lane] = winc - ws;   // exclusive prefix of the warp sums
+            if (lane == 31) total_s = winc;
+        }
+        __syncthreads();
+        const uint32_t excl = carry_s + wsum[w] + (inc - tsum);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = i0 + j;
+            if (i < n) out[i] = excl + v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += total_s;
+        __syncthreads();
+    }
+    if (write_total && threadIdx.x == 0) out[n] = carry_s;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t *__restrict__ keys_in,
+                                                                const uint32_t *__restrict__ vals_in,
+                                                                uint32_t *__restrict__ keys_out,
+                                                                uint32_t *__restrict__ vals_out, int n, int pass,
+                                                                const uint32_t *__restrict__ hist, int tiles,
+                                                                uint32_t val_base, const GridParams *__restrict__ gpp) {
+    if (!gpp->ok) return;
+    extern __shared__ uint32_t smem[];
+    const int bits = gpp->sort_bits, shift = pass * bits;
+    const int nb = 1 << bits;
+    constexpr int NW = SORT_THREADS / 32;
+    uint32_t *gbase = smem;                                          // [nb]
+    uint16_t *cnt = reinterpret_cast<uint16_t *>(smem + nb);         // [NW][nb]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < nb; i += SORT_THREADS) gbase[i] = hist[(size_t) i * tiles + blockIdx.x];
+    for (int i = threadIdx.x; i < NW * nb; i += SORT_THREADS) cnt[i] = 0;
+    __syncthreads();
+    const uint32_t mask = (uint32_t) nb - 1;
+    const int base = blockIdx.x * SORT_TILE + w * (SORT_IPT * 32);
+    uint32_t key[SORT_IPT], rank[SORT_IPT];
+    uint16_t *mycnt = cnt + w * nb;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; r++) {
+        const int i = base + r * 32 + lane;
+        const bool valid = i < n;
+        key[r] = valid ? keys_in[i] : 0xffffffffu;
+        const uint32_t d = valid ? ((key[r] >> shift) & mask) : (uint32_t) nb;   // sentinel digit groups the tail
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader && valid) {
+            old = mycnt[d];
+            mycnt[d] = (uint16_t) (old + __popc(peers));
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive prefix over warps, per digit
+    for (int d = threadIdx.x; d < nb; d += SORT_THREADS) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++) {
+            const uint32_t t = cnt[ww * nb + d];
+            cnt[ww * nb + d] = (uint16_t) run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; r++) {
+        const int i = base + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (key[r] >> shift) & mask;
+            const uint32_t pos = gbase[d] + mycnt[d] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = vals_in ? vals_in[i] : (val_base + (uint32_t) i);
+        }
+    }
+}
+
+// After the sort: box_start[] by boundary detection (no atomics, empty boxes included) and the in-box
+// coordinates in sorted order.  box id = by*B + bx.
+template <int D>
+__global__ void __launch_bounds__(256) k_post_sort(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ perm,
+                                                   const float *__restrict__ Y, int n,
+                                                   const GridParams *__restrict__ gpp, uint32_t *__restrict__ box_start,
+                                                   float *__restrict__ sorted_u) {
+    const GridParams &gp = *gpp;
+    if (!gp.ok) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t key = skeys[k];
+    const uint32_t xmask = (1u << gp.xbits) - 1u;
+    const int box = D == 2 ? (int) (key >> gp.xbits) * gp.B + (int) (key & xmask) : (int) key;
+    int lo;   // boxes (lo, box] start at k
+    if (k == 0) lo = -1;
+    else {
+        const uint32_t pk = skeys[k - 1];
+        lo = D == 2 ? (int) (pk >> gp.xbits) * gp.B + (int) (pk & xmask) : (int) pk;
+    }
+    for (int b = lo + 1; b <= box; b++) box_start[b] = (uint32_t) k;
+    if (k == n - 1) for (int b = box + 1; b <= gp.nb; b++) box_start[b] = (uint32_t) n;
+    const uint32_t pi = perm[k];
+    if (D == 2) {
+        const float2 y = reinterpret_cast<const float2 *>(Y)[pi];
+        float2 u;
+        box_of<true>(y.x, gp, u.x);
+        box_of<true>(y.y, gp, u.y);
+        reinterpret_cast<float2 *>(sorted_u)[k] = u;
+    } else {
+        float u;
+        box_of<false>(Y[pi], gp, u);
+        sorted_u[k] = u;
+    }
+}
+
+// --------------------------------------------------------------------------------------------- spread --
+
+template <int P>
+__device__ __forceinline__ float lagrange1(const GridParams &gp, int p, int j, float u) {
+    float v = gp.inv_den[j];
+    if (P > 0) {
+#pragma unroll
+        for (int k = 0; k < P; k++) if (k != j) v *= (u - gp.s[k]);
+    } else {
+        for (int k = 0; k < p; k++) if (k != j) v *= (u - gp.s[k]);
+    }
+    return v;
+}
+
+// One thread per (chunk of <= CHUNK box-sorted points, interpolation node): serial, fixed-order accumulation
+// of (L, L*bx, L*by, L*|b|^2) -- no atomics.  partial[chunk][node] is a float4.
+//   2-D: node = a*p + b, a = y node, b = x node.   1-D: node = a, components (L, L*b, L*b^2, 0).
+template <int D, int P>
+__global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__ sorted_u,
+                                                       const uint32_t *__restrict__ box_start,
+                                                       const uint32_t *__restrict__ chunk_off,
+                                                       const GridParams *__restrict__ gpp, int chunks_per_block,
+                                                       float4 *__restrict__ partial) {
+    __shared__ GridParams gps;
+    for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
+        reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
+    __syncthreads();
+    const GridParams &gp = gps;
+    if (!gp.ok) return;
+    const int p = P > 0 ? P : gp.p;
+    const int nodes = D == 2 ? p * p : p;
+    const int cl = threadIdx.x / nodes;
+    if (cl >= chunks_per_block) return;
+    const int node = threadIdx.x - cl * nodes;
+    const uint32_t c = (uint32_t) blockIdx.x * chunks_per_block + cl;
+    const int nb = gp.nb;
+    if (c >= chunk_off[nb]) return;
+    // last box b with chunk_off[b] <= c  (empty boxes repeat the offset, so search for the upper bound)
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_off[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int box = lo;
+    const uint32_t kb = box_start[box] + (c - chunk_off[box]) * CHUNK;
+    const uint32_t ke = min(kb + CHUNK, box_start[box + 1]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float bw = gp.bwf;
+    if (D == 2) {
+        const int a = node / p, b = node - a * p;
+        const float sa = gp.s[a], sb = gp.s[b];
+        for (uint32_t k = kb; k < ke; k++) {
+            const float2 u = reinterpret_cast<const float2 *>(sorted_u)[k];
+            const float L = lagrange1<P>(gp, p, a, u.y) * lagrange1<P>(gp, p, b, u.x);
+            const float ox = bw * (u.x - sb), oy = bw * (u.y - sa);
+            acc.x += L;
+            acc.y += L * ox;
+            acc.z += L * oy;
+            acc.w += L * (ox * ox + oy * oy);
+        }
+    } else {
+        const float sa = gp.s[node];
+        for (uint32_t k = kb; k < ke; k++) {
+            const float u = sorted_u[k];
+            const float L = lagrange1<P>(gp, p, node, u);
+            const float o = bw * (u - sa);
+            acc.x += L;
+            acc.y += L * o;
+            acc.z += L * o * o;
+        }
+    }
+    partial[(size_t) c * nodes + node] = acc;
+}
+
+// One thread per element of the zero-padded FFT input plane (M^D): inside the G^D corner, sum the node's
+// chunk partials in chunk order; outside, write the zero padding (so no memset is needed when G changes and
+// the launch shape depends on M only).  Grid row = y node, column = x node.
+// Multi-GPU (compact != nullptr): write instead a dense [n_fwd][Gcap^D] buffer (G^D values then zeros per
+// plane, Gcap = M/2) that is all-reduced and then expanded by k_pad_grids.
+template <int D>
+__global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ partial,
+                                                        const uint32_t *__restrict__ chunk_off,
+                                                        const GridParams *__restrict__ gpp, int n_fwd,
+                                                        float *__restrict__ fft_in, float *__restrict__ compact) {
+    const GridParams &gp = *gpp;
+    if (!gp.ok) return;
+    const int G = gp.G, p = gp.p, M = gp.M;
+    const size_t id = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
+    const int Gc = M / 2;
+    const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
+    int row = 0, col;
+    bool inside;
+    size_t out;
+    if (!compact) {
+        if (id >= plane) return;
+        if (D == 2) { row = (int) (id / M); col = (int) (id - (size_t) row * M); } else col = (int) id;
+        inside = col < G && row < G;
+        out = id;
+    } else {
+        if (id >= cplane) return;
+        const size_t GG = D == 2 ? (size_t) G * G : (size_t) G;
+        inside = id < GG;
+        if (D == 2) { row = (int) (id / G); col = (int) (id - (size_t) row * G); } else col = (int) id;
+        out = id;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) {
+        int box, node, nodes;
+        if (D == 2) {
+            const int by = row / p, a = row - by * p, bx = col / p, b = col - bx * p;
+            box = by * gp.B + bx; node = a * p + b; nodes = p * p;
+        } else {
+            box = col / p; node = col - box * p; nodes = p;
+        }
+        const uint32_t c0 = chunk_off[box], c1 = chunk_off[box + 1];
+        const float4 *src = partial + (size_t) c0 * nodes + node;
+        uint32_t c = c0;
+        for (; c + 4 <= c1; c += 4) {      // 4 independent loads in flight, summed in chunk order
+            const float4 v0 = src[0], v1 = src[nodes], v2 = src[2 * (size_t) nodes], v3 = src[3 * (size_t) nodes];
+            acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+            acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+            acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+            acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+            src += 4 * (size_t) nodes;
+        }
+        for (; c < c1; c++) {
+            const float4 v = *src;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            src += nodes;
+        }
+    }
+    float *dst = compact ? compact : fft_in;
+    const size_t stride = compact ? cplane : plane;
+    dst[out] = acc.x;
+    dst[stride + out] = acc.y;
+    dst[2 * stride + out] = acc.z;
+    if (n_fwd > 3) dst[3 * stride + out] = acc.w;
+}
+
+// multi-GPU: expand the all-reduced compact grids into the zero-padded FFT input planes
+template <int D>
+__global__ void __launch_bounds__(256) k_pad_grids(const float *__restrict__ compact, const GridParams *__restrict__ gpp,
+                                                   int n_fwd, float *__restrict__ fft_in) {
+    const GridParams &gp = *gpp;
+    if (!gp.ok) return;
+    const int G = gp.G, M = gp.M, Gc = M / 2;
+    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
+    const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
+    const size_t id = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= plane) return;
+    int row = 0, col;
+    if (D == 2) { row = (int) (id / M); col = (int) (id - (size_t) row * M); } else col = (int) id;
+    const bool inside = col < G && row < G;
+    const size_t src = D == 2 ? (size_t) row * G + col : (size_t) col;
+    for (int t = 0; t < n_fwd; t++) fft_in[t * plane + id] = inside ? compact[t * cplane + src] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------ kernel samples --
+// Real kernels on the wrap-around node-offset lattice, offsets d in (-G, G) stored at index d mod M
+// (the reference's 2G circulant embedding, nbodyfft.cpp:52-61, with M >= 2G).  Planes written at
+// fft_in[plane0 + j]:  j=0: Ksq=(1+r2/df)^-(df+1)   j=1..D: R_k*Ksq   j=D+1: Kb=(1+r2/df)^-df
+// (tsne.cpp:69-94).  Values carry the 1/M^D inverse-FFT normalisation.
+template <int D>
+__global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restrict__ gpp, double df, int plane0,
+                                                     float *__restrict__ fft_in) {
+    const GridParams &gp = *gpp;
+    if (!gp.ok) return;
+    const int M = gp.M, G = gp.G;
+    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
+    const size_t id = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= plane) return;
+    int r = 0, c;
+    if (D == 2) { r = (int) (id / M); c = (int) (id - (size_t) r * M); } else c = (int) id;
+    const int dc = c < G ? c : (c > M - G ? c - M : 0);
+    const int dr = r < G ? r : (r > M - G ? r - M : 0);
+    const bool valid = (c < G || c > M - G) && (D == 1 || r < G || r > M - G);
+    float *base = fft_in + (size_t) plane0 * plane + id;
+    if (!valid) {
+        for (int j = 0; j < D + 2; j++) base[j * plane] = 0.f;
+        return;
+    }
+    const double rx = gp.h * (double) dc, ry = gp.h * (double) dr;
+    const double r2 = rx * rx + (D == 2 ? ry * ry : 0.0);
+    double kb, ksq;
+    if (df == 1.0) {
+        kb = 1.0 / (1.0 + r2);
+        ksq = kb * kb;
+    } else {
+        const double t = 1.0 + r2 / df;
+        kb = pow(t, -df);
+        ksq = pow(t, -(df + 1.0));
+    }
+    kb *= gp.inv_norm; ksq *= gp.inv_norm;
+    base[0] = (float) ksq;
+    base[plane] = (float) (rx * ksq);
+    if (D == 2) base[2 * plane] = (float) (ry * ksq);
+    base[(D + 1) * plane] = (float) kb;
+}
+
+// ------------------------------------------------------------------------------ Hadamard + sum_Q terms --
+// spec planes: [0..n_fwd) = FFT of (w1, delta_1..D, [wbb]);  [ks..ks+D+2) = FFT of (Ksq, Kgrad_1..D, Kb).
+// Overwrites planes 0..D with  v1 = Ksq.w1,  B_k = Kgrad_k.w1 - Ksq.delta_k  and accumulates, by Parseval,
+//   df==1: <w1,Kb*w1> + 2<wbb,v1> + sum_k (4<delta_k,Kgrad_k*w1> - 2<delta_k,Ksq*delta_k>)   (tsne.cpp:1101-1110)
+//   df!=1: <w1,Kb*w1>                                                                          (tsne.cpp:950-955)
+// in fp64; half-spectrum columns 1..ceil(M/2)-1 count twice.
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double re_conj_mul(float2 a, float2 b) { return (double) a.x * (double) b.x + (double) a.y * (double) b.y; }
+
+template <int D>
+__global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ spec, const GridParams *__restrict__ gpp, int n_fwd,
+                                                  int ks, int df_is_one, double *__restrict__ zpartial) {
+    __shared__ double sm[32];
+    const GridParams &gp = *gpp;
+    if (!gp.ok) return;
+    const int M = gp.M, MH = M / 2 + 1;
+    const size_t nfreq = D == 2 ? (size_t) M * MH : (size_t) MH;
+    double zacc = 0;
+    for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < nfreq; e += (size_t) gridDim.x * blockDim.x) {
+        const int col = D == 2 ? (int) (e % MH) : (int) e;
+        const double wt = (col == 0 || (2 * col == M)) ? 1.0 : 2.0;
+        const float2 w1 = spec[e];
+        const float2 ksq = spec[(size_t) ks * nfreq + e];
+        const float2 kb = spec[(size_t) (ks + D + 1) * nfreq + e];
+        const float2 v1 = cmul(ksq, w1);
+        double z = re_conj_mul(w1, cmul(kb, w1));
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const float2 dk = spec[(size_t) (1 + k) * nfreq + e];
+            const float2 kg = spec[(size_t) (ks + 1 + k) * nfreq + e];
+            const float2 kgw = cmul(kg, w1);
+            const float2 ksd = cmul(ksq, dk);
+            if (df_is_one) z += 4.0 * re_conj_mul(dk, kgw) - 2.0 * re_conj_mul(dk, ksd);
+            spec[(size_t) (1 + k) * nfreq + e] = make_float2(kgw.x - ksd.x, kgw.y - ksd.y);
+        }
+        if (df_is_one) {
+            const float2 wbb = spec[(size_t) (1 + D) * nfreq + e];
+            z += 2.0 * re_conj_mul(wbb, v1);
+        }
+        spec[e] = v1;
+        zacc += wt * z;
+    }
+    const double r = block_sum(zacc, sm);
+    if (threadIdx.x == 0) zpartial[blockIdx.x] = r;
+}
+
+__global__ void __launch_bounds__(256) k_finalize_z(const double *__restrict__ zpartial, int nparts, int N,
+                                                    const GridParams *__restrict__ gpp, Scalars *__restrict__ sc) {
+    __shared__ double sm[32];
+    if (!gpp->ok) return;
+    double s = 0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += zpartial[i];
+    const double r = block_sum(s, sm);
+    if (threadIdx.x == 0) {
+        const double Z = r - (double) N;      // "- N": the sums include i == j (tsne.cpp:1110)
+        sc->Z = Z;
+        sc->inv_Z = (float) (1.0 / Z);
+    }
+}
+
+// --------------------------------------------------------------------------------------------- gather --
+// One thread per box-sorted point: F_rep/Z = (1/Z) sum_nodes L * (a_k * v1 + B_k) with a = y - X_node;
+// written to the point's ORIGINAL index (frep[perm[k]]), so the update runs coalesced in point order.
+template <int D, int P>
+__global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
+                                                const uint32_t *__restrict__ perm, int n,
+                                                const GridParams *__restrict__ gpp, const Scalars *__restrict__ sc,
+                                                const float *__restrict__ fft_out, float *__restrict__ frep) {
+    __shared__ GridParams gps;
+    for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
+        reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
+    __syncthreads();
+    const GridParams &gp = gps;
+    if (!gp.ok) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int p = P > 0 ? P : gp.p;
+    const int M = gp.M;
+    const float bw = gp.bwf, inv_Z = sc->inv_Z;
+    const uint32_t key = skeys[k];
+    if (D == 2) {
+        const size_t plane = (size_t) M * M;
+        const int by = (int) (key >> gp.xbits), bx = (int) (key & ((1u << gp.xbits) - 1u));
+        const float2 u = reinterpret_cast<const float2 *>(sorted_u)[k];
+        float Lx[P > 0 ? P : PMAX], ox[P > 0 ? P : PMAX];
+#pragma unroll(P > 0 ? P : 1)
+        for (int b = 0; b < (P > 0 ? P : PMAX); b++) {
+            if (b < p) { Lx[b] = lagrange1<P>(gp, p, b, u.x); ox[b] = bw * (u.x - gp.s[b]); }
+        }
+        float fx = 0.f, fy = 0.f;
+        const float *g0 = fft_out + (size_t) (by * p) * M + bx * p;
+#pragma unroll(P > 0 ? P : 1)
+        for (int a = 0; a < (P > 0 ? P : PMAX); a++) {
+            if (a < p) {
+                const float Ly = lagrange1<P>(gp, p, a, u.y);
+                const float oy = bw * (u.y - gp.s[a]);
+                const float *row = g0 + (size_t) a * M;
+#pragma unroll(P > 0 ? P : 1)
+                for (int b = 0; b < (P > 0 ? P : PMAX); b++) {
+                    if (b < p) {
+                        const float L = Ly * Lx[b];
+                        const float v1 = __ldg(row + b), Bx = __ldg(row + plane + b), By = __ldg(row + 2 * plane + b);
+                        fx += L * (ox[b] * v1 + Bx);
+                        fy += L * (oy * v1 + By);
+                    }
+                }
+            }
+        }
+        reinterpret_cast<float2 *>(frep)[perm[k]] = make_float2(fx * inv_Z, fy * inv_Z);
+    } else {
+        const float u = sorted_u[k];
+        const float *g0 = fft_out + (size_t) key * p;
+        float f = 0.f;
+        for (int a = 0; a < p; a++) {
+            const float L = lagrange1<P>(gp, p, a, u);
+            const float o = bw * (u - gp.s[a]);
+            f += L * (o * __ldg(g0 + a) + __ldg(g0 + M + a));
+        }
+        frep[perm[k]] = f * inv_Z;
+    }
+}
+
+// ------------------------------------------------------------------- attractive term + optimiser step --
+// LPR lanes cooperate on one CSR row: F_attr = sum_j p_ij q_ij (y_i - y_j), q = 1/(1+d2/df)
+// (tsne.cpp:1121-1137), then dC = alpha*F_attr - F_rep/Z (tsne.cpp:1153-1154) and either
+//   UPDATE=false: write dC (parity entry point), or
+//   UPDATE=true : gains / momentum / clipping / Y += uY  (tsne.cpp:479-513) into Ynext (un-centred).
+// Row offsets are local to this rank's edge slice: edges of row i are [row_P[i]-edge_base, row_P[i+1]-edge_base).
+__device__ __forceinline__ float sgnf(float x) { return x == 0.f ? 0.f : (x < 0.f ? -1.f : 1.f); }
+
+template <int D, int LPR, bool UPDATE>
+__global__ void __launch_bounds__(256) k_attract_update(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
+                                                        const float *__restrict__ val_P, uint32_t edge_base,
+                                                        const float *__restrict__ Y, const float *__restrict__ frep,
+                                                        int row_begin, int row_end, const StepParams *__restrict__ spp,
+                                                        const GridParams *__restrict__ gpp,
+                                                        float *__restrict__ dC_out, float *__restrict__ uY,
+                                                        float *__restrict__ gains, float *__restrict__ Ynext) {
+    if (!gpp->ok) return;
+    const StepParams sp = *spp;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = gid % LPR;
+    const int row = row_begin + gid / LPR;
+    const bool active = row < row_end;
+    float ax = 0.f, ay = 0.f;
+    float yix = 0.f, yiy = 0.f;
+    if (active) {
+        if (D == 2) { const float2 yi = reinterpret_cast<const float2 *>(Y)[row]; yix = yi.x; yiy = yi.y; }
+        else yix = Y[row];
+        const uint32_t e0 = row_P[row] - edge_base, e1 = row_P[row + 1] - edge_base;
+        for (uint32_t e = e0 + sub; e < e1; e += LPR) {
+            const uint32_t j = col_P[e];
+            const float pv = val_P[e];
+            if (D == 2) {
+                const float2 yj = __ldg(reinterpret_cast<const float2 *>(Y) + j);
+                const float dx = yix - yj.x, dy = yiy - yj.y;
+                const float q = pv / (1.f + (dx * dx + dy * dy) * sp.inv_df);
+                ax += q * dx; ay += q * dy;
+            } else {
+                const float dx = yix - __ldg(Y + j);
+                const float q = pv / (1.f + dx * dx * sp.inv_df);
+                ax += q * dx;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        if (D == 2) ay += __shfl_xor_sync(0xffffffffu, ay, o);
+    }
+    if (!active || sub != 0) return;
+    float d0, d1 = 0.f;
+    if (D == 2) {
+        const float2 fr = reinterpret_cast<const float2 *>(frep)[row];
+        d0 = sp.alpha * ax - fr.x; d1 = sp.alpha * ay - fr.y;
+    } else d0 = sp.alpha * ax - frep[row];
+    if (!UPDATE) {
+        if (D == 2) reinterpret_cast<float2 *>(dC_out)[row] = make_float2(d0, d1);
+        else dC_out[row] = d0;
+        return;
+    }
+    if (sp.mode == 2) {   // plain gradient descent, no learning rate (tsne.cpp:489)
+        if (D == 2) reinterpret_cast<float2 *>(Ynext)[row] = make_float2(yix - d0, yiy - d1);
+        else Ynext[row] = yix - d0;
+        return;
+    }
+    float u0, u1 = 0.f, g0, g1 = 1.f;
+    if (D == 2) {
+        const float2 u = reinterpret_cast<const float2 *>(uY)[row], g = reinterpret_cast<const float2 *>(gains)[row];
+        u0 = u.x; u1 = u.y; g0 = g.x; g1 = g.y;
+    } else { u0 = uY[row]; g0 = gains[row]; }
+    g0 = (sgnf(d0) != sgnf(u0)) ? (g0 + .2f) : (g0 * .8f);
+    if (g0 < .01f) g0 = .01f;
+    u0 = sp.momentum * u0 - sp.lr * g0 * d0;
+    if (D == 2) {
+        g1 = (sgnf(d1) != sgnf(u1)) ? (g1 + .2f) : (g1 * .8f);
+        if (g1 < .01f) g1 = .01f;
+        u1 = sp.momentum * u1 - sp.lr * g1 * d1;
+    }
+    if (sp.mode == 0 && sp.max_step_norm > 0.f) {
+        const float step = sqrtf(u0 * u0 + u1 * u1);
+        if (step > sp.max_step_norm) { const float f = sp.max_step_norm / step; u0 *= f; u1 *= f; }
+    }
+    if (D == 2) {
+        reinterpret_cast<float2 *>(gains)[row] = make_float2(g0, g1);
+        reinterpret_cast<float2 *>(uY)[row] = make_float2(u0, u1);
+        reinterpret_cast<float2 *>(Ynext)[row] = make_float2(yix + u0, yiy + u1);
+    } else {
+        gains[row] = g0; uY[row] = u0; Ynext[row] = yix + u0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ KL --
+// sum_edges (alpha p) log((alpha p + FLT_MIN) / (q + FLT_MIN)), q = (1+d2/df)^-df / sum_Q  (tsne.cpp:1340-1348);
+// per-row sums in fp64, per-block partials reduced in fixed order by k_finalize_kl.
+template <int D>
+__global__ void __launch_bounds__(256) k_kl(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
+                                            const float *__restrict__ val_P, uint32_t edge_base, const float *__restrict__ Y,
+                                            int row_begin, int row_end, double alpha, double df,
+                                            const Scalars *__restrict__ sc, double *__restrict__ partial) {
+    __shared__ double sm[32];
+    const double Z = sc->Z;
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    double acc = 0;
+    for (int row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_end; row += warps_total) {
+        float yix, yiy = 0.f;
+        if (D == 2) { const float2 yi = reinterpret_cast<const float2 *>(Y)[row]; yix = yi.x; yiy = yi.y; }
+        else yix = Y[row];
+        const uint32_t e0 = row_P[row] - edge_base, e1 = row_P[row + 1] - edge_base;
+        for (uint32_t e = e0 + lane; e < e1; e += 32) {
+            const uint32_t j = col_P[e];
+            const double pv = alpha * (double) val_P[e];
+            double d2;
+            if (D == 2) {
+                const float2 yj = reinterpret_cast<const float2 *>(Y)[j];
+                const double dx = (double) yix - (double) yj.x, dy = (double) yiy - (double) yj.y;
+                d2 = dx * dx + dy * dy;
+            } else {
+                const double dx = (double) yix - (double) Y[j];
+                d2 = dx * dx;
+            }
+            double q = 1.0 / (1.0 + d2 / df);
+            if (df != 1.0) q = pow(q, df);
+            q /= Z;
+            acc += pv * log((pv + (double) FLT_MIN) / (q + (double) FLT_MIN));
+        }
+    }
+    const double r = block_sum(acc, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+__global__ void __launch_bounds__(256) k_finalize_kl(const double *__restrict__ partial, int nparts, Scalars *__restrict__ sc) {
+    __shared__ double sm[32];
+    double s = 0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
+    const double r = block_sum(s, sm);
+    if (threadIdx.x == 0) sc->kl = r;
+}
+
+// max row sum of P for the automatic exaggeration coefficient (tsne.cpp:392-399)
+__global__ void __launch_bounds__(256) k_row_sum_max(const uint32_t *__restrict__ row_P, const float *__restrict__ val_P,
+                                                     uint32_t edge_base, int row_begin, int row_end,
+                                                     double *__restrict__ partial) {
+    __shared__ double sm[32];
+    double mx = 0;
+    for (int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += gridDim.x * blockDim.x) {
+        double s = 0;
+        for (uint32_t e = row_P[row] - edge_base; e < row_P[row + 1] - edge_base; e++) s += (double) val_P[e];
+        mx = fmax(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int) (blockDim.x >> 5); i++) mx = fmax(mx, sm[i]);
+        partial[blockIdx.x] = mx;
+    }
+}
+
+// fp64 host data <-> fp32 device data
+__global__ void k_d2f(const double *__restrict__ in, float *__restrict__ out, size_t n) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float) in[i];
+}
+__global__ void k_f2d(const float *__restrict__ in, double *__restrict__ out, size_t n) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double) in[i];
+}
+__global__ void k_fill(float *__restrict__ out, float v, size_t n) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+}  // namespace fk

@@ -1,0 +1,241 @@
+"""fitsne_b200 -- ctypes binding of libfitsne_b200.so (include/fitsne_b200.h).
+
+Python-side mirror of the C ABI that replaces the per-iteration loop of the reference's TSNE::run
+(/root/reference/src/tsne.cpp:437-577).  This module holds no numerics: every call goes to the CUDA library,
+and importing/using it without the built library or without a CUDA device raises -- there is no CPU fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfitsne_b200.so")
+
+STEP_MOMENTUM_CLIP, STEP_MOMENTUM, STEP_PLAIN_GD = 0, 1, 2
+FLAG_NO_GRAPH, FLAG_TIMERS = 1, 2
+PHASES = ["bounds", "sort", "spread", "kernel_spectrum", "fft", "gather", "attract_update", "center", "kl",
+          "collectives"]
+
+EXPORTS = [
+    "fitsne_create", "fitsne_create_sharded", "fitsne_nccl_unique_id", "fitsne_destroy", "fitsne_last_error",
+    "fitsne_set_Y", "fitsne_get_Y", "fitsne_set_optimizer_state", "fitsne_get_optimizer_state", "fitsne_gradient",
+    "fitsne_step", "fitsne_kl", "fitsne_run", "fitsne_run_host", "fitsne_synchronize", "fitsne_get_stats",
+    "fitsne_reset_stats", "fitsne_last_run_ms", "fitsne_debug_copy", "fitsne_version",
+]
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("nterms", ctypes.c_int), ("intervals_per_integer", ctypes.c_double),
+                ("min_num_intervals", ctypes.c_int), ("df", ctypes.c_double), ("device", ctypes.c_int),
+                ("flags", ctypes.c_int)]
+
+
+class StepParams(ctypes.Structure):
+    _fields_ = [("exaggeration", ctypes.c_double), ("momentum", ctypes.c_double), ("learning_rate", ctypes.c_double),
+                ("max_step_norm", ctypes.c_double), ("mode", ctypes.c_int)]
+
+
+class Schedule(ctypes.Structure):
+    _fields_ = [("max_iter", ctypes.c_int), ("stop_lying_iter", ctypes.c_int), ("mom_switch_iter", ctypes.c_int),
+                ("start_late_exag_iter", ctypes.c_int), ("momentum", ctypes.c_double),
+                ("final_momentum", ctypes.c_double), ("learning_rate", ctypes.c_double),
+                ("early_exag_coeff", ctypes.c_double), ("late_exag_coeff", ctypes.c_double),
+                ("max_step_norm", ctypes.c_double), ("no_momentum_during_exag", ctypes.c_int),
+                ("verbose", ctypes.c_int)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("iterations", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
+                ("graph_launches", ctypes.c_uint64), ("regrids", ctypes.c_uint64), ("n_boxes", ctypes.c_int),
+                ("grid_side", ctypes.c_int), ("fft_side", ctypes.c_int), ("min_coord", ctypes.c_double),
+                ("max_coord", ctypes.c_double), ("phase_ms", ctypes.c_double * 16)]
+
+
+class FitsneError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libfitsne_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the CUDA library; raises OSError if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is None:
+        lib = ctypes.CDLL(path or LIB_PATH)
+        lib.fitsne_last_error.restype = ctypes.c_char_p
+        lib.fitsne_last_error.argtypes = [ctypes.c_void_p]
+        lib.fitsne_version.restype = ctypes.c_char_p
+        _lib = lib
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def make_schedule(max_iter=750, stop_lying_iter=250, mom_switch_iter=250, start_late_exag_iter=-1, momentum=0.5,
+                  final_momentum=0.8, learning_rate=200.0, early_exag_coeff=12.0, late_exag_coeff=-1.0,
+                  max_step_norm=5.0, no_momentum_during_exag=False, verbose=False):
+    """Defaults are those of the reference wrapper (fast_tsne.py:19-51)."""
+    return Schedule(int(max_iter), int(stop_lying_iter), int(mom_switch_iter), int(start_late_exag_iter),
+                    float(momentum), float(final_momentum), float(learning_rate), float(early_exag_coeff),
+                    float(late_exag_coeff), float(max_step_norm), int(bool(no_momentum_during_exag)),
+                    int(bool(verbose)))
+
+
+def shard_range(N, rank, world):
+    per = (N + world - 1) // world
+    return rank * per, min(N, (rank + 1) * per)
+
+
+class FitSNE:
+    """Device-resident t-SNE optimiser state for a fixed CSR P (row_P, col_P, val_P as in tsne.cpp:168-170)."""
+
+    def __init__(self, row_P, col_P, val_P, Y0, nterms=3, intervals_per_integer=1.0, min_num_intervals=50, df=1.0,
+                 device=-1, flags=0, rank=0, world=1, nccl_id=None):
+        self._h = ctypes.c_void_p()
+        self._lib = load_library()
+        Y0 = np.ascontiguousarray(Y0, dtype=np.float64)
+        if Y0.ndim == 1:
+            Y0 = Y0[:, None]
+        self.N, self.no_dims = Y0.shape
+        row = np.ascontiguousarray(row_P, dtype=np.uint32)
+        if row.shape[0] != self.N + 1:
+            raise ValueError("row_P must have N+1 entries")
+        b, e = shard_range(self.N, rank, world)
+        col = np.ascontiguousarray(col_P, dtype=np.uint32)
+        val = np.ascontiguousarray(val_P, dtype=np.float64)
+        if world > 1 and col.shape[0] == int(row[-1]):   # full arrays given: slice this rank's edges
+            col = np.ascontiguousarray(col[row[b]:row[e]])
+            val = np.ascontiguousarray(val[row[b]:row[e]])
+        cfg = Config(int(nterms), float(intervals_per_integer), int(min_num_intervals), float(df), int(device),
+                     int(flags))
+        idbuf = None
+        if world > 1:
+            idbuf = (ctypes.c_char * 128).from_buffer_copy(bytes(nccl_id))
+        rc = self._lib.fitsne_create_sharded(ctypes.byref(cfg), self.N, self.no_dims, _dp(row),
+                                             _dp(col) if col.size else None, _dp(val) if val.size else None,
+                                             _dp(Y0), int(rank), int(world), int(b), int(e), idbuf,
+                                             ctypes.byref(self._h))
+        if rc != 0:
+            raise FitsneError(rc, self._lib.fitsne_last_error(None).decode())
+        self.row_begin, self.row_end = b, e
+
+    # -- plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise FitsneError(rc, self._lib.fitsne_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._lib.fitsne_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- state
+    def set_Y(self, Y):
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        assert Y.size == self.N * self.no_dims
+        self._ck(self._lib.fitsne_set_Y(self._h, _dp(Y)))
+
+    def get_Y(self):
+        Y = np.empty((self.N, self.no_dims))
+        self._ck(self._lib.fitsne_get_Y(self._h, _dp(Y)))
+        return Y
+
+    def set_optimizer_state(self, uY=None, gains=None):
+        uY = None if uY is None else np.ascontiguousarray(uY, dtype=np.float64)
+        gains = None if gains is None else np.ascontiguousarray(gains, dtype=np.float64)
+        self._ck(self._lib.fitsne_set_optimizer_state(self._h, _dp(uY), _dp(gains)))
+
+    def get_optimizer_state(self):
+        uY = np.empty((self.N, self.no_dims))
+        gains = np.empty((self.N, self.no_dims))
+        self._ck(self._lib.fitsne_get_optimizer_state(self._h, _dp(uY), _dp(gains)))
+        return uY, gains
+
+    # -- hot path
+    def gradient(self, exaggeration=1.0):
+        """(dC, sum_Q) for the current Y -- computeFftGradient* of the reference."""
+        dC = np.empty((self.N, self.no_dims))
+        z = ctypes.c_double(0)
+        self._ck(self._lib.fitsne_gradient(self._h, ctypes.c_double(exaggeration), _dp(dC), ctypes.byref(z)))
+        return dC, z.value
+
+    def step(self, exaggeration=1.0, momentum=0.5, learning_rate=200.0, max_step_norm=5.0, mode=STEP_MOMENTUM_CLIP):
+        sp = StepParams(float(exaggeration), float(momentum), float(learning_rate), float(max_step_norm), int(mode))
+        self._ck(self._lib.fitsne_step(self._h, ctypes.byref(sp)))
+
+    def kl(self, exaggeration=1.0):
+        c = ctypes.c_double(0)
+        self._ck(self._lib.fitsne_kl(self._h, ctypes.c_double(exaggeration), ctypes.byref(c)))
+        return c.value
+
+    def run(self, schedule=None, fetch_Y=True, **kw):
+        """The loop of TSNE::run; returns (Y or None, costs)."""
+        s = schedule or make_schedule(**kw)
+        costs = np.zeros(s.max_iter)
+        Y = np.empty((self.N, self.no_dims)) if fetch_Y else None
+        self._ck(self._lib.fitsne_run(self._h, ctypes.byref(s), _dp(costs), _dp(Y)))
+        return Y, costs
+
+    def synchronize(self):
+        self._ck(self._lib.fitsne_synchronize(self._h))
+
+    def last_run_ms(self):
+        ms = ctypes.c_double(0)
+        self._ck(self._lib.fitsne_last_run_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def stats(self):
+        st = Stats()
+        self._ck(self._lib.fitsne_get_stats(self._h, ctypes.byref(st)))
+        d = {k: getattr(st, k) for k, _ in Stats._fields_ if k != "phase_ms"}
+        d["phase_ms"] = {PHASES[i]: st.phase_ms[i] for i in range(len(PHASES))}
+        return d
+
+    def reset_stats(self):
+        self._ck(self._lib.fitsne_reset_stats(self._h))
+
+    def debug(self, what, dtype):
+        need = ctypes.c_size_t(0)
+        self._ck(self._lib.fitsne_debug_copy(self._h, what.encode(), None, 0, ctypes.byref(need)))
+        out = np.empty(need.value // np.dtype(dtype).itemsize, dtype=dtype)
+        self._ck(self._lib.fitsne_debug_copy(self._h, what.encode(), _dp(out), ctypes.c_size_t(out.nbytes),
+                                             ctypes.byref(need)))
+        return out
+
+
+def run_host(row_P, col_P, val_P, Y0, schedule=None, nterms=3, intervals_per_integer=1.0, min_num_intervals=50,
+             df=1.0, device=-1, flags=0, **kw):
+    """fitsne_run_host: host CSR P + host Y in, host Y + costs out (the call a patched tsne.cpp makes)."""
+    lib = load_library()
+    s = schedule or make_schedule(**kw)
+    Y = np.array(Y0, dtype=np.float64, order="C")
+    if Y.ndim == 1:
+        Y = Y[:, None]
+    N, d = Y.shape
+    row = np.ascontiguousarray(row_P, dtype=np.uint32)
+    col = np.ascontiguousarray(col_P, dtype=np.uint32)
+    val = np.ascontiguousarray(val_P, dtype=np.float64)
+    costs = np.zeros(s.max_iter)
+    cfg = Config(int(nterms), float(intervals_per_integer), int(min_num_intervals), float(df), int(device), int(flags))
+    rc = lib.fitsne_run_host(ctypes.byref(cfg), ctypes.byref(s), N, d, _dp(row), _dp(col), _dp(val), _dp(Y), _dp(costs))
+    if rc != 0:
+        raise FitsneError(rc, lib.fitsne_last_error(None).decode())
+    return Y, costs
