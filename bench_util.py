@@ -56,37 +56,60 @@ def early_embedding(N, dims, seed=2):
     return (rng.standard_normal((N, dims)) * 1e-4).astype(np.float32).astype(np.float64)
 
 
+def write_data_dat(path, X, theta=0.5, perplexity=30.0, perplexity_list=None, no_dims=2, max_iter=750,
+                   stop_lying_iter=250, mom_switch_iter=250, momentum=0.5, final_momentum=0.8, learning_rate=200.0,
+                   max_step_norm=5.0, K=-1, sigma=-1.0, nbody_algo=2, knn_algo=1, early_exag_coeff=12.0,
+                   no_momentum_during_exag=0, n_trees=50, search_k=-1, start_late_exag_iter=-1, late_exag_coeff=-1.0,
+                   nterms=3, intervals_per_integer=1.0, min_num_intervals=50, seed=-1, df=1.0, load_affinities=0,
+                   initialization=None):
+    """Our own writer of the data.dat protocol (field order and packing of /root/reference/fast_tsne.py:259-297,
+    read by src/tsne.cpp:1915-1985).  tests/test_protocol.py checks it byte for byte against the reference wrapper."""
+    import struct
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n, d = X.shape
+    with open(path, "wb") as f:
+        f.write(struct.pack("=i", n)); f.write(struct.pack("=i", d))
+        f.write(struct.pack("=d", theta)); f.write(struct.pack("=d", perplexity))
+        if perplexity == 0:
+            f.write(struct.pack("=i", len(perplexity_list)))
+            for pp in perplexity_list:
+                f.write(struct.pack("=d", pp))
+        f.write(struct.pack("=i", no_dims)); f.write(struct.pack("=i", max_iter))
+        f.write(struct.pack("=i", stop_lying_iter)); f.write(struct.pack("=i", mom_switch_iter))
+        f.write(struct.pack("=d", momentum)); f.write(struct.pack("=d", final_momentum))
+        f.write(struct.pack("=d", learning_rate)); f.write(struct.pack("=d", max_step_norm))
+        f.write(struct.pack("=i", K)); f.write(struct.pack("=d", sigma))
+        f.write(struct.pack("=i", nbody_algo)); f.write(struct.pack("=i", knn_algo))
+        f.write(struct.pack("=d", early_exag_coeff)); f.write(struct.pack("=i", no_momentum_during_exag))
+        f.write(struct.pack("=i", n_trees)); f.write(struct.pack("=i", search_k))
+        f.write(struct.pack("=i", start_late_exag_iter)); f.write(struct.pack("=d", late_exag_coeff))
+        f.write(struct.pack("=i", nterms)); f.write(struct.pack("=d", intervals_per_integer))
+        f.write(struct.pack("=i", min_num_intervals))
+        f.write(X.tobytes())
+        f.write(struct.pack("=i", seed)); f.write(struct.pack("=d", df)); f.write(struct.pack("=i", load_affinities))
+        if initialization is not None:
+            f.write(np.ascontiguousarray(initialization, dtype=np.float64).tobytes())
+
+
 def write_reference_inputs(dirname, row, col, val, Y0, max_iter, no_dims, learning_rate, stop_lying_iter,
                            mom_switch_iter, early_exag=12.0, df=1.0, nterms=3, ipi=1.0, min_int=50,
                            max_step_norm=5.0, start_late_exag_iter=-1, late_exag_coeff=-1.0, momentum=0.5,
                            final_momentum=0.8, no_momentum_during_exag=0):
-    """data.dat + P_row/P_col/P_val.dat for `fast_tsne <ver> data.dat result.dat <nthreads>` with
-    load_affinities=1 (byte layout: /root/reference/fast_tsne.py:259-297 == src/tsne.cpp:1915-1985)."""
+    """data.dat + P_row/P_col/P_val.dat for `fast_tsne 1.2.1 data.dat result.dat <nthreads>` with load_affinities=1
+    (the reference's own injection hook, src/tsne.cpp:236-281): X is an N x 1 dummy, kNN is bypassed."""
     import os
-    import struct
     os.makedirs(dirname, exist_ok=True)
     N = len(Y0)
     np.ascontiguousarray(row, np.uint32).tofile(os.path.join(dirname, "P_row.dat"))
     np.ascontiguousarray(col, np.uint32).tofile(os.path.join(dirname, "P_col.dat"))
     np.ascontiguousarray(val, np.float64).tofile(os.path.join(dirname, "P_val.dat"))
-    with open(os.path.join(dirname, "data.dat"), "wb") as f:
-        D = 1
-        f.write(struct.pack("=i", N)); f.write(struct.pack("=i", D))
-        f.write(struct.pack("=d", 0.5))            # theta
-        f.write(struct.pack("=d", -1.0))           # perplexity < 0: manual sigma/K branch (never reached with load)
-        f.write(struct.pack("=i", no_dims)); f.write(struct.pack("=i", max_iter))
-        f.write(struct.pack("=i", stop_lying_iter)); f.write(struct.pack("=i", mom_switch_iter))
-        f.write(struct.pack("=d", momentum)); f.write(struct.pack("=d", final_momentum))
-        f.write(struct.pack("=d", learning_rate)); f.write(struct.pack("=d", max_step_norm))
-        f.write(struct.pack("=i", 1)); f.write(struct.pack("=d", 1.0))     # K, sigma
-        f.write(struct.pack("=i", 2)); f.write(struct.pack("=i", 1))       # nbody_algo=FFT, knn_algo
-        f.write(struct.pack("=d", early_exag)); f.write(struct.pack("=i", no_momentum_during_exag))
-        f.write(struct.pack("=i", 1)); f.write(struct.pack("=i", 1))       # n_trees, search_k
-        f.write(struct.pack("=i", start_late_exag_iter)); f.write(struct.pack("=d", late_exag_coeff))
-        f.write(struct.pack("=i", nterms)); f.write(struct.pack("=d", ipi)); f.write(struct.pack("=i", min_int))
-        f.write(np.zeros(N * D, np.float64).tobytes())
-        f.write(struct.pack("=i", 42)); f.write(struct.pack("=d", df)); f.write(struct.pack("=i", 1))
-        f.write(np.ascontiguousarray(Y0, np.float64).tobytes())
+    write_data_dat(os.path.join(dirname, "data.dat"), np.zeros((N, 1)), theta=0.5, perplexity=-1.0, no_dims=no_dims,
+                   max_iter=max_iter, stop_lying_iter=stop_lying_iter, mom_switch_iter=mom_switch_iter, momentum=momentum,
+                   final_momentum=final_momentum, learning_rate=learning_rate, max_step_norm=max_step_norm, K=1, sigma=1.0,
+                   nbody_algo=2, knn_algo=1, early_exag_coeff=early_exag, no_momentum_during_exag=no_momentum_during_exag,
+                   n_trees=1, search_k=1, start_late_exag_iter=start_late_exag_iter, late_exag_coeff=late_exag_coeff,
+                   nterms=nterms, intervals_per_integer=ipi, min_num_intervals=min_int, seed=42, df=df, load_affinities=1,
+                   initialization=Y0)
 
 
 def read_result(path):

@@ -1,0 +1,73 @@
+"""bin/fast_tsne (our host shell + CUDA loop) driven through the reference's file protocol on a GPU box."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import bench_util
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "bin", "fast_tsne")
+
+
+def run_bin(cwd, threads=4):
+    out = subprocess.run([BIN, "1.2.1", "data.dat", "result.dat", str(threads)], cwd=cwd, capture_output=True, text=True)
+    return out
+
+
+def test_binary_with_injected_affinities_matches_reference_golden(tmp_path, golden_graph, golden_runs):
+    row, col, val, _ = golden_graph
+    g = golden_runs
+    name = "run2d_default"
+    kw = {k: v for k, v in zip(g[name + "__kwkeys"], g[name + "__kwvals"])}
+    bench_util.write_reference_inputs(str(tmp_path), row, col, val.astype(np.float64), g[name + "__Y0"].astype(np.float64),
+                                      max_iter=int(kw["max_iter"]), no_dims=2, learning_rate=kw["learning_rate"],
+                                      stop_lying_iter=int(kw["stop_lying_iter"]), mom_switch_iter=int(kw["mom_switch_iter"]),
+                                      early_exag=kw["early_exag_coeff"], max_step_norm=kw["max_step_norm"])
+    out = run_bin(tmp_path)
+    assert out.returncode == 0, out.stdout[-800:] + out.stderr[-400:]
+    assert "Iteration 50 (50 iterations in" in out.stdout and "Wrote the 3000 x 2 data matrix successfully." in out.stdout
+    Y, costs = bench_util.read_result(str(tmp_path / "result.dat"))
+    ref = g[name + "__costs"]
+    assert np.array_equal(costs != 0, ref != 0)
+    nz = ref != 0
+    assert np.all(np.abs(costs[nz] - ref[nz]) / ref[nz] < 1e-2)      # north_star: final KL within 1 %
+    assert Y.shape == (3000, 2) and abs(Y.mean()) < 1e-4
+
+
+def test_binary_end_to_end_from_raw_data(tmp_path):
+    """Full path: X -> (host) kNN + perplexity + symmetrise -> (B200) loop; clusters must come apart and KL must drop."""
+    rng = np.random.default_rng(0)
+    N, D, C = 2000, 20, 5
+    labels = rng.integers(0, C, N)
+    X = rng.standard_normal((C, D))[labels] * 6 + rng.standard_normal((N, D))
+    init = rng.standard_normal((N, 2)) * 1e-4
+    bench_util.write_data_dat(str(tmp_path / "data.dat"), X, perplexity=20.0, max_iter=300, stop_lying_iter=100, mom_switch_iter=100,
+                              learning_rate=200.0, knn_algo=2, seed=3, initialization=init, load_affinities=2)
+    out = run_bin(tmp_path)
+    assert out.returncode == 0, out.stdout[-800:] + out.stderr[-400:]
+    Y, costs = bench_util.read_result(str(tmp_path / "result.dat"))
+    kl = costs[costs != 0]
+    assert len(kl) == 6 and kl[-1] < kl[0] and kl[-1] < 2.0
+    cent = np.stack([Y[labels == c].mean(0) for c in range(C)])
+    within = np.mean([np.linalg.norm(Y[labels == c] - cent[c], axis=1).mean() for c in range(C)])
+    between = np.mean([np.linalg.norm(cent[a] - cent[b]) for a in range(C) for b in range(a + 1, C)])
+    assert between > 3 * within
+    # load_affinities=2 wrote the P files in the reference's layout (tsne.cpp:334-358)
+    r = np.fromfile(tmp_path / "P_row.dat", np.uint32)
+    assert len(r) == N + 1 and np.fromfile(tmp_path / "P_col.dat", np.uint32).size == r[-1]
+    assert abs(np.fromfile(tmp_path / "P_val.dat", np.float64).sum() - 1) < 1e-9
+
+
+def test_binary_rejects_bad_version_and_unsupported_modes(tmp_path):
+    out = subprocess.run([BIN, "1.0.0"], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode != 0 and "wrong version number" in out.stdout
+    X = np.random.default_rng(1).standard_normal((100, 4))
+    bench_util.write_data_dat(str(tmp_path / "data.dat"), X, perplexity=10.0, nbody_algo=1, max_iter=10)
+    out = run_bin(tmp_path)
+    assert out.returncode == 2 and "FFT-interpolation path only" in out.stdout
+    bench_util.write_data_dat(str(tmp_path / "data.dat"), X, perplexity=40.0, max_iter=10)
+    out = run_bin(tmp_path)
+    assert out.returncode == 1 and "Perplexity too large" in out.stdout       # tsne.cpp:128-131
