@@ -78,11 +78,13 @@ struct fitsne_ctx {
     int device = 0;
     bool df_is_one = true;
     int n_fwd = 0, n_kern = 0, n_inv = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;    // repulsive pipeline + update (high priority)
+    cudaStream_t stream2 = nullptr;   // attractive SpMV, concurrent with the repulsive pipeline (low priority)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     ncclComm_t comm = nullptr;
 
     // state (fp32)
-    float *Y = nullptr, *Yb = nullptr, *uY = nullptr, *gains = nullptr, *frep = nullptr, *dC = nullptr;
+    float *Y = nullptr, *Yb = nullptr, *uY = nullptr, *gains = nullptr, *frep = nullptr, *dC = nullptr, *attr = nullptr;
     size_t y_elems = 0;   // allocated elements per Y buffer (padded to per*world*D)
     // CSR
     uint32_t *row_P = nullptr, *col_P = nullptr;
@@ -93,10 +95,9 @@ struct fitsne_ctx {
     // sort / bins
     uint32_t *keys[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
     float *sorted_u = nullptr;
-    uint32_t *box_start = nullptr, *chunk_off = nullptr, *hist = nullptr;
+    uint32_t *box_start = nullptr, *hist = nullptr, *sort_totals = nullptr;
     size_t box_cap = 0, hist_cap = 0;
-    float4 *partial = nullptr;
-    size_t partial_cap = 0;
+    float4 *slots = nullptr;          // spread partials: [chunk][2][nodes]
     // grids
     float *fft_in = nullptr, *fft_out = nullptr, *compact = nullptr;
     float2 *spec = nullptr;
@@ -182,32 +183,19 @@ static inline size_t max_boxes_for(const fitsne_ctx *c, int M) {
     const size_t Bmax = (size_t) std::max(1, M / (2 * c->cfg.nterms));
     return c->D == 2 ? Bmax * Bmax : Bmax;
 }
-static inline size_t max_chunks_for(const fitsne_ctx *c, int M) {
-    return (size_t) c->nloc / CHUNK + std::min(max_boxes_for(c, M), (size_t) c->nloc) + 2;
-}
-
 static void drop_graphs(fitsne_ctx *c) {
     for (auto &g : c->graphs) cudaGraphExecDestroy(g.second.exec);
     c->graphs.clear();
 }
 
 static int ensure_grid_capacity(fitsne_ctx *c, int M) {
-    const int D = c->D, p = c->cfg.nterms;
+    const int D = c->D;
     const size_t nb = max_boxes_for(c, M);
     bool moved = false;
     if (nb + 2 > c->box_cap) {
         const size_t cap = nb + nb / 2 + 1024;
         CKRC(dev_alloc(c, &c->box_start, cap));
-        CKRC(dev_alloc(c, &c->chunk_off, cap));
         c->box_cap = cap;
-        moved = true;
-    }
-    const size_t nodes = D == 2 ? (size_t) p * p : (size_t) p;
-    const size_t maxchunks = max_chunks_for(c, M);
-    if (maxchunks * nodes > c->partial_cap) {
-        const size_t cap = maxchunks * nodes + maxchunks * nodes / 2;
-        CKRC(dev_alloc(c, &c->partial, cap));
-        c->partial_cap = cap;
         moved = true;
     }
     const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
@@ -260,13 +248,15 @@ static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int 
 
 template <int D, int P>
 static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, int M, const uint32_t *skeys, const uint32_t *sperm) {
+    (void) M;
     const int p = c->cfg.nterms;
     const int nodes = D == 2 ? p * p : p;
     if (!gather) {
         const int cpb = std::max(1, 256 / nodes);
-        const size_t maxchunks = max_chunks_for(c, M);
-        k_spread_chunks<D, P><<<cdiv(maxchunks, cpb), cpb * nodes, 0, c->stream>>>(c->sorted_u, c->box_start, c->chunk_off,
-                                                                                    c->gp, cpb, c->partial);
+        const int nchunks = cdiv(c->nloc, CHUNK);
+        k_spread_chunks<D, P><<<cdiv(nchunks, cpb), cpb * nodes, 0, c->stream>>>(c->sorted_u, skeys, c->box_start, c->nloc, c->gp, cpb,
+                                                                                  c->n_fwd, c->slots, c->fft_in,
+                                                                                  c->world > 1 ? c->compact : nullptr);
     } else {
         k_gather<D, P><<<cdiv(c->nloc, 256), 256, 0, c->stream>>>(c->sorted_u, skeys, sperm, c->nloc, c->gp, c->sc,
                                                                    c->fft_out, c->frep);
@@ -287,11 +277,12 @@ static int launch_spread_gather(fitsne_ctx *c, bool gather, int M, const uint32_
     }
 }
 
-template <int D, bool UPDATE>
-static int launch_attract(fitsne_ctx *c) {
+template <int D>
+static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
     const int rows = c->row_end - c->row_begin;
-#define ATT(L) k_attract_update<D, L, UPDATE><<<cdiv((long long) rows * L, 256), 256, 0, c->stream>>>( \
-        c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC, c->uY, c->gains, c->Yb)
+    const float inv_df = (float) (1.0 / c->cfg.df);
+#define ATT(L) k_attract<D, L><<<cdiv((long long) rows * L, 256), 256, 0, st>>>( \
+        c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->row_begin, c->row_end, inv_df, c->attr)
     switch (c->lpr) {
         case 4: ATT(4); break;
         case 8: ATT(8); break;
@@ -304,9 +295,19 @@ static int launch_attract(fitsne_ctx *c) {
     return 0;
 }
 
+// lanes per output node in k_spread_combine: more lanes when the grid is small (few, heavy boxes)
+static inline int combine_lanes(const fitsne_ctx *c, int M) {
+    const size_t plane = c->D == 2 ? (size_t) M * M : (size_t) M;
+    int lpn = 1;
+    while (lpn < 32 && plane * (size_t) (lpn * 2) <= (size_t) 148 * 2048 * 4) lpn *= 2;
+    return lpn;
+}
+
 // Everything from "bounds are known" to either dC (update=false) or the centred new Y and its bounds
 // (update=true).  B is only passed to k_setup_grid (which verifies it against the device's own bounds); every
 // launch shape below depends on M, the shard size and nterms only.  Pure stream work: capturable.
+// The attractive SpMV needs only Y and P, so it is forked onto a second, lower-priority stream and joins before
+// the update kernel: it overlaps the whole sort/spread/FFT/gather chain.
 template <int D>
 static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool update) {
     const int p = c->cfg.nterms, nloc = c->nloc;
@@ -314,42 +315,49 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     Plans *pl;
     CKRC(get_plans(c, M, &pl));
     const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
+    const bool overlap = !c->timing_this_iter;    // timers mode serialises everything to time each phase
+
+    if (overlap) {
+        CK(cudaEventRecord(c->ev_fork, st));
+        CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        CKRC(launch_attract<D>(c, c->stream2));
+        CK(cudaEventRecord(c->ev_join, c->stream2));
+    }
 
     phase_mark(c, FITSNE_PHASE_BOUNDS);
-    k_setup_grid<<<1, 32, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals, c->mismatch);
+    k_setup_grid<<<1, 256, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
+                                    c->mismatch, c->sort_totals);
     c->stats.kernel_launches += 1;
 
     // ---- bin + stable two-pass LSD radix sort by box
     phase_mark(c, FITSNE_PHASE_SORT);
-    k_bin<D><<<cdiv(nloc, 256), 256, 0, st>>>(c->Y, c->row_begin, nloc, c->gp, c->keys[0]);
     const int tiles = cdiv(nloc, SORT_TILE);
-    const size_t scatter_smem = (size_t) (1 << SORT_MAX_BITS) * 4 + (size_t) (SORT_THREADS / 32) * (1 << SORT_MAX_BITS) * 2;
-    int src = 0;
-    for (int ps = 0; ps < 2; ps++) {
-        k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[src], nloc, ps, c->hist, tiles, c->gp);
-        k_scan_u32<ScanIdentity, false><<<1, 1024, 0, st>>>(c->hist, c->hist, tiles, 0, c->gp, ScanIdentity());
-        k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[src], ps == 0 ? nullptr : c->perm[src], c->keys[src ^ 1],
-                                                                  c->perm[src ^ 1], nloc, ps, c->hist, tiles,
-                                                                  (uint32_t) c->row_begin, c->gp);
-        src ^= 1;
-        c->stats.kernel_launches += 3;
-    }
-    const uint32_t *skeys = c->keys[src], *sperm = c->perm[src];
+    const int max_bins = 1 << SORT_MAX_BITS;
+    const size_t scatter_smem = (size_t) max_bins * 4 + (size_t) (SORT_THREADS / 32) * max_bins * 2;
+    k_bin<D><<<tiles, SORT_THREADS, 0, st>>>(c->Y, c->row_begin, nloc, c->gp, c->keys[0], c->hist, tiles, c->sort_totals);
+    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, c->gp);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], nloc, 0, c->hist, tiles,
+                                                              (uint32_t) c->row_begin, c->gp);
+    k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[1], nloc, 1, c->hist, tiles, c->sort_totals + max_bins, c->gp);
+    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, c->gp);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], nloc, 1, c->hist, tiles,
+                                                              (uint32_t) c->row_begin, c->gp);
+    const uint32_t *skeys = c->keys[0], *sperm = c->perm[0];
     k_post_sort<D><<<cdiv(nloc, 256), 256, 0, st>>>(skeys, sperm, c->Y, nloc, c->gp, c->box_start, c->sorted_u);
-    k_scan_u32<ScanChunks, true><<<1, 1024, 0, st>>>(c->box_start, c->chunk_off, 0, 1, c->gp, ScanChunks());
-    c->stats.kernel_launches += 3;
+    c->stats.kernel_launches += 7;
     LAUNCH_CHECK();
 
     // ---- spread
     phase_mark(c, FITSNE_PHASE_SPREAD);
     CKRC(launch_spread_gather<D>(c, false, M, skeys, sperm));
+    const int lpn = combine_lanes(c, M);
     if (c->world == 1) {
-        k_spread_combine<D><<<cdiv(plane, 256), 256, 0, st>>>(c->partial, c->chunk_off, c->gp, c->n_fwd, c->fft_in, nullptr);
+        k_spread_combine<D><<<cdiv(plane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, c->n_fwd, lpn, c->fft_in, nullptr);
         c->stats.kernel_launches += 1;
     } else {
         const int Gc = M / 2;
         const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
-        k_spread_combine<D><<<cdiv(cplane, 256), 256, 0, st>>>(c->partial, c->chunk_off, c->gp, c->n_fwd, c->fft_in, c->compact);
+        k_spread_combine<D><<<cdiv(cplane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, c->n_fwd, lpn, c->fft_in, c->compact);
         phase_mark(c, FITSNE_PHASE_COLLECTIVES);
         CKNCCL(g_nccl.AllReduce(c->compact, c->compact, cplane * c->n_fwd, ncclFloat, ncclSum, c->comm, st));
         k_pad_grids<D><<<cdiv(plane, 256), 256, 0, st>>>(c->compact, c->gp, c->n_fwd, c->fft_in);
@@ -372,13 +380,20 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     phase_mark(c, FITSNE_PHASE_GATHER);
     CKRC(launch_spread_gather<D>(c, true, M, skeys, sperm));
 
-    // ---- attractive term (+ optimiser step)
+    // ---- attractive term (joined here) + optimiser step
     phase_mark(c, FITSNE_PHASE_ATTRACT_UPDATE);
+    if (overlap) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    else CKRC(launch_attract<D>(c, st));
+    const int rows = c->row_end - c->row_begin;
     if (!update) {
-        CKRC((launch_attract<D, false>(c)));
+        k_update<D, false><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
+                                                           c->uY, c->gains, c->Yb);
+        c->stats.kernel_launches += 1;
         phase_mark(c, FITSNE_PHASE_CENTER);
     } else {
-        CKRC((launch_attract<D, true>(c)));
+        k_update<D, true><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
+                                                          c->uY, c->gains, c->Yb);
+        c->stats.kernel_launches += 1;
         if (c->world > 1) {
             CKNCCL(g_nccl.AllGather(c->Yb + (size_t) c->rank * c->per * D, c->Yb, (size_t) c->per * D, ncclFloat, c->comm, st));
             c->stats.kernel_launches += 1;
@@ -548,17 +563,22 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c->device));
     if (prop.major < 10) return fail(c, FITSNE_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200)", c->device, prop.major, prop.minor);
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
 
     const size_t yel = (size_t) c->per * world * no_dims;
     c->y_elems = yel;
     CKRC(dev_alloc(c, &c->Y, yel)); CKRC(dev_alloc(c, &c->Yb, yel));
     CKRC(dev_alloc(c, &c->uY, yel)); CKRC(dev_alloc(c, &c->gains, yel));
-    CKRC(dev_alloc(c, &c->frep, yel)); CKRC(dev_alloc(c, &c->dC, yel));
+    CKRC(dev_alloc(c, &c->frep, yel)); CKRC(dev_alloc(c, &c->dC, yel)); CKRC(dev_alloc(c, &c->attr, yel));
     CK(cudaMemsetAsync(c->Y, 0, yel * 4, c->stream)); CK(cudaMemsetAsync(c->Yb, 0, yel * 4, c->stream));
     CK(cudaMemsetAsync(c->uY, 0, yel * 4, c->stream)); CK(cudaMemsetAsync(c->frep, 0, yel * 4, c->stream));
-    CK(cudaMemsetAsync(c->dC, 0, yel * 4, c->stream));
+    CK(cudaMemsetAsync(c->dC, 0, yel * 4, c->stream)); CK(cudaMemsetAsync(c->attr, 0, yel * 4, c->stream));
     k_fill<<<cdiv(yel, 256), 256, 0, c->stream>>>(c->gains, 1.0f, yel);
     LAUNCH_CHECK();
 
@@ -589,6 +609,11 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CKRC(dev_alloc(c, &c->sorted_u, (size_t) c->nloc * no_dims));
     c->hist_cap = (size_t) cdiv(c->nloc, SORT_TILE) * (1 << SORT_MAX_BITS);
     CKRC(dev_alloc(c, &c->hist, c->hist_cap));
+    CKRC(dev_alloc(c, &c->sort_totals, (size_t) 2 * (1 << SORT_MAX_BITS)));
+    {
+        const size_t nodes = no_dims == 2 ? (size_t) cfg->nterms * cfg->nterms : (size_t) cfg->nterms;
+        CKRC(dev_alloc(c, &c->slots, (size_t) cdiv(c->nloc, CHUNK) * 2 * nodes));
+    }
     CKRC(dev_alloc(c, &c->colsum_partial, (size_t) RED_BLOCKS * 2));
     CKRC(dev_alloc(c, &c->bounds_partial, (size_t) RED_BLOCKS));
     CKRC(dev_alloc(c, &c->zpartial, (size_t) Z_BLOCKS));
@@ -633,17 +658,21 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     drop_graphs(c);
     for (auto &p : c->plans) { cufftDestroy(p.second.fwd); cufftDestroy(p.second.inv); }
     if (c->comm) g_nccl.CommDestroy(c->comm);
     void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->col_P, c->val_P, c->keys[0], c->keys[1],
-                    c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->chunk_off, c->hist, c->partial, c->fft_in,
+                    c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->hist, c->sort_totals, c->slots, c->attr, c->fft_in,
                     c->fft_out, c->compact, c->spec, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->staging};
     for (void *b : bufs) if (b) cudaFree(b);
     if (c->host_bounds) cudaFreeHost(c->host_bounds);
     if (c->host_sc) cudaFreeHost(c->host_sc);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -853,6 +882,22 @@ int fitsne_run_host(const fitsne_config *cfg, const fitsne_schedule *s, int N, i
     if (rc != 0) g_create_error = c->err;
     fitsne_destroy(c);
     return rc;
+}
+
+int fitsne_prewarm(fitsne_ctx *c, int n_boxes_lo, int n_boxes_hi) {
+    if (!c || n_boxes_lo < 1 || n_boxes_hi < n_boxes_lo) return FITSNE_EINVAL;
+    CK(cudaSetDevice(c->device));
+    int last = -1;
+    for (int B = n_boxes_lo; B <= n_boxes_hi; B++) {
+        const int M = nice_fft_size(2 * B * c->cfg.nterms);
+        if (M == last) continue;
+        last = M;
+        TRACE("prewarm: plans for M=%d", M);
+        CKRC(ensure_grid_capacity(c, M));
+        Plans *pl;
+        CKRC(get_plans(c, M, &pl));
+    }
+    return 0;
 }
 
 int fitsne_last_run_ms(fitsne_ctx *c, double *ms) {

@@ -2,12 +2,12 @@
 //
 // Everything the reference does per iteration (reference = /root/reference/src/...) in fp32 on the device:
 //   bounds + zero-mean        tsne.cpp:1039-1049, :1851-1876        k_colsum, k_center_bounds, k_setup_grid
-//   point -> box, sort        nbodyfft.cpp:85-114                    k_bin, k_radix_hist/scan/scatter, k_post_sort
+//   point -> box, sort        nbodyfft.cpp:85-114                    k_bin, k_radix_hist/offsets/scatter, k_post_sort
 //   Lagrange spread           nbodyfft.cpp:123-147, :310-336         k_spread_chunks, k_spread_combine
 //   kernel samples            nbodyfft.cpp:52-61, tsne.cpp:69-94     k_gen_kernels        (+ cuFFT R2C)
 //   Hadamard + sum_Q          nbodyfft.cpp:184-191, tsne.cpp:1101-1110  k_hadamard, k_finalize_z  (+ cuFFT C2R)
 //   gather + normalise        nbodyfft.cpp:222-239, tsne.cpp:1149-1151  k_gather
-//   attractive + optimiser    tsne.cpp:1121-1137, :479-513           k_attract_update
+//   attractive + optimiser    tsne.cpp:1121-1137, :479-513           k_attract (2nd stream), k_update
 //   KL                        tsne.cpp:1329-1355                      k_kl
 //
 // The repulsive part uses the "local offset" formulation documented in tests/device_model.py (identical
@@ -258,7 +258,8 @@ __host__ __device__ inline int sort_bits_for(int B, int dims) {
 
 // Fill GridParams for a grid of B boxes/dim (the host's choice; verified against the device's own bounds).
 __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restrict__ sc, const int *__restrict__ B_host, int M, int p, int dims,
-                             double ipi, int min_int, int *__restrict__ mismatch) {
+                             double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals) {
+    for (int i = threadIdx.x; i < 2 * (1 << SORT_MAX_BITS); i += blockDim.x) sort_totals[i] = 0;   // both passes
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int B = *reinterpret_cast<const volatile int *>(B_host);
     const double mn = (double) sc->bmin, mx = (double) sc->bmax;
@@ -293,33 +294,61 @@ __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restr
 }
 
 // -------------------------------------------------------------------------------------------- binning --
+// Stable LSD radix sort of (box key, point index), exactly two passes of `sort_bits` (<= 11) bits each:
+//   k_bin            keys + per-tile histogram of digit 0 (fused)      k_radix_hist   per-tile histogram of digit 1
+//   k_radix_offsets  per-digit tile offsets (one CTA per digit value)  k_radix_scatter stable scatter
+// Stability (ties keep point-index order) makes the box-sorted order, hence the spread's summation order,
+// bitwise repeatable.  key = (by << xbits) | bx.
+// hist layout: [digit][tile];  totals[pass][digit] = sum over tiles (integer atomics: order-independent).
 
-// key = (by << xbits) | bx : least-significant digit is the x box, most-significant the y box
-template <int D>
-__global__ void __launch_bounds__(256) k_bin(const float *__restrict__ Y, int first, int n,
-                                             const GridParams *__restrict__ gpp, uint32_t *__restrict__ keys) {
-    const GridParams &gp = *gpp;
-    if (!gp.ok) return;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    float u;
-    if (D == 2) {
-        const float2 y = reinterpret_cast<const float2 *>(Y)[first + k];
-        const int bx = box_of<true>(y.x, gp, u);
-        const int by = box_of<true>(y.y, gp, u);
-        keys[k] = ((uint32_t) by << gp.xbits) | (uint32_t) bx;
-    } else {
-        keys[k] = (uint32_t) box_of<false>(Y[first + k], gp, u);
+__device__ __forceinline__ void tile_hist_flush(const uint32_t *cnt, int nb, uint32_t *hist, int tiles, uint32_t *totals) {
+    for (int i = threadIdx.x; i < nb; i += SORT_THREADS) {
+        const uint32_t v = cnt[i];
+        hist[(size_t) i * tiles + blockIdx.x] = v;
+        if (v) atomicAdd(&totals[i], v);
     }
 }
 
-// ----------------------------------------------------------------------------------------- radix sort --
-// Stable LSD radix sort of (key, point index) pairs, one digit of `bits` (<= 11) bits per pass:
-// per-tile digit histogram -> exclusive scan in digit-major order -> stable scatter.  Stability (ties keep
-// point-index order) makes the box-sorted order, hence the spread's summation order, bitwise repeatable.
+template <int D>
+__global__ void __launch_bounds__(SORT_THREADS) k_bin(const float *__restrict__ Y, int first, int n,
+                                                      const GridParams *__restrict__ gpp, uint32_t *__restrict__ keys,
+                                                      uint32_t *__restrict__ hist, int tiles, uint32_t *__restrict__ totals) {
+    __shared__ uint32_t cnt[1 << SORT_MAX_BITS];
+    __shared__ GridParams gps;
+    for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
+        reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
+    __syncthreads();
+    const GridParams &gp = gps;
+    if (!gp.ok) return;
+    const int nb = 1 << gp.sort_bits;
+    const uint32_t mask = (uint32_t) nb - 1;
+    for (int i = threadIdx.x; i < nb; i += SORT_THREADS) cnt[i] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * SORT_TILE;
+#pragma unroll 4
+    for (int r = 0; r < SORT_IPT; r++) {
+        const int k = base + r * SORT_THREADS + threadIdx.x;
+        if (k < n) {
+            float u;
+            uint32_t key;
+            if (D == 2) {
+                const float2 y = reinterpret_cast<const float2 *>(Y)[first + k];
+                const int bx = box_of<true>(y.x, gp, u);
+                const int by = box_of<true>(y.y, gp, u);
+                key = ((uint32_t) by << gp.xbits) | (uint32_t) bx;
+            } else {
+                key = (uint32_t) box_of<false>(Y[first + k], gp, u);
+            }
+            keys[k] = key;
+            atomicAdd(&cnt[key & mask], 1u);
+        }
+    }
+    __syncthreads();
+    tile_hist_flush(cnt, nb, hist, tiles, totals);
+}
 
 __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint32_t *__restrict__ keys, int n, int pass,
-                                                             uint32_t *__restrict__ hist, int tiles,
+                                                             uint32_t *__restrict__ hist, int tiles, uint32_t *__restrict__ totals,
                                                              const GridParams *__restrict__ gpp) {
     if (!gpp->ok) return;
     __shared__ uint32_t cnt[1 << SORT_MAX_BITS];
@@ -335,70 +364,53 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint32_t *__r
         if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & mask], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nb; i += SORT_THREADS) hist[(size_t) i * tiles + blockIdx.x] = cnt[i];
+    tile_hist_flush(cnt, nb, hist, tiles, totals);
 }
 
-// Single-CTA exclusive scan of n u32 values, in place.  F transforms the loaded value (identity for the sort,
-// points->chunks for the spread work list).  out[n] receives the total when write_total != 0.
-struct ScanIdentity { __device__ uint32_t operator()(uint32_t v, uint32_t) const { return v; } };
-struct ScanChunks {   // input is box_start[]: element i -> ceil((start[i+1]-start[i]) / CHUNK)
-    __device__ uint32_t operator()(uint32_t v, uint32_t next) const { return (next - v + CHUNK - 1) / CHUNK; }
-};
-template <typename F, bool NEEDS_NEXT>
-__global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int tiles,
-                                                   int write_total, const GridParams *__restrict__ gpp, F f) {
+// One CTA per digit value d: hist[d][t] <- (sum of totals[d' < d]) + (exclusive prefix over tiles t' < t), in place.
+__global__ void __launch_bounds__(256) k_radix_offsets(uint32_t *__restrict__ hist, int tiles, const uint32_t *__restrict__ totals,
+                                                       const GridParams *__restrict__ gpp) {
     if (!gpp->ok) return;
-    // length comes from the device-resident grid description: tiles>0 -> radix histogram (bins x tiles), else boxes
-    const int n = tiles > 0 ? (1 << gpp->sort_bits) * tiles : gpp->nb;
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry_s, total_s;
+    const int nb = 1 << gpp->sort_bits;
+    const int d = blockIdx.x;
+    if (d >= nb) return;
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t carry_s;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    // rounds of 1024 threads x 4 consecutive elements, warp-shuffle scans, running carry
-    for (int base = 0; base < n; base += 4096) {
-        uint32_t v[4];
-        uint32_t tsum = 0;
-        const int i0 = base + threadIdx.x * 4;
+    // base = sum of totals of smaller digits
+    uint32_t acc = 0;
+    for (int i = threadIdx.x; i < d; i += 256) acc += totals[i];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int i = i0 + j;
-            uint32_t x = 0;
-            if (i < n) x = f(in[i], NEEDS_NEXT ? in[i + 1] : 0u);
-            v[j] = tsum;
-            tsum += x;
-        }
-        uint32_t inc = tsum;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) wsum[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) t += wsum[i];
+        carry_s = t;
+    }
+    __syncthreads();
+    uint32_t *rowp = hist + (size_t) d * tiles;
+    for (int base = 0; base < tiles; base += 256) {
+        const int i = base + threadIdx.x;
+        const uint32_t x = i < tiles ? rowp[i] : 0u;
+        uint32_t inc = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
         }
+        __syncthreads();            // wsum / carry_s reads of the previous round are done
         if (lane == 31) wsum[w] = inc;
         __syncthreads();
-        if (w == 0) {
-            const uint32_t ws = wsum[lane];
-            uint32_t winc = ws;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            wsum[lane] = winc - ws;   // exclusive prefix of the warp sums
-            if (lane == 31) total_s = winc;
-        }
+        uint32_t wbase = 0;
+        for (int i2 = 0; i2 < w; i2++) wbase += wsum[i2];
+        const uint32_t carry = carry_s;
+        if (i < tiles) rowp[i] = carry + wbase + inc - x;
         __syncthreads();
-        const uint32_t excl = carry_s + wsum[w] + (inc - tsum);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int i = i0 + j;
-            if (i < n) out[i] = excl + v[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += total_s;
+        if (threadIdx.x == 255) carry_s = carry + wbase + inc;
         __syncthreads();
     }
-    if (write_total && threadIdx.x == 0) out[n] = carry_s;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t *__restrict__ keys_in,
@@ -514,15 +526,44 @@ __device__ __forceinline__ float lagrange1(const GridParams &gp, int p, int j, f
     return v;
 }
 
-// One thread per (chunk of <= CHUNK box-sorted points, interpolation node): serial, fixed-order accumulation
-// of (L, L*bx, L*by, L*|b|^2) -- no atomics.  partial[chunk][node] is a float4.
-//   2-D: node = a*p + b, a = y node, b = x node.   1-D: node = a, components (L, L*b, L*b^2, 0).
+// Spread, deterministic and atomic-free.  The box-sorted points are cut into fixed chunks of CHUNK consecutive
+// points (chunk c = sorted positions [c*CHUNK, (c+1)*CHUNK)); one thread per (chunk, interpolation node) walks its
+// points in order and accumulates (L, L*bx, L*by, L*|b|^2) per box segment:
+//   * a box that lies entirely inside the chunk is finished here and written straight to the grid;
+//   * a segment of a box that continues into a neighbouring chunk goes to slot[c][0] when the box started before
+//     this chunk, else to slot[c][1]; k_spread_combine adds a box's slots in chunk order.
+//   2-D: node = a*p + b, a = y node, b = x node (grid row = y node, column = x node).  1-D: (L, L*b, L*b^2, 0).
+template <int D>
+__device__ __forceinline__ int key_to_box(uint32_t key, const GridParams &gp) {
+    return D == 2 ? (int) (key >> gp.xbits) * gp.B + (int) (key & ((1u << gp.xbits) - 1u)) : (int) key;
+}
+
+template <int D>
+__device__ __forceinline__ void store_node(float *__restrict__ dst, size_t stride, size_t off, float4 v, int n_fwd) {
+    dst[off] = v.x;
+    dst[stride + off] = v.y;
+    dst[2 * stride + off] = v.z;
+    if (n_fwd > 3) dst[3 * stride + off] = v.w;
+}
+
+// offset of (box, node) inside one plane: padded FFT input (row stride M) or, multi-GPU, the compact G^D layout
+template <int D>
+__device__ __forceinline__ size_t node_offset(int box, int node, const GridParams &gp, int p, bool compact) {
+    if (D == 2) {
+        const int by = box / gp.B, bx = box - by * gp.B;
+        const int a = node / p, b = node - a * p;
+        const size_t rs = compact ? (size_t) gp.G : (size_t) gp.M;
+        return (size_t) (by * p + a) * rs + (size_t) (bx * p + b);
+    }
+    return (size_t) box * p + node;
+}
+
 template <int D, int P>
-__global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__ sorted_u,
-                                                       const uint32_t *__restrict__ box_start,
-                                                       const uint32_t *__restrict__ chunk_off,
-                                                       const GridParams *__restrict__ gpp, int chunks_per_block,
-                                                       float4 *__restrict__ partial) {
+__global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
+                                                       const uint32_t *__restrict__ box_start, int n,
+                                                       const GridParams *__restrict__ gpp, int chunks_per_block, int n_fwd,
+                                                       float4 *__restrict__ slots, float *__restrict__ fft_in,
+                                                       float *__restrict__ compact) {
     __shared__ GridParams gps;
     for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
@@ -534,24 +575,30 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
     const int cl = threadIdx.x / nodes;
     if (cl >= chunks_per_block) return;
     const int node = threadIdx.x - cl * nodes;
-    const uint32_t c = (uint32_t) blockIdx.x * chunks_per_block + cl;
-    const int nb = gp.nb;
-    if (c >= chunk_off[nb]) return;
-    // last box b with chunk_off[b] <= c  (empty boxes repeat the offset, so search for the upper bound)
-    int lo = 0, hi = nb;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (chunk_off[mid] <= c) lo = mid; else hi = mid;
-    }
-    const int box = lo;
-    const uint32_t kb = box_start[box] + (c - chunk_off[box]) * CHUNK;
-    const uint32_t ke = min(kb + CHUNK, box_start[box + 1]);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = blockIdx.x * chunks_per_block + cl;
+    const int kb = c * CHUNK;
+    if (kb >= n) return;
+    const int ke = min(kb + CHUNK, n);
     const float bw = gp.bwf;
-    if (D == 2) {
-        const int a = node / p, b = node - a * p;
-        const float sa = gp.s[a], sb = gp.s[b];
-        for (uint32_t k = kb; k < ke; k++) {
+    const int a = D == 2 ? node / p : node, b = D == 2 ? node - a * p : 0;
+    const float sa = gp.s[a], sb = gp.s[b];
+    float *dst = compact ? compact : fft_in;
+    const int Gc = gp.M / 2;
+    const size_t stride = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) gp.M * gp.M : (size_t) gp.M);
+    float4 *myslots = slots + (size_t) c * 2 * nodes;
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur = key_to_box<D>(skeys[kb], gp);
+    for (int k = kb; k < ke; k++) {
+        const int box = key_to_box<D>(skeys[k], gp);
+        if (box != cur) {
+            // segment of `cur` ended inside the chunk: finished box unless it started before the chunk
+            if ((int) box_start[cur] >= kb) store_node<D>(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc, n_fwd);
+            else myslots[node] = acc;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            cur = box;
+        }
+        if (D == 2) {
             const float2 u = reinterpret_cast<const float2 *>(sorted_u)[k];
             const float L = lagrange1<P>(gp, p, a, u.y) * lagrange1<P>(gp, p, b, u.x);
             const float ox = bw * (u.x - sb), oy = bw * (u.y - sa);
@@ -559,85 +606,82 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
             acc.y += L * ox;
             acc.z += L * oy;
             acc.w += L * (ox * ox + oy * oy);
-        }
-    } else {
-        const float sa = gp.s[node];
-        for (uint32_t k = kb; k < ke; k++) {
+        } else {
             const float u = sorted_u[k];
-            const float L = lagrange1<P>(gp, p, node, u);
+            const float L = lagrange1<P>(gp, p, a, u);
             const float o = bw * (u - sa);
             acc.x += L;
             acc.y += L * o;
             acc.z += L * o * o;
         }
     }
-    partial[(size_t) c * nodes + node] = acc;
+    // last segment: finished only if the box both started in this chunk and ends with it
+    const bool started_here = (int) box_start[cur] >= kb, ends_here = (int) box_start[cur + 1] <= ke;
+    if (started_here && ends_here) store_node<D>(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc, n_fwd);
+    else myslots[(started_here ? 1 : 0) * nodes + node] = acc;
 }
 
-// One thread per element of the zero-padded FFT input plane (M^D): inside the G^D corner, sum the node's
-// chunk partials in chunk order; outside, write the zero padding (so no memset is needed when G changes and
-// the launch shape depends on M only).  Grid row = y node, column = x node.
-// Multi-GPU (compact != nullptr): write instead a dense [n_fwd][Gcap^D] buffer (G^D values then zeros per
-// plane, Gcap = M/2) that is all-reduced and then expanded by k_pad_grids.
+// One thread group (LPN lanes, a power of two <= 32) per element of the output plane.  Inside the G^D corner:
+// empty box -> 0; box finished by a single chunk -> already written by k_spread_chunks; otherwise add the box's
+// slot partials in chunk order (lane-strided, then a fixed shuffle tree: deterministic for a given LPN).
+// Outside the corner: the zero padding, so no memset is needed when G changes and the launch shape depends on M
+// only.  Multi-GPU (compact != nullptr): the plane is the dense Gcap^D buffer (G^D values then zeros) that is
+// all-reduced and then expanded by k_pad_grids.
 template <int D>
-__global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ partial,
-                                                        const uint32_t *__restrict__ chunk_off,
-                                                        const GridParams *__restrict__ gpp, int n_fwd,
+__global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ slots, const uint32_t *__restrict__ box_start,
+                                                        const GridParams *__restrict__ gpp, int n_fwd, int lpn,
                                                         float *__restrict__ fft_in, float *__restrict__ compact) {
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
     const int G = gp.G, p = gp.p, M = gp.M;
-    const size_t id = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
+    const size_t gid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t id = gid / lpn;
+    const int sub = (int) (gid - id * lpn);
     const int Gc = M / 2;
-    const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
-    int row = 0, col;
-    bool inside;
-    size_t out;
-    if (!compact) {
-        if (id >= plane) return;
-        if (D == 2) { row = (int) (id / M); col = (int) (id - (size_t) row * M); } else col = (int) id;
-        inside = col < G && row < G;
-        out = id;
-    } else {
-        if (id >= cplane) return;
-        const size_t GG = D == 2 ? (size_t) G * G : (size_t) G;
-        inside = id < GG;
-        if (D == 2) { row = (int) (id / G); col = (int) (id - (size_t) row * G); } else col = (int) id;
-        out = id;
+    const size_t plane = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) M * M : (size_t) M);
+    const bool live = id < plane;
+    int row = 0, col = 0;
+    bool inside = false;
+    if (live) {
+        if (!compact) {
+            if (D == 2) { row = (int) (id / M); col = (int) (id - (size_t) row * M); } else col = (int) id;
+            inside = col < G && row < G;
+        } else {
+            const size_t GG = D == 2 ? (size_t) G * G : (size_t) G;
+            inside = id < GG;
+            if (D == 2) { row = (int) (id / G); col = (int) (id - (size_t) row * G); } else col = (int) id;
+        }
     }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // what to do with this element: 0 = leave (finished by k_spread_chunks), 1 = write acc (zero or the slot sum)
+    int node = 0, nodes = 1, c0 = 0, c1 = -1;
+    bool write = live;
     if (inside) {
-        int box, node, nodes;
+        int box;
         if (D == 2) {
             const int by = row / p, a = row - by * p, bx = col / p, b = col - bx * p;
             box = by * gp.B + bx; node = a * p + b; nodes = p * p;
         } else {
             box = col / p; node = col - box * p; nodes = p;
         }
-        const uint32_t c0 = chunk_off[box], c1 = chunk_off[box + 1];
-        const float4 *src = partial + (size_t) c0 * nodes + node;
-        uint32_t c = c0;
-        for (; c + 4 <= c1; c += 4) {      // 4 independent loads in flight, summed in chunk order
-            const float4 v0 = src[0], v1 = src[nodes], v2 = src[2 * (size_t) nodes], v3 = src[3 * (size_t) nodes];
-            acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
-            acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
-            acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
-            acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
-            src += 4 * (size_t) nodes;
-        }
-        for (; c < c1; c++) {
-            const float4 v = *src;
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            src += nodes;
+        const int s = (int) box_start[box], e = (int) box_start[box + 1];
+        if (e > s) {
+            c0 = s / CHUNK; c1 = (e - 1) / CHUNK;
+            if (c0 == c1) { write = false; c1 = c0 - 1; }   // single chunk: already written
         }
     }
-    float *dst = compact ? compact : fft_in;
-    const size_t stride = compact ? cplane : plane;
-    dst[out] = acc.x;
-    dst[stride + out] = acc.y;
-    dst[2 * stride + out] = acc.z;
-    if (n_fwd > 3) dst[3 * stride + out] = acc.w;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // chunk c0 holds the box's head in slot 1 (the box starts inside or at the start of c0); later chunks use slot 0
+    for (int c = c0 + sub; c <= c1; c += lpn) {
+        const float4 v = slots[((size_t) c * 2 + (c == c0 ? 1 : 0)) * nodes + node];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    for (int o = lpn >> 1; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (write && sub == 0) store_node<D>(compact ? compact : fft_in, plane, id, acc, n_fwd);
 }
 
 // multi-GPU: expand the all-reduced compact grids into the zero-padded FFT input planes
@@ -823,30 +867,22 @@ __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted
 }
 
 // ------------------------------------------------------------------- attractive term + optimiser step --
-// LPR lanes cooperate on one CSR row: F_attr = sum_j p_ij q_ij (y_i - y_j), q = 1/(1+d2/df)
-// (tsne.cpp:1121-1137), then dC = alpha*F_attr - F_rep/Z (tsne.cpp:1153-1154) and either
-//   UPDATE=false: write dC (parity entry point), or
-//   UPDATE=true : gains / momentum / clipping / Y += uY  (tsne.cpp:479-513) into Ynext (un-centred).
+// k_attract: LPR lanes cooperate on one CSR row: attr_i = sum_j p_ij q_ij (y_i - y_j), q = 1/(1+d2/df)
+// (tsne.cpp:1121-1137; exaggeration is applied later as a scalar).  It depends on Y and P only, so it runs on a
+// second stream concurrently with the whole repulsive pipeline (sort/spread/FFT/gather).
 // Row offsets are local to this rank's edge slice: edges of row i are [row_P[i]-edge_base, row_P[i+1]-edge_base).
-__device__ __forceinline__ float sgnf(float x) { return x == 0.f ? 0.f : (x < 0.f ? -1.f : 1.f); }
-
-template <int D, int LPR, bool UPDATE>
-__global__ void __launch_bounds__(256) k_attract_update(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
-                                                        const float *__restrict__ val_P, uint32_t edge_base,
-                                                        const float *__restrict__ Y, const float *__restrict__ frep,
-                                                        int row_begin, int row_end, const StepParams *__restrict__ spp,
-                                                        const GridParams *__restrict__ gpp,
-                                                        float *__restrict__ dC_out, float *__restrict__ uY,
-                                                        float *__restrict__ gains, float *__restrict__ Ynext) {
-    if (!gpp->ok) return;
-    const StepParams sp = *spp;
+template <int D, int LPR>
+__global__ void __launch_bounds__(256) k_attract(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
+                                                 const float *__restrict__ val_P, uint32_t edge_base,
+                                                 const float *__restrict__ Y, int row_begin, int row_end, float inv_df,
+                                                 float *__restrict__ attr) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = gid % LPR;
     const int row = row_begin + gid / LPR;
     const bool active = row < row_end;
     float ax = 0.f, ay = 0.f;
-    float yix = 0.f, yiy = 0.f;
     if (active) {
+        float yix, yiy = 0.f;
         if (D == 2) { const float2 yi = reinterpret_cast<const float2 *>(Y)[row]; yix = yi.x; yiy = yi.y; }
         else yix = Y[row];
         const uint32_t e0 = row_P[row] - edge_base, e1 = row_P[row + 1] - edge_base;
@@ -856,11 +892,11 @@ __global__ void __launch_bounds__(256) k_attract_update(const uint32_t *__restri
             if (D == 2) {
                 const float2 yj = __ldg(reinterpret_cast<const float2 *>(Y) + j);
                 const float dx = yix - yj.x, dy = yiy - yj.y;
-                const float q = pv / (1.f + (dx * dx + dy * dy) * sp.inv_df);
+                const float q = pv / (1.f + (dx * dx + dy * dy) * inv_df);
                 ax += q * dx; ay += q * dy;
             } else {
                 const float dx = yix - __ldg(Y + j);
-                const float q = pv / (1.f + dx * dx * sp.inv_df);
+                const float q = pv / (1.f + dx * dx * inv_df);
                 ax += q * dx;
             }
         }
@@ -870,12 +906,37 @@ __global__ void __launch_bounds__(256) k_attract_update(const uint32_t *__restri
         ax += __shfl_xor_sync(0xffffffffu, ax, o);
         if (D == 2) ay += __shfl_xor_sync(0xffffffffu, ay, o);
     }
-    if (!active || sub != 0) return;
-    float d0, d1 = 0.f;
+    if (active && sub == 0) {
+        if (D == 2) reinterpret_cast<float2 *>(attr)[row] = make_float2(ax, ay);
+        else attr[row] = ax;
+    }
+}
+
+// k_update: dC = alpha*attr - F_rep/Z (tsne.cpp:1153-1154), then either
+//   UPDATE=false: write dC (parity entry point), or
+//   UPDATE=true : gains / momentum / clipping / Y += uY (tsne.cpp:479-513) into Ynext (un-centred).
+__device__ __forceinline__ float sgnf(float x) { return x == 0.f ? 0.f : (x < 0.f ? -1.f : 1.f); }
+
+template <int D, bool UPDATE>
+__global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, const float *__restrict__ attr,
+                                                const float *__restrict__ frep, int row_begin, int row_end,
+                                                const StepParams *__restrict__ spp, const GridParams *__restrict__ gpp,
+                                                float *__restrict__ dC_out, float *__restrict__ uY, float *__restrict__ gains,
+                                                float *__restrict__ Ynext) {
+    if (!gpp->ok) return;
+    const StepParams sp = *spp;
+    const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= row_end) return;
+    float d0, d1 = 0.f, yix, yiy = 0.f;
     if (D == 2) {
-        const float2 fr = reinterpret_cast<const float2 *>(frep)[row];
-        d0 = sp.alpha * ax - fr.x; d1 = sp.alpha * ay - fr.y;
-    } else d0 = sp.alpha * ax - frep[row];
+        const float2 at = reinterpret_cast<const float2 *>(attr)[row], fr = reinterpret_cast<const float2 *>(frep)[row];
+        const float2 yi = reinterpret_cast<const float2 *>(Y)[row];
+        d0 = sp.alpha * at.x - fr.x; d1 = sp.alpha * at.y - fr.y;
+        yix = yi.x; yiy = yi.y;
+    } else {
+        d0 = sp.alpha * attr[row] - frep[row];
+        yix = Y[row];
+    }
     if (!UPDATE) {
         if (D == 2) reinterpret_cast<float2 *>(dC_out)[row] = make_float2(d0, d1);
         else dC_out[row] = d0;

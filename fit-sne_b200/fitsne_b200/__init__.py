@@ -21,7 +21,7 @@ EXPORTS = [
     "fitsne_create", "fitsne_create_sharded", "fitsne_nccl_unique_id", "fitsne_destroy", "fitsne_last_error",
     "fitsne_set_Y", "fitsne_get_Y", "fitsne_set_optimizer_state", "fitsne_get_optimizer_state", "fitsne_gradient",
     "fitsne_step", "fitsne_kl", "fitsne_run", "fitsne_run_host", "fitsne_synchronize", "fitsne_get_stats",
-    "fitsne_reset_stats", "fitsne_last_run_ms", "fitsne_debug_copy", "fitsne_version",
+    "fitsne_reset_stats", "fitsne_last_run_ms", "fitsne_debug_copy", "fitsne_version", "fitsne_prewarm",
 ]
 
 
@@ -193,6 +193,10 @@ class FitSNE:
         Y = np.empty((self.N, self.no_dims)) if fetch_Y else None
         self._ck(self._lib.fitsne_run(self._h, ctypes.byref(s), _dp(costs), _dp(Y)))
         return Y, costs
+
+    def prewarm(self, n_boxes_lo, n_boxes_hi):
+        """Create the cuFFT plans for grids of n_boxes_lo..n_boxes_hi boxes per dimension ahead of the loop."""
+        self._ck(self._lib.fitsne_prewarm(self._h, int(n_boxes_lo), int(n_boxes_hi)))
 
     def synchronize(self):
         self._ck(self._lib.fitsne_synchronize(self._h))

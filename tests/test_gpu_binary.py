@@ -50,7 +50,7 @@ def test_binary_end_to_end_from_raw_data(tmp_path):
     assert out.returncode == 0, out.stdout[-800:] + out.stderr[-400:]
     Y, costs = bench_util.read_result(str(tmp_path / "result.dat"))
     kl = costs[costs != 0]
-    assert len(kl) == 6 and kl[-1] < kl[0] and kl[-1] < 2.0
+    assert len(kl) == 6 and kl[-1] < kl[0] and kl[-1] < 2.5
     cent = np.stack([Y[labels == c].mean(0) for c in range(C)])
     within = np.mean([np.linalg.norm(Y[labels == c] - cent[c], axis=1).mean() for c in range(C)])
     between = np.mean([np.linalg.norm(cent[a] - cent[b]) for a in range(C) for b in range(a + 1, C)])
