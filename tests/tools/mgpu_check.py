@@ -19,20 +19,22 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        buf = (ctypes.c_char * 128)()
-        assert fb.load_library().fitsne_nccl_unique_id(buf) == 0
-        idt.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    nccl_id = idt.cpu().numpy().tobytes()
+    def fresh_id():
+        """every sharded context is its own NCCL communicator and needs its own ncclUniqueId"""
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = (ctypes.c_char * 128)()
+            assert fb.load_library().fitsne_nccl_unique_id(buf) == 0
+            idt.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        return idt.cpu().numpy().tobytes()
 
     N = 200003   # not divisible by the world size on purpose
     row, col, val, labels = bench_util.knn_like_graph(N, 8, seed=3)
     ok = True
     for dims, df, span in ((2, 1.0, 60.0), (1, 0.5, 120.0)):
         Y0 = bench_util.clustered_embedding(labels, dims, span, seed=5)
-        t = fb.FitSNE(row, col, val, Y0, df=df, device=local, rank=rank, world=world, nccl_id=nccl_id)
+        t = fb.FitSNE(row, col, val, Y0, df=df, device=local, rank=rank, world=world, nccl_id=fresh_id())
         dC, Z = t.gradient(4.0)
         kl = t.kl(4.0)
         b, e = t.row_begin, t.row_end
