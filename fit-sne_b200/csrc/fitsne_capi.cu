@@ -92,6 +92,20 @@ struct fitsne_ctx {
     uint32_t edge_base = 0;
     size_t E = 0;
     int lpr = 32;
+    // locality re-ordering + tiled attractive term (single-GPU contexts)
+    uint32_t *orig_of = nullptr, *orig_tmp = nullptr, *pos_of = nullptr, *rank_map = nullptr;   // u32[N]
+    uint32_t *row_P2 = nullptr, *col_P2 = nullptr;   // second CSR buffer (re-labelled copy is built here, then swapped)
+    float *val_P2 = nullptr;
+    uint32_t *tile_cnt = nullptr, *tile_start = nullptr, *tile_cur = nullptr, *tile_pack = nullptr, *nonempty = nullptr;
+    float *tile_val = nullptr;
+    GridParams *gp_reorder = nullptr;
+    TileGeom tg{};
+    size_t ntiles = 0;
+    bool reordered = false, use_tiles = false;
+    uint64_t last_reorder_iter = 0, reorder_interval = 50, reorders = 0;
+    uint32_t nonempty_tiles = 0;
+    float tile_fix32 = 1.0f;
+    uint64_t kernel_launches_reorder = 0;
     // sort / bins
     uint32_t *keys[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
     float *sorted_u = nullptr;
@@ -239,7 +253,8 @@ static inline void phase_mark(fitsne_ctx *c, int phase) {
 template <int D>
 static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int do_center) {
     k_center_bounds<D><<<RED_BLOCKS, 256, 0, c->stream>>>(Yin, Yout, c->N, c->colsum_partial, RED_BLOCKS, do_center,
-                                                          c->bounds_partial, c->sc);
+                                                          c->bounds_partial, c->sc, c->reordered ? c->orig_of : nullptr,
+                                                          c->reordered ? c->pos_of : nullptr);
     k_reduce_bounds<<<1, 256, 0, c->stream>>>(c->bounds_partial, RED_BLOCKS, c->sc, c->host_bounds_dev);
     LAUNCH_CHECK();
     c->stats.kernel_launches += 2;
@@ -277,10 +292,28 @@ static int launch_spread_gather(fitsne_ctx *c, bool gather, int M, const uint32_
     }
 }
 
+static inline size_t tiles_smem_bytes(int D) {
+    const size_t yt = D == 2 ? sizeof(float2) : sizeof(float);
+    return (size_t) TILE_ROWS * yt + (size_t) TILE_ROWS * D * sizeof(long long) + (size_t) TILE_COLS * yt;
+}
+
 template <int D>
 static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
     const int rows = c->row_end - c->row_begin;
     const float inv_df = (float) (1.0 / c->cfg.df);
+    if (c->use_tiles) {
+        // accumulation: 32-bit fixed point scaled by the largest row sum of P (|attr_i| <= rowsum_i / 2) -- native
+        // shared-memory integer atomics, order-independent => bitwise repeatable.  FITSNE_TILE_ACC overrides (experiments).
+        static const int acc_mode = getenv("FITSNE_TILE_ACC") ? atoi(getenv("FITSNE_TILE_ACC")) : 2;
+        const float fix32 = c->tile_fix32;
+#define TILES(A) k_attract_tiles<D, A><<<c->tg.nchunks, 1024, tiles_smem_bytes(D), st>>>(c->Y, c->N, c->tg, c->tile_start, c->tile_pack, \
+                                                                           c->tile_val, inv_df, fix32, c->attr)
+        if (acc_mode == 1) TILES(1); else if (acc_mode == 2) TILES(2); else if (acc_mode == 3) TILES(3); else TILES(0);
+#undef TILES
+        LAUNCH_CHECK();
+        c->stats.kernel_launches += 1;
+        return 0;
+    }
 #define ATT(L) k_attract<D, L><<<cdiv((long long) rows * L, 256), 256, 0, st>>>( \
         c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->row_begin, c->row_end, inv_df, c->attr)
     switch (c->lpr) {
@@ -429,9 +462,118 @@ static int push_step_params(fitsne_ctx *c, const StepParams &sp) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------ locality re-ordering --
+// Physically re-order the points along a Morton curve of the current embedding, re-label the CSR and regroup
+// its edges into (row chunk x column block) tiles for k_attract_tiles.  Rare (iterations 0, 50, 150, 350, ...),
+// so it favours simplicity: a handful of streaming kernels, ~E*40 bytes of traffic.
+static int reorder_points(fitsne_ctx *c) {
+    const int N = c->N, D = c->D;
+    cudaStream_t st = c->stream;
+    CK(cudaStreamSynchronize(c->stream2));
+    const size_t E = c->E;
+    if (!c->orig_of) {
+        CKRC(dev_alloc(c, &c->orig_of, (size_t) N)); CKRC(dev_alloc(c, &c->orig_tmp, (size_t) N));
+        CKRC(dev_alloc(c, &c->pos_of, (size_t) N)); CKRC(dev_alloc(c, &c->rank_map, (size_t) N));
+        CKRC(dev_alloc(c, &c->row_P2, (size_t) N + 1)); CKRC(dev_alloc(c, &c->col_P2, E + 1)); CKRC(dev_alloc(c, &c->val_P2, E + 1));
+        CKRC(dev_alloc(c, &c->tile_pack, E + 1)); CKRC(dev_alloc(c, &c->tile_val, E + 1));
+        const int w = std::max(1, cdiv(N, 148 * TILE_ROWS));            // waves of 148 row chunks
+        c->tg.rows_per_chunk = std::min(TILE_ROWS, std::max(64, cdiv(N, 148 * w)));
+        c->tg.nchunks = cdiv(N, c->tg.rows_per_chunk);
+        c->tg.ncb = cdiv(N, TILE_COLS);
+        c->ntiles = (size_t) c->tg.nchunks * c->tg.ncb;
+        CKRC(dev_alloc(c, &c->tile_cnt, c->ntiles + 1)); CKRC(dev_alloc(c, &c->tile_start, c->ntiles + 1));
+        CKRC(dev_alloc(c, &c->tile_cur, c->ntiles + 1)); CKRC(dev_alloc(c, &c->nonempty, (size_t) 1));
+        CKRC(dev_alloc(c, &c->gp_reorder, (size_t) 1));
+        GridParams g;
+        memset(&g, 0, sizeof g);
+        g.ok = 1; g.sort_bits = SORT_MAX_BITS;
+        CK(cudaMemcpyAsync(c->gp_reorder, &g, sizeof g, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        {   // fixed-point scale of the tiled kernel: 2^30 / max row sum
+            const int blocks = 1024;
+            k_row_sum_max<<<blocks, 256, 0, st>>>(c->row_P, c->val_P, c->edge_base, c->row_begin, c->row_end, c->kl_partial);
+            std::vector<double> h(blocks);
+            CK(cudaMemcpyAsync(h.data(), c->kl_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            double mx = 0;
+            for (double v : h) mx = std::max(mx, v);
+            c->tile_fix32 = (float) (1073741824.0 / std::max(mx, 1e-300));
+        }
+#define SETSM(DD, A) CK(cudaFuncSetAttribute(k_attract_tiles<DD, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tiles_smem_bytes(DD)))
+        if (D == 2) { SETSM(2, 0); SETSM(2, 1); SETSM(2, 2); SETSM(2, 3); } else { SETSM(1, 0); SETSM(1, 1); SETSM(1, 2); SETSM(1, 3); }
+#undef SETSM
+    }
+    CKRC(refresh_bounds(c));     // sc->bmin / bmax of the current Y
+    // 1. locality keys, stable 2 x 11-bit LSD sort (same kernels as the per-iteration box sort)
+    const int tiles = cdiv(N, SORT_TILE);
+    const int max_bins = 1 << SORT_MAX_BITS;
+    const size_t scatter_smem = (size_t) max_bins * 4 + (size_t) (SORT_THREADS / 32) * max_bins * 2;
+    if (D == 2) k_morton_keys<2><<<cdiv(N, 256), 256, 0, st>>>(c->Y, N, c->sc, c->keys[0]);
+    else k_morton_keys<1><<<cdiv(N, 256), 256, 0, st>>>(c->Y, N, c->sc, c->keys[0]);
+    CK(cudaMemsetAsync(c->sort_totals, 0, sizeof(uint32_t) * 2 * max_bins, st));
+    k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[0], N, 0, c->hist, tiles, c->sort_totals, c->gp_reorder);
+    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, c->gp_reorder);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], N, 0, c->hist, tiles, 0u, c->gp_reorder);
+    k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[1], N, 1, c->hist, tiles, c->sort_totals + max_bins, c->gp_reorder);
+    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, c->gp_reorder);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], N, 1, c->hist, tiles, 0u, c->gp_reorder);
+    LAUNCH_CHECK();
+    // 2. maps
+    k_reorder_maps<<<cdiv(N, 256), 256, 0, st>>>(c->perm[0], N, c->rank_map, c->reordered ? c->orig_of : nullptr, c->orig_tmp, c->pos_of);
+    CK(cudaMemcpyAsync(c->orig_of, c->orig_tmp, (size_t) N * 4, cudaMemcpyDeviceToDevice, st));
+    // 3. per-point state
+    const size_t bytes = (size_t) N * D * sizeof(float);
+    float *state[3] = {c->Y, c->uY, c->gains};
+    for (float *buf : state) {
+        if (D == 2) k_permute_rows<2><<<cdiv(N, 256), 256, 0, st>>>(buf, c->Yb, c->perm[0], N);
+        else k_permute_rows<1><<<cdiv(N, 256), 256, 0, st>>>(buf, c->Yb, c->perm[0], N);
+        CK(cudaMemcpyAsync(buf, c->Yb, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    // 4. CSR relabel + tiles (keys[1] is free again: row lengths)
+    uint32_t *new_len = c->keys[1];
+    CK(cudaMemsetAsync(c->tile_cnt, 0, (c->ntiles + 1) * 4, st));
+    CK(cudaMemsetAsync(c->tile_cur, 0, (c->ntiles + 1) * 4, st));
+    CK(cudaMemsetAsync(c->nonempty, 0, 4, st));
+    k_relabel_csr<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(0, c->row_P, c->col_P, c->val_P, c->rank_map, N, c->tg, new_len, c->tile_cnt,
+                                                                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_scan_excl<<<1, 1024, 0, st>>>(new_len, c->row_P2, N);
+    k_scan_excl<<<1, 1024, 0, st>>>(c->tile_cnt, c->tile_start, (int) c->ntiles);
+    k_relabel_csr<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(1, c->row_P, c->col_P, c->val_P, c->rank_map, N, c->tg, new_len, c->tile_cnt,
+                                                                 c->row_P2, c->col_P2, c->val_P2, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val);
+    k_count_nonempty<<<cdiv(c->ntiles, 256), 256, 0, st>>>(c->tile_cnt, c->ntiles, c->nonempty);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(&c->nonempty_tiles, c->nonempty, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::swap(c->row_P, c->row_P2); std::swap(c->col_P, c->col_P2); std::swap(c->val_P, c->val_P2);
+    c->reordered = true;
+    c->reorders++;
+    // 5. which attractive kernel: modelled cost of the tiled path (column-block fills from L2 + the edge stream) vs
+    //    the CSR gather path (~2 cycles per divergent gather per SM; measured 6.9 ps/edge chip-wide on B200)
+    // (calibrated on B200, N=1M/E=30M: 4393 non-empty tiles -> 340 us without accumulation => ~78 ns per column-block fill)
+    const double est_tiles_us = (double) c->nonempty_tiles * 0.078 + (double) E * 8.0 / 5.0e6 + 5.0;
+    const double est_csr_us = (double) E * 6.9e-6 + 5.0;
+    c->use_tiles = est_tiles_us < est_csr_us;
+    if (c->cfg.flags & FITSNE_FLAG_FORCE_TILES) c->use_tiles = true;
+    if (c->cfg.flags & FITSNE_FLAG_NO_TILES) c->use_tiles = false;
+    TRACE("reorder #%llu: %u of %zu tiles non-empty, est tiles %.0f us vs csr %.0f us -> %s", (unsigned long long) c->reorders,
+          c->nonempty_tiles, c->ntiles, est_tiles_us, est_csr_us, c->use_tiles ? "tiles" : "csr");
+    drop_graphs(c);              // CSR pointers and the attractive kernel changed
+    c->kernel_launches_reorder += 20;
+    return 0;
+}
+
+static int maybe_reorder(fitsne_ctx *c) {
+    if (c->world > 1 || (c->cfg.flags & FITSNE_FLAG_NO_REORDER) || c->E == 0) return 0;
+    if (c->reordered && c->stats.iterations - c->last_reorder_iter < c->reorder_interval) return 0;
+    if (c->reordered) c->reorder_interval = std::min<uint64_t>(c->reorder_interval * 2, 400);
+    c->last_reorder_iter = c->stats.iterations;
+    return reorder_points(c);
+}
+
 // Decide the grid from the (host-visible) bounds and run one iteration, through a cached CUDA graph unless
 // disabled.  The one host<->device handshake per iteration is the 8-byte bounds read.
 static int run_iteration(fitsne_ctx *c, bool update) {
+    CKRC(maybe_reorder(c));
     CKRC(refresh_bounds(c));
     TRACE("iteration: waiting for bounds");
     CK(cudaStreamSynchronize(c->stream));
@@ -507,17 +649,28 @@ static int run_iteration(fitsne_ctx *c, bool update) {
 }
 
 // ------------------------------------------------------------------------------------------ transfers --
-static int upload_as_float(fitsne_ctx *c, const double *host, float *dev, size_t n) {
+// Host arrays are always in the caller's ORIGINAL point order; the device may have re-ordered the points.
+static int upload_as_float(fitsne_ctx *c, const double *host, float *dev, size_t n, bool per_point = true) {
     if (n > c->staging_elems) { CKRC(dev_alloc(c, &c->staging, n)); c->staging_elems = n; }
     CK(cudaMemcpyAsync(c->staging, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_d2f<<<cdiv(n, 256), 256, 0, c->stream>>>(c->staging, dev, n);
+    if (per_point && c->reordered) {
+        if (c->D == 2) k_d2f_ordered<2><<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->staging, dev, c->orig_of, c->N);
+        else k_d2f_ordered<1><<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->staging, dev, c->orig_of, c->N);
+    } else {
+        k_d2f<<<cdiv(n, 256), 256, 0, c->stream>>>(c->staging, dev, n);
+    }
     LAUNCH_CHECK();
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
-static int download_as_double(fitsne_ctx *c, const float *dev, double *host, size_t n) {
+static int download_as_double(fitsne_ctx *c, const float *dev, double *host, size_t n, bool per_point = true) {
     if (n > c->staging_elems) { CKRC(dev_alloc(c, &c->staging, n)); c->staging_elems = n; }
-    k_f2d<<<cdiv(n, 256), 256, 0, c->stream>>>(dev, c->staging, n);
+    if (per_point && c->reordered) {
+        if (c->D == 2) k_f2d_ordered<2><<<cdiv(c->N, 256), 256, 0, c->stream>>>(dev, c->staging, c->orig_of, c->N);
+        else k_f2d_ordered<1><<<cdiv(c->N, 256), 256, 0, c->stream>>>(dev, c->staging, c->orig_of, c->N);
+    } else {
+        k_f2d<<<cdiv(n, 256), 256, 0, c->stream>>>(dev, c->staging, n);
+    }
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(host, c->staging, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -665,7 +818,9 @@ int fitsne_destroy(fitsne_ctx *c) {
     void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->col_P, c->val_P, c->keys[0], c->keys[1],
                     c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->hist, c->sort_totals, c->slots, c->attr, c->fft_in,
                     c->fft_out, c->compact, c->spec, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
-                    c->gp, c->sp, c->sc, c->mismatch, c->staging};
+                    c->gp, c->sp, c->sc, c->mismatch, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
+                    c->row_P2, c->col_P2, c->val_P2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
+                    c->nonempty, c->gp_reorder};
     for (void *b : bufs) if (b) cudaFree(b);
     if (c->host_bounds) cudaFreeHost(c->host_bounds);
     if (c->host_sc) cudaFreeHost(c->host_sc);
@@ -929,7 +1084,15 @@ int fitsne_debug_copy(fitsne_ctx *c, const char *what, void *dst, size_t dst_byt
     const void *src = nullptr;
     size_t bytes = 0;
     const int sorted_buf = 0;   // two LSD passes: sorted data ends up back in buffer 0
-    if (!strcmp(what, "frep")) { src = c->frep; bytes = (size_t) c->N * c->D * 4; }
+    if (!strcmp(what, "frep")) {
+        src = c->frep; bytes = (size_t) c->N * c->D * 4;
+        if (c->reordered) {   // hand it back in the caller's point order
+            if (c->D == 2) k_f2f_ordered<2><<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->frep, c->dC, c->orig_of, c->N);
+            else k_f2f_ordered<1><<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->frep, c->dC, c->orig_of, c->N);
+            CK(cudaStreamSynchronize(c->stream));
+            src = c->dC;
+        }
+    }
     else if (!strcmp(what, "perm")) { src = c->perm[sorted_buf]; bytes = (size_t) c->nloc * 4; }
     else if (!strcmp(what, "keys")) { src = c->keys[sorted_buf]; bytes = (size_t) c->nloc * 4; }
     else if (!strcmp(what, "box_start")) { src = c->box_start; bytes = ((c->D == 2 ? (size_t) c->cur_B * c->cur_B : (size_t) c->cur_B) + 1) * 4; }

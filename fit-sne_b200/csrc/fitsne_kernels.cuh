@@ -18,6 +18,7 @@
 #include <cufft.h>
 #include <stdint.h>
 #include <float.h>
+#include <type_traits>
 
 namespace fk {
 
@@ -137,7 +138,8 @@ template <int D>
 __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__ Yin, float *__restrict__ Yout, int N,
                                                        const double *__restrict__ colsum_partial, int nparts,
                                                        int do_center, float2 *__restrict__ bounds_partial,
-                                                       Scalars *__restrict__ sc) {
+                                                       Scalars *__restrict__ sc, const uint32_t *__restrict__ orig_of,
+                                                       const uint32_t *__restrict__ pos_of) {
     __shared__ double smd[32];
     __shared__ float smf[64];
     __shared__ double mean_s[2];
@@ -160,8 +162,9 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
         int t = 0;
         if (D == 2) {
             float run = -INFINITY;
-            while (t < nflat) {
-                float v = (float) ((double) Yin[t] - mean[t & 1]);
+            while (t < nflat) {   // walk the points in ORIGINAL order (the device may have re-ordered them)
+                const size_t pos = pos_of ? (size_t) pos_of[t >> 1] : (size_t) (t >> 1);
+                float v = (float) ((double) Yin[pos * 2 + (t & 1)] - mean[t & 1]);
                 if (v > run) { run = v; t++; } else break;
             }
         }
@@ -179,8 +182,9 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
             v.y = (float) ((double) v.y - mean[1]);
             if (do_center) reinterpret_cast<float2 *>(Yout)[i] = v;
             mx = fmaxf(mx, fmaxf(v.x, v.y));
-            if (2 * i >= t0) mn = fminf(mn, v.x);
-            if (2 * i + 1 >= t0) mn = fminf(mn, v.y);
+            const long long fo = orig_of ? 2ll * (long long) orig_of[i] : 2ll * i;   // flat index in original order
+            if (fo >= t0) mn = fminf(mn, v.x);
+            if (fo + 1 >= t0) mn = fminf(mn, v.y);
         } else {
             float v = (float) ((double) Yin[i] - mean[0]);
             if (do_center) Yout[i] = v;
@@ -970,6 +974,259 @@ __global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, con
         reinterpret_cast<float2 *>(Ynext)[row] = make_float2(yix + u0, yiy + u1);
     } else {
         gains[row] = g0; uY[row] = u0; Ynext[row] = yix + u0;
+    }
+}
+
+// ------------------------------------------------------------- locality re-ordering + tiled attractive term --
+// k_attract over a plain CSR is bound by L1 gather wavefronts (one 128-byte line per random neighbour), not by
+// DRAM.  The tiled path removes that bound: every few hundred iterations the points are physically re-ordered
+// along a Morton curve of the current embedding (neighbours in P are neighbours in Y by then), the edges are
+// regrouped into tiles (row chunk of <= TILE_ROWS points) x (column block of TILE_COLS points), and
+// k_attract_tiles keeps the chunk's own positions, its accumulators and one column block of Y in shared memory:
+// neighbour gathers become shared-memory reads, the edge stream (8 B/edge) is the only HBM traffic.
+// Row sums are accumulated as 64-bit fixed point (2^-60) with shared-memory integer atomics: integer addition is
+// associative, so the result does not depend on the order edges arrive in -- bitwise repeatable.
+constexpr int TILE_ROWS = 4096;    // max points per row chunk  (row-local index fits 16 bits)
+constexpr int TILE_COLS = 14336;   // points per column block    (112 KB of float2)
+constexpr float FIX_SCALE = 1152921504606846976.f;          // 2^60
+constexpr double FIX_INV = 1.0 / 1152921504606846976.0;
+
+struct TileGeom {
+    int rows_per_chunk, nchunks, ncb;   // chunk c = rows [c*rows_per_chunk, ...), column block b = points [b*TILE_COLS, ...)
+};
+
+__device__ __forceinline__ uint32_t spread_bits11(uint32_t v) {   // 11 bits -> every other bit of 22
+    v &= 0x7ffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// 22-bit locality key of every point: Morton code of the position quantised to 2048 cells per axis (2-D) or the
+// 22-bit quantised coordinate (1-D).
+template <int D>
+__global__ void __launch_bounds__(256) k_morton_keys(const float *__restrict__ Y, int n, const Scalars *__restrict__ sc,
+                                                     uint32_t *__restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float mn = sc->bmin, inv = 1.f / fmaxf(sc->bmax - sc->bmin, 1e-30f);
+    if (D == 2) {
+        const float2 y = reinterpret_cast<const float2 *>(Y)[i];
+        const int qx = min(2047, max(0, (int) ((y.x - mn) * inv * 2048.f)));
+        const int qy = min(2047, max(0, (int) ((y.y - mn) * inv * 2048.f)));
+        keys[i] = spread_bits11((uint32_t) qx) | (spread_bits11((uint32_t) qy) << 1);
+    } else {
+        keys[i] = (uint32_t) min(4194303, max(0, (int) ((Y[i] - mn) * inv * 4194304.f)));
+    }
+}
+
+// after sorting: perm[k] = previous position of the point that moves to position k.
+// orig_of[k] = ORIGINAL index of the point now at k; pos_of[o] = current position of original point o;
+// rank[prev] = new position (used to relabel the CSR columns).
+__global__ void __launch_bounds__(256) k_reorder_maps(const uint32_t *__restrict__ perm, int n, uint32_t *__restrict__ rank,
+                                                      const uint32_t *__restrict__ orig_old, uint32_t *__restrict__ orig_new,
+                                                      uint32_t *__restrict__ pos_of) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t prev = perm[k];
+    rank[prev] = (uint32_t) k;
+    const uint32_t o = orig_old ? orig_old[prev] : prev;
+    orig_new[k] = o;
+    pos_of[o] = (uint32_t) k;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_permute_rows(const float *__restrict__ in, float *__restrict__ out,
+                                                      const uint32_t *__restrict__ perm, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (D == 2) reinterpret_cast<float2 *>(out)[k] = reinterpret_cast<const float2 *>(in)[perm[k]];
+    else out[k] = in[perm[k]];
+}
+
+// host <-> device transfers in ORIGINAL point order: dev[k] corresponds to host[orig_of[k]]
+template <int D>
+__global__ void __launch_bounds__(256) k_d2f_ordered(const double *__restrict__ in, float *__restrict__ out,
+                                                     const uint32_t *__restrict__ orig_of, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t o = orig_of[k];
+    for (int d = 0; d < D; d++) out[(size_t) k * D + d] = (float) in[o * D + d];
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_f2d_ordered(const float *__restrict__ in, double *__restrict__ out,
+                                                     const uint32_t *__restrict__ orig_of, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t o = orig_of[k];
+    for (int d = 0; d < D; d++) out[o * D + d] = (double) in[(size_t) k * D + d];
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_f2f_ordered(const float *__restrict__ in, float *__restrict__ out,
+                                                     const uint32_t *__restrict__ orig_of, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t o = orig_of[k];
+    for (int d = 0; d < D; d++) out[o * D + d] = in[(size_t) k * D + d];
+}
+
+// single-CTA exclusive scan (re-ordering time only); out[n] = total
+__global__ void __launch_bounds__(1024) k_scan_excl(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int n) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s, total_s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 4096) {
+        uint32_t v[4], tsum = 0;
+        const int i0 = base + threadIdx.x * 4;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int i = i0 + j; const uint32_t x = i < n ? in[i] : 0u; v[j] = tsum; tsum += x; }
+        uint32_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t ws = wsum[lane];
+            uint32_t winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+            wsum[lane] = winc - ws;
+            if (lane == 31) total_s = winc;
+        }
+        __syncthreads();
+        const uint32_t excl = carry_s + wsum[w] + (inc - tsum);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int i = i0 + j; if (i < n) out[i] = excl + v[j]; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += total_s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+// Relabel the CSR into the new point order.  One 8-lane group per OLD row i (new row r = rank[i]).
+//   PASS 0: new_len[r] = len(i); tile_cnt[tile(r, rank[col])]++
+//   PASS 1: copy the row's edges to new_row_P[r] (relabelled columns) and scatter them into their tiles
+__global__ void __launch_bounds__(256) k_relabel_csr(int pass, const uint32_t *__restrict__ row_old, const uint32_t *__restrict__ col_old,
+                                                     const float *__restrict__ val_old, const uint32_t *__restrict__ rank, int n,
+                                                     TileGeom tg, uint32_t *__restrict__ new_len, uint32_t *__restrict__ tile_cnt,
+                                                     const uint32_t *__restrict__ row_new, uint32_t *__restrict__ col_new,
+                                                     float *__restrict__ val_new, const uint32_t *__restrict__ tile_start,
+                                                     uint32_t *__restrict__ tile_cur, uint32_t *__restrict__ tile_pack,
+                                                     float *__restrict__ tile_val) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = gid & 7, i = gid >> 3;
+    if (i >= n) return;
+    const uint32_t r = rank[i];
+    const uint32_t e0 = row_old[i], e1 = row_old[i + 1];
+    const uint32_t rc = r / (uint32_t) tg.rows_per_chunk, rl = r - rc * (uint32_t) tg.rows_per_chunk;
+    if (pass == 0) {
+        if (sub == 0) new_len[r] = e1 - e0;
+        for (uint32_t e = e0 + sub; e < e1; e += 8) {
+            const uint32_t c = rank[col_old[e]];
+            atomicAdd(&tile_cnt[(size_t) rc * tg.ncb + c / TILE_COLS], 1u);
+        }
+    } else {
+        const uint32_t nb = row_new[r];
+        for (uint32_t e = e0 + sub; e < e1; e += 8) {
+            const uint32_t c = rank[col_old[e]];
+            const float v = val_old[e];
+            col_new[nb + (e - e0)] = c;
+            val_new[nb + (e - e0)] = v;
+            const uint32_t cb = c / TILE_COLS;
+            const size_t t = (size_t) rc * tg.ncb + cb;
+            const uint32_t pos = tile_start[t] + atomicAdd(&tile_cur[t], 1u);
+            tile_pack[pos] = (rl << 16) | (c - cb * TILE_COLS);
+            tile_val[pos] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_count_nonempty(const uint32_t *__restrict__ tile_cnt, size_t ntiles, uint32_t *__restrict__ out) {
+    const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ne = t < ntiles && tile_cnt[t] != 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, ne);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (uint32_t) __popc(m));
+}
+
+// One CTA per row chunk.  Shared memory: own positions [R] | fixed-point accumulators [R][D] | column block [TILE_COLS].
+// ACC: 0 = 64-bit fixed point, 1 = float atomics (experiment), 2 = 32-bit fixed point, 3 = no accumulation (experiment)
+template <int D, int ACC>
+__global__ void __launch_bounds__(1024, 1) k_attract_tiles(const float *__restrict__ Y, int n, TileGeom tg,
+                                                           const uint32_t *__restrict__ tile_start,
+                                                           const uint32_t *__restrict__ tile_pack, const float *__restrict__ tile_val,
+                                                           float inv_df, float fix32, float *__restrict__ attr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = tg.rows_per_chunk;
+    using YT = typename std::conditional<D == 2, float2, float>::type;
+    YT *yrow = reinterpret_cast<YT *>(smem_raw);
+    long long *acc = reinterpret_cast<long long *>(smem_raw + (size_t) TILE_ROWS * sizeof(YT));
+    YT *ycol = reinterpret_cast<YT *>(smem_raw + (size_t) TILE_ROWS * sizeof(YT) + (size_t) TILE_ROWS * D * sizeof(long long));
+    const int rc = blockIdx.x;
+    const int r0 = rc * R, rn = min(R, n - r0);
+    const YT *Yt = reinterpret_cast<const YT *>(Y);
+    for (int i = threadIdx.x; i < rn; i += blockDim.x) yrow[i] = Yt[r0 + i];
+    for (int i = threadIdx.x; i < rn * D; i += blockDim.x) acc[i] = 0;
+    const uint32_t *ts = tile_start + (size_t) rc * tg.ncb;
+    for (int cb = 0; cb < tg.ncb; cb++) {
+        const uint32_t e0 = ts[cb], e1 = ts[cb + 1];
+        if (e0 == e1) continue;                       // uniform across the CTA
+        __syncthreads();                              // previous block's readers are done (also covers the init above)
+        const int c0 = cb * TILE_COLS, cn = min(TILE_COLS, n - c0);
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) ycol[i] = Yt[c0 + i];
+        __syncthreads();
+        // 4 independent edges per thread per trip: keeps enough 8-byte loads in flight to stream at HBM rate
+        for (uint32_t eb = e0 + threadIdx.x; eb < e1; eb += 4 * blockDim.x) {
+            uint32_t pk[4];
+            float pv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t e = eb + u * blockDim.x;
+                pk[u] = e < e1 ? tile_pack[e] : 0u;
+                pv[u] = e < e1 ? tile_val[e] : 0.f;      // weight 0 contributes exactly 0
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (eb + u * blockDim.x >= e1) break;
+                const uint32_t rl = pk[u] >> 16, cl = pk[u] & 0xffffu;
+                if (D == 2) {
+                    const float2 yi = reinterpret_cast<const float2 *>(yrow)[rl], yj = reinterpret_cast<const float2 *>(ycol)[cl];
+                    const float dx = yi.x - yj.x, dy = yi.y - yj.y;
+                    const float q = pv[u] / (1.f + (dx * dx + dy * dy) * inv_df);
+                    if (ACC == 0) {
+                        atomicAdd(reinterpret_cast<unsigned long long *>(&acc[2 * rl]), (unsigned long long) __float2ll_rn(q * dx * FIX_SCALE));
+                        atomicAdd(reinterpret_cast<unsigned long long *>(&acc[2 * rl + 1]), (unsigned long long) __float2ll_rn(q * dy * FIX_SCALE));
+                    } else if (ACC == 1) {
+                        atomicAdd(reinterpret_cast<float *>(&acc[2 * rl]), q * dx);
+                        atomicAdd(reinterpret_cast<float *>(&acc[2 * rl + 1]), q * dy);
+                    } else if (ACC == 2) {
+                        atomicAdd(reinterpret_cast<int *>(&acc[2 * rl]), __float2int_rn(q * dx * fix32));
+                        atomicAdd(reinterpret_cast<int *>(&acc[2 * rl + 1]), __float2int_rn(q * dy * fix32));
+                    } else {
+                        if (q * dx == 123.456f) acc[0] = 1;
+                    }
+                } else {
+                    const float dx = reinterpret_cast<const float *>(yrow)[rl] - reinterpret_cast<const float *>(ycol)[cl];
+                    const float q = pv[u] / (1.f + dx * dx * inv_df);
+                    if (ACC == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc[rl]), (unsigned long long) __float2ll_rn(q * dx * FIX_SCALE));
+                    else if (ACC == 1) atomicAdd(reinterpret_cast<float *>(&acc[rl]), q * dx);
+                    else if (ACC == 2) atomicAdd(reinterpret_cast<int *>(&acc[rl]), __float2int_rn(q * dx * fix32));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < rn; i += blockDim.x) {
+        float a0, a1 = 0.f;
+        if (ACC == 0) { a0 = (float) ((double) acc[(D == 2 ? 2 : 1) * i] * FIX_INV); if (D == 2) a1 = (float) ((double) acc[2 * i + 1] * FIX_INV); }
+        else if (ACC == 2) { a0 = (float) ((double) *reinterpret_cast<int *>(&acc[(D == 2 ? 2 : 1) * i]) / (double) fix32); if (D == 2) a1 = (float) ((double) *reinterpret_cast<int *>(&acc[2 * i + 1]) / (double) fix32); }
+        else { a0 = *reinterpret_cast<float *>(&acc[(D == 2 ? 2 : 1) * i]); if (D == 2) a1 = *reinterpret_cast<float *>(&acc[2 * i + 1]); }
+        if (D == 2) reinterpret_cast<float2 *>(attr)[r0 + i] = make_float2(a0, a1);
+        else attr[r0 + i] = a0;
     }
 }
 

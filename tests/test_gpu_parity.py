@@ -144,3 +144,36 @@ def test_errors_are_loud(fb, golden_graph):
     with pytest.raises(fb.FitsneError):
         t = fb.FitSNE(row, col, val.astype(np.float64), np.zeros((N, 2)))
         t.gradient(1.0)                                                        # degenerate embedding
+
+
+def test_reordering_and_tiled_attractive_kernel_match_plain_csr(fb, golden_graph, golden_gradients):
+    """Device-side Morton re-ordering + the shared-memory tiled SpMV are invisible from outside: same dC (original point
+    order), same optimiser trajectory, as the plain CSR kernel without re-ordering."""
+    row, col, val, _ = golden_graph
+    val64 = val.astype(np.float64)
+    for name in ("g2d_mid", "g1d_late"):
+        g = golden_gradients
+        dims, df, nterms, ipi, min_int, Z, kl = g[name + "__meta"]
+        Y = g[name + "__Y"].astype(np.float64)
+        out = {}
+        for label, flags in (("plain", fb.FLAG_NO_REORDER), ("tiles", fb.FLAG_FORCE_TILES), ("reorder_csr", fb.FLAG_NO_TILES)):
+            with fb.FitSNE(row, col, val64, Y, nterms=int(nterms), df=df, flags=flags) as t:
+                dC, z = t.gradient(3.0)
+                k = t.kl(3.0)
+                for _ in range(3):
+                    t.step(exaggeration=3.0, momentum=0.5, learning_rate=100.0, max_step_norm=5.0)
+                Y3 = t.get_Y()
+                uY3, g3 = t.get_optimizer_state()
+                dC_again, _ = t.gradient(3.0)
+                dC_again2, _ = t.gradient(3.0)
+                assert np.array_equal(dC_again, dC_again2)         # integer-atomic accumulation: bitwise repeatable
+            out[label] = (dC, z, k, Y3, uY3, g3)
+        ref = g[name + "__dC"] + 2.0 * (g[name + "__dC"] - g[name + "__dC_rep"])     # exaggeration 3 on the attractive part
+        for label in out:
+            assert rel(out[label][0], ref) < GRAD_TOL
+        for label in ("tiles", "reorder_csr"):
+            assert rel(out[label][0], out["plain"][0]) < 2e-6
+            assert abs(out[label][1] - out["plain"][1]) / out["plain"][1] < 1e-6
+            assert abs(out[label][2] - out["plain"][2]) / abs(out["plain"][2]) < 1e-6
+            assert rel(out[label][3], out["plain"][3]) < 1e-5
+            assert rel(out[label][4], out["plain"][4]) < 1e-3
