@@ -1,9 +1,10 @@
 // fitsne_capi.cu -- context, per-iteration launch sequence, CUDA-graph cache and the C ABI
-// (include/fitsne_b200.h) of libfitsne_b200.so.  Kernels live in fitsne_kernels.cuh; cuFFT R2C/C2R is the one
-// library call on the path; NCCL (loaded with dlopen, only for sharded runs) carries the grid all-reduce and
-// the Y all-gather.  There is no CPU fallback anywhere in this file.
+// (include/fitsne_b200.h) of libfitsne_b200.so.  Kernels live in fitsne_kernels.cuh and fitsne_fft.cuh (no library
+// call is left on the path: the FFTs are our own); NCCL (loaded with dlopen, only for sharded runs) carries the grid
+// all-reduce and the Y all-gather.  There is no CPU fallback anywhere in this file.
 #include "../../include/fitsne_b200.h"
 #include "fitsne_kernels.cuh"
+#include "fitsne_fft.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -56,8 +57,11 @@ struct NcclApi {
 NcclApi g_nccl;
 std::string g_create_error;
 
-struct Plans {
-    cufftHandle fwd = 0, inv = 0;
+struct Plans {          // per FFT length: radix plan + twiddle table (no library plans, nothing to JIT)
+    FftPlan plan{};
+    float2 *W = nullptr;
+    int lines = 1;          // rows / columns per CTA tile
+    size_t smem = 0;
 };
 
 // The launch sequence depends on the FFT length M only (n_boxes and all grid geometry are read from the
@@ -113,9 +117,8 @@ struct fitsne_ctx {
     size_t box_cap = 0, hist_cap = 0;
     float4 *slots = nullptr;          // spread partials: [chunk][2][nodes]
     // grids
-    float *fft_in = nullptr, *fft_out = nullptr, *compact = nullptr;
-    float2 *spec = nullptr;
-    size_t plane_cap = 0, compact_cap = 0;   // capacity in real elements per plane
+    float2 *planes = nullptr, *compact = nullptr;   // 4 packed complex planes [M^D]; multi-GPU compact grids
+    size_t plane_cap = 0;                            // capacity in complex elements per plane
     // small stuff
     double *colsum_partial = nullptr, *zpartial = nullptr, *kl_partial = nullptr;
     float2 *bounds_partial = nullptr;
@@ -155,8 +158,6 @@ static int fail(fitsne_ctx *c, int code, const char *fmt, ...) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return fail(c, e_ == cudaErrorMemoryAllocation ? FITSNE_ENOMEM : FITSNE_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
-#define CKFFT(call) do { cufftResult r_ = (call); if (r_ != CUFFT_SUCCESS) \
-    return fail(c, FITSNE_ECUDA, "%s failed: cufft error %d (%s:%d)", #call, (int) r_, __FILE__, __LINE__); } while (0)
 #define CKNCCL(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) \
     return fail(c, FITSNE_ENCCL, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); } while (0)
 #define CKRC(call) do { int rc_ = (call); if (rc_ != 0) return rc_; } while (0)
@@ -171,18 +172,18 @@ static double now_ms() {
 static inline int cdiv(long long a, long long b) { return (int) ((a + b - 1) / b); }
 
 // FFT length for a grid of side G.  Any M >= 2G-1 gives the same linear convolution (the reference uses 2G,
-// nbodyfft.cpp:155-156), so M is taken from a coarse ladder of cuFFT-friendly lengths -- 2^a 3^b 5^c 7^d that
-// are multiples of 32 (16 below 512) -- to keep the number of distinct plans / graphs over a run small:
-// plan creation costs from milliseconds to seconds per new length (cuFFT JIT-compiles kernels on sm_100).
+// nbodyfft.cpp:155-156); M is the next 2^a 3^b 5^c that is a multiple of 16 (32 above 512) -- the lengths our
+// mixed-radix shared-memory FFT handles, on a ladder coarse enough that CUDA graphs are re-captured rarely.
 static int nice_fft_size(int n) {
     const int q = n <= 512 ? 16 : 32;
     n = (n + q - 1) / q * q;
     for (;; n += q) {
         int m = n;
-        for (int f : {2, 3, 5, 7}) while (m % f == 0) m /= f;
+        for (int f : {2, 3, 5}) while (m % f == 0) m /= f;
         if (m == 1) return n;
     }
 }
+static inline int max_fft_len(int D) { return D == 2 ? 4096 : FFT_EPT * FFT_THREADS; }
 
 template <typename T>
 static int dev_alloc(fitsne_ctx *c, T **p, size_t count) {
@@ -215,12 +216,8 @@ static int ensure_grid_capacity(fitsne_ctx *c, int M) {
     const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
     if (plane > c->plane_cap) {
         const size_t cap = plane + plane / 2;
-        const size_t cplane = D == 2 ? (size_t) M * (M / 2 + 1) : (size_t) (M / 2 + 1);
-        const size_t ccap = cplane + cplane / 2 + 64;
-        CKRC(dev_alloc(c, &c->fft_in, cap * (c->n_fwd + c->n_kern)));
-        CKRC(dev_alloc(c, &c->spec, ccap * (c->n_fwd + c->n_kern)));
-        CKRC(dev_alloc(c, &c->fft_out, cap * c->n_inv));
-        if (c->world > 1) CKRC(dev_alloc(c, &c->compact, cap * c->n_fwd / 4 + 1024));
+        CKRC(dev_alloc(c, &c->planes, cap * 4));
+        if (c->world > 1) CKRC(dev_alloc(c, &c->compact, cap / 2 + 1024));
         c->plane_cap = cap;
         moved = true;
     }
@@ -232,14 +229,18 @@ static int get_plans(fitsne_ctx *c, int M, Plans **out) {
     auto it = c->plans.find(M);
     if (it != c->plans.end()) { *out = &it->second; return 0; }
     Plans pl;
-    const int D = c->D;
-    int n[2] = {M, M};
-    const int rank = D;
-    const int rdist = D == 2 ? M * M : M, cdist = D == 2 ? M * (M / 2 + 1) : (M / 2 + 1);
-    CKFFT(cufftPlanMany(&pl.fwd, rank, n, nullptr, 1, rdist, nullptr, 1, cdist, CUFFT_R2C, c->n_fwd + c->n_kern));
-    CKFFT(cufftPlanMany(&pl.inv, rank, n, nullptr, 1, cdist, nullptr, 1, rdist, CUFFT_C2R, c->n_inv));
-    CKFFT(cufftSetStream(pl.fwd, c->stream));
-    CKFFT(cufftSetStream(pl.inv, c->stream));
+    if (!fft_make_plan(M, &pl.plan)) return fail(c, FITSNE_EINVAL, "FFT length %d is not of the form 2^a 3^b 5^c", M);
+    CK(cudaMalloc((void **) &pl.W, (size_t) M * sizeof(float2)));
+    k_fft_twiddles<<<cdiv(M, 256), 256, 0, c->stream>>>(pl.W, M);
+    LAUNCH_CHECK();
+    CK(cudaStreamSynchronize(c->stream));
+    // tile: up to 8 lines (64-byte column segments) per CTA, bounded by the per-thread load budget
+    // (M * lines <= FFT_EPT * FFT_THREADS) and by shared memory (two ping-pong buffers + the twiddle table)
+    pl.lines = c->D == 2 ? 8 : 1;
+    while (pl.lines > 1 && ((size_t) M * pl.lines > (size_t) FFT_EPT * FFT_THREADS ||
+                            ((size_t) 2 * pl.lines * fft_buf_len(M) + M) * sizeof(float2) > (size_t) 110 * 1024)) pl.lines /= 2;   // power of two; two CTAs per SM
+    if ((size_t) M * pl.lines > (size_t) FFT_EPT * FFT_THREADS) return fail(c, FITSNE_EINVAL, "FFT length %d too long", M);
+    pl.smem = ((size_t) 2 * pl.lines * fft_buf_len(M) + M) * sizeof(float2);
     c->plans[M] = pl;
     *out = &c->plans[M];
     return 0;
@@ -270,11 +271,11 @@ static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, int M, const
         const int cpb = std::max(1, 256 / nodes);
         const int nchunks = cdiv(c->nloc, CHUNK);
         k_spread_chunks<D, P><<<cdiv(nchunks, cpb), cpb * nodes, 0, c->stream>>>(c->sorted_u, skeys, c->box_start, c->nloc, c->gp, cpb,
-                                                                                  c->n_fwd, c->slots, c->fft_in,
+                                                                                  c->slots, c->planes,
                                                                                   c->world > 1 ? c->compact : nullptr);
     } else {
         k_gather<D, P><<<cdiv(c->nloc, 256), 256, 0, c->stream>>>(c->sorted_u, skeys, sperm, c->nloc, c->gp, c->sc,
-                                                                   c->fft_out, c->frep);
+                                                                   c->planes, c->frep);
     }
     LAUNCH_CHECK();
     c->stats.kernel_launches += 1;
@@ -385,28 +386,43 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     CKRC(launch_spread_gather<D>(c, false, M, skeys, sperm));
     const int lpn = combine_lanes(c, M);
     if (c->world == 1) {
-        k_spread_combine<D><<<cdiv(plane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, c->n_fwd, lpn, c->fft_in, nullptr);
+        k_spread_combine<D><<<cdiv(plane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, lpn, c->planes, nullptr);
         c->stats.kernel_launches += 1;
     } else {
         const int Gc = M / 2;
         const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
-        k_spread_combine<D><<<cdiv(cplane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, c->n_fwd, lpn, c->fft_in, c->compact);
+        k_spread_combine<D><<<cdiv(cplane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, lpn, c->planes, c->compact);
         phase_mark(c, FITSNE_PHASE_COLLECTIVES);
-        CKNCCL(g_nccl.AllReduce(c->compact, c->compact, cplane * c->n_fwd, ncclFloat, ncclSum, c->comm, st));
-        k_pad_grids<D><<<cdiv(plane, 256), 256, 0, st>>>(c->compact, c->gp, c->n_fwd, c->fft_in);
+        CKNCCL(g_nccl.AllReduce(c->compact, c->compact, cplane * 4, ncclFloat, ncclSum, c->comm, st));   // 2 planes x float2
+        k_pad_grids<D><<<cdiv(plane, 256), 256, 0, st>>>(c->compact, c->gp, c->planes);
         c->stats.kernel_launches += 3;
     }
 
-    // ---- kernel samples + one batched R2C over (grids, kernels)
+    // ---- kernel samples, then the convolution: forward FFTs of the 4 packed planes, Hadamard (+ sum_Q), inverse FFTs
     phase_mark(c, FITSNE_PHASE_KERNEL_SPECTRUM);
-    k_gen_kernels<D><<<cdiv(plane, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->n_fwd, c->fft_in);
+    k_gen_kernels<D><<<cdiv(plane, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->planes);
     LAUNCH_CHECK();
     phase_mark(c, FITSNE_PHASE_FFT);
-    CKFFT(cufftExecR2C(pl->fwd, c->fft_in, reinterpret_cast<cufftComplex *>(c->spec)));
-    k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->spec, c->gp, c->n_fwd, c->n_fwd, c->df_is_one ? 1 : 0, c->zpartial);
+    const int *gG = &c->gp->G, *gok = &c->gp->ok;
+    const int L = pl->lines;
+    if (D == 2) {
+        // rows: the charge planes (0,1) are zero beyond row G -> pruned; the kernel planes (2,3) need every row
+        k_fft_pass<false><<<dim3(cdiv(M, L), 4), FFT_THREADS, pl->smem, st>>>(c->planes, plane, M, L, pl->plan, pl->W, 0, 0x3u, gG, gok);
+        k_fft_pass<true><<<dim3(cdiv(M, L), 4), FFT_THREADS, pl->smem, st>>>(c->planes, plane, M, L, pl->plan, pl->W, 0, 0u, gG, gok);
+    } else {
+        k_fft_pass<false><<<dim3(1, 4), FFT_THREADS, pl->smem, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok);
+    }
+    k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial);
     k_finalize_z<<<1, 256, 0, st>>>(c->zpartial, Z_BLOCKS, c->N, c->gp, c->sc);
-    CKFFT(cufftExecC2R(pl->inv, reinterpret_cast<cufftComplex *>(c->spec), c->fft_out));
-    c->stats.kernel_launches += 5;
+    if (D == 2) {
+        // inverse: columns first (all of them), then only the G rows the gather reads
+        k_fft_pass<true><<<dim3(cdiv(M, L), 2), FFT_THREADS, pl->smem, st>>>(c->planes, plane, M, L, pl->plan, pl->W, 1, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(cdiv(M, L), 2), FFT_THREADS, pl->smem, st>>>(c->planes, plane, M, L, pl->plan, pl->W, 1, 0x3u, gG, gok);
+        c->stats.kernel_launches += 6;
+    } else {
+        k_fft_pass<false><<<dim3(1, 1), FFT_THREADS, pl->smem, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok);
+        c->stats.kernel_launches += 4;
+    }
     LAUNCH_CHECK();
 
     // ---- gather (+ 1/Z)
@@ -584,6 +600,7 @@ static int run_iteration(fitsne_ctx *c, bool update) {
     if (sort_bits_for(B, c->D) > SORT_MAX_BITS || (long long) G * 2 > 65536)
         return fail(c, FITSNE_EINVAL, "grid too large: n_boxes=%d", B);
     const int M = nice_fft_size(2 * G);
+    if (M > max_fft_len(c->D)) return fail(c, FITSNE_EINVAL, "grid too large: n_boxes=%d needs FFT length %d > %d", B, M, max_fft_len(c->D));
     TRACE("bounds [%g, %g] -> B=%d G=%d M=%d", mn, mx, B, G, M);
     CKRC(ensure_grid_capacity(c, M));
     if (B != c->cur_B || M != c->cur_M) {
@@ -723,6 +740,8 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
+    CK(cudaFuncSetAttribute(k_fft_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_fft_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 
     const size_t yel = (size_t) c->per * world * no_dims;
     c->y_elems = yel;
@@ -813,11 +832,11 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     drop_graphs(c);
-    for (auto &p : c->plans) { cufftDestroy(p.second.fwd); cufftDestroy(p.second.inv); }
+    for (auto &p : c->plans) if (p.second.W) cudaFree(p.second.W);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->col_P, c->val_P, c->keys[0], c->keys[1],
-                    c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->hist, c->sort_totals, c->slots, c->attr, c->fft_in,
-                    c->fft_out, c->compact, c->spec, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
+                    c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->hist, c->sort_totals, c->slots, c->attr, c->planes,
+                    c->compact, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->col_P2, c->val_P2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
                     c->nonempty, c->gp_reorder};
@@ -1096,7 +1115,7 @@ int fitsne_debug_copy(fitsne_ctx *c, const char *what, void *dst, size_t dst_byt
     else if (!strcmp(what, "perm")) { src = c->perm[sorted_buf]; bytes = (size_t) c->nloc * 4; }
     else if (!strcmp(what, "keys")) { src = c->keys[sorted_buf]; bytes = (size_t) c->nloc * 4; }
     else if (!strcmp(what, "box_start")) { src = c->box_start; bytes = ((c->D == 2 ? (size_t) c->cur_B * c->cur_B : (size_t) c->cur_B) + 1) * 4; }
-    else if (!strcmp(what, "fft_out")) { src = c->fft_out; bytes = (c->D == 2 ? (size_t) c->cur_M * c->cur_M : (size_t) c->cur_M) * c->n_inv * 4; }
+    else if (!strcmp(what, "planes")) { src = c->planes; bytes = (c->D == 2 ? (size_t) c->cur_M * c->cur_M : (size_t) c->cur_M) * 4 * sizeof(float2); }
     else return fail(c, FITSNE_EINVAL, "unknown debug array '%s'", what);
     if (needed) *needed = bytes;
     if (!dst) return 0;

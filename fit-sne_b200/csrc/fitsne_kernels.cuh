@@ -15,7 +15,6 @@
 // evaluated in fp64 with the reference's exact operation order.
 #pragma once
 #include <cuda_runtime.h>
-#include <cufft.h>
 #include <stdint.h>
 #include <float.h>
 #include <type_traits>
@@ -542,12 +541,14 @@ __device__ __forceinline__ int key_to_box(uint32_t key, const GridParams &gp) {
     return D == 2 ? (int) (key >> gp.xbits) * gp.B + (int) (key & ((1u << gp.xbits) - 1u)) : (int) key;
 }
 
-template <int D>
-__device__ __forceinline__ void store_node(float *__restrict__ dst, size_t stride, size_t off, float4 v, int n_fwd) {
-    dst[off] = v.x;
-    dst[stride + off] = v.y;
-    dst[2 * stride + off] = v.z;
-    if (n_fwd > 3) dst[3 * stride + off] = v.w;
+// Spread results live in two packed complex planes (two real grids per complex transform, see fitsne_fft.cuh):
+//   plane 0 = (w1, delta_x)   plane 1 = (delta_y, wbb)        [1-D: (w1, delta), (wbb, 0)]
+// delta and wbb are kept in BOX UNITS (offsets / box width): every plane is then O(w1) whatever the embedding's
+// scale, which is what makes packing two real planes into one fp32 complex transform safe (a 1e-5-scale plane
+// packed beside an O(1) plane would lose 5 digits in the separation).
+__device__ __forceinline__ void store_node(float2 *__restrict__ dst, size_t stride, size_t off, float4 v) {
+    dst[off] = make_float2(v.x, v.y);
+    dst[stride + off] = make_float2(v.z, v.w);
 }
 
 // offset of (box, node) inside one plane: padded FFT input (row stride M) or, multi-GPU, the compact G^D layout
@@ -565,9 +566,9 @@ __device__ __forceinline__ size_t node_offset(int box, int node, const GridParam
 template <int D, int P>
 __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
                                                        const uint32_t *__restrict__ box_start, int n,
-                                                       const GridParams *__restrict__ gpp, int chunks_per_block, int n_fwd,
-                                                       float4 *__restrict__ slots, float *__restrict__ fft_in,
-                                                       float *__restrict__ compact) {
+                                                       const GridParams *__restrict__ gpp, int chunks_per_block,
+                                                       float4 *__restrict__ slots, float2 *__restrict__ fft_in,
+                                                       float2 *__restrict__ compact) {
     __shared__ GridParams gps;
     for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
@@ -583,10 +584,9 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
     const int kb = c * CHUNK;
     if (kb >= n) return;
     const int ke = min(kb + CHUNK, n);
-    const float bw = gp.bwf;
     const int a = D == 2 ? node / p : node, b = D == 2 ? node - a * p : 0;
     const float sa = gp.s[a], sb = gp.s[b];
-    float *dst = compact ? compact : fft_in;
+    float2 *dst = compact ? compact : fft_in;
     const int Gc = gp.M / 2;
     const size_t stride = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) gp.M * gp.M : (size_t) gp.M);
     float4 *myslots = slots + (size_t) c * 2 * nodes;
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
         const int box = key_to_box<D>(skeys[k], gp);
         if (box != cur) {
             // segment of `cur` ended inside the chunk: finished box unless it started before the chunk
-            if ((int) box_start[cur] >= kb) store_node<D>(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc, n_fwd);
+            if ((int) box_start[cur] >= kb) store_node(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc);
             else myslots[node] = acc;
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
             cur = box;
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
         if (D == 2) {
             const float2 u = reinterpret_cast<const float2 *>(sorted_u)[k];
             const float L = lagrange1<P>(gp, p, a, u.y) * lagrange1<P>(gp, p, b, u.x);
-            const float ox = bw * (u.x - sb), oy = bw * (u.y - sa);
+            const float ox = u.x - sb, oy = u.y - sa;      // offsets in BOX UNITS (x bw later): keeps the packed planes O(w1)
             acc.x += L;
             acc.y += L * ox;
             acc.z += L * oy;
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
         } else {
             const float u = sorted_u[k];
             const float L = lagrange1<P>(gp, p, a, u);
-            const float o = bw * (u - sa);
+            const float o = u - sa;                         // box units
             acc.x += L;
             acc.y += L * o;
             acc.z += L * o * o;
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
     }
     // last segment: finished only if the box both started in this chunk and ends with it
     const bool started_here = (int) box_start[cur] >= kb, ends_here = (int) box_start[cur + 1] <= ke;
-    if (started_here && ends_here) store_node<D>(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc, n_fwd);
+    if (started_here && ends_here) store_node(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc);
     else myslots[(started_here ? 1 : 0) * nodes + node] = acc;
 }
 
@@ -633,8 +633,8 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
 // all-reduced and then expanded by k_pad_grids.
 template <int D>
 __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ slots, const uint32_t *__restrict__ box_start,
-                                                        const GridParams *__restrict__ gpp, int n_fwd, int lpn,
-                                                        float *__restrict__ fft_in, float *__restrict__ compact) {
+                                                        const GridParams *__restrict__ gpp, int lpn,
+                                                        float2 *__restrict__ fft_in, float2 *__restrict__ compact) {
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
     const int G = gp.G, p = gp.p, M = gp.M;
@@ -685,13 +685,13 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
         acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
         acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
-    if (write && sub == 0) store_node<D>(compact ? compact : fft_in, plane, id, acc, n_fwd);
+    if (write && sub == 0) store_node(compact ? compact : fft_in, plane, id, acc);
 }
 
 // multi-GPU: expand the all-reduced compact grids into the zero-padded FFT input planes
 template <int D>
-__global__ void __launch_bounds__(256) k_pad_grids(const float *__restrict__ compact, const GridParams *__restrict__ gpp,
-                                                   int n_fwd, float *__restrict__ fft_in) {
+__global__ void __launch_bounds__(256) k_pad_grids(const float2 *__restrict__ compact, const GridParams *__restrict__ gpp,
+                                                   float2 *__restrict__ fft_in) {
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
     const int G = gp.G, M = gp.M, Gc = M / 2;
@@ -703,17 +703,19 @@ __global__ void __launch_bounds__(256) k_pad_grids(const float *__restrict__ com
     if (D == 2) { row = (int) (id / M); col = (int) (id - (size_t) row * M); } else col = (int) id;
     const bool inside = col < G && row < G;
     const size_t src = D == 2 ? (size_t) row * G + col : (size_t) col;
-    for (int t = 0; t < n_fwd; t++) fft_in[t * plane + id] = inside ? compact[t * cplane + src] : 0.f;
+    const float2 z = make_float2(0.f, 0.f);
+    fft_in[id] = inside ? compact[src] : z;
+    fft_in[plane + id] = inside ? compact[cplane + src] : z;
 }
 
 // ------------------------------------------------------------------------------------ kernel samples --
 // Real kernels on the wrap-around node-offset lattice, offsets d in (-G, G) stored at index d mod M
-// (the reference's 2G circulant embedding, nbodyfft.cpp:52-61, with M >= 2G).  Planes written at
-// fft_in[plane0 + j]:  j=0: Ksq=(1+r2/df)^-(df+1)   j=1..D: R_k*Ksq   j=D+1: Kb=(1+r2/df)^-df
-// (tsne.cpp:69-94).  Values carry the 1/M^D inverse-FFT normalisation.
+// (the reference's 2G circulant embedding, nbodyfft.cpp:52-61, with M >= 2G), packed two per complex plane:
+//   plane 2 = (Ksq, Kb)   plane 3 = (Kgrad_x, Kgrad_y)  [1-D: (Kgrad, 0)]
+//   Ksq=(1+r2/df)^-(df+1)   Kgrad_k = (R_k/bw)*Ksq  (box units)   Kb=(1+r2/df)^-df      (tsne.cpp:69-94)
+// Values carry the 1/M^D inverse-FFT normalisation (nbodyfft.cpp:202-203).
 template <int D>
-__global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restrict__ gpp, double df, int plane0,
-                                                     float *__restrict__ fft_in) {
+__global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restrict__ gpp, double df, float2 *__restrict__ planes) {
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
     const int M = gp.M, G = gp.G;
@@ -725,70 +727,91 @@ __global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restric
     const int dc = c < G ? c : (c > M - G ? c - M : 0);
     const int dr = r < G ? r : (r > M - G ? r - M : 0);
     const bool valid = (c < G || c > M - G) && (D == 1 || r < G || r > M - G);
-    float *base = fft_in + (size_t) plane0 * plane + id;
-    if (!valid) {
-        for (int j = 0; j < D + 2; j++) base[j * plane] = 0.f;
-        return;
+    float2 k1 = make_float2(0.f, 0.f), k2 = make_float2(0.f, 0.f);
+    if (valid) {
+        const double rx = gp.h * (double) dc, ry = gp.h * (double) dr;
+        const double r2 = rx * rx + (D == 2 ? ry * ry : 0.0);
+        double kb, ksq;
+        if (df == 1.0) {
+            kb = 1.0 / (1.0 + r2);
+            ksq = kb * kb;
+        } else {
+            const double t = 1.0 + r2 / df;
+            kb = pow(t, -df);
+            ksq = pow(t, -(df + 1.0));
+        }
+        kb *= gp.inv_norm; ksq *= gp.inv_norm;
+        k1 = make_float2((float) ksq, (float) kb);
+        // gradient kernels in box units as well: R_k / bw = (lattice offset) / p
+        const double ux = (double) dc / (double) gp.p, uy = (double) dr / (double) gp.p;
+        k2 = make_float2((float) (ux * ksq), D == 2 ? (float) (uy * ksq) : 0.f);
     }
-    const double rx = gp.h * (double) dc, ry = gp.h * (double) dr;
-    const double r2 = rx * rx + (D == 2 ? ry * ry : 0.0);
-    double kb, ksq;
-    if (df == 1.0) {
-        kb = 1.0 / (1.0 + r2);
-        ksq = kb * kb;
-    } else {
-        const double t = 1.0 + r2 / df;
-        kb = pow(t, -df);
-        ksq = pow(t, -(df + 1.0));
-    }
-    kb *= gp.inv_norm; ksq *= gp.inv_norm;
-    base[0] = (float) ksq;
-    base[plane] = (float) (rx * ksq);
-    if (D == 2) base[2 * plane] = (float) (ry * ksq);
-    base[(D + 1) * plane] = (float) kb;
+    planes[2 * plane + id] = k1;
+    planes[3 * plane + id] = k2;
 }
 
 // ------------------------------------------------------------------------------ Hadamard + sum_Q terms --
-// spec planes: [0..n_fwd) = FFT of (w1, delta_1..D, [wbb]);  [ks..ks+D+2) = FFT of (Ksq, Kgrad_1..D, Kb).
-// Overwrites planes 0..D with  v1 = Ksq.w1,  B_k = Kgrad_k.w1 - Ksq.delta_k  and accumulates, by Parseval,
+// Input: the (full, M^D) spectra of the four packed planes.  A packed spectrum Z = FFT(A + iB) of two REAL arrays
+// separates as  A^[k] = (Z[k] + conj(Z[-k]))/2,  B^[k] = (Z[k] - conj(Z[-k]))/(2i);  one thread owns the frequency
+// pair (k, -k), so everything is done in place:
+//   plane 0 <- V1 = v1^ + i*B1^      v1 = Ksq*w1,  B_k = Kgrad_k*w1 - Ksq*delta_k     (nbodyfft.cpp:184-191)
+//   plane 1 <- V2 = B2^              (2-D only)
+// and, by Parseval in fp64, the sum_Q terms
 //   df==1: <w1,Kb*w1> + 2<wbb,v1> + sum_k (4<delta_k,Kgrad_k*w1> - 2<delta_k,Ksq*delta_k>)   (tsne.cpp:1101-1110)
 //   df!=1: <w1,Kb*w1>                                                                          (tsne.cpp:950-955)
-// in fp64; half-spectrum columns 1..ceil(M/2)-1 count twice.
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 __device__ __forceinline__ double re_conj_mul(float2 a, float2 b) { return (double) a.x * (double) b.x + (double) a.y * (double) b.y; }
+// split Z[k], Z[-k] of a packed pair into the spectra of its real part (A) and imaginary part (B) at k
+__device__ __forceinline__ void unpack_pair(float2 zk, float2 zm, float2 &A, float2 &B) {
+    A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+    B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+}
 
 template <int D>
-__global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ spec, const GridParams *__restrict__ gpp, int n_fwd,
-                                                  int ks, int df_is_one, double *__restrict__ zpartial) {
+__global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, const GridParams *__restrict__ gpp,
+                                                  int df_is_one, double *__restrict__ zpartial) {
     __shared__ double sm[32];
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
-    const int M = gp.M, MH = M / 2 + 1;
-    const size_t nfreq = D == 2 ? (size_t) M * MH : (size_t) MH;
+    const int M = gp.M;
+    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
+    float2 *Z1 = planes, *Z2 = planes + plane;
+    const float2 *K1 = planes + 2 * plane, *K2 = planes + 3 * plane;
+    const double bw2 = gp.bw * gp.bw;
     double zacc = 0;
-    for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < nfreq; e += (size_t) gridDim.x * blockDim.x) {
-        const int col = D == 2 ? (int) (e % MH) : (int) e;
-        const double wt = (col == 0 || (2 * col == M)) ? 1.0 : 2.0;
-        const float2 w1 = spec[e];
-        const float2 ksq = spec[(size_t) ks * nfreq + e];
-        const float2 kb = spec[(size_t) (ks + D + 1) * nfreq + e];
+    for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < plane; e += (size_t) gridDim.x * blockDim.x) {
+        size_t em;
+        if (D == 2) {
+            const int k1 = (int) (e / M), k2 = (int) (e - (size_t) k1 * M);
+            em = (size_t) ((M - k1) % M) * M + (size_t) ((M - k2) % M);
+        } else em = (size_t) ((M - (int) e) % M);
+        if (em < e) continue;                       // the partner thread owns this pair
+        const double wt = em == e ? 1.0 : 2.0;
+        float2 w1, d1, d2, wbb, ksq, kb, kg1, kg2;
+        unpack_pair(Z1[e], Z1[em], w1, d1);
+        unpack_pair(Z2[e], Z2[em], d2, wbb);        // 1-D: d2 = wbb-plane real part, see below
+        unpack_pair(K1[e], K1[em], ksq, kb);
+        unpack_pair(K2[e], K2[em], kg1, kg2);
+        if (D == 1) { wbb = d2; }                   // 1-D plane 1 = (wbb, 0)
         const float2 v1 = cmul(ksq, w1);
+        const float2 kgw1 = cmul(kg1, w1), ksd1 = cmul(ksq, d1);
+        const float2 B1 = make_float2(kgw1.x - ksd1.x, kgw1.y - ksd1.y);
+        // delta, wbb, Kgrad and B are in box units: the physical sum_Q terms carry bw^2
         double z = re_conj_mul(w1, cmul(kb, w1));
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-            const float2 dk = spec[(size_t) (1 + k) * nfreq + e];
-            const float2 kg = spec[(size_t) (ks + 1 + k) * nfreq + e];
-            const float2 kgw = cmul(kg, w1);
-            const float2 ksd = cmul(ksq, dk);
-            if (df_is_one) z += 4.0 * re_conj_mul(dk, kgw) - 2.0 * re_conj_mul(dk, ksd);
-            spec[(size_t) (1 + k) * nfreq + e] = make_float2(kgw.x - ksd.x, kgw.y - ksd.y);
+        double zb = 0;
+        if (df_is_one) zb += 2.0 * re_conj_mul(wbb, v1) + 4.0 * re_conj_mul(d1, kgw1) - 2.0 * re_conj_mul(d1, ksd1);
+        // V1 = v1 + i*B1 at k; at -k both spectra are conjugated (real arrays): V1[-k] = conj(v1) + i*conj(B1)
+        Z1[e] = make_float2(v1.x - B1.y, v1.y + B1.x);
+        if (em != e) Z1[em] = make_float2(v1.x + B1.y, -v1.y + B1.x);
+        if (D == 2) {
+            const float2 kgw2 = cmul(kg2, w1), ksd2 = cmul(ksq, d2);
+            const float2 B2 = make_float2(kgw2.x - ksd2.x, kgw2.y - ksd2.y);
+            if (df_is_one) zb += 4.0 * re_conj_mul(d2, kgw2) - 2.0 * re_conj_mul(d2, ksd2);
+            Z2[e] = B2;
+            if (em != e) Z2[em] = cconj(B2);
         }
-        if (df_is_one) {
-            const float2 wbb = spec[(size_t) (1 + D) * nfreq + e];
-            z += 2.0 * re_conj_mul(wbb, v1);
-        }
-        spec[e] = v1;
-        zacc += wt * z;
+        zacc += wt * (z + bw2 * zb);
     }
     const double r = block_sum(zacc, sm);
     if (threadIdx.x == 0) zpartial[blockIdx.x] = r;
@@ -815,7 +838,7 @@ template <int D, int P>
 __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
                                                 const uint32_t *__restrict__ perm, int n,
                                                 const GridParams *__restrict__ gpp, const Scalars *__restrict__ sc,
-                                                const float *__restrict__ fft_out, float *__restrict__ frep) {
+                                                const float2 *__restrict__ planes, float *__restrict__ frep) {
     __shared__ GridParams gps;
     for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
@@ -835,38 +858,41 @@ __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted
         float Lx[P > 0 ? P : PMAX], ox[P > 0 ? P : PMAX];
 #pragma unroll(P > 0 ? P : 1)
         for (int b = 0; b < (P > 0 ? P : PMAX); b++) {
-            if (b < p) { Lx[b] = lagrange1<P>(gp, p, b, u.x); ox[b] = bw * (u.x - gp.s[b]); }
+            if (b < p) { Lx[b] = lagrange1<P>(gp, p, b, u.x); ox[b] = u.x - gp.s[b]; }
         }
         float fx = 0.f, fy = 0.f;
-        const float *g0 = fft_out + (size_t) (by * p) * M + bx * p;
+        const float2 *g0 = planes + (size_t) (by * p) * M + bx * p;   // plane 0 = (v1, Bx), plane 1 = (By, .)
 #pragma unroll(P > 0 ? P : 1)
         for (int a = 0; a < (P > 0 ? P : PMAX); a++) {
             if (a < p) {
                 const float Ly = lagrange1<P>(gp, p, a, u.y);
-                const float oy = bw * (u.y - gp.s[a]);
-                const float *row = g0 + (size_t) a * M;
+                const float oy = u.y - gp.s[a];
+                const float2 *row = g0 + (size_t) a * M;
 #pragma unroll(P > 0 ? P : 1)
                 for (int b = 0; b < (P > 0 ? P : PMAX); b++) {
                     if (b < p) {
                         const float L = Ly * Lx[b];
-                        const float v1 = __ldg(row + b), Bx = __ldg(row + plane + b), By = __ldg(row + 2 * plane + b);
-                        fx += L * (ox[b] * v1 + Bx);
-                        fy += L * (oy * v1 + By);
+                        const float2 vb = __ldg(row + b);
+                        const float By = __ldg(reinterpret_cast<const float *>(row + plane + b));
+                        fx += L * (ox[b] * vb.x + vb.y);
+                        fy += L * (oy * vb.x + By);
                     }
                 }
             }
         }
-        reinterpret_cast<float2 *>(frep)[perm[k]] = make_float2(fx * inv_Z, fy * inv_Z);
+        // offsets and B planes are in box units: one factor bw restores the physical force
+        reinterpret_cast<float2 *>(frep)[perm[k]] = make_float2(fx * bw * inv_Z, fy * bw * inv_Z);
     } else {
         const float u = sorted_u[k];
-        const float *g0 = fft_out + (size_t) key * p;
+        const float2 *g0 = planes + (size_t) key * p;                  // plane 0 = (v1, B)
         float f = 0.f;
         for (int a = 0; a < p; a++) {
             const float L = lagrange1<P>(gp, p, a, u);
-            const float o = bw * (u - gp.s[a]);
-            f += L * (o * __ldg(g0 + a) + __ldg(g0 + M + a));
+            const float o = u - gp.s[a];
+            const float2 vb = __ldg(g0 + a);
+            f += L * (o * vb.x + vb.y);
         }
-        frep[perm[k]] = f * inv_Z;
+        frep[perm[k]] = f * bw * inv_Z;
     }
 }
 
