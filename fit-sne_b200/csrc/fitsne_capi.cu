@@ -60,8 +60,8 @@ std::string g_create_error;
 struct Plans {          // per FFT length: radix plan + twiddle table (no library plans, nothing to JIT)
     FftPlan plan{};
     float2 *W = nullptr;
-    int lines = 1;          // rows / columns per CTA tile
-    size_t smem = 0;
+    int lines_rows = 1, lines_cols = 1;          // rows / columns per CTA tile
+    size_t smem_rows = 0, smem_cols = 0;
 };
 
 // The launch sequence depends on the FFT length M only (n_boxes and all grid geometry are read from the
@@ -234,13 +234,20 @@ static int get_plans(fitsne_ctx *c, int M, Plans **out) {
     k_fft_twiddles<<<cdiv(M, 256), 256, 0, c->stream>>>(pl.W, M);
     LAUNCH_CHECK();
     CK(cudaStreamSynchronize(c->stream));
-    // tile: up to 8 lines (64-byte column segments) per CTA, bounded by the per-thread load budget
-    // (M * lines <= FFT_EPT * FFT_THREADS) and by shared memory (two ping-pong buffers + the twiddle table)
-    pl.lines = c->D == 2 ? 8 : 1;
-    while (pl.lines > 1 && ((size_t) M * pl.lines > (size_t) FFT_EPT * FFT_THREADS ||
-                            ((size_t) 2 * pl.lines * fft_buf_len(M) + M) * sizeof(float2) > (size_t) 110 * 1024)) pl.lines /= 2;   // power of two; two CTAs per SM
-    if ((size_t) M * pl.lines > (size_t) FFT_EPT * FFT_THREADS) return fail(c, FITSNE_EINVAL, "FFT length %d too long", M);
-    pl.smem = ((size_t) 2 * pl.lines * fft_buf_len(M) + M) * sizeof(float2);
+    // tiles: column passes take 4 adjacent columns per CTA (32-byte segments = one sector per row); row passes are
+    // contiguous anyway, so they use 2 rows per CTA and get twice the CTAs per SM to overlap loads with butterflies.
+    // Bounds: M * lines <= FFT_EPT * FFT_THREADS (register staging) and the two ping-pong buffers + twiddles in smem.
+    auto fit = [&](int want) {
+        int l = c->D == 2 ? want : 1;
+        while (l > 1 && ((size_t) M * l > (size_t) FFT_EPT * FFT_THREADS ||
+                         ((size_t) 2 * l * fft_buf_len(M, l) + M) * sizeof(float2) > (size_t) 110 * 1024)) l /= 2;
+        return l;
+    };
+    pl.lines_cols = fit(4);
+    pl.lines_rows = fit(2);
+    if ((size_t) M * pl.lines_cols > (size_t) FFT_EPT * FFT_THREADS) return fail(c, FITSNE_EINVAL, "FFT length %d too long", M);
+    pl.smem_cols = ((size_t) 2 * pl.lines_cols * fft_buf_len(M, pl.lines_cols) + M) * sizeof(float2);
+    pl.smem_rows = ((size_t) 2 * pl.lines_rows * fft_buf_len(M, pl.lines_rows) + M) * sizeof(float2);
     c->plans[M] = pl;
     *out = &c->plans[M];
     return 0;
@@ -315,9 +322,13 @@ static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
         c->stats.kernel_launches += 1;
         return 0;
     }
-#define ATT(L) k_attract<D, L><<<cdiv((long long) rows * L, 256), 256, 0, st>>>( \
+    // persistent grid: `per_sm` CTAs of 256 threads per SM (never more than the row groups there are)
+    static const int per_sm = getenv("FITSNE_SPMV_CTAS_PER_SM") ? atoi(getenv("FITSNE_SPMV_CTAS_PER_SM")) : 8;
+    static const int lpr_env = getenv("FITSNE_LPR") ? atoi(getenv("FITSNE_LPR")) : 0;
+    static const int dummy_smem = getenv("FITSNE_SPMV_SMEM_KB") ? atoi(getenv("FITSNE_SPMV_SMEM_KB")) * 1024 : 0;
+#define ATT(L) k_attract<D, L><<<std::min(cdiv((long long) rows * L, 256), 148 * per_sm), 256, dummy_smem, st>>>( \
         c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->row_begin, c->row_end, inv_df, c->attr)
-    switch (c->lpr) {
+    switch (lpr_env ? lpr_env : c->lpr) {
         case 4: ATT(4); break;
         case 8: ATT(8); break;
         case 16: ATT(16); break;
@@ -404,23 +415,23 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     LAUNCH_CHECK();
     phase_mark(c, FITSNE_PHASE_FFT);
     const int *gG = &c->gp->G, *gok = &c->gp->ok;
-    const int L = pl->lines;
+    const int LR = pl->lines_rows, LC = pl->lines_cols;
     if (D == 2) {
         // rows: the charge planes (0,1) are zero beyond row G -> pruned; the kernel planes (2,3) need every row
-        k_fft_pass<false><<<dim3(cdiv(M, L), 4), FFT_THREADS, pl->smem, st>>>(c->planes, plane, M, L, pl->plan, pl->W, 0, 0x3u, gG, gok);
-        k_fft_pass<true><<<dim3(cdiv(M, L), 4), FFT_THREADS, pl->smem, st>>>(c->planes, plane, M, L, pl->plan, pl->W, 0, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(cdiv(M, LR), 4), FFT_THREADS, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok);
+        k_fft_pass<true><<<dim3(cdiv(M, LC), 4), FFT_THREADS, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 0, 0u, gG, gok);
     } else {
-        k_fft_pass<false><<<dim3(1, 4), FFT_THREADS, pl->smem, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(1, 4), FFT_THREADS, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok);
     }
     k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial);
     k_finalize_z<<<1, 256, 0, st>>>(c->zpartial, Z_BLOCKS, c->N, c->gp, c->sc);
     if (D == 2) {
         // inverse: columns first (all of them), then only the G rows the gather reads
-        k_fft_pass<true><<<dim3(cdiv(M, L), 2), FFT_THREADS, pl->smem, st>>>(c->planes, plane, M, L, pl->plan, pl->W, 1, 0u, gG, gok);
-        k_fft_pass<false><<<dim3(cdiv(M, L), 2), FFT_THREADS, pl->smem, st>>>(c->planes, plane, M, L, pl->plan, pl->W, 1, 0x3u, gG, gok);
+        k_fft_pass<true><<<dim3(cdiv(M, LC), 2), FFT_THREADS, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(cdiv(M, LR), 2), FFT_THREADS, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok);
         c->stats.kernel_launches += 6;
     } else {
-        k_fft_pass<false><<<dim3(1, 1), FFT_THREADS, pl->smem, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(1, 1), FFT_THREADS, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok);
         c->stats.kernel_launches += 4;
     }
     LAUNCH_CHECK();
@@ -740,6 +751,10 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
+    CK(cudaFuncSetAttribute(k_attract<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_attract<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_attract<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_attract<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_fft_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(k_fft_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 
@@ -774,7 +789,7 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
         }
     }
     const double avg = (double) c->E / (double) std::max(1, c->nloc);
-    c->lpr = avg > 48 ? 32 : avg > 20 ? 16 : avg > 8 ? 8 : 4;
+    c->lpr = avg > 96 ? 32 : avg > 40 ? 16 : avg > 6 ? 8 : 4;   // lanes per CSR row (B200 sweep at 30 nnz/row: 8 lanes best)
 
     CKRC(dev_alloc(c, &c->keys[0], (size_t) c->nloc)); CKRC(dev_alloc(c, &c->keys[1], (size_t) c->nloc));
     CKRC(dev_alloc(c, &c->perm[0], (size_t) c->nloc)); CKRC(dev_alloc(c, &c->perm[1], (size_t) c->nloc));

@@ -24,7 +24,14 @@ constexpr int FFT_THREADS = 512;
 // shared-memory index skew: one pad slot every 8 elements turns the stride-R / stride-8R writes of the first Stockham
 // stages (which would hit 2 of the 16 eight-byte bank pairs) into conflict-free or 2-way patterns
 __host__ __device__ __forceinline__ int fft_phys(int i) { return i + (i >> 3); }
-__host__ __device__ __forceinline__ int fft_buf_len(int n) { return n + (n >> 3) + 1; }
+// per-sequence buffer stride: skewed length rounded up so that stride % 16 == 16 / lines -- the `lines` sequences of a
+// column tile then start in different 8-byte bank pairs and the transposing stage-in/out is conflict-free
+__host__ __device__ __forceinline__ int fft_buf_len(int n, int lines) {
+    int len = n + (n >> 3) + 1;
+    const int want = lines >= 16 ? 1 : 16 / (lines < 1 ? 1 : lines);
+    while ((len & 15) != (want & 15)) len++;
+    return len;
+}
 
 // exact division of small non-negative integers (n < 2^20) by an invariant: shifts for powers of two, multiply-high else
 struct FastDiv {
@@ -200,7 +207,7 @@ __device__ __forceinline__ float2 *fft_smem(float2 *a, float2 *b, int NS, int ba
 //   rows: grid = (ceil(rows_total / lines), nplanes); prune_mask bit i set => plane i only needs rows < *g_rows
 //         (g_rows points at GridParams::G on the device)
 //   cols: grid = (ceil(M / lines), nplanes)
-// Dynamic smem: (2 * lines * fft_buf_len(M) + M) float2.  Requires M * lines <= FFT_EPT * FFT_THREADS.
+// Dynamic smem: (2 * lines * fft_buf_len(M, lines) + M) float2.  Requires M * lines <= FFT_EPT * FFT_THREADS.
 constexpr int FFT_EPT = 24;
 
 template <bool COLS>
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_pass(float2 *__restrict__ d
     __shared__ FftPlan plan_s;
     for (int i = threadIdx.x; i < (int) (sizeof(FftPlan) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&plan_s)[i] = reinterpret_cast<const int *>(&plan)[i];
-    const int M = plan.n, NS = fft_buf_len(M);
+    const int M = plan.n, NS = fft_buf_len(M, lines);
     const int l0 = blockIdx.x * lines;
     int limit = COLS ? M : rows_total;
     if (!COLS && ((prune_mask >> blockIdx.y) & 1u)) limit = min(limit, *g_rows);

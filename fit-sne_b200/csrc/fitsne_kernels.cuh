@@ -901,44 +901,50 @@ __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted
 // (tsne.cpp:1121-1137; exaggeration is applied later as a scalar).  It depends on Y and P only, so it runs on a
 // second stream concurrently with the whole repulsive pipeline (sort/spread/FFT/gather).
 // Row offsets are local to this rank's edge slice: edges of row i are [row_P[i]-edge_base, row_P[i+1]-edge_base).
+// Persistent form: a fixed grid (a few CTAs per SM, set by the host) strides over the row groups, so the kernel
+// never occupies more than its share of each SM and the repulsive pipeline's kernels co-run beside it.
 template <int D, int LPR>
 __global__ void __launch_bounds__(256) k_attract(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
                                                  const float *__restrict__ val_P, uint32_t edge_base,
                                                  const float *__restrict__ Y, int row_begin, int row_end, float inv_df,
                                                  float *__restrict__ attr) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int sub = gid % LPR;
-    const int row = row_begin + gid / LPR;
-    const bool active = row < row_end;
-    float ax = 0.f, ay = 0.f;
-    if (active) {
-        float yix, yiy = 0.f;
-        if (D == 2) { const float2 yi = reinterpret_cast<const float2 *>(Y)[row]; yix = yi.x; yiy = yi.y; }
-        else yix = Y[row];
-        const uint32_t e0 = row_P[row] - edge_base, e1 = row_P[row + 1] - edge_base;
-        for (uint32_t e = e0 + sub; e < e1; e += LPR) {
-            const uint32_t j = col_P[e];
-            const float pv = val_P[e];
-            if (D == 2) {
-                const float2 yj = __ldg(reinterpret_cast<const float2 *>(Y) + j);
-                const float dx = yix - yj.x, dy = yiy - yj.y;
-                const float q = pv / (1.f + (dx * dx + dy * dy) * inv_df);
-                ax += q * dx; ay += q * dy;
-            } else {
-                const float dx = yix - __ldg(Y + j);
-                const float q = pv / (1.f + dx * dx * inv_df);
-                ax += q * dx;
+    constexpr int RPB = 256 / LPR;                       // rows per CTA per trip
+    const int sub = threadIdx.x % LPR;
+    const int nrows = row_end - row_begin;
+    for (int base = blockIdx.x * RPB; base < nrows; base += gridDim.x * RPB) {
+        const int row = row_begin + base + threadIdx.x / LPR;
+        const bool active = row < row_end;
+        float ax = 0.f, ay = 0.f;
+        if (active) {
+            float yix, yiy = 0.f;
+            if (D == 2) { const float2 yi = reinterpret_cast<const float2 *>(Y)[row]; yix = yi.x; yiy = yi.y; }
+            else yix = Y[row];
+            const uint32_t e0 = row_P[row] - edge_base, e1 = row_P[row + 1] - edge_base;
+#pragma unroll 4
+            for (uint32_t e = e0 + sub; e < e1; e += LPR) {
+                const uint32_t j = col_P[e];
+                const float pv = val_P[e];
+                if (D == 2) {
+                    const float2 yj = __ldg(reinterpret_cast<const float2 *>(Y) + j);
+                    const float dx = yix - yj.x, dy = yiy - yj.y;
+                    const float q = __fdividef(pv, 1.f + (dx * dx + dy * dy) * inv_df);
+                    ax += q * dx; ay += q * dy;
+                } else {
+                    const float dx = yix - __ldg(Y + j);
+                    const float q = __fdividef(pv, 1.f + dx * dx * inv_df);
+                    ax += q * dx;
+                }
             }
         }
-    }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
-        ax += __shfl_xor_sync(0xffffffffu, ax, o);
-        if (D == 2) ay += __shfl_xor_sync(0xffffffffu, ay, o);
-    }
-    if (active && sub == 0) {
-        if (D == 2) reinterpret_cast<float2 *>(attr)[row] = make_float2(ax, ay);
-        else attr[row] = ax;
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            ax += __shfl_xor_sync(0xffffffffu, ax, o);
+            if (D == 2) ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        }
+        if (active && sub == 0) {
+            if (D == 2) reinterpret_cast<float2 *>(attr)[row] = make_float2(ax, ay);
+            else attr[row] = ax;
+        }
     }
 }
 
