@@ -39,13 +39,13 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def workload(points, phase, K_nn=15):
+def workload(points, phase, K_nn=15, dims=2):
     row, col, val, labels = bench_util.knn_like_graph(points, K_nn, seed=0)
     if phase == "early":
-        Y0 = bench_util.early_embedding(points, 2)
+        Y0 = bench_util.early_embedding(points, dims)
         sched = dict(early_exag_coeff=12.0, stop_lying_iter=10 ** 9, mom_switch_iter=10 ** 9, momentum=0.5, final_momentum=0.8)
     else:
-        Y0 = bench_util.clustered_embedding(labels, 2, 170.0)
+        Y0 = bench_util.clustered_embedding(labels, dims, 170.0)
         # late phase: exaggeration off (coefficient 1 from the start), final momentum
         sched = dict(early_exag_coeff=1.0, stop_lying_iter=-1, mom_switch_iter=-1, momentum=0.8, final_momentum=0.8)
     sched.update(learning_rate=points / 12.0, max_step_norm=5.0, start_late_exag_iter=-1, late_exag_coeff=-1.0)
@@ -97,14 +97,14 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------- reference arm --
-def run_reference(points, phase, steps, threads, keep_dir=None):
+def run_reference(points, phase, steps, threads, keep_dir=None, dims=2, df=1.0):
     """Time the unmodified reference binary's own loop (its 'N iterations in X seconds' lines, tsne.cpp:574)."""
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "fast_tsne_ref")
     if not os.path.exists(ref_bin):
         return None, "oracle/_ref/fast_tsne_ref missing (built by __graft_entry__.build() where /root/reference exists)"
-    row, col, val, Y0, sched = workload(points, phase)
+    row, col, val, Y0, sched = workload(points, phase, dims=dims)
     with tempfile.TemporaryDirectory(dir=keep_dir) as td:
-        bench_util.write_reference_inputs(td, row, col, val, Y0, max_iter=steps, no_dims=2, learning_rate=sched["learning_rate"],
+        bench_util.write_reference_inputs(td, row, col, val, Y0, max_iter=steps, no_dims=dims, df=df, learning_rate=sched["learning_rate"],
                                           stop_lying_iter=sched["stop_lying_iter"] if sched["stop_lying_iter"] < 10 ** 8 else steps + 1,
                                           mom_switch_iter=sched["mom_switch_iter"] if sched["mom_switch_iter"] < 10 ** 8 else steps + 1,
                                           early_exag=sched["early_exag_coeff"], momentum=sched["momentum"],
@@ -133,6 +133,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1000000)
     ap.add_argument("--phase", default="late", choices=["late", "early"])
+    ap.add_argument("--dims", type=int, default=2, choices=[1, 2], help="embedding dimension (BASELINE config 5 uses 1)")
+    ap.add_argument("--df", type=float, default=1.0, help="t-kernel degrees of freedom (config 5 uses 0.5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -142,7 +144,7 @@ def main():
     threads = os.cpu_count() or 1
     config = {"workload": "BASELINE config 3: synthetic N=%d, 2-D, lr=N/12, fixed kNN-style graph (K=15 same-cluster neighbours, "
                           "symmetrised, ~30 nnz/row) injected as load_affinities=1; %s phase" % (args.points, args.phase),
-              "points": args.points, "phase": args.phase, "nterms": 3, "intervals_per_integer": 1, "min_num_intervals": 50,
+              "points": args.points, "phase": args.phase, "dims": args.dims, "df": args.df, "nterms": 3, "intervals_per_integer": 1, "min_num_intervals": 50,
               "l2": "inputs larger than L2: the CSR P (~8 B/edge, ~240 MB at 1M points) is streamed from HBM every step",
               "sharding": "points/rows sharded across %d rank(s); NCCL grid all-reduce + Y all-gather" % max(world, 1)}
 
@@ -150,7 +152,7 @@ def main():
         if rank != 0:
             return 0
         steps = min(args.steps, 60 if args.points >= 500000 else 1000)
-        res, err = run_reference(args.points, args.phase, steps, threads)
+        res, err = run_reference(args.points, args.phase, steps, threads, dims=args.dims, df=args.df)
         if res is None:
             print(json.dumps({"impl": "reference", "unavailable": err}))
             return 0
@@ -189,14 +191,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    row, col, val, Y0, sched = workload(args.points, args.phase)
+    row, col, val, Y0, sched = workload(args.points, args.phase, dims=args.dims)
     N, E = args.points, int(len(col))
-    t = fb.FitSNE(row, col, val, Y0, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
-    # warm-up: W untimed steps (graph capture, clocks) + cuFFT plans for every grid size the run can drift through
-    # (plan creation JIT-finalises kernels: seconds per new FFT length on a fresh machine, cached by the driver after)
+    t = fb.FitSNE(row, col, val, Y0, df=args.df, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
+    # warm-up: W untimed steps (graph capture, clocks)
     t.run(fetch_Y=False, max_iter=max(args.warmup, 3), **sched)
     b0 = t.stats()["n_boxes"]
-    t.prewarm(max(25, b0 - 60), b0 + 90)
+    t.prewarm(max(25, b0 - 60), b0 + 90)     # twiddle tables for the FFT lengths the run can drift through (milliseconds)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -221,7 +222,7 @@ def main():
     if rank == 0:
         peak, peak_src = load_peaks()
         nsteps_t = 30
-        tt = fb.FitSNE(row, col, val, t.get_Y(), device=local_rank, flags=fb.FLAG_TIMERS) if world == 1 else None
+        tt = fb.FitSNE(row, col, val, t.get_Y(), df=args.df, device=local_rank, flags=fb.FLAG_TIMERS) if world == 1 else None
         if tt is not None:
             tt.prewarm(max(25, st["n_boxes"] - 30), st["n_boxes"] + 30)
         if tt is not None:
@@ -236,8 +237,9 @@ def main():
             sst = tt.stats()
             G, M = sst["grid_side"], sst["fft_side"]
             # algorithmic bytes per launch
-            algo = {"attract_update": 8 * E + 60 * N, "spread": 12 * N + 16 * G * G, "gather": 20 * N + 16 * G * G,
-                    "sort": 16 * N + 2 * 16 * N, "fft": 4 * 28 * M * M + 12 * M * M, "center": 24 * N}
+            d = args.dims
+            algo = {"attract_update": 8 * E + 30 * d * N, "spread": (4 + 4 * d) * N + 16 * G ** d, "gather": (12 + 4 * d) * N + 16 * G ** d,
+                    "sort": 16 * N + 2 * 16 * N, "fft": 4 * 28 * M ** d + 12 * M ** d, "center": 12 * d * N}
             for k, b in algo.items():
                 dur = sst["phase_ms"][k] / nsteps_t
                 if k == "fft":
@@ -246,9 +248,12 @@ def main():
                     kern[k] = {"ms": round(dur, 5), "algorithmic_bytes": int(b), "gbs": round(b / dur / 1e6, 1), "frac": round(b / dur / 1e6 / peak, 4)}
             tt.close()
             dom = "attract_update"
-            roofline = {"kernel": "k_attract_update (CSR SpMV + gains/momentum/clip/Y update)", "bound": "hbm",
+            # traffic: dram__bytes_read+write of k_attract from the committed ncu --set full capture of this exact workload
+            # (profiles/r1_ncu_full_top_kernels.txt: 252.4 MB + 9.9 MB per launch); null for any other workload
+            traffic = 262.3e6 if (N == 1000000 and d == 2 and args.phase == "late") else None
+            roofline = {"kernel": "k_attract + k_update (CSR SpMV on its own stream, then exaggeration/gains/momentum/clip/Y update)", "bound": "hbm",
                         "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
-                        "traffic": None, "peak_source": peak_src,
+                        "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"], "avg_launch_ms": kern[dom]["ms"]}
 
     # end to end through the C ABI with host buffers: upload P + Y0, run K iterations, download Y + costs
@@ -259,7 +264,7 @@ def main():
         t.close()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        Yout, costs2 = fb.run_host(prow, pcol, pval, pY, max_iter=args.steps, device=local_rank, **sched)
+        Yout, costs2 = fb.run_host(prow, pcol, pval, pY, max_iter=args.steps, device=local_rank, df=args.df, **sched)
         dt = time.perf_counter() - t0
         h2d = prow.nbytes + pcol.nbytes + pval.nbytes + pY.nbytes
         d2h = Yout.nbytes + costs2.nbytes
@@ -269,7 +274,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         steps_ref = 20 if args.points >= 500000 else 200
-        res, err = run_reference(args.points, args.phase, steps_ref, threads)
+        res, err = run_reference(args.points, args.phase, steps_ref, threads, dims=args.dims, df=args.df)
         if res is not None:
             cpu_baseline = {"value": res["it_per_s"], "unit": UNIT, "cores": threads, "kind": "reference",
                             "sample": "%d iterations of the same workload by oracle/_ref/fast_tsne_ref (unmodified reference, FFTW->MKL shim), %d threads" % (steps_ref, threads)}

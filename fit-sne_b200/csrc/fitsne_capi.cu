@@ -344,7 +344,7 @@ static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
 static inline int combine_lanes(const fitsne_ctx *c, int M) {
     const size_t plane = c->D == 2 ? (size_t) M * M : (size_t) M;
     int lpn = 1;
-    while (lpn < 32 && plane * (size_t) (lpn * 2) <= (size_t) 148 * 2048 * 4) lpn *= 2;
+    while (lpn < 32 && plane * (size_t) (lpn * 2) <= (size_t) 8 << 20) lpn *= 2;   // up to ~8M threads: cheap, and heavy boxes (early exaggeration) get a full warp per node
     return lpn;
 }
 
