@@ -183,7 +183,7 @@ static int nice_fft_size(int n) {
         if (m == 1) return n;
     }
 }
-static inline int max_fft_len(int D) { return D == 2 ? 4096 : FFT_EPT * FFT_THREADS; }
+static inline int max_fft_len(int D) { return D == 2 ? 4096 : 8192; }   // 1-D: two buffers + twiddles must fit in shared memory
 
 template <typename T>
 static int dev_alloc(fitsne_ctx *c, T **p, size_t count) {
@@ -234,20 +234,25 @@ static int get_plans(fitsne_ctx *c, int M, Plans **out) {
     k_fft_twiddles<<<cdiv(M, 256), 256, 0, c->stream>>>(pl.W, M);
     LAUNCH_CHECK();
     CK(cudaStreamSynchronize(c->stream));
-    // tiles: column passes take 4 adjacent columns per CTA (32-byte segments = one sector per row); row passes are
-    // contiguous anyway, so they use 2 rows per CTA and get twice the CTAs per SM to overlap loads with butterflies.
+    // tiles: column passes take up to 8 adjacent columns per CTA (64-byte segments), row passes up to 4 rows.
     // Bounds: M * lines <= FFT_EPT * FFT_THREADS (register staging) and the two ping-pong buffers + twiddles in smem.
     auto fit = [&](int want) {
         int l = c->D == 2 ? want : 1;
         while (l > 1 && ((size_t) M * l > (size_t) FFT_EPT * FFT_THREADS ||
-                         ((size_t) 2 * l * fft_buf_len(M, l) + M) * sizeof(float2) > (size_t) 110 * 1024)) l /= 2;
+                         ((size_t) 2 * l * fft_buf_len(M, l) + M) * sizeof(float2) > (size_t) 200 * 1024)) l /= 2;
         return l;
     };
-    pl.lines_cols = fit(4);
-    pl.lines_rows = fit(2);
+    // B200 sweep at M=1280 (tests/tools/fft_sweep.py): 8 columns / 4 rows per 512-thread CTA is the best of a flat
+    // optimum (0.20-0.23 ms for the whole convolution)
+    static const int env_lc = getenv("FITSNE_FFT_LINES_COLS") ? atoi(getenv("FITSNE_FFT_LINES_COLS")) : 8;
+    static const int env_lr = getenv("FITSNE_FFT_LINES_ROWS") ? atoi(getenv("FITSNE_FFT_LINES_ROWS")) : 4;
+    pl.lines_cols = fit(env_lc);
+    pl.lines_rows = fit(env_lr);
     if ((size_t) M * pl.lines_cols > (size_t) FFT_EPT * FFT_THREADS) return fail(c, FITSNE_EINVAL, "FFT length %d too long", M);
     pl.smem_cols = ((size_t) 2 * pl.lines_cols * fft_buf_len(M, pl.lines_cols) + M) * sizeof(float2);
     pl.smem_rows = ((size_t) 2 * pl.lines_rows * fft_buf_len(M, pl.lines_rows) + M) * sizeof(float2);
+    if (pl.smem_rows > (size_t) 220 * 1024 || pl.smem_cols > (size_t) 220 * 1024)
+        return fail(c, FITSNE_EINVAL, "FFT length %d does not fit in shared memory", M);
     c->plans[M] = pl;
     *out = &c->plans[M];
     return 0;
@@ -416,22 +421,23 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     phase_mark(c, FITSNE_PHASE_FFT);
     const int *gG = &c->gp->G, *gok = &c->gp->ok;
     const int LR = pl->lines_rows, LC = pl->lines_cols;
+    const int FT = FFT_THREADS;
     if (D == 2) {
         // rows: the charge planes (0,1) are zero beyond row G -> pruned; the kernel planes (2,3) need every row
-        k_fft_pass<false><<<dim3(cdiv(M, LR), 4), FFT_THREADS, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok);
-        k_fft_pass<true><<<dim3(cdiv(M, LC), 4), FFT_THREADS, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 0, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(cdiv(M, LR), 4), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok);
+        k_fft_pass<true><<<dim3(cdiv(M, LC), 4), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 0, 0u, gG, gok);
     } else {
-        k_fft_pass<false><<<dim3(1, 4), FFT_THREADS, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(1, 4), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok);
     }
     k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial);
     k_finalize_z<<<1, 256, 0, st>>>(c->zpartial, Z_BLOCKS, c->N, c->gp, c->sc);
     if (D == 2) {
         // inverse: columns first (all of them), then only the G rows the gather reads
-        k_fft_pass<true><<<dim3(cdiv(M, LC), 2), FFT_THREADS, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok);
-        k_fft_pass<false><<<dim3(cdiv(M, LR), 2), FFT_THREADS, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok);
+        k_fft_pass<true><<<dim3(cdiv(M, LC), 2), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(cdiv(M, LR), 2), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok);
         c->stats.kernel_launches += 6;
     } else {
-        k_fft_pass<false><<<dim3(1, 1), FFT_THREADS, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(1, 1), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok);
         c->stats.kernel_launches += 4;
     }
     LAUNCH_CHECK();

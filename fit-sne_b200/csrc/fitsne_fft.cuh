@@ -155,7 +155,7 @@ __device__ __forceinline__ void fft_stage(const float2 *__restrict__ x, float2 *
     const int per = N / R;
     const int sm_ = s * m;
     const int tpl = 1 << tpl_log2;
-    const int ts = threadIdx.x & (tpl - 1), lb = threadIdx.x >> tpl_log2, lgroups = blockDim.x >> tpl_log2;
+    const int ts = threadIdx.x & (tpl - 1), lb = threadIdx.x >> tpl_log2, lgroups = max(1, (int) blockDim.x >> tpl_log2);
     for (int t = ts; t < per; t += tpl) {
         const int p = fastdiv(t, div_s), q = t - p * s;
         const int i0 = q + s * p, o0 = q + s * R * p;
