@@ -154,10 +154,9 @@ int fitsne_run_host(const fitsne_config *cfg, const fitsne_schedule *s, int N, i
                     const unsigned int *row_P, const unsigned int *col_P, const double *val_P, double *Y,
                     double *costs);
 
-/* Create the cuFFT plans for every FFT length a grid of n_boxes_lo..n_boxes_hi boxes per dimension can need.
- * Plan creation is the one slow host-side step (cuFFT finalises kernels at plan time: milliseconds with a warm
- * driver compute cache, seconds per new length on a machine that has never seen it); calling this up front keeps
- * it out of the iteration loop.  Optional: plans are otherwise created on first use. */
+/* Prepare (twiddle tables, buffers) every FFT length a grid of n_boxes_lo..n_boxes_hi boxes per dimension can need,
+ * so that no allocation happens inside the iteration loop.  Optional and cheap (the FFTs are our own kernels: there
+ * are no library plans to create); lengths are otherwise prepared on first use. */
 int fitsne_prewarm(fitsne_ctx *ctx, int n_boxes_lo, int n_boxes_hi);
 
 /* ---- introspection -------------------------------------------------------------------------------- */
