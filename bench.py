@@ -259,8 +259,8 @@ def main():
     # end to end through the C ABI with host buffers: upload P + Y0, run K iterations, download Y + costs
     e2e = None
     if rank == 0 and world == 1 and not args.no_e2e:
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
-        prow, pcol, pval, pY = pin(row), pin(col), pin(val), pin(Y0)
+        pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (row, col, val, Y0)]   # keep the owners alive
+        prow, pcol, pval, pY = [p_.numpy() for p_ in pinned]
         t.close()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -270,6 +270,7 @@ def main():
         d2h = Yout.nbytes + costs2.nbytes
         e2e = {"value": args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                "call": "fitsne_run_host (create + %d iterations + download), host wall clock" % args.steps}
+        del prow, pcol, pval, pY, pinned       # release the pinned buffers while the CUDA context is still alive
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

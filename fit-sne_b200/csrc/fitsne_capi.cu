@@ -171,18 +171,6 @@ static double now_ms() {
 
 static inline int cdiv(long long a, long long b) { return (int) ((a + b - 1) / b); }
 
-// FFT length for a grid of side G.  Any M >= 2G-1 gives the same linear convolution (the reference uses 2G,
-// nbodyfft.cpp:155-156); M is the next 2^a 3^b 5^c that is a multiple of 16 (32 above 512) -- the lengths our
-// mixed-radix shared-memory FFT handles, on a ladder coarse enough that CUDA graphs are re-captured rarely.
-static int nice_fft_size(int n) {
-    const int q = n <= 512 ? 16 : 32;
-    n = (n + q - 1) / q * q;
-    for (;; n += q) {
-        int m = n;
-        for (int f : {2, 3, 5}) while (m % f == 0) m /= f;
-        if (m == 1) return n;
-    }
-}
 static inline int max_fft_len(int D) { return D == 2 ? 4096 : 8192; }   // 1-D: two buffers + twiddles must fit in shared memory
 
 template <typename T>
@@ -265,10 +253,12 @@ static inline void phase_mark(fitsne_ctx *c, int phase) {
 
 template <int D>
 static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int do_center) {
+    // do_center == 1: closing kernels of an optimiser step (skipped, like the rest, when the grid check failed)
+    const GridParams *gate = do_center ? c->gp : nullptr;
     k_center_bounds<D><<<RED_BLOCKS, 256, 0, c->stream>>>(Yin, Yout, c->N, c->colsum_partial, RED_BLOCKS, do_center,
                                                           c->bounds_partial, c->sc, c->reordered ? c->orig_of : nullptr,
-                                                          c->reordered ? c->pos_of : nullptr);
-    k_reduce_bounds<<<1, 256, 0, c->stream>>>(c->bounds_partial, RED_BLOCKS, c->sc, c->host_bounds_dev);
+                                                          c->reordered ? c->pos_of : nullptr, gate);
+    k_reduce_bounds<<<1, 256, 0, c->stream>>>(c->bounds_partial, RED_BLOCKS, c->sc, c->host_bounds_dev, gate);
     LAUNCH_CHECK();
     c->stats.kernel_launches += 2;
     return 0;
@@ -465,7 +455,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
             c->stats.kernel_launches += 1;
         }
         phase_mark(c, FITSNE_PHASE_CENTER);
-        k_colsum<D><<<RED_BLOCKS, 256, 0, st>>>(c->Yb, c->N, c->colsum_partial);
+        k_colsum<D><<<RED_BLOCKS, 256, 0, st>>>(c->Yb, c->N, c->colsum_partial, c->gp);
         c->stats.kernel_launches += 1;
         CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1));
     }
@@ -603,13 +593,34 @@ static int maybe_reorder(fitsne_ctx *c) {
     return reorder_points(c);
 }
 
-// Decide the grid from the (host-visible) bounds and run one iteration, through a cached CUDA graph unless
-// disabled.  The one host<->device handshake per iteration is the 8-byte bounds read.
-static int run_iteration(fitsne_ctx *c, bool update) {
-    CKRC(maybe_reorder(c));
-    CKRC(refresh_bounds(c));
-    TRACE("iteration: waiting for bounds");
-    CK(cudaStreamSynchronize(c->stream));
+// The captured CUDA graph of one iteration for FFT length M (kind: gradient only / full step); created on first use.
+static int get_graph(fitsne_ctx *c, int M, bool update, fitsne_ctx::GraphEntry **out) {
+    const GraphKey key{M, update ? 1 : 0};
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+        Plans *pl;
+        TRACE("new graph for M=%d kind=%d", M, update ? 1 : 0);
+        CKRC(get_plans(c, M, &pl));   // twiddle tables are computed outside the capture
+        cudaGraph_t graph;
+        const uint64_t launches_before = c->stats.kernel_launches;
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_iteration_d(c, M, update);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc != 0) return rc;
+        if (e != cudaSuccess) return fail(c, FITSNE_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        cudaGraphExec_t exec;
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        c->graphs[key] = fitsne_ctx::GraphEntry{exec, c->stats.kernel_launches - launches_before};
+        it = c->graphs.find(key);
+        c->stats.kernel_launches = launches_before;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+// Host-side grid choice from the last published bounds (the stream must be idle).
+static int choose_grid(fitsne_ctx *c, int *B_out, int *M_out) {
     const double mn = (double) c->host_bounds[0], mx = (double) c->host_bounds[1];
     if (!(mx > mn)) return fail(c, FITSNE_EINVAL, "degenerate embedding: max_coord (%g) <= min_coord (%g)", mx, mn);
     const int B = choose_n_boxes(mn, mx, c->cfg.intervals_per_integer, c->cfg.min_num_intervals, c->D);
@@ -618,15 +629,60 @@ static int run_iteration(fitsne_ctx *c, bool update) {
         return fail(c, FITSNE_EINVAL, "grid too large: n_boxes=%d", B);
     const int M = nice_fft_size(2 * G);
     if (M > max_fft_len(c->D)) return fail(c, FITSNE_EINVAL, "grid too large: n_boxes=%d needs FFT length %d > %d", B, M, max_fft_len(c->D));
-    TRACE("bounds [%g, %g] -> B=%d G=%d M=%d", mn, mx, B, G, M);
     CKRC(ensure_grid_capacity(c, M));
-    if (B != c->cur_B || M != c->cur_M) {
-        c->cur_B = B; c->cur_M = M;
-        c->stats.regrids++;
-    }
-    *c->host_B = B;
+    if (B != c->cur_B || M != c->cur_M) { c->cur_B = B; c->cur_M = M; c->stats.regrids++; }
     c->stats.n_boxes = B; c->stats.grid_side = G; c->stats.fft_side = M;
     c->stats.min_coord = mn; c->stats.max_coord = mx;
+    *B_out = B; *M_out = M;
+    return 0;
+}
+
+static int run_iteration(fitsne_ctx *c, bool update);
+
+// Speculative batch: enqueue up to `n` full optimiser steps back to back with NO host round trip in between.  Each
+// step sizes its own grid on the device (k_setup_grid); a step whose grid no longer maps to this graph's FFT length
+// turns itself -- and, since nothing changed, every later step of the batch -- into a no-op.  One synchronisation at
+// the end tells how many steps really ran (Scalars::iter_done, mirrored in mapped host memory).
+static int run_batch(fitsne_ctx *c, int n, int *done) {
+    CKRC(maybe_reorder(c));
+    CKRC(refresh_bounds(c));
+    CK(cudaStreamSynchronize(c->stream));
+    int B, M;
+    CKRC(choose_grid(c, &B, &M));
+    fitsne_ctx::GraphEntry *ge;
+    CKRC(get_graph(c, M, true, &ge));
+    *c->host_B = 0;                                           // let the device choose n_boxes
+    volatile unsigned long long *host_iter = reinterpret_cast<volatile unsigned long long *>(c->host_bounds + 4);
+    const unsigned long long before = *host_iter;
+    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(ge->exec, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int ran = (int) (*host_iter - before);
+    c->stats.graph_launches += n;
+    c->stats.kernel_launches += ge->launches * (uint64_t) ran;   // no-op launches are not counted as work
+    c->stats.iterations += ran;
+    c->have_grad = c->have_grad || ran > 0;
+    c->bounds_valid = true;
+    TRACE("batch of %d at M=%d: %d ran", n, M, ran);
+    *done = ran;
+    if (ran == 0) {
+        // even the first step refused: the published bounds must map to a different M than the one just chosen --
+        // impossible unless something is inconsistent; fall back to one host-sized step
+        CKRC(run_iteration(c, true));
+        *done = 1;
+    }
+    return 0;
+}
+
+// Decide the grid from the (host-visible) bounds and run one iteration, through a cached CUDA graph unless
+// disabled.  The one host<->device handshake per iteration is the 8-byte bounds read.
+static int run_iteration(fitsne_ctx *c, bool update) {
+    CKRC(maybe_reorder(c));
+    CKRC(refresh_bounds(c));
+    TRACE("iteration: waiting for bounds");
+    CK(cudaStreamSynchronize(c->stream));
+    int B, M;
+    CKRC(choose_grid(c, &B, &M));
+    *c->host_B = B;
 
     const bool timers = (c->cfg.flags & FITSNE_FLAG_TIMERS) != 0;
     const bool use_graph = !(c->cfg.flags & FITSNE_FLAG_NO_GRAPH) && !timers;
@@ -634,31 +690,10 @@ static int run_iteration(fitsne_ctx *c, bool update) {
     if (!use_graph) {
         CKRC(enqueue_iteration_d(c, M, update));
     } else {
-        const GraphKey key{M, update ? 1 : 0};
-        auto it = c->graphs.find(key);
-        if (it == c->graphs.end()) {
-            Plans *pl;
-            TRACE("new graph for M=%d kind=%d: plans", M, update ? 1 : 0);
-            CKRC(get_plans(c, M, &pl));   // plan creation is not capturable
-            TRACE("capture");
-            cudaGraph_t graph;
-            const uint64_t launches_before = c->stats.kernel_launches;
-            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue_iteration_d(c, M, update);
-            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
-            if (rc != 0) return rc;
-            if (e != cudaSuccess) return fail(c, FITSNE_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
-            cudaGraphExec_t exec;
-            TRACE("instantiate");
-            CK(cudaGraphInstantiate(&exec, graph, 0));
-            cudaGraphDestroy(graph);
-            TRACE("graph ready");
-            c->graphs[key] = fitsne_ctx::GraphEntry{exec, c->stats.kernel_launches - launches_before};
-            it = c->graphs.find(key);
-            c->stats.kernel_launches = launches_before;
-        }
-        c->stats.kernel_launches += it->second.launches;
-        CK(cudaGraphLaunch(it->second.exec, c->stream));
+        fitsne_ctx::GraphEntry *ge;
+        CKRC(get_graph(c, M, update, &ge));
+        c->stats.kernel_launches += ge->launches;
+        CK(cudaGraphLaunch(ge->exec, c->stream));
         c->stats.graph_launches++;
     }
     if (timers) {
@@ -1025,34 +1060,46 @@ int fitsne_run(fitsne_ctx *c, const fitsne_schedule *s, double *costs, double *Y
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, c->stream));
     auto t0 = std::chrono::steady_clock::now();
-    for (int iter = 0; iter < s->max_iter; iter++) {
-        fitsne_step_params sp;
-        sp.exaggeration = alpha; sp.momentum = momentum; sp.learning_rate = s->learning_rate;
-        sp.max_step_norm = s->max_step_norm;
-        sp.mode = FITSNE_STEP_MOMENTUM_CLIP;
-        if (s->no_momentum_during_exag) sp.mode = iter > s->stop_lying_iter ? FITSNE_STEP_MOMENTUM : FITSNE_STEP_PLAIN_GD;
-        CKRC(push_step_params(c, make_sp(c, sp.exaggeration, sp.momentum, sp.learning_rate, sp.max_step_norm, sp.mode)));
-        CKRC(run_iteration(c, true));
+    const bool batched = !(c->cfg.flags & (FITSNE_FLAG_NO_GRAPH | FITSNE_FLAG_TIMERS | FITSNE_FLAG_NO_SPECULATION));
+    int iter = 0;
+    while (iter < s->max_iter) {
+        int mode = FITSNE_STEP_MOMENTUM_CLIP;
+        if (s->no_momentum_during_exag) mode = iter > s->stop_lying_iter ? FITSNE_STEP_MOMENTUM : FITSNE_STEP_PLAIN_GD;
+        CKRC(push_step_params(c, make_sp(c, alpha, momentum, s->learning_rate, s->max_step_norm, mode)));
+        // the batch [iter, end] shares one set of step parameters: it stops at the next schedule event, KL evaluation,
+        // point re-ordering or after 64 steps, whichever comes first
+        int end = std::min(s->max_iter - 1, iter + 63);
+        auto clip = [&](long long ev) { if (ev >= iter && ev < end) end = (int) ev; };
+        clip(s->stop_lying_iter); clip(s->start_late_exag_iter); clip(s->mom_switch_iter);
+        clip((long long) (iter / 50 + 1) * 50 - 1);
+        if (c->world == 1 && !(c->cfg.flags & FITSNE_FLAG_NO_REORDER) && c->reordered)
+            clip((long long) iter + (long long) (c->last_reorder_iter + c->reorder_interval - c->stats.iterations) - 1);
+        int ran = 1;
+        if (batched) CKRC(run_batch(c, end - iter + 1, &ran));
+        else { CKRC(run_iteration(c, true)); end = iter; }
+        iter += ran;
+        if (iter <= end) continue;          // a step refused its grid: re-plan from the fresh bounds
+        const int last = end;
         // schedule changes take effect after the step of that iteration (tsne.cpp:534-544).  The reference
         // un-exaggerates by dividing and late-exaggerates by multiplying the stored P.
-        if (iter == s->stop_lying_iter) {
+        if (last == s->stop_lying_iter) {
             if (s->verbose) printf("Unexaggerating Ps by %f\n", early);
             alpha /= early;
         }
-        if (iter == s->start_late_exag_iter) {
+        if (last == s->start_late_exag_iter) {
             if (s->verbose) printf("Exaggerating Ps by %f\n", s->late_exag_coeff);
             alpha *= s->late_exag_coeff;
         }
-        if (iter == s->mom_switch_iter) momentum = s->final_momentum;
-        if ((iter + 1) % 50 == 0 || iter == s->max_iter - 1) {
+        if (last == s->mom_switch_iter) momentum = s->final_momentum;
+        if ((last + 1) % 50 == 0 || last == s->max_iter - 1) {
             double C = 0;
             CKRC(kl_impl(c, alpha, &C));
-            if (iter < s->stop_lying_iter && s->stop_lying_iter != -1) C = C / early - log(early);
-            if (iter >= s->start_late_exag_iter && s->start_late_exag_iter != -1) C = C / s->late_exag_coeff - log(s->late_exag_coeff);
-            if (costs) costs[iter] = C;
+            if (last < s->stop_lying_iter && s->stop_lying_iter != -1) C = C / early - log(early);
+            if (last >= s->start_late_exag_iter && s->start_late_exag_iter != -1) C = C / s->late_exag_coeff - log(s->late_exag_coeff);
+            if (costs) costs[last] = C;
             if (s->verbose) {
                 auto t1 = std::chrono::steady_clock::now();
-                printf("Iteration %d (50 iterations in %.2f seconds), cost %f\n", iter + 1,
+                printf("Iteration %d (50 iterations in %.2f seconds), cost %f\n", last + 1,
                        std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count() / (float) 1000.0, C);
                 t0 = std::chrono::steady_clock::now();
             }

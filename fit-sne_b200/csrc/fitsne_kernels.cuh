@@ -61,6 +61,7 @@ struct Scalars {          // small device-resident results
     double mean[2];
     float bmin, bmax;     // bounds of the current Y (with the 2-D scan quirk)
     double kl;
+    unsigned long long iter_done;   // optimiser steps that really executed (speculative launches that found a grid mismatch do not count)
 };
 
 // ------------------------------------------------------------------------------------------ helpers --
@@ -110,8 +111,10 @@ __device__ __forceinline__ int box_of(float y, const GridParams &gp, float &u) {
 
 // partial[b*D+d] = sum of Y[:,d] over block b's contiguous slice (fixed order -> deterministic)
 template <int D>
-__global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ Y, int N, double *__restrict__ partial) {
+__global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ Y, int N, double *__restrict__ partial,
+                                                const GridParams *__restrict__ gpp) {
     __shared__ double sm[32];
+    if (gpp && !gpp->ok) return;
     const int per = (N + gridDim.x - 1) / gridDim.x;
     const int b = blockIdx.x * per, e = min(N, b + per);
     double s0 = 0, s1 = 0;
@@ -138,8 +141,9 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
                                                        const double *__restrict__ colsum_partial, int nparts,
                                                        int do_center, float2 *__restrict__ bounds_partial,
                                                        Scalars *__restrict__ sc, const uint32_t *__restrict__ orig_of,
-                                                       const uint32_t *__restrict__ pos_of) {
+                                                       const uint32_t *__restrict__ pos_of, const GridParams *__restrict__ gpp) {
     __shared__ double smd[32];
+    if (gpp && !gpp->ok) return;
     __shared__ float smf[64];
     __shared__ double mean_s[2];
     __shared__ int t_s;
@@ -214,8 +218,10 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
 
 // Reduce the per-block bounds; publish them to the device scalars and to a host-mapped word pair.
 __global__ void __launch_bounds__(256) k_reduce_bounds(const float2 *__restrict__ bounds_partial, int nparts,
-                                                       Scalars *__restrict__ sc, volatile float *host_bounds) {
+                                                       Scalars *__restrict__ sc, volatile float *host_bounds,
+                                                       const GridParams *__restrict__ gpp) {
     __shared__ float smf[64];
+    if (gpp && !gpp->ok) return;
     float mn = INFINITY, mx = -INFINITY;
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
         float2 v = bounds_partial[i];
@@ -232,7 +238,26 @@ __global__ void __launch_bounds__(256) k_reduce_bounds(const float2 *__restrict_
     if (threadIdx.x == 0) {
         for (int i = 1; i < (int) (blockDim.x >> 5); i++) { mn = fminf(mn, smf[i]); mx = fmaxf(mx, smf[32 + i]); }
         sc->bmin = mn; sc->bmax = mx;
-        if (host_bounds) { host_bounds[0] = mn; host_bounds[1] = mx; }
+        if (gpp) sc->iter_done += 1;      // closing kernel of a full optimiser step
+        if (host_bounds) {
+            host_bounds[0] = mn; host_bounds[1] = mx;
+            if (gpp) *reinterpret_cast<volatile unsigned long long *>(host_bounds + 4) = sc->iter_done;
+        }
+    }
+}
+
+// FFT length for a grid of side G = n/2.  Any M >= 2G-1 gives the same linear convolution (the reference uses 2G,
+// nbodyfft.cpp:155-156); M is the next 2^a 3^b 5^c that is a multiple of 16 (32 above 512) -- the lengths the
+// mixed-radix shared-memory FFT handles, on a ladder coarse enough that CUDA graphs are re-captured rarely.
+__host__ __device__ inline int nice_fft_size(int n) {
+    const int q = n <= 512 ? 16 : 32;
+    n = (n + q - 1) / q * q;
+    for (;; n += q) {
+        int m = n;
+        while (m % 2 == 0) m /= 2;
+        while (m % 3 == 0) m /= 3;
+        while (m % 5 == 0) m /= 5;
+        if (m == 1) return n;
     }
 }
 
@@ -264,10 +289,13 @@ __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restr
                              double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals) {
     for (int i = threadIdx.x; i < 2 * (1 << SORT_MAX_BITS); i += blockDim.x) sort_totals[i] = 0;   // both passes
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int B = *reinterpret_cast<const volatile int *>(B_host);
+    // B_host > 0: the host sized the grid after reading the bounds (single-step API); 0: speculative launch, the device
+    // sizes the grid itself and the whole iteration becomes a no-op if that grid does not belong to this graph's M
+    const int hostB = *reinterpret_cast<const volatile int *>(B_host);
     const double mn = (double) sc->bmin, mx = (double) sc->bmax;
     const int want = choose_n_boxes(mn, mx, ipi, min_int, dims);
-    gp->ok = (want == B) && (2 * B * p <= M);
+    const int B = hostB > 0 ? hostB : want;
+    gp->ok = (want == B) && (mx > mn) && (nice_fft_size(2 * B * p) == M);
     if (!gp->ok) *mismatch = want;
     gp->mn = mn; gp->mx = mx;
     gp->B = B; gp->p = p; gp->G = B * p; gp->M = M;

@@ -230,3 +230,25 @@ def test_edge_cases_match_oracle(fb, oracle):
         assert rel(dC, ref) < tol, (N, dims, df, nterms, rel(dC, ref))
         assert abs(z - zr) / abs(zr) < 1e-5
         assert abs(kl - oracle.kl(Y, row2, col2, val2, zr, df=df)) / abs(kl) < 1e-5
+
+
+def test_speculative_batches_equal_stepwise_run(fb, golden_graph):
+    """fitsne_run launches iterations in batches with no host round trip in between (the device sizes each grid and a step
+    that no longer fits the captured FFT length voids itself).  Must be bitwise identical to the one-sync-per-iteration
+    path, including across grid changes."""
+    row, col, val, labels = golden_graph
+    import bench_util
+    Y0 = bench_util.clustered_embedding(labels.astype(np.int64), 2, 46.0, seed=4)
+    kw = dict(max_iter=130, stop_lying_iter=20, mom_switch_iter=20, learning_rate=2000.0, early_exag_coeff=2.0,
+              start_late_exag_iter=90, late_exag_coeff=1.5, max_step_norm=5.0)
+    res = {}
+    for label, flags in (("batched", 0), ("stepwise", fb.FLAG_NO_SPECULATION)):
+        with fb.FitSNE(row, col, val.astype(np.float64), Y0, flags=flags) as t:
+            Y, costs = t.run(**kw)
+            st = t.stats()
+        res[label] = (Y, costs, st)
+    assert res["batched"][2]["iterations"] == res["stepwise"][2]["iterations"] == 130
+    assert res["stepwise"][2]["regrids"] >= 2, res["stepwise"][2]          # the run really crosses grid sizes
+    assert np.array_equal(res["batched"][1], res["stepwise"][1])
+    assert np.array_equal(res["batched"][0], res["stepwise"][0])
+    assert res["batched"][2]["graph_launches"] >= 130
