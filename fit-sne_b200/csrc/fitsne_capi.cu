@@ -108,6 +108,7 @@ struct fitsne_ctx {
     bool reordered = false, use_tiles = false;
     uint64_t last_reorder_iter = 0, reorder_interval = 50, reorders = 0;
     uint32_t nonempty_tiles = 0;
+    unsigned long long kc_hits_base = 0;
     float tile_fix32 = 1.0f;
     uint64_t kernel_launches_reorder = 0;
     // sort / bins
@@ -204,7 +205,8 @@ static int ensure_grid_capacity(fitsne_ctx *c, int M) {
     const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
     if (plane > c->plane_cap) {
         const size_t cap = plane + plane / 2;
-        CKRC(dev_alloc(c, &c->planes, cap * 4));
+        CKRC(dev_alloc(c, &c->planes, cap * 6));      // 2 charge + 2 kernel + 2 kernel-derivative planes
+        CK(cudaMemsetAsync(&c->sc->kc_valid, 0, sizeof(int), c->stream));   // cached spectra are gone
         if (c->world > 1) CKRC(dev_alloc(c, &c->compact, cap / 2 + 1024));
         c->plane_cap = cap;
         moved = true;
@@ -366,7 +368,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
 
     phase_mark(c, FITSNE_PHASE_BOUNDS);
     k_setup_grid<<<1, 256, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
-                                    c->mismatch, c->sort_totals);
+                                    c->mismatch, c->sort_totals, c->sc, (c->cfg.flags & FITSNE_FLAG_NO_KERNEL_CACHE) ? 0 : 1);
     c->stats.kernel_launches += 1;
 
     // ---- bin + stable two-pass LSD radix sort by box
@@ -374,14 +376,16 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     const int tiles = cdiv(nloc, SORT_TILE);
     const int max_bins = 1 << SORT_MAX_BITS;
     const size_t scatter_smem = (size_t) max_bins * 4 + (size_t) (SORT_THREADS / 32) * max_bins * 2;
-    k_bin<D><<<tiles, SORT_THREADS, 0, st>>>(c->Y, c->row_begin, nloc, c->gp, c->keys[0], c->hist, tiles, c->sort_totals);
-    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, c->gp);
+    // (one-pass layout: k_bin writes keys[1] + the pass-1 histogram + in-box coordinates (staged in frep, free until the
+    //  gather), the pass-0 kernels return at once, the pass-1 scatter produces keys[0]/perm[0]/sorted_u and box_start)
+    k_bin<D><<<tiles, SORT_THREADS, 0, st>>>(c->Y, c->row_begin, nloc, c->gp, c->keys[0], c->keys[1], c->frep, c->hist, tiles, c->sort_totals);
+    k_radix_offsets<D><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, 0, nloc, nullptr, c->gp);
     k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], nloc, 0, c->hist, tiles,
-                                                              (uint32_t) c->row_begin, c->gp);
+                                                              (uint32_t) c->row_begin, c->gp, nullptr, nullptr, D);
     k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[1], nloc, 1, c->hist, tiles, c->sort_totals + max_bins, c->gp);
-    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, c->gp);
+    k_radix_offsets<D><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, 1, nloc, c->box_start, c->gp);
     k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], nloc, 1, c->hist, tiles,
-                                                              (uint32_t) c->row_begin, c->gp);
+                                                              (uint32_t) c->row_begin, c->gp, c->frep, c->sorted_u, D);
     const uint32_t *skeys = c->keys[0], *sperm = c->perm[0];
     k_post_sort<D><<<cdiv(nloc, 256), 256, 0, st>>>(skeys, sperm, c->Y, nloc, c->gp, c->box_start, c->sorted_u);
     c->stats.kernel_launches += 7;
@@ -410,24 +414,26 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     LAUNCH_CHECK();
     phase_mark(c, FITSNE_PHASE_FFT);
     const int *gG = &c->gp->G, *gok = &c->gp->ok;
+    const unsigned *gskip = &c->gp->fft_skip;
     const int LR = pl->lines_rows, LC = pl->lines_cols;
     const int FT = FFT_THREADS;
     if (D == 2) {
-        // rows: the charge planes (0,1) are zero beyond row G -> pruned; the kernel planes (2,3) need every row
-        k_fft_pass<false><<<dim3(cdiv(M, LR), 4), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok);
-        k_fft_pass<true><<<dim3(cdiv(M, LC), 4), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 0, 0u, gG, gok);
+        // rows: the charge planes (0,1) are zero beyond row G -> pruned; the kernel planes (2..5) need every row and are
+        // skipped altogether (device-side mask) on iterations that re-use the cached kernel spectra
+        k_fft_pass<false><<<dim3(cdiv(M, LR), 6), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
+        k_fft_pass<true><<<dim3(cdiv(M, LC), 6), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
     } else {
-        k_fft_pass<false><<<dim3(1, 4), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(1, 6), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
     }
     k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial);
     k_finalize_z<<<1, 256, 0, st>>>(c->zpartial, Z_BLOCKS, c->N, c->gp, c->sc);
     if (D == 2) {
         // inverse: columns first (all of them), then only the G rows the gather reads
-        k_fft_pass<true><<<dim3(cdiv(M, LC), 2), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok);
-        k_fft_pass<false><<<dim3(cdiv(M, LR), 2), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok);
+        k_fft_pass<true><<<dim3(cdiv(M, LC), 2), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
+        k_fft_pass<false><<<dim3(cdiv(M, LR), 2), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok, nullptr);
         c->stats.kernel_launches += 6;
     } else {
-        k_fft_pass<false><<<dim3(1, 1), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok);
+        k_fft_pass<false><<<dim3(1, 1), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
         c->stats.kernel_launches += 4;
     }
     LAUNCH_CHECK();
@@ -509,7 +515,7 @@ static int reorder_points(fitsne_ctx *c) {
         CKRC(dev_alloc(c, &c->gp_reorder, (size_t) 1));
         GridParams g;
         memset(&g, 0, sizeof g);
-        g.ok = 1; g.sort_bits = SORT_MAX_BITS;
+        g.ok = 1; g.sort_bits = 11; g.sort_passes = 2;      // 22-bit locality keys: two passes of 11 bits
         CK(cudaMemcpyAsync(c->gp_reorder, &g, sizeof g, cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));
         {   // fixed-point scale of the tiled kernel: 2^30 / max row sum
@@ -535,11 +541,11 @@ static int reorder_points(fitsne_ctx *c) {
     else k_morton_keys<1><<<cdiv(N, 256), 256, 0, st>>>(c->Y, N, c->sc, c->keys[0]);
     CK(cudaMemsetAsync(c->sort_totals, 0, sizeof(uint32_t) * 2 * max_bins, st));
     k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[0], N, 0, c->hist, tiles, c->sort_totals, c->gp_reorder);
-    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, c->gp_reorder);
-    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], N, 0, c->hist, tiles, 0u, c->gp_reorder);
+    k_radix_offsets<2><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, 0, N, nullptr, c->gp_reorder);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], N, 0, c->hist, tiles, 0u, c->gp_reorder, nullptr, nullptr, D);
     k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[1], N, 1, c->hist, tiles, c->sort_totals + max_bins, c->gp_reorder);
-    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, c->gp_reorder);
-    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], N, 1, c->hist, tiles, 0u, c->gp_reorder);
+    k_radix_offsets<2><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, 1, N, nullptr, c->gp_reorder);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], N, 1, c->hist, tiles, 0u, c->gp_reorder, nullptr, nullptr, D);
     LAUNCH_CHECK();
     // 2. maps
     k_reorder_maps<<<cdiv(N, 256), 256, 0, st>>>(c->perm[0], N, c->rank_map, c->reordered ? c->orig_of : nullptr, c->orig_tmp, c->pos_of);
@@ -625,7 +631,7 @@ static int choose_grid(fitsne_ctx *c, int *B_out, int *M_out) {
     if (!(mx > mn)) return fail(c, FITSNE_EINVAL, "degenerate embedding: max_coord (%g) <= min_coord (%g)", mx, mn);
     const int B = choose_n_boxes(mn, mx, c->cfg.intervals_per_integer, c->cfg.min_num_intervals, c->D);
     const int G = B * c->cfg.nterms;
-    if (sort_bits_for(B, c->D) > SORT_MAX_BITS || (long long) G * 2 > 65536)
+    if (sort_bits_for(B, c->D) > SORT_MAX_BITS || (long long) G * 2 > 65536)   // two passes of <= 11 bits
         return fail(c, FITSNE_EINVAL, "grid too large: n_boxes=%d", B);
     const int M = nice_fft_size(2 * G);
     if (M > max_fft_len(c->D)) return fail(c, FITSNE_EINVAL, "grid too large: n_boxes=%d needs FFT length %d > %d", B, M, max_fft_len(c->D));
@@ -796,6 +802,7 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaFuncSetAttribute(k_attract<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_attract<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_attract<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_fft_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(k_fft_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 
@@ -1151,6 +1158,9 @@ int fitsne_last_run_ms(fitsne_ctx *c, double *ms) {
 int fitsne_get_stats(fitsne_ctx *c, fitsne_stats *out) {
     if (!c || !out) return FITSNE_EINVAL;
     CK(cudaStreamSynchronize(c->stream));
+    CKRC(read_scalars(c));
+    c->stats.spectrum_cache_hits = c->host_sc->kc_hits - c->kc_hits_base;
+    c->stats.reorders = c->reorders;
     *out = c->stats;
     return 0;
 }
@@ -1158,6 +1168,7 @@ int fitsne_get_stats(fitsne_ctx *c, fitsne_stats *out) {
 int fitsne_reset_stats(fitsne_ctx *c) {
     if (!c) return FITSNE_EINVAL;
     const fitsne_stats old = c->stats;
+    if (read_scalars(c) == 0) c->kc_hits_base = c->host_sc->kc_hits;
     c->stats = fitsne_stats{};
     c->stats.n_boxes = old.n_boxes; c->stats.grid_side = old.grid_side; c->stats.fft_side = old.fft_side;
     c->stats.min_coord = old.min_coord; c->stats.max_coord = old.max_coord;

@@ -213,8 +213,10 @@ constexpr int FFT_EPT = 24;
 template <bool COLS>
 __global__ void __launch_bounds__(FFT_THREADS) k_fft_pass(float2 *__restrict__ data, size_t plane, int rows_total, int lines,
                                                              FftPlan plan, const float2 *__restrict__ W, int inverse, unsigned prune_mask,
-                                                             const int *__restrict__ g_rows, const int *__restrict__ ok) {
+                                                             const int *__restrict__ g_rows, const int *__restrict__ ok,
+                                                             const unsigned *__restrict__ skip_mask) {
     if (ok && !*ok) return;
+    if (skip_mask && ((*skip_mask >> blockIdx.y) & 1u)) return;      // plane keeps its (cached) contents this iteration
     extern __shared__ float2 fft_sm[];
     // the stage loop indexes the plan dynamically: keep it in shared memory, not in the (slow to index) parameter bank
     __shared__ FftPlan plan_s;

@@ -26,7 +26,9 @@ constexpr int CHUNK = 32;         // points per spread work item
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
-constexpr int SORT_MAX_BITS = 11;
+constexpr int SORT_MAX_BITS = 11;     // widest radix digit
+constexpr int SORT_ONE_PASS_BITS = 8; // keys this short sort in ONE pass.  (Measured on B200: a single 12-bit pass -- 4096 bins --
+                                      // is slower than two 6-bit passes: 84 vs 70 us at N=1M; so only short 1-D keys qualify.)
 constexpr int RED_BLOCKS = 592;   // 4 x 148 SMs: partial-reduction width for bounds / column sums
 constexpr int Z_BLOCKS = 592;
 
@@ -41,7 +43,12 @@ struct GridParams {
     double inv_norm;      // 1/M^dims, folded into the kernel spectra (nbodyfft.cpp:202-203)
     float bwf;
     int B, G, M, p, xbits, nb, ok;
-    int sort_bits;        // radix digit width: the key (dims*xbits bits) is sorted in exactly two LSD passes
+    int sort_bits;        // radix digit width
+    int sort_passes;      // 1: the whole key is one digit (<= SORT_MAX_BITS bits); 2: two LSD passes of sort_bits each
+    int kmode;            // kernel spectra this iteration: 0 = sample + transform at h, 1 = first-order Taylor from the cache
+    int with_deriv;       // kmode 0 only: also sample + transform dK/dh (so that later iterations can use kmode 1)
+    unsigned fft_skip;    // bit i set: forward FFT passes leave plane i alone this iteration
+    float dh;             // h - h0 of the cached spectra (kmode 1)
     int pad_;
     float s[PMAX];        // in-box node positions (k+1/2)/p, accumulated like nbodyfft.cpp:30-34
     float inv_den[PMAX];  // 1/prod_{j!=i}(s_i-s_j)          nbodyfft.cpp:313-321
@@ -62,7 +69,22 @@ struct Scalars {          // small device-resident results
     float bmin, bmax;     // bounds of the current Y (with the 2-D scan quirk)
     double kl;
     unsigned long long iter_done;   // optimiser steps that really executed (speculative launches that found a grid mismatch do not count)
+    // kernel-spectrum cache (planes 2..5 hold K^(h0) and dK^/dh(h0)): see k_setup_grid
+    double kc_h0, kc_hprev;
+    int kc_B, kc_M, kc_valid, kc_has_deriv;
+    unsigned long long kc_hits;     // iterations served from the cache
 };
+
+// Kernel-spectrum cache.  The kernel samples depend on the grid only through the node spacing h (and n_boxes / M), and
+// h drifts by ~1e-4 per iteration late in a run.  Instead of re-sampling and re-transforming the four kernel planes
+// every iteration (~45 % of the convolution), iterations whose h is within KC_MAX_REL of the cached h0 use
+//   K^(h) = K^(h0) + (h - h0) * dK^/dh (h0)
+// (second-order term <= 10 (dh/h)^2 relative = 1e-5 at the limit: two decades inside the 1e-4 gradient tolerance).
+// dK/dh planes are only built when h moved slowly since the previous iteration, so the fast-drift early phase pays
+// nothing extra.  Exactness is restored at every refresh; reference parity is kept (tests/test_gpu_parity.py).
+constexpr double KC_MAX_REL = 1.0e-3;    // |h - h0| / h0 beyond which the spectra are refreshed
+constexpr double KC_SLOW_REL = 2.5e-4;   // |h - h_prev| / h below which a refresh also builds dK/dh
+
 
 // ------------------------------------------------------------------------------------------ helpers --
 
@@ -276,17 +298,25 @@ __host__ __device__ inline int choose_n_boxes(double mn, double mx, double ipi, 
     return n;
 }
 
-// Two LSD passes always (so the launch sequence does not depend on B): digit width = ceil(key bits / 2).
-__host__ __device__ inline int sort_bits_for(int B, int dims) {
+// Sort layout for n_boxes = B: one pass when the key (dims*xbits bits) fits a single digit, else two LSD passes of
+// ceil(key bits / 2).  The launch sequence is the same either way (kernels of the unused pass return at once).
+__host__ __device__ inline void sort_layout(int B, int dims, int *bits, int *passes) {
     int xb = 0;
     while ((1 << xb) < B) xb++;
     const int kb = dims * xb > 1 ? dims * xb : 1;
-    return (kb + 1) / 2;
+    if (kb <= SORT_ONE_PASS_BITS) { *passes = 1; *bits = kb; }
+    else { *passes = 2; *bits = (kb + 1) / 2; }
+}
+__host__ __device__ inline int sort_bits_for(int B, int dims) {
+    int bits, passes;
+    sort_layout(B, dims, &bits, &passes);
+    return bits;
 }
 
 // Fill GridParams for a grid of B boxes/dim (the host's choice; verified against the device's own bounds).
 __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restrict__ sc, const int *__restrict__ B_host, int M, int p, int dims,
-                             double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals) {
+                             double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals,
+                             Scalars *__restrict__ scw, int use_kernel_cache) {
     for (int i = threadIdx.x; i < 2 * (1 << SORT_MAX_BITS); i += blockDim.x) sort_totals[i] = 0;   // both passes
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     // B_host > 0: the host sized the grid after reading the bounds (single-step API); 0: speculative launch, the device
@@ -309,9 +339,31 @@ __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restr
     int xb = 0;
     while ((1 << xb) < B) xb++;
     gp->xbits = xb;
-    gp->sort_bits = sort_bits_for(B, dims);
+    sort_layout(B, dims, &gp->sort_bits, &gp->sort_passes);
     gp->pad_ = 0;
     gp->nb = dims == 2 ? B * B : B;
+    // kernel-spectrum cache decision (only for iterations that will really run)
+    gp->kmode = 0; gp->with_deriv = 0; gp->dh = 0.f; gp->fft_skip = 0x30u;   // planes 4,5 (dK/dh) idle by default
+    if (gp->ok) {
+        const double h = gp->h;
+        if (use_kernel_cache) {
+            const bool same = scw->kc_valid && scw->kc_B == B && scw->kc_M == M;
+            if (same && scw->kc_has_deriv && fabs(h - scw->kc_h0) <= KC_MAX_REL * scw->kc_h0) {
+                gp->kmode = 1;
+                scw->kc_hits += 1;
+                gp->dh = (float) (h - scw->kc_h0);
+                gp->fft_skip = 0x3cu;                    // kernel planes 2..5 keep the cached spectra
+            } else {
+                const bool slow = !scw->kc_valid || (scw->kc_B == B && fabs(h - scw->kc_hprev) <= KC_SLOW_REL * h);
+                gp->with_deriv = slow ? 1 : 0;
+                gp->fft_skip = slow ? 0u : 0x30u;
+                scw->kc_h0 = h; scw->kc_B = B; scw->kc_M = M; scw->kc_valid = 1; scw->kc_has_deriv = slow ? 1 : 0;
+            }
+        } else {
+            scw->kc_valid = 0;
+        }
+        scw->kc_hprev = h;
+    }
     double s[PMAX];
     const double hh = 1.0 / (double) p;
     s[0] = hh / 2;
@@ -325,7 +377,8 @@ __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restr
 }
 
 // -------------------------------------------------------------------------------------------- binning --
-// Stable LSD radix sort of (box key, point index), exactly two passes of `sort_bits` (<= 11) bits each:
+// Stable LSD radix sort of (box key, point index): one pass when the key has <= SORT_ONE_PASS_BITS bits, else two
+// passes of `sort_bits` bits each:
 //   k_bin            keys + per-tile histogram of digit 0 (fused)      k_radix_hist   per-tile histogram of digit 1
 //   k_radix_offsets  per-digit tile offsets (one CTA per digit value)  k_radix_scatter stable scatter
 // Stability (ties keep point-index order) makes the box-sorted order, hence the spread's summation order,
@@ -342,7 +395,8 @@ __device__ __forceinline__ void tile_hist_flush(const uint32_t *cnt, int nb, uin
 
 template <int D>
 __global__ void __launch_bounds__(SORT_THREADS) k_bin(const float *__restrict__ Y, int first, int n,
-                                                      const GridParams *__restrict__ gpp, uint32_t *__restrict__ keys,
+                                                      const GridParams *__restrict__ gpp, uint32_t *__restrict__ keys_two_pass,
+                                                      uint32_t *__restrict__ keys_one_pass, float *__restrict__ ubuf,
                                                       uint32_t *__restrict__ hist, int tiles, uint32_t *__restrict__ totals) {
     __shared__ uint32_t cnt[1 << SORT_MAX_BITS];
     __shared__ GridParams gps;
@@ -351,6 +405,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_bin(const float *__restrict__ 
     __syncthreads();
     const GridParams &gp = gps;
     if (!gp.ok) return;
+    // one-pass layout: this histogram (whole key) is the one the single scatter uses -> it goes to the pass-1 totals,
+    // the keys go to the scatter's input buffer, and the in-box coordinates ride along (no k_post_sort needed)
+    const bool one = gp.sort_passes == 1;
+    uint32_t *keys = one ? keys_one_pass : keys_two_pass;
+    uint32_t *tot = one ? totals + (1 << SORT_MAX_BITS) : totals;
     const int nb = 1 << gp.sort_bits;
     const uint32_t mask = (uint32_t) nb - 1;
     for (int i = threadIdx.x; i < nb; i += SORT_THREADS) cnt[i] = 0;
@@ -360,28 +419,31 @@ __global__ void __launch_bounds__(SORT_THREADS) k_bin(const float *__restrict__ 
     for (int r = 0; r < SORT_IPT; r++) {
         const int k = base + r * SORT_THREADS + threadIdx.x;
         if (k < n) {
-            float u;
             uint32_t key;
             if (D == 2) {
                 const float2 y = reinterpret_cast<const float2 *>(Y)[first + k];
-                const int bx = box_of<true>(y.x, gp, u);
-                const int by = box_of<true>(y.y, gp, u);
+                float2 u;
+                const int bx = box_of<true>(y.x, gp, u.x);
+                const int by = box_of<true>(y.y, gp, u.y);
                 key = ((uint32_t) by << gp.xbits) | (uint32_t) bx;
+                if (one) reinterpret_cast<float2 *>(ubuf)[k] = u;
             } else {
+                float u;
                 key = (uint32_t) box_of<false>(Y[first + k], gp, u);
+                if (one) ubuf[k] = u;
             }
             keys[k] = key;
             atomicAdd(&cnt[key & mask], 1u);
         }
     }
     __syncthreads();
-    tile_hist_flush(cnt, nb, hist, tiles, totals);
+    tile_hist_flush(cnt, nb, hist, tiles, tot);
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint32_t *__restrict__ keys, int n, int pass,
                                                              uint32_t *__restrict__ hist, int tiles, uint32_t *__restrict__ totals,
                                                              const GridParams *__restrict__ gpp) {
-    if (!gpp->ok) return;
+    if (!gpp->ok || gpp->sort_passes == 1) return;      // one-pass layout: k_bin already produced the histogram
     __shared__ uint32_t cnt[1 << SORT_MAX_BITS];
     const int bits = gpp->sort_bits, shift = pass * bits;
     const int nb = 1 << bits;
@@ -399,9 +461,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint32_t *__r
 }
 
 // One CTA per digit value d: hist[d][t] <- (sum of totals[d' < d]) + (exclusive prefix over tiles t' < t), in place.
+template <int D>
 __global__ void __launch_bounds__(256) k_radix_offsets(uint32_t *__restrict__ hist, int tiles, const uint32_t *__restrict__ totals,
+                                                       int pass, int n, uint32_t *__restrict__ box_start,
                                                        const GridParams *__restrict__ gpp) {
     if (!gpp->ok) return;
+    const bool one = gpp->sort_passes == 1;
+    if (one && pass == 0) return;
     const int nb = 1 << gpp->sort_bits;
     const int d = blockIdx.x;
     if (d >= nb) return;
@@ -419,6 +485,15 @@ __global__ void __launch_bounds__(256) k_radix_offsets(uint32_t *__restrict__ hi
         uint32_t t = 0;
         for (int i = 0; i < 8; i++) t += wsum[i];
         carry_s = t;
+        if (one && box_start) {
+            // the digit IS the box key: its global base is the box's first sorted position (keys are ordered like boxes)
+            const int B = gpp->B;
+            if (D == 2) {
+                const int by = d >> gpp->xbits, bx = d & ((1 << gpp->xbits) - 1);
+                if (bx < B && by < B) box_start[by * B + bx] = t;
+            } else if (d < B) box_start[d] = t;
+            if (d == 0) box_start[gpp->nb] = (uint32_t) n;
+        }
     }
     __syncthreads();
     uint32_t *rowp = hist + (size_t) d * tiles;
@@ -449,10 +524,14 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t *
                                                                 uint32_t *__restrict__ keys_out,
                                                                 uint32_t *__restrict__ vals_out, int n, int pass,
                                                                 const uint32_t *__restrict__ hist, int tiles,
-                                                                uint32_t val_base, const GridParams *__restrict__ gpp) {
+                                                                uint32_t val_base, const GridParams *__restrict__ gpp,
+                                                                const float *__restrict__ ubuf, float *__restrict__ sorted_u, int dims) {
     if (!gpp->ok) return;
+    const bool one = gpp->sort_passes == 1;
+    if (one && pass == 0) return;
+    if (one) vals_in = nullptr;                           // single pass: values are the identity (+ val_base)
     extern __shared__ uint32_t smem[];
-    const int bits = gpp->sort_bits, shift = pass * bits;
+    const int bits = gpp->sort_bits, shift = one ? 0 : pass * bits;
     const int nb = 1 << bits;
     constexpr int NW = SORT_THREADS / 32;
     uint32_t *gbase = smem;                                          // [nb]
@@ -503,6 +582,10 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t *
             const uint32_t pos = gbase[d] + mycnt[d] + rank[r];
             keys_out[pos] = key[r];
             vals_out[pos] = vals_in ? vals_in[i] : (val_base + (uint32_t) i);
+            if (one && ubuf) {                            // in-box coordinates computed by k_bin ride along
+                if (dims == 2) reinterpret_cast<float2 *>(sorted_u)[pos] = reinterpret_cast<const float2 *>(ubuf)[i];
+                else sorted_u[pos] = ubuf[i];
+            }
         }
     }
 }
@@ -515,7 +598,7 @@ __global__ void __launch_bounds__(256) k_post_sort(const uint32_t *__restrict__ 
                                                    const GridParams *__restrict__ gpp, uint32_t *__restrict__ box_start,
                                                    float *__restrict__ sorted_u) {
     const GridParams &gp = *gpp;
-    if (!gp.ok) return;
+    if (!gp.ok || gp.sort_passes == 1) return;           // one-pass layout: box_start and sorted_u are already there
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t key = skeys[k];
@@ -739,13 +822,13 @@ __global__ void __launch_bounds__(256) k_pad_grids(const float2 *__restrict__ co
 // ------------------------------------------------------------------------------------ kernel samples --
 // Real kernels on the wrap-around node-offset lattice, offsets d in (-G, G) stored at index d mod M
 // (the reference's 2G circulant embedding, nbodyfft.cpp:52-61, with M >= 2G), packed two per complex plane:
-//   plane 2 = (Ksq, Kb)   plane 3 = (Kgrad_x, Kgrad_y)  [1-D: (Kgrad, 0)]
+//   plane 2 = (Ksq, Kb)   plane 3 = (Kgrad_x, Kgrad_y)  [1-D: (Kgrad, 0)]   planes 4, 5 = d/dh of planes 2, 3 (with_deriv)
 //   Ksq=(1+r2/df)^-(df+1)   Kgrad_k = (R_k/bw)*Ksq  (box units)   Kb=(1+r2/df)^-df      (tsne.cpp:69-94)
 // Values carry the 1/M^D inverse-FFT normalisation (nbodyfft.cpp:202-203).
 template <int D>
 __global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restrict__ gpp, double df, float2 *__restrict__ planes) {
     const GridParams &gp = *gpp;
-    if (!gp.ok) return;
+    if (!gp.ok || gp.kmode == 1) return;          // kmode 1: the cached spectra (planes 2..5) stay as they are
     const int M = gp.M, G = gp.G;
     const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
     const size_t id = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -755,27 +838,39 @@ __global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restric
     const int dc = c < G ? c : (c > M - G ? c - M : 0);
     const int dr = r < G ? r : (r > M - G ? r - M : 0);
     const bool valid = (c < G || c > M - G) && (D == 1 || r < G || r > M - G);
-    float2 k1 = make_float2(0.f, 0.f), k2 = make_float2(0.f, 0.f);
+    float2 k1 = make_float2(0.f, 0.f), k2 = make_float2(0.f, 0.f), d1 = k1, d2 = k1;
     if (valid) {
-        const double rx = gp.h * (double) dc, ry = gp.h * (double) dr;
-        const double r2 = rx * rx + (D == 2 ? ry * ry : 0.0);
-        double kb, ksq;
+        const double d2l = (double) dc * (double) dc + (D == 2 ? (double) dr * (double) dr : 0.0);   // lattice distance^2
+        const double r2 = gp.h * gp.h * d2l;
+        double kb, ksq, dksq;
         if (df == 1.0) {
             kb = 1.0 / (1.0 + r2);
             ksq = kb * kb;
+            dksq = -4.0 * gp.h * d2l * ksq * kb;                       // d/dh (1+h^2 d2)^-2
         } else {
             const double t = 1.0 + r2 / df;
             kb = pow(t, -df);
             ksq = pow(t, -(df + 1.0));
+            dksq = -(df + 1.0) * (2.0 * gp.h * d2l / df) * ksq / t;   // d/dh (1+h^2 d2/df)^-(df+1)
         }
+        const double dkb = -2.0 * gp.h * d2l * ksq;                    // d/dh (1+h^2 d2/df)^-df
         kb *= gp.inv_norm; ksq *= gp.inv_norm;
         k1 = make_float2((float) ksq, (float) kb);
         // gradient kernels in box units as well: R_k / bw = (lattice offset) / p
         const double ux = (double) dc / (double) gp.p, uy = (double) dr / (double) gp.p;
         k2 = make_float2((float) (ux * ksq), D == 2 ? (float) (uy * ksq) : 0.f);
+        if (gp.with_deriv) {
+            const double a = dksq * gp.inv_norm, bb = dkb * gp.inv_norm;
+            d1 = make_float2((float) a, (float) bb);
+            d2 = make_float2((float) (ux * a), D == 2 ? (float) (uy * a) : 0.f);
+        }
     }
     planes[2 * plane + id] = k1;
     planes[3 * plane + id] = k2;
+    if (gp.with_deriv) {
+        planes[4 * plane + id] = d1;
+        planes[5 * plane + id] = d2;
+    }
 }
 
 // ------------------------------------------------------------------------------ Hadamard + sum_Q terms --
@@ -805,7 +900,9 @@ __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, c
     const int M = gp.M;
     const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
     float2 *Z1 = planes, *Z2 = planes + plane;
-    const float2 *K1 = planes + 2 * plane, *K2 = planes + 3 * plane;
+    const float2 *K1 = planes + 2 * plane, *K2 = planes + 3 * plane, *dK1 = planes + 4 * plane, *dK2 = planes + 5 * plane;
+    const bool taylor = gp.kmode == 1;
+    const float dh = gp.dh;
     const double bw2 = gp.bw * gp.bw;
     double zacc = 0;
     for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < plane; e += (size_t) gridDim.x * blockDim.x) {
@@ -819,8 +916,14 @@ __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, c
         float2 w1, d1, d2, wbb, ksq, kb, kg1, kg2;
         unpack_pair(Z1[e], Z1[em], w1, d1);
         unpack_pair(Z2[e], Z2[em], d2, wbb);        // 1-D: d2 = wbb-plane real part, see below
-        unpack_pair(K1[e], K1[em], ksq, kb);
-        unpack_pair(K2[e], K2[em], kg1, kg2);
+        float2 k1e = K1[e], k1m = K1[em], k2e = K2[e], k2m = K2[em];
+        if (taylor) {      // K^(h) = K^(h0) + dh * dK^/dh(h0), on the packed values (the unpacking is linear)
+            const float2 a1 = dK1[e], b1 = dK1[em], a2 = dK2[e], b2 = dK2[em];
+            k1e.x += dh * a1.x; k1e.y += dh * a1.y; k1m.x += dh * b1.x; k1m.y += dh * b1.y;
+            k2e.x += dh * a2.x; k2e.y += dh * a2.y; k2m.x += dh * b2.x; k2m.y += dh * b2.y;
+        }
+        unpack_pair(k1e, k1m, ksq, kb);
+        unpack_pair(k2e, k2m, kg1, kg2);
         if (D == 1) { wbb = d2; }                   // 1-D plane 1 = (wbb, 0)
         const float2 v1 = cmul(ksq, w1);
         const float2 kgw1 = cmul(kg1, w1), ksd1 = cmul(ksq, d1);

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfitsne_b200.so")
 
 STEP_MOMENTUM_CLIP, STEP_MOMENTUM, STEP_PLAIN_GD = 0, 1, 2
-FLAG_NO_GRAPH, FLAG_TIMERS, FLAG_NO_REORDER, FLAG_FORCE_TILES, FLAG_NO_TILES, FLAG_NO_SPECULATION = 1, 2, 4, 8, 16, 32
+FLAG_NO_GRAPH, FLAG_TIMERS, FLAG_NO_REORDER, FLAG_FORCE_TILES, FLAG_NO_TILES, FLAG_NO_SPECULATION, FLAG_NO_KERNEL_CACHE = 1, 2, 4, 8, 16, 32, 64
 PHASES = ["bounds", "sort", "spread", "kernel_spectrum", "fft", "gather", "attract_update", "center", "kl",
           "collectives"]
 
@@ -49,7 +49,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
                 ("graph_launches", ctypes.c_uint64), ("regrids", ctypes.c_uint64), ("n_boxes", ctypes.c_int),
                 ("grid_side", ctypes.c_int), ("fft_side", ctypes.c_int), ("min_coord", ctypes.c_double),
-                ("max_coord", ctypes.c_double), ("phase_ms", ctypes.c_double * 16)]
+                ("max_coord", ctypes.c_double), ("phase_ms", ctypes.c_double * 16),
+                ("spectrum_cache_hits", ctypes.c_uint64), ("reorders", ctypes.c_uint64)]
 
 
 class FitsneError(RuntimeError):

@@ -50,6 +50,7 @@ typedef struct fitsne_config {
 #define FITSNE_FLAG_FORCE_TILES 8 /* always use the tiled attractive kernel after a re-ordering            */
 #define FITSNE_FLAG_NO_TILES 16   /* re-order for locality but keep the CSR attractive kernel              */
 #define FITSNE_FLAG_NO_SPECULATION 32 /* fitsne_run: one host round trip per iteration instead of batches  */
+#define FITSNE_FLAG_NO_KERNEL_CACHE 64 /* re-sample + re-transform the kernel planes every iteration (no Taylor re-use) */
 
 /* One optimiser step's parameters: the state TSNE::run carries across iterations (tsne.cpp:437-544). */
 typedef struct fitsne_step_params {
@@ -91,6 +92,8 @@ typedef struct fitsne_stats {
     int fft_side;                 /* last FFT length per dimension                               */
     double min_coord, max_coord;  /* last bounds used for the grid                               */
     double phase_ms[16];          /* FITSNE_PHASE_* accumulators (only with FITSNE_FLAG_TIMERS)  */
+    uint64_t spectrum_cache_hits; /* iterations that re-used the cached kernel spectra (Taylor step in h) */
+    uint64_t reorders;            /* device-side Morton re-orderings of the points                */
 } fitsne_stats;
 
 enum {
