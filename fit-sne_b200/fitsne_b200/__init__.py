@@ -244,3 +244,108 @@ def run_host(row_P, col_P, val_P, Y0, schedule=None, nterms=3, intervals_per_int
     if rc != 0:
         raise FitsneError(rc, lib.fitsne_last_error(None).decode())
     return Y, costs
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# In-process mirror of the reference wrapper's fast_tsne() (fast_tsne.py:19-51): same arguments and defaults, but no
+# data.dat / result.dat round trip and no subprocess -- host preprocessing by libfitsne_host.so (exact kNN, perplexity
+# calibration, symmetrisation: the reference's own semantics, see host/tsne_host.cpp), gradient loop by libfitsne_b200.so.
+HOSTLIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfitsne_host.so")
+_hostlib = None
+
+
+def _load_hostlib():
+    global _hostlib
+    if _hostlib is None:
+        _hostlib = ctypes.CDLL(HOSTLIB_PATH)
+    return _hostlib
+
+
+def input_similarities(X, perplexity=30.0, K=-1, sigma=-1.0, perplexity_list=None, nthreads=0):
+    """CSR P (row u32, col u32, val f64) exactly as TSNE::run builds it before the loop (tsne.cpp:153-161,282-330)."""
+    lib = _load_hostlib()
+    X = np.array(X, dtype=np.float64, order="C")
+    X -= X.mean(0)
+    if perplexity_list is not None:
+        perplexity = 0.0
+    if perplexity >= 0:
+        X /= np.abs(X).max()
+        K_use = int(3 * (perplexity if perplexity > 0 else max(perplexity_list)))
+        sigma_use = -1.0
+    else:
+        K_use, sigma_use = int(K), float(sigma)
+    row, col, val = ctypes.POINTER(ctypes.c_uint)(), ctypes.POINTER(ctypes.c_uint)(), ctypes.POINTER(ctypes.c_double)()
+    pl = np.ascontiguousarray(perplexity_list if perplexity_list is not None else [0.0], np.float64)
+    rc = lib.fitsne_host_similarities(_dp(X), X.shape[0], X.shape[1], ctypes.c_double(perplexity), K_use, ctypes.c_double(sigma_use),
+                                      len(pl) if perplexity_list is not None else 0, _dp(pl), int(nthreads or os.cpu_count() or 1),
+                                      ctypes.byref(row), ctypes.byref(col), ctypes.byref(val))
+    if rc != 0:
+        raise RuntimeError("input_similarities failed (%d)" % rc)
+    N = X.shape[0]
+    r = np.ctypeslib.as_array(row, shape=(N + 1,)).copy()
+    c = np.ctypeslib.as_array(col, shape=(int(r[-1]),)).copy()
+    v = np.ctypeslib.as_array(val, shape=(int(r[-1]),)).copy()
+    for ptr in (row, col, val):
+        lib.fitsne_host_free(ptr)
+    return r, c, v
+
+
+def fast_tsne(X, theta=0.5, perplexity=30, map_dims=2, max_iter=750, stop_early_exag_iter=250, K=-1, sigma=-1, nbody_algo="FFT",
+              knn_algo="annoy", mom_switch_iter=250, momentum=0.5, final_momentum=0.8, learning_rate="auto", early_exag_coeff=12,
+              no_momentum_during_exag=False, n_trees=50, search_k=None, start_late_exag_iter="auto", late_exag_coeff=-1, nterms=3,
+              intervals_per_integer=1, min_num_intervals=50, seed=-1, initialization="pca", load_affinities=None,
+              perplexity_list=None, df=1, return_loss=False, nthreads=-1, max_step_norm=5, device=-1):
+    """Drop-in for the reference wrapper's fast_tsne() (same parameters, fast_tsne.py:19-51) running in-process on a B200."""
+    if nbody_algo != "FFT" or theta == 0:
+        raise ValueError("this build accelerates the FFT-interpolation path only (nbody_algo='FFT', theta > 0)")
+    if map_dims not in (1, 2):
+        raise ValueError("FFT interpolation scheme supports only 1 or 2 output dimensions")
+    X = np.array(X).astype(float)
+    N = X.shape[0]
+    if learning_rate == "auto":
+        learning_rate = max(200, N / early_exag_coeff)
+    if start_late_exag_iter == "auto":
+        start_late_exag_iter = stop_early_exag_iter if late_exag_coeff > 0 else -1
+    if max_step_norm == "none":
+        max_step_norm = -1
+    rng = np.random.default_rng(None if seed == -1 else seed)
+    if isinstance(initialization, str) and initialization == "pca":
+        Xc = X - X.mean(0)
+        # leading principal components by SVD of the (thin) data matrix, scaled to std 1e-4 like the wrapper
+        U, S, _ = np.linalg.svd(Xc, full_matrices=False) if min(Xc.shape) <= 2000 else _randomized_svd(Xc, map_dims, rng)
+        Y0 = U[:, :map_dims] * S[:map_dims]
+        Y0 = Y0 / np.std(Y0[:, 0]) * 0.0001
+    elif isinstance(initialization, str) and initialization == "random":
+        Y0 = rng.standard_normal((N, map_dims)) * 0.0001
+    else:
+        Y0 = np.array(initialization).astype(float).reshape(N, map_dims)
+    if sigma > 0 and K > 0:
+        perplexity = -1
+    if N - 1 < 3 * (perplexity if perplexity_list is None else max(perplexity_list)):
+        raise ValueError("Perplexity too large for the number of data points!")
+    if load_affinities == "load":
+        row = np.fromfile("P_row.dat", np.uint32); col = np.fromfile("P_col.dat", np.uint32); val = np.fromfile("P_val.dat", np.float64)
+    else:
+        row, col, val = input_similarities(X, float(perplexity), K, sigma, perplexity_list, 0 if nthreads == -1 else nthreads)
+        if load_affinities == "save":
+            row.tofile("P_row.dat"); col.tofile("P_col.dat"); val.tofile("P_val.dat")
+    Y, costs = run_host(row, col, val, Y0, nterms=nterms, intervals_per_integer=intervals_per_integer,
+                        min_num_intervals=min_num_intervals, df=df, device=device, max_iter=max_iter,
+                        stop_lying_iter=stop_early_exag_iter, mom_switch_iter=mom_switch_iter,
+                        start_late_exag_iter=start_late_exag_iter, momentum=momentum, final_momentum=final_momentum,
+                        learning_rate=learning_rate, early_exag_coeff=early_exag_coeff, late_exag_coeff=late_exag_coeff,
+                        max_step_norm=max_step_norm, no_momentum_during_exag=no_momentum_during_exag)
+    if return_loss:
+        loss = costs.copy()
+        loss[np.arange(1, max_iter + 1) % 50 > 0] = np.nan          # like the wrapper (fast_tsne.py:328)
+        return Y, loss
+    return Y
+
+
+def _randomized_svd(A, k, rng, oversample=8, iters=4):
+    """Small randomized range finder for the PCA initialisation of large inputs (the wrapper uses sklearn's arpack)."""
+    Q = np.linalg.qr(A @ rng.standard_normal((A.shape[1], k + oversample)))[0]
+    for _ in range(iters):
+        Q = np.linalg.qr(A @ (A.T @ Q))[0]
+    Ub, S, Vt = np.linalg.svd(Q.T @ A, full_matrices=False)
+    return Q @ Ub, S, Vt

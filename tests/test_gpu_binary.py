@@ -71,3 +71,29 @@ def test_binary_rejects_bad_version_and_unsupported_modes(tmp_path):
     bench_util.write_data_dat(str(tmp_path / "data.dat"), X, perplexity=40.0, max_iter=10)
     out = run_bin(tmp_path)
     assert out.returncode == 1 and "Perplexity too large" in out.stdout       # tsne.cpp:128-131
+
+
+def test_in_process_fast_tsne_matches_binary(tmp_path):
+    """fitsne_b200.fast_tsne() (same signature as the reference wrapper, no files) == bin/fast_tsne on the same input."""
+    import fitsne_b200 as fb
+    rng = np.random.default_rng(5)
+    N, D, C = 1500, 12, 4
+    labels = rng.integers(0, C, N)
+    X = rng.standard_normal((C, D))[labels] * 5 + rng.standard_normal((N, D))
+    init = rng.standard_normal((N, 2)) * 1e-4
+    kw = dict(perplexity=15, max_iter=200, stop_early_exag_iter=80, mom_switch_iter=80, learning_rate=150.0, late_exag_coeff=1.5,
+              knn_algo="vp-tree", df=0.9, initialization=init)
+    Y, loss = fb.fast_tsne(X, return_loss=True, **kw)
+    bench_util.write_data_dat(str(tmp_path / "data.dat"), X, perplexity=15.0, max_iter=200, stop_lying_iter=80, mom_switch_iter=80,
+                              learning_rate=150.0, start_late_exag_iter=80, late_exag_coeff=1.5, knn_algo=2, df=0.9, seed=-1,
+                              initialization=init, search_k=15 * 3 * 50)
+    out = run_bin(tmp_path)
+    assert out.returncode == 0, out.stdout[-600:]
+    Yb, costs = bench_util.read_result(str(tmp_path / "result.dat"))
+    nz = costs != 0
+    assert np.array_equal(np.isfinite(loss), nz)
+    assert np.allclose(loss[nz], costs[nz], rtol=1e-9)
+    assert np.allclose(Y, Yb, rtol=0, atol=1e-9 * np.abs(Yb).max())
+    # PCA / random initialisations and the 1-D path at least run and separate the clusters
+    Y1 = fb.fast_tsne(X, perplexity=15, max_iter=250, map_dims=1, seed=3)
+    assert Y1.shape == (N, 1) and np.isfinite(Y1).all()
