@@ -121,12 +121,13 @@ struct fitsne_ctx {
     float2 *planes = nullptr, *compact = nullptr;   // 4 packed complex planes [M^D]; multi-GPU compact grids
     size_t plane_cap = 0;                            // capacity in complex elements per plane
     // small stuff
-    double *colsum_partial = nullptr, *zpartial = nullptr, *kl_partial = nullptr;
+    double *colsum_partial = nullptr, *zpartial = nullptr, *kl_partial = nullptr, *update_partial = nullptr;
     float2 *bounds_partial = nullptr;
     GridParams *gp = nullptr;
     StepParams *sp = nullptr;
     Scalars *sc = nullptr;
     int *mismatch = nullptr;
+    unsigned int *tickets = nullptr;   // last-block-done counters: [0] hadamard, [1] centre/bounds, [2] update
     float *host_bounds = nullptr, *host_bounds_dev = nullptr;   // mapped pinned
     int *host_B = nullptr, *host_B_dev = nullptr;               // mapped pinned: the host's n_boxes for this iteration
     Scalars *host_sc = nullptr;                                 // pinned staging for scalar read-back
@@ -254,15 +255,16 @@ static inline void phase_mark(fitsne_ctx *c, int phase) {
 }
 
 template <int D>
-static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int do_center) {
-    // do_center == 1: closing kernels of an optimiser step (skipped, like the rest, when the grid check failed)
+static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int do_center, int mean_ready = 0) {
+    // do_center == 1: closing kernel of an optimiser step (skipped, like the rest, when the grid check failed).
+    // The last block to finish combines the per-block bounds and publishes them (no second launch).
     const GridParams *gate = do_center ? c->gp : nullptr;
     k_center_bounds<D><<<RED_BLOCKS, 256, 0, c->stream>>>(Yin, Yout, c->N, c->colsum_partial, RED_BLOCKS, do_center,
                                                           c->bounds_partial, c->sc, c->reordered ? c->orig_of : nullptr,
-                                                          c->reordered ? c->pos_of : nullptr, gate);
-    k_reduce_bounds<<<1, 256, 0, c->stream>>>(c->bounds_partial, RED_BLOCKS, c->sc, c->host_bounds_dev, gate);
+                                                          c->reordered ? c->pos_of : nullptr, gate, c->host_bounds_dev,
+                                                          c->tickets + 1, mean_ready);
     LAUNCH_CHECK();
-    c->stats.kernel_launches += 2;
+    c->stats.kernel_launches += 1;
     return 0;
 }
 
@@ -425,16 +427,15 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     } else {
         k_fft_pass<false><<<dim3(1, 6), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
     }
-    k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial);
-    k_finalize_z<<<1, 256, 0, st>>>(c->zpartial, Z_BLOCKS, c->N, c->gp, c->sc);
+    k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0);
     if (D == 2) {
         // inverse: columns first (all of them), then only the G rows the gather reads
         k_fft_pass<true><<<dim3(cdiv(M, LC), 2), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
         k_fft_pass<false><<<dim3(cdiv(M, LR), 2), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok, nullptr);
-        c->stats.kernel_launches += 6;
+        c->stats.kernel_launches += 5;
     } else {
         k_fft_pass<false><<<dim3(1, 1), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
-        c->stats.kernel_launches += 4;
+        c->stats.kernel_launches += 3;
     }
     LAUNCH_CHECK();
 
@@ -449,21 +450,25 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     const int rows = c->row_end - c->row_begin;
     if (!update) {
         k_update<D, false><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
-                                                           c->uY, c->gains, c->Yb);
+                                                           c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         c->stats.kernel_launches += 1;
         phase_mark(c, FITSNE_PHASE_CENTER);
+    } else if (c->world == 1) {
+        // single GPU: k_update also produces the column means of the new positions (last-block reduction), the
+        // centring kernel subtracts them, finds the bounds and publishes them -- two launches for the whole tail
+        k_update<D, true><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
+                                                          c->uY, c->gains, c->Yb, c->update_partial, c->N, c->sc, c->tickets + 2);
+        c->stats.kernel_launches += 1;
+        phase_mark(c, FITSNE_PHASE_CENTER);
+        CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1, 1));
     } else {
         k_update<D, true><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
-                                                          c->uY, c->gains, c->Yb);
-        c->stats.kernel_launches += 1;
-        if (c->world > 1) {
-            CKNCCL(g_nccl.AllGather(c->Yb + (size_t) c->rank * c->per * D, c->Yb, (size_t) c->per * D, ncclFloat, c->comm, st));
-            c->stats.kernel_launches += 1;
-        }
+                                                          c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
+        CKNCCL(g_nccl.AllGather(c->Yb + (size_t) c->rank * c->per * D, c->Yb, (size_t) c->per * D, ncclFloat, c->comm, st));
         phase_mark(c, FITSNE_PHASE_CENTER);
         k_colsum<D><<<RED_BLOCKS, 256, 0, st>>>(c->Yb, c->N, c->colsum_partial, c->gp);
-        c->stats.kernel_launches += 1;
-        CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1));
+        c->stats.kernel_launches += 3;
+        CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1, 0));
     }
     phase_mark(c, FITSNE_PHASE_COUNT);
     LAUNCH_CHECK();
@@ -850,11 +855,14 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
         CKRC(dev_alloc(c, &c->slots, (size_t) cdiv(c->nloc, CHUNK) * 2 * nodes));
     }
     CKRC(dev_alloc(c, &c->colsum_partial, (size_t) RED_BLOCKS * 2));
+    CKRC(dev_alloc(c, &c->update_partial, (size_t) cdiv(c->nloc, 256) * 2 + 2));
     CKRC(dev_alloc(c, &c->bounds_partial, (size_t) RED_BLOCKS));
     CKRC(dev_alloc(c, &c->zpartial, (size_t) Z_BLOCKS));
     CKRC(dev_alloc(c, &c->kl_partial, (size_t) 4096));
     CKRC(dev_alloc(c, &c->gp, (size_t) 1)); CKRC(dev_alloc(c, &c->sp, (size_t) 1)); CKRC(dev_alloc(c, &c->sc, (size_t) 1));
     CKRC(dev_alloc(c, &c->mismatch, (size_t) 1));
+    CKRC(dev_alloc(c, &c->tickets, (size_t) 8));
+    CK(cudaMemsetAsync(c->tickets, 0, 8 * sizeof(unsigned int), c->stream));
     CK(cudaMemsetAsync(c->gp, 0, sizeof(GridParams), c->stream));
     CK(cudaMemsetAsync(c->sc, 0, sizeof(Scalars), c->stream));
     CK(cudaMemsetAsync(c->mismatch, 0, sizeof(int), c->stream));
@@ -899,8 +907,8 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (c->comm) g_nccl.CommDestroy(c->comm);
     void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->col_P, c->val_P, c->keys[0], c->keys[1],
                     c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->hist, c->sort_totals, c->slots, c->attr, c->planes,
-                    c->compact, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
-                    c->gp, c->sp, c->sc, c->mismatch, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
+                    c->compact, c->colsum_partial, c->update_partial, c->zpartial, c->kl_partial, c->bounds_partial,
+                    c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->col_P2, c->val_P2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
                     c->nonempty, c->gp_reorder};
     for (void *b : bufs) if (b) cudaFree(b);
@@ -1125,9 +1133,12 @@ int fitsne_run(fitsne_ctx *c, const fitsne_schedule *s, double *costs, double *Y
 int fitsne_run_host(const fitsne_config *cfg, const fitsne_schedule *s, int N, int no_dims, const unsigned int *row_P,
                     const unsigned int *col_P, const double *val_P, double *Y, double *costs) {
     fitsne_ctx *c = nullptr;
+    TRACE("run_host: create");
     int rc = fitsne_create(cfg, N, no_dims, row_P, col_P, val_P, Y, &c);
     if (rc != 0) return rc;
+    TRACE("run_host: run");
     rc = fitsne_run(c, s, costs, Y);
+    TRACE("run_host: destroy");
     if (rc != 0) g_create_error = c->err;
     fitsne_destroy(c);
     return rc;

@@ -115,6 +115,22 @@ __device__ __forceinline__ T block_sum(T v, T *sm) {
     return r;
 }
 
+// "Last block done": every block deposits its partial result, then calls this; it returns true (in all threads) only
+// in the block that arrives last, which can then reduce the partials in a FIXED order -- a deterministic two-level
+// reduction without a second kernel launch.  The ticket counter resets itself for the next launch.
+__device__ __forceinline__ bool last_block_done(unsigned int *counter) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *counter = 0;
+    }
+    __syncthreads();
+    return is_last;
+}
+
 // box index and in-box coordinate of one coordinate, fp64, reference operation order
 // (nbodyfft.cpp:86-113 / :350-363); __d*_rn keeps nvcc from contracting into FMAs the CPU does not use.
 template <bool CLAMP_LOW>
@@ -163,7 +179,9 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
                                                        const double *__restrict__ colsum_partial, int nparts,
                                                        int do_center, float2 *__restrict__ bounds_partial,
                                                        Scalars *__restrict__ sc, const uint32_t *__restrict__ orig_of,
-                                                       const uint32_t *__restrict__ pos_of, const GridParams *__restrict__ gpp) {
+                                                       const uint32_t *__restrict__ pos_of, const GridParams *__restrict__ gpp,
+                                                       volatile float *host_bounds, unsigned int *__restrict__ ticket,
+                                                       int mean_ready) {
     __shared__ double smd[32];
     if (gpp && !gpp->ok) return;
     __shared__ float smf[64];
@@ -171,16 +189,20 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
     __shared__ int t_s;
     double mean[2] = {0, 0};
     if (do_center) {
-        // every block re-reduces the (few hundred) partials in the same fixed order
-        for (int d = 0; d < D; d++) {
-            double s = 0;
-            for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += colsum_partial[i * D + d];
-            double r = block_sum(s, smd);
-            if (threadIdx.x == 0) mean_s[d] = r / (double) N;
+        if (mean_ready) {            // k_update's last block already reduced the column sums (single-GPU path)
+            for (int d = 0; d < D; d++) mean[d] = sc->mean[d];
+        } else {
+            // every block re-reduces the (few hundred) partials in the same fixed order
+            for (int d = 0; d < D; d++) {
+                double s = 0;
+                for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += colsum_partial[i * D + d];
+                double r = block_sum(s, smd);
+                if (threadIdx.x == 0) mean_s[d] = r / (double) N;
+            }
+            __syncthreads();
+            for (int d = 0; d < D; d++) mean[d] = mean_s[d];
+            if (blockIdx.x == 0 && threadIdx.x == 0) { sc->mean[0] = mean[0]; sc->mean[1] = mean[1]; }
         }
-        __syncthreads();
-        for (int d = 0; d < D; d++) mean[d] = mean_s[d];
-        if (blockIdx.x == 0 && threadIdx.x == 0) { sc->mean[0] = mean[0]; sc->mean[1] = mean[1]; }
     }
     const int nflat = N * D;
     if (threadIdx.x == 0) {
@@ -236,8 +258,35 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
         }
         if (lane == 0) bounds_partial[blockIdx.x] = make_float2(mn, mx);
     }
+    // last block: combine the per-block bounds and publish them (device scalars + host-mapped words); closing a full
+    // optimiser step (gpp != nullptr) also bumps the executed-iterations counter
+    if (last_block_done(ticket)) {
+        float bmn = INFINITY, bmx = -INFINITY;
+        for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) {
+            const float2 v = bounds_partial[i];
+            bmn = fminf(bmn, v.x); bmx = fmaxf(bmx, v.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bmn = fminf(bmn, __shfl_xor_sync(0xffffffffu, bmn, o));
+            bmx = fmaxf(bmx, __shfl_xor_sync(0xffffffffu, bmx, o));
+        }
+        __syncthreads();
+        if (lane == 0) { smf[w] = bmn; smf[32 + w] = bmx; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < (int) (blockDim.x >> 5); i++) { bmn = fminf(bmn, smf[i]); bmx = fmaxf(bmx, smf[32 + i]); }
+            sc->bmin = bmn; sc->bmax = bmx;
+            if (gpp) sc->iter_done += 1;
+            if (host_bounds) {
+                host_bounds[0] = bmn; host_bounds[1] = bmx;
+                if (gpp) *reinterpret_cast<volatile unsigned long long *>(host_bounds + 4) = sc->iter_done;
+            }
+        }
+    }
 }
 
+// (superseded by the last-block epilogue of k_center_bounds; kept for reference / sharded experiments)
 // Reduce the per-block bounds; publish them to the device scalars and to a host-mapped word pair.
 __global__ void __launch_bounds__(256) k_reduce_bounds(const float2 *__restrict__ bounds_partial, int nparts,
                                                        Scalars *__restrict__ sc, volatile float *host_bounds,
@@ -893,7 +942,8 @@ __device__ __forceinline__ void unpack_pair(float2 zk, float2 zm, float2 &A, flo
 
 template <int D>
 __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, const GridParams *__restrict__ gpp,
-                                                  int df_is_one, double *__restrict__ zpartial) {
+                                                  int df_is_one, double *__restrict__ zpartial, int N, Scalars *__restrict__ sc,
+                                                  unsigned int *__restrict__ ticket) {
     __shared__ double sm[32];
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
@@ -946,6 +996,16 @@ __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, c
     }
     const double r = block_sum(zacc, sm);
     if (threadIdx.x == 0) zpartial[blockIdx.x] = r;
+    if (last_block_done(ticket)) {           // sum_Q = (sum of the partials, in index order) - N   (tsne.cpp:1110)
+        double s2 = 0;
+        for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) s2 += zpartial[i];
+        const double tot = block_sum(s2, sm);
+        if (threadIdx.x == 0) {
+            const double Z = tot - (double) N;
+            sc->Z = Z;
+            sc->inv_Z = (float) (1.0 / Z);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_finalize_z(const double *__restrict__ zpartial, int nparts, int N,
@@ -1085,15 +1145,10 @@ __global__ void __launch_bounds__(256) k_attract(const uint32_t *__restrict__ ro
 __device__ __forceinline__ float sgnf(float x) { return x == 0.f ? 0.f : (x < 0.f ? -1.f : 1.f); }
 
 template <int D, bool UPDATE>
-__global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, const float *__restrict__ attr,
-                                                const float *__restrict__ frep, int row_begin, int row_end,
-                                                const StepParams *__restrict__ spp, const GridParams *__restrict__ gpp,
-                                                float *__restrict__ dC_out, float *__restrict__ uY, float *__restrict__ gains,
-                                                float *__restrict__ Ynext) {
-    if (!gpp->ok) return;
-    const StepParams sp = *spp;
-    const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= row_end) return;
+__device__ __forceinline__ void update_row(int row, const float *__restrict__ Y, const float *__restrict__ attr,
+                                           const float *__restrict__ frep, const StepParams &sp, float *__restrict__ dC_out,
+                                           float *__restrict__ uY, float *__restrict__ gains, float *__restrict__ Ynext,
+                                           float &new0, float &new1) {
     float d0, d1 = 0.f, yix, yiy = 0.f;
     if (D == 2) {
         const float2 at = reinterpret_cast<const float2 *>(attr)[row], fr = reinterpret_cast<const float2 *>(frep)[row];
@@ -1110,8 +1165,9 @@ __global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, con
         return;
     }
     if (sp.mode == 2) {   // plain gradient descent, no learning rate (tsne.cpp:489)
-        if (D == 2) reinterpret_cast<float2 *>(Ynext)[row] = make_float2(yix - d0, yiy - d1);
-        else Ynext[row] = yix - d0;
+        new0 = yix - d0; new1 = yiy - d1;
+        if (D == 2) reinterpret_cast<float2 *>(Ynext)[row] = make_float2(new0, new1);
+        else Ynext[row] = new0;
         return;
     }
     float u0, u1 = 0.f, g0, g1 = 1.f;
@@ -1131,14 +1187,48 @@ __global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, con
         const float step = sqrtf(u0 * u0 + u1 * u1);
         if (step > sp.max_step_norm) { const float f = sp.max_step_norm / step; u0 *= f; u1 *= f; }
     }
+    new0 = yix + u0; new1 = yiy + u1;
     if (D == 2) {
         reinterpret_cast<float2 *>(gains)[row] = make_float2(g0, g1);
         reinterpret_cast<float2 *>(uY)[row] = make_float2(u0, u1);
-        reinterpret_cast<float2 *>(Ynext)[row] = make_float2(yix + u0, yiy + u1);
+        reinterpret_cast<float2 *>(Ynext)[row] = make_float2(new0, new1);
     } else {
-        gains[row] = g0; uY[row] = u0; Ynext[row] = yix + u0;
+        gains[row] = g0; uY[row] = u0; Ynext[row] = new0;
     }
 }
+
+template <int D, bool UPDATE>
+__global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, const float *__restrict__ attr,
+                                                const float *__restrict__ frep, int row_begin, int row_end,
+                                                const StepParams *__restrict__ spp, const GridParams *__restrict__ gpp,
+                                                float *__restrict__ dC_out, float *__restrict__ uY, float *__restrict__ gains,
+                                                float *__restrict__ Ynext, double *__restrict__ colsum_partial, int N_total,
+                                                Scalars *__restrict__ sc, unsigned int *__restrict__ ticket) {
+    if (!gpp->ok) return;
+    const StepParams sp = *spp;
+    const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    float new0 = 0.f, new1 = 0.f;           // this thread's new (un-centred) position, 0 beyond the slice
+    if (row < row_end) update_row<D, UPDATE>(row, Y, attr, frep, sp, dC_out, uY, gains, Ynext, new0, new1);
+    if (!UPDATE || colsum_partial == nullptr) return;
+    // column sums of Ynext for the zero-mean step (tsne.cpp:1851-1876): per-block partials in a fixed tree, then the
+    // last block adds the partials in index order -- no separate reduction pass over Ynext
+    __shared__ double smu[32];
+    const double s0 = block_sum((double) new0, smu);
+    if (threadIdx.x == 0) colsum_partial[blockIdx.x * D] = s0;
+    if (D == 2) {
+        const double s1 = block_sum((double) new1, smu);
+        if (threadIdx.x == 0) colsum_partial[blockIdx.x * D + 1] = s1;
+    }
+    if (last_block_done(ticket)) {
+        for (int d = 0; d < D; d++) {
+            double s = 0;
+            for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) s += colsum_partial[i * D + d];
+            const double r = block_sum(s, smu);
+            if (threadIdx.x == 0) sc->mean[d] = r / (double) N_total;
+        }
+    }
+}
+
 
 // ------------------------------------------------------------- locality re-ordering + tiled attractive term --
 // k_attract over a plain CSR is bound by L1 gather wavefronts (one 128-byte line per random neighbour), not by

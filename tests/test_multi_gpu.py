@@ -24,7 +24,7 @@ def test_sharded_matches_single_gpu():
     n = min(_n_gpus(), 4)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
                           "--master-addr", "127.0.0.1", "--master-port", "29517",
-                          os.path.join(ROOT, "tests", "tools", "mgpu_check.py")], capture_output=True, text=True, timeout=900)
+                          os.path.join(ROOT, "tests", "tools", "mgpu_check.py")], capture_output=True, text=True, timeout=300)
     assert "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
