@@ -1075,7 +1075,9 @@ int fitsne_run(fitsne_ctx *c, const fitsne_schedule *s, double *costs, double *Y
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, c->stream));
     auto t0 = std::chrono::steady_clock::now();
-    const bool batched = !(c->cfg.flags & (FITSNE_FLAG_NO_GRAPH | FITSNE_FLAG_TIMERS | FITSNE_FLAG_NO_SPECULATION));
+    // Sharded runs keep one host round trip per iteration for now: speculative batches of graphs that contain NCCL nodes
+    // hung in the second communicator of a process and ran 2x slower on 2 GPUs (round-1 finding).
+    const bool batched = !(c->cfg.flags & (FITSNE_FLAG_NO_GRAPH | FITSNE_FLAG_TIMERS | FITSNE_FLAG_NO_SPECULATION)) && c->world == 1;
     int iter = 0;
     while (iter < s->max_iter) {
         int mode = FITSNE_STEP_MOMENTUM_CLIP;

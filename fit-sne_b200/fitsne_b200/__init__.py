@@ -113,6 +113,7 @@ class FitSNE:
         if world > 1 and col.shape[0] == int(row[-1]):   # full arrays given: slice this rank's edges
             col = np.ascontiguousarray(col[row[b]:row[e]])
             val = np.ascontiguousarray(val[row[b]:row[e]])
+        flags = int(flags) | int(os.environ.get("FITSNE_FLAGS", "0"))      # diagnostics: OR extra FLAG_* bits into every context
         cfg = Config(int(nterms), float(intervals_per_integer), int(min_num_intervals), float(df), int(device),
                      int(flags))
         idbuf = None
