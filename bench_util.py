@@ -8,7 +8,31 @@ import numpy as np
 
 
 def knn_like_graph(N, K, seed=0, n_clusters=10):
-    """CSR (row u32, col u32, val f64-of-f32) of a symmetric same-cluster random-neighbour graph, sum(val)=1."""
+    """CSR (row u32, col u32, val f64-of-f32) of a symmetric same-cluster random-neighbour graph, sum(val)=1.
+    With FITSNE_BENCH_CACHE=<dir> the (deterministic) result is kept as an .npz there: torchrun ranks and repeated
+    bench runs on one box then generate a 10M-point graph once instead of once per process."""
+    import os
+    cache = os.environ.get("FITSNE_BENCH_CACHE")
+    path = os.path.join(cache, "knn_like_%d_%d_%d_%d.npz" % (N, K, seed, n_clusters)) if cache else None
+    if path and os.path.exists(path):
+        try:
+            z = np.load(path)
+            return z["row"], z["col"], z["val"], z["labels"]
+        except Exception:
+            pass
+    out = _knn_like_graph(N, K, seed, n_clusters)
+    if path:
+        try:
+            os.makedirs(cache, exist_ok=True)
+            tmp = "%s.%d.tmp.npz" % (path, os.getpid())
+            np.savez(tmp, row=out[0], col=out[1], val=out[2], labels=out[3])
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return out
+
+
+def _knn_like_graph(N, K, seed=0, n_clusters=10):
     rng = np.random.default_rng(seed)
     labels = rng.integers(0, n_clusters, N).astype(np.int32)
     order = np.argsort(labels, kind="stable")

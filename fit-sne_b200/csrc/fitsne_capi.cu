@@ -84,8 +84,13 @@ struct fitsne_ctx {
     int n_fwd = 0, n_kern = 0, n_inv = 0;
     cudaStream_t stream = nullptr;    // repulsive pipeline + update (high priority)
     cudaStream_t stream2 = nullptr;   // attractive SpMV, concurrent with the repulsive pipeline (low priority)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ag = nullptr;
     ncclComm_t comm = nullptr;
+    // sharded runs: per-rank reduction records (all-gathered, 128 B each) and whether c->Y currently holds every rank's slice
+    ShardStats *shard_stats = nullptr;
+    double *shard_sum_partial = nullptr;
+    float4 *shard_mm_partial = nullptr;
+    bool y_whole = true;
 
     // state (fp32)
     float *Y = nullptr, *Yb = nullptr, *uY = nullptr, *gains = nullptr, *frep = nullptr, *dC = nullptr, *attr = nullptr;
@@ -127,7 +132,7 @@ struct fitsne_ctx {
     StepParams *sp = nullptr;
     Scalars *sc = nullptr;
     int *mismatch = nullptr;
-    unsigned int *tickets = nullptr;   // last-block-done counters: [0] hadamard, [1] centre/bounds, [2] update
+    unsigned int *tickets = nullptr;   // last-block-done counters: [0] hadamard, [1] centre/bounds, [2] update, [3] shard stats
     float *host_bounds = nullptr, *host_bounds_dev = nullptr;   // mapped pinned
     int *host_B = nullptr, *host_B_dev = nullptr;               // mapped pinned: the host's n_boxes for this iteration
     Scalars *host_sc = nullptr;                                 // pinned staging for scalar read-back
@@ -341,9 +346,9 @@ static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
 
 // lanes per output node in k_spread_combine: more lanes when the grid is small (few, heavy boxes)
 static inline int combine_lanes(const fitsne_ctx *c, int M) {
-    const size_t plane = c->D == 2 ? (size_t) M * M : (size_t) M;
+    const size_t space = c->D == 2 ? (size_t) (M / 2) * (M / 2) : (size_t) M;      // k_spread_combine's index space
     int lpn = 1;
-    while (lpn < 32 && plane * (size_t) (lpn * 2) <= (size_t) 8 << 20) lpn *= 2;   // up to ~8M threads: cheap, and heavy boxes (early exaggeration) get a full warp per node
+    while (lpn < 32 && space * (size_t) (lpn * 2) <= (size_t) 3 << 20) lpn *= 2;   // up to ~3M threads: cheap, and heavy boxes (early exaggeration) get a full warp per node
     return lpn;
 }
 
@@ -361,12 +366,23 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
     const bool overlap = !c->timing_this_iter;    // timers mode serialises everything to time each phase
 
+    // Sharded: after an optimiser step every rank only holds ITS slice of the new Y.  The all-gather that completes Y is
+    // issued here, on the SpMV's stream: the SpMV is its only consumer inside the iteration (bin / sort / spread / gather /
+    // update read the local slice), so the transfer overlaps this iteration's sort and spread.  NCCL calls on one
+    // communicator must keep one order on every rank: Y all-gather -> grid all-reduce -> stats all-gather, enforced by ev_ag.
     if (overlap) {
         CK(cudaEventRecord(c->ev_fork, st));
         CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        if (c->world > 1) {
+            CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, c->stream2));
+            CK(cudaEventRecord(c->ev_ag, c->stream2));
+        }
         CKRC(launch_attract<D>(c, c->stream2));
         CK(cudaEventRecord(c->ev_join, c->stream2));
+    } else if (c->world > 1) {      // timers mode: everything on one stream (this transfer is outside the phase timers)
+        CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, st));
     }
+    c->y_whole = true;
 
     phase_mark(c, FITSNE_PHASE_BOUNDS);
     k_setup_grid<<<1, 256, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
@@ -397,16 +413,18 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     phase_mark(c, FITSNE_PHASE_SPREAD);
     CKRC(launch_spread_gather<D>(c, false, M, skeys, sperm));
     const int lpn = combine_lanes(c, M);
+    const int Gc = M / 2;
+    const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
     if (c->world == 1) {
-        k_spread_combine<D><<<cdiv(plane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, lpn, c->planes, nullptr);
+        // 2-D: only the (M/2)^2 corner is touched (the zero padding is substituted inside the forward FFT passes)
+        k_spread_combine<D><<<cdiv((D == 2 ? cplane : plane) * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, lpn, c->planes, nullptr);
         c->stats.kernel_launches += 1;
     } else {
-        const int Gc = M / 2;
-        const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
         k_spread_combine<D><<<cdiv(cplane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, lpn, c->planes, c->compact);
         phase_mark(c, FITSNE_PHASE_COLLECTIVES);
+        if (overlap) CK(cudaStreamWaitEvent(st, c->ev_ag, 0));       // collective order: Y all-gather first (see above)
         CKNCCL(g_nccl.AllReduce(c->compact, c->compact, cplane * 4, ncclFloat, ncclSum, c->comm, st));   // 2 planes x float2
-        k_pad_grids<D><<<cdiv(plane, 256), 256, 0, st>>>(c->compact, c->gp, c->planes);
+        k_pad_grids<D><<<cdiv(D == 2 ? cplane : plane, 256), 256, 0, st>>>(c->compact, c->gp, c->planes);
         c->stats.kernel_launches += 3;
     }
 
@@ -423,7 +441,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         // rows: the charge planes (0,1) are zero beyond row G -> pruned; the kernel planes (2..5) need every row and are
         // skipped altogether (device-side mask) on iterations that re-use the cached kernel spectra
         k_fft_pass<false><<<dim3(cdiv(M, LR), 6), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
-        k_fft_pass<true><<<dim3(cdiv(M, LC), 6), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
+        k_fft_pass<true><<<dim3(cdiv(M, LC), 6), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
     } else {
         k_fft_pass<false><<<dim3(1, 6), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
     }
@@ -462,13 +480,18 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         phase_mark(c, FITSNE_PHASE_CENTER);
         CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1, 1));
     } else {
+        // sharded tail: local update -> local sums / bounds -> 128-byte records all-gathered -> every rank centres its own
+        // slice with the global mean and publishes the (identical) global bounds.  Y itself is gathered next iteration.
         k_update<D, true><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
                                                           c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
-        CKNCCL(g_nccl.AllGather(c->Yb + (size_t) c->rank * c->per * D, c->Yb, (size_t) c->per * D, ncclFloat, c->comm, st));
         phase_mark(c, FITSNE_PHASE_CENTER);
-        k_colsum<D><<<RED_BLOCKS, 256, 0, st>>>(c->Yb, c->N, c->colsum_partial, c->gp);
+        k_shard_stats<D><<<SHARD_BLOCKS, 256, 0, st>>>(c->Yb, c->row_begin, c->row_end, c->rank, c->gp, c->shard_sum_partial,
+                                                      c->shard_mm_partial, c->shard_stats + c->rank, c->tickets + 3);
+        CKNCCL(g_nccl.AllGather(c->shard_stats + c->rank, c->shard_stats, sizeof(ShardStats), ncclChar, c->comm, st));
+        k_center_shard<D><<<cdiv(rows, 256), 256, 0, st>>>(c->Yb, c->Y, c->row_begin, c->row_end, c->N, c->shard_stats, c->world,
+                                                          c->gp, c->sc, c->host_bounds_dev);
         c->stats.kernel_launches += 3;
-        CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1, 0));
+        c->y_whole = false;
     }
     phase_mark(c, FITSNE_PHASE_COUNT);
     LAUNCH_CHECK();
@@ -480,8 +503,19 @@ static int enqueue_iteration_d(fitsne_ctx *c, int M, bool update) {
     return c->D == 2 ? enqueue_iteration<2>(c, c->host_B_dev, M, update) : enqueue_iteration<1>(c, c->host_B_dev, M, update);
 }
 
+// Sharded: make c->Y hold every rank's slice again (after a step only the local slice is current; the next iteration's
+// own all-gather does this on the second stream, anything else that reads foreign rows -- KL, downloads, a bounds scan --
+// calls this first).  Collective: every rank reaches it at the same point of the call sequence.
+static int ensure_whole_Y(fitsne_ctx *c) {
+    if (c->world == 1 || c->y_whole) return 0;
+    CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * c->D, c->Y, (size_t) c->per * c->D, ncclFloat, c->comm, c->stream));
+    c->y_whole = true;
+    return 0;
+}
+
 static int refresh_bounds(fitsne_ctx *c) {
     if (c->bounds_valid) return 0;
+    CKRC(ensure_whole_Y(c));
     if (c->D == 2) CKRC(launch_bounds_only<2>(c, c->Y, c->Y, 0)); else CKRC(launch_bounds_only<1>(c, c->Y, c->Y, 0));
     c->bounds_valid = true;
     return 0;
@@ -660,20 +694,38 @@ static int run_batch(fitsne_ctx *c, int n, int *done) {
     CK(cudaStreamSynchronize(c->stream));
     int B, M;
     CKRC(choose_grid(c, &B, &M));
-    fitsne_ctx::GraphEntry *ge;
-    CKRC(get_graph(c, M, true, &ge));
     *c->host_B = 0;                                           // let the device choose n_boxes
     volatile unsigned long long *host_iter = reinterpret_cast<volatile unsigned long long *>(c->host_bounds + 4);
     const unsigned long long before = *host_iter;
-    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(ge->exec, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    const int ran = (int) (*host_iter - before);
-    c->stats.graph_launches += n;
-    c->stats.kernel_launches += ge->launches * (uint64_t) ran;   // no-op launches are not counted as work
+    int ran = 0;
+    if (c->world == 1) {
+        fitsne_ctx::GraphEntry *ge;
+        CKRC(get_graph(c, M, true, &ge));
+        for (int i = 0; i < n; i++) CK(cudaGraphLaunch(ge->exec, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        ran = (int) (*host_iter - before);
+        c->stats.graph_launches += n;
+        c->stats.kernel_launches += ge->launches * (uint64_t) ran;   // no-op launches are not counted as work
+    } else {
+        // sharded: plain stream launches (the NCCL calls stay ordinary stream operations on two streams); the host runs
+        // ahead of the device by up to the whole batch, so launch latency is hidden just the same.  Every rank sees the
+        // same bounds (derived from the same all-gathered bytes), hence takes the same decisions: collectives stay matched.
+        const uint64_t l0 = c->stats.kernel_launches;
+        uint64_t per_iter = 0;
+        c->timing_this_iter = false;
+        for (int i = 0; i < n; i++) {
+            CKRC(enqueue_iteration_d(c, M, true));
+            if (i == 0) per_iter = c->stats.kernel_launches - l0;
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        ran = (int) (*host_iter - before);
+        c->stats.kernel_launches = l0 + per_iter * (uint64_t) ran;
+    }
     c->stats.iterations += ran;
     c->have_grad = c->have_grad || ran > 0;
     c->bounds_valid = true;
     TRACE("batch of %d at M=%d: %d ran", n, M, ran);
+    if (ran < 0 || ran > n) return fail(c, FITSNE_ESTATE, "executed-iterations counter out of range (%d of %d)", ran, n);
     *done = ran;
     if (ran == 0) {
         // even the first step refused: the published bounds must map to a different M than the one just chosen --
@@ -696,7 +748,7 @@ static int run_iteration(fitsne_ctx *c, bool update) {
     *c->host_B = B;
 
     const bool timers = (c->cfg.flags & FITSNE_FLAG_TIMERS) != 0;
-    const bool use_graph = !(c->cfg.flags & FITSNE_FLAG_NO_GRAPH) && !timers;
+    const bool use_graph = !(c->cfg.flags & FITSNE_FLAG_NO_GRAPH) && !timers && c->world == 1;   // sharded: plain launches
     c->timing_this_iter = timers;
     if (!use_graph) {
         CKRC(enqueue_iteration_d(c, M, update));
@@ -802,6 +854,7 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_ag, cudaEventDisableTiming));
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_attract<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_attract<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -862,15 +915,26 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CKRC(dev_alloc(c, &c->gp, (size_t) 1)); CKRC(dev_alloc(c, &c->sp, (size_t) 1)); CKRC(dev_alloc(c, &c->sc, (size_t) 1));
     CKRC(dev_alloc(c, &c->mismatch, (size_t) 1));
     CKRC(dev_alloc(c, &c->tickets, (size_t) 8));
+    if (world > 1) {
+        CKRC(dev_alloc(c, &c->shard_stats, (size_t) world));
+        CKRC(dev_alloc(c, &c->shard_sum_partial, (size_t) SHARD_BLOCKS * 2));
+        CKRC(dev_alloc(c, &c->shard_mm_partial, (size_t) SHARD_BLOCKS));
+        CK(cudaMemsetAsync(c->shard_stats, 0, sizeof(ShardStats) * world, c->stream));
+    }
     CK(cudaMemsetAsync(c->tickets, 0, 8 * sizeof(unsigned int), c->stream));
     CK(cudaMemsetAsync(c->gp, 0, sizeof(GridParams), c->stream));
     CK(cudaMemsetAsync(c->sc, 0, sizeof(Scalars), c->stream));
     CK(cudaMemsetAsync(c->mismatch, 0, sizeof(int), c->stream));
     CK(cudaHostAlloc((void **) &c->host_bounds, 64, cudaHostAllocMapped));
+    // pinned allocations are recycled by the driver WITHOUT being cleared: a later context of the same process would
+    // otherwise start from the previous context's bounds / executed-iterations word (run_batch reads the latter before
+    // its first launch) -- found as a wrong iteration count + out-of-range costs[] write in the third context of a process
+    memset(c->host_bounds, 0, 64);
     CK(cudaHostGetDevicePointer((void **) &c->host_bounds_dev, c->host_bounds, 0));
     c->host_B = reinterpret_cast<int *>(c->host_bounds + 8);
     c->host_B_dev = reinterpret_cast<int *>(c->host_bounds_dev + 8);
     CK(cudaHostAlloc((void **) &c->host_sc, sizeof(Scalars), cudaHostAllocDefault));
+    memset(c->host_sc, 0, sizeof(Scalars));
     if (Y0) CKRC(upload_as_float(c, Y0, c->Y, (size_t) N * no_dims));
 
     if (world > 1) {
@@ -910,13 +974,14 @@ int fitsne_destroy(fitsne_ctx *c) {
                     c->compact, c->colsum_partial, c->update_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->col_P2, c->val_P2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
-                    c->nonempty, c->gp_reorder};
+                    c->nonempty, c->gp_reorder, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial};
     for (void *b : bufs) if (b) cudaFree(b);
     if (c->host_bounds) cudaFreeHost(c->host_bounds);
     if (c->host_sc) cudaFreeHost(c->host_sc);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_ag) cudaEventDestroy(c->ev_ag);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -957,12 +1022,14 @@ int fitsne_set_Y(fitsne_ctx *c, const double *Y) {
     if (!c || !Y) return FITSNE_EINVAL;
     CK(cudaSetDevice(c->device));
     c->bounds_valid = false;
+    c->y_whole = true;
     return upload_as_float(c, Y, c->Y, (size_t) c->N * c->D);
 }
 
 int fitsne_get_Y(fitsne_ctx *c, double *Y) {
     if (!c || !Y) return FITSNE_EINVAL;
     CK(cudaSetDevice(c->device));
+    CKRC(ensure_whole_Y(c));
     return download_as_double(c, c->Y, Y, (size_t) c->N * c->D);
 }
 
@@ -1016,6 +1083,7 @@ int fitsne_step(fitsne_ctx *c, const fitsne_step_params *p) {
 
 static int kl_impl(fitsne_ctx *c, double exaggeration, double *C_out) {
     if (!c->have_grad) return fail(c, FITSNE_ESTATE, "fitsne_kl needs the sum_Q of a previous gradient/step");
+    CKRC(ensure_whole_Y(c));
     const int blocks = std::min(4096, std::max(1, cdiv((long long) (c->row_end - c->row_begin) * 32, 256)));
     if (c->D == 2)
         k_kl<2><<<blocks, 256, 0, c->stream>>>(c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->row_begin, c->row_end,
@@ -1075,9 +1143,11 @@ int fitsne_run(fitsne_ctx *c, const fitsne_schedule *s, double *costs, double *Y
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, c->stream));
     auto t0 = std::chrono::steady_clock::now();
-    // Sharded runs keep one host round trip per iteration for now: speculative batches of graphs that contain NCCL nodes
-    // hung in the second communicator of a process and ran 2x slower on 2 GPUs (round-1 finding).
-    const bool batched = !(c->cfg.flags & (FITSNE_FLAG_NO_GRAPH | FITSNE_FLAG_TIMERS | FITSNE_FLAG_NO_SPECULATION)) && c->world == 1;
+    // Sharded runs batch too, but with plain launches instead of graphs (run_batch); FITSNE_SHARDED_SYNC=1 restores one
+    // host round trip per iteration there (diagnostics).
+    static const bool sharded_sync = getenv("FITSNE_SHARDED_SYNC") && atoi(getenv("FITSNE_SHARDED_SYNC")) != 0;
+    const bool batched = c->world == 1 ? !(c->cfg.flags & (FITSNE_FLAG_NO_GRAPH | FITSNE_FLAG_TIMERS | FITSNE_FLAG_NO_SPECULATION))
+                                       : !(c->cfg.flags & (FITSNE_FLAG_TIMERS | FITSNE_FLAG_NO_SPECULATION)) && !sharded_sync;
     int iter = 0;
     while (iter < s->max_iter) {
         int mode = FITSNE_STEP_MOMENTUM_CLIP;
@@ -1128,6 +1198,7 @@ int fitsne_run(fitsne_ctx *c, const fitsne_schedule *s, double *costs, double *Y
     CK(cudaEventElapsedTime(&ms, e0, e1));
     c->last_run_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CKRC(ensure_whole_Y(c));
     if (Y_out) CKRC(download_as_double(c, c->Y, Y_out, (size_t) c->N * c->D));
     return 0;
 }

@@ -207,6 +207,9 @@ __device__ __forceinline__ float2 *fft_smem(float2 *a, float2 *b, int NS, int ba
 //   rows: grid = (ceil(rows_total / lines), nplanes); prune_mask bit i set => plane i only needs rows < *g_rows
 //         (g_rows points at GridParams::G on the device)
 //   cols: grid = (ceil(M / lines), nplanes)
+//   forward passes (inverse == 0): prune_mask bit i also says "plane i is a zero-padded G x G corner": everything outside
+//   the corner is taken as zero WITHOUT being read (rows pass: columns >= G; columns pass: rows >= G), so the padding never
+//   has to be written to memory and whatever an earlier iteration left there is ignored.
 // Dynamic smem: (2 * lines * fft_buf_len(M, lines) + M) float2.  Requires M * lines <= FFT_EPT * FFT_THREADS.
 constexpr int FFT_EPT = 24;
 
@@ -228,6 +231,8 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_pass(float2 *__restrict__ d
     if (!COLS && ((prune_mask >> blockIdx.y) & 1u)) limit = min(limit, *g_rows);
     if (l0 >= limit) return;
     const int nl = min(lines, limit - l0);
+    const bool zpad = !inverse && ((prune_mask >> blockIdx.y) & 1u);
+    const int gz = zpad ? *g_rows : M;                                 // data extent along the transformed axis
     float2 *bufa = fft_sm, *bufb = fft_sm + (size_t) lines * NS, *Ws = fft_sm + (size_t) 2 * lines * NS;
     for (int i = threadIdx.x; i < M; i += blockDim.x) Ws[i] = W[i];
     float2 *base = data + (size_t) blockIdx.y * plane + (COLS ? (size_t) l0 : (size_t) l0 * M);
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_pass(float2 *__restrict__ d
 #pragma unroll
         for (int u = 0; u < FFT_EPT; u++) {
             const int i = threadIdx.x + u * blockDim.x;
-            if (i < total) v[u] = base[(size_t) (i >> lg) * M + (i & (lines - 1))];
+            if (i < total) v[u] = (i >> lg) < gz ? base[(size_t) (i >> lg) * M + (i & (lines - 1))] : make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < FFT_EPT; u++) {
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_pass(float2 *__restrict__ d
             float2 *dst = bufa + ln * NS;
 #pragma unroll 2
             for (int pos = threadIdx.x; pos < M; pos += blockDim.x) {
-                float2 v = src[pos];
+                float2 v = pos < gz ? src[pos] : make_float2(0.f, 0.f);
                 if (inverse) v.y = -v.y;
                 dst[fft_phys(pos)] = v;
             }

@@ -31,6 +31,7 @@ constexpr int SORT_ONE_PASS_BITS = 8; // keys this short sort in ONE pass.  (Mea
                                       // is slower than two 6-bit passes: 84 vs 70 us at N=1M; so only short 1-D keys qualify.)
 constexpr int RED_BLOCKS = 592;   // 4 x 148 SMs: partial-reduction width for bounds / column sums
 constexpr int Z_BLOCKS = 592;
+constexpr int SHARD_BLOCKS = 148;  // one CTA per SM: per-rank sums / bounds of the local slice (sharded runs)
 
 // Device-resident description of this iteration's interpolation grid.  Rewritten every iteration by
 // k_setup_grid from the bounds; all kernels read it from memory so that one captured CUDA graph serves every
@@ -119,17 +120,22 @@ __device__ __forceinline__ T block_sum(T v, T *sm) {
 // in the block that arrives last, which can then reduce the partials in a FIXED order -- a deterministic two-level
 // reduction without a second kernel launch.  The ticket counter resets itself for the next launch.
 __device__ __forceinline__ bool last_block_done(unsigned int *counter) {
+    // Contract: the block's partial result was written by THREAD 0 (block_sum / the warp-0 reductions leave it there).
+    // Only that thread has to make it visible before taking a ticket; a __threadfence() in every thread would make all
+    // warps wait for the acknowledgement of their own bulk stores (Y, uY, gains ...) before they can retire.
     __shared__ bool is_last;
-    __threadfence();
-    __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         const unsigned int t = atomicAdd(counter, 1u);
         is_last = (t == gridDim.x - 1);
-        if (is_last) *counter = 0;
+        if (is_last) { *counter = 0; __threadfence(); }
     }
     __syncthreads();
     return is_last;
 }
+// partials written by other blocks are read around L1 (ld.global.cg) in the last block
+__device__ __forceinline__ double ld_partial(const double *p) { return __ldcg(p); }
+__device__ __forceinline__ float2 ld_partial(const float2 *p) { return __ldcg(p); }
 
 // box index and in-box coordinate of one coordinate, fp64, reference operation order
 // (nbodyfft.cpp:86-113 / :350-363); __d*_rn keeps nvcc from contracting into FMAs the CPU does not use.
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
     if (last_block_done(ticket)) {
         float bmn = INFINITY, bmx = -INFINITY;
         for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) {
-            const float2 v = bounds_partial[i];
+            const float2 v = ld_partial(bounds_partial + i);
             bmn = fminf(bmn, v.x); bmx = fmaxf(bmx, v.y);
         }
 #pragma unroll
@@ -788,9 +794,11 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
 // One thread group (LPN lanes, a power of two <= 32) per element of the output plane.  Inside the G^D corner:
 // empty box -> 0; box finished by a single chunk -> already written by k_spread_chunks; otherwise add the box's
 // slot partials in chunk order (lane-strided, then a fixed shuffle tree: deterministic for a given LPN).
-// Outside the corner: the zero padding, so no memset is needed when G changes and the launch shape depends on M
-// only.  Multi-GPU (compact != nullptr): the plane is the dense Gcap^D buffer (G^D values then zeros) that is
-// all-reduced and then expanded by k_pad_grids.
+// 2-D: the index space is the (M/2)^2 corner that can hold data (G <= M/2); elements of it outside G^2 are left alone
+// and the zero padding of the FFT input is never materialised -- the forward FFT passes substitute zeros for everything
+// outside the G^2 corner while loading (k_fft_pass, prune_mask), so the launch shape still depends on M only.
+// 1-D: the whole length-M line, zeros included (tiny).  Multi-GPU (compact != nullptr): the plane is the dense Gcap^D
+// buffer (G^D values then zeros) that is all-reduced and then copied into the corner by k_pad_grids.
 template <int D>
 __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ slots, const uint32_t *__restrict__ box_start,
                                                         const GridParams *__restrict__ gpp, int lpn,
@@ -802,13 +810,14 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
     const size_t id = gid / lpn;
     const int sub = (int) (gid - id * lpn);
     const int Gc = M / 2;
-    const size_t plane = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) M * M : (size_t) M);
-    const bool live = id < plane;
+    const size_t space = D == 2 ? (size_t) Gc * Gc : (compact ? (size_t) Gc : (size_t) M);      // index space of this launch
+    const size_t stride = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) M * M : (size_t) M);   // plane 0 -> plane 1
+    const bool live = id < space;
     int row = 0, col = 0;
     bool inside = false;
     if (live) {
         if (!compact) {
-            if (D == 2) { row = (int) (id / M); col = (int) (id - (size_t) row * M); } else col = (int) id;
+            if (D == 2) { row = (int) (id / Gc); col = (int) (id - (size_t) row * Gc); } else col = (int) id;
             inside = col < G && row < G;
         } else {
             const size_t GG = D == 2 ? (size_t) G * G : (size_t) G;
@@ -818,7 +827,7 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
     }
     // what to do with this element: 0 = leave (finished by k_spread_chunks), 1 = write acc (zero or the slot sum)
     int node = 0, nodes = 1, c0 = 0, c1 = -1;
-    bool write = live;
+    bool write = live && (inside || compact != nullptr || D == 1);
     if (inside) {
         int box;
         if (D == 2) {
@@ -845,7 +854,8 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
         acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
         acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
-    if (write && sub == 0) store_node(compact ? compact : fft_in, plane, id, acc);
+    const size_t off = (compact || D == 1) ? id : (size_t) row * M + col;
+    if (write && sub == 0) store_node(compact ? compact : fft_in, stride, off, acc);
 }
 
 // multi-GPU: expand the all-reduced compact grids into the zero-padded FFT input planes
@@ -858,14 +868,20 @@ __global__ void __launch_bounds__(256) k_pad_grids(const float2 *__restrict__ co
     const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
     const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
     const size_t id = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= plane) return;
-    int row = 0, col;
-    if (D == 2) { row = (int) (id / M); col = (int) (id - (size_t) row * M); } else col = (int) id;
-    const bool inside = col < G && row < G;
-    const size_t src = D == 2 ? (size_t) row * G + col : (size_t) col;
-    const float2 z = make_float2(0.f, 0.f);
-    fft_in[id] = inside ? compact[src] : z;
-    fft_in[plane + id] = inside ? compact[cplane + src] : z;
+    if (D == 2) {           // copy the G^2 corner; the padding is substituted by the FFT passes (see k_spread_combine)
+        if (id >= cplane) return;
+        const int row = (int) (id / Gc), col = (int) (id - (size_t) row * Gc);
+        if (row >= G || col >= G) return;
+        const size_t src = (size_t) row * G + col, dst = (size_t) row * M + col;
+        fft_in[dst] = compact[src];
+        fft_in[plane + dst] = compact[cplane + src];
+    } else {
+        if (id >= plane) return;
+        const bool inside = (int) id < G;
+        const float2 z = make_float2(0.f, 0.f);
+        fft_in[id] = inside ? compact[id] : z;
+        fft_in[plane + id] = inside ? compact[cplane + id] : z;
+    }
 }
 
 // ------------------------------------------------------------------------------------ kernel samples --
@@ -998,7 +1014,7 @@ __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, c
     if (threadIdx.x == 0) zpartial[blockIdx.x] = r;
     if (last_block_done(ticket)) {           // sum_Q = (sum of the partials, in index order) - N   (tsne.cpp:1110)
         double s2 = 0;
-        for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) s2 += zpartial[i];
+        for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) s2 += ld_partial(zpartial + i);
         const double tot = block_sum(s2, sm);
         if (threadIdx.x == 0) {
             const double Z = tot - (double) N;
@@ -1222,13 +1238,150 @@ __global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, con
     if (last_block_done(ticket)) {
         for (int d = 0; d < D; d++) {
             double s = 0;
-            for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) s += colsum_partial[i * D + d];
+            for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) s += ld_partial(colsum_partial + i * D + d);
             const double r = block_sum(s, smu);
             if (threadIdx.x == 0) sc->mean[d] = r / (double) N_total;
         }
     }
 }
 
+
+// ------------------------------------------------------------------------- sharded zero-mean + bounds --
+// Multi-GPU tail of an optimiser step.  Each rank has just written the new, un-centred positions of ITS points
+// (Ynext[row_begin..row_end)).  Instead of all-gathering Y first and then reducing over all N points on every GPU, each
+// rank reduces its own slice (k_shard_stats), the per-rank records (128 bytes) are all-gathered, and every rank derives
+// the same global column means and bounds from the same bytes (k_center_shard) while centring only its own slice.  The
+// big Y all-gather then runs on the second stream at the start of the NEXT iteration, overlapped with that iteration's
+// sort / spread (which only read the local slice).
+//
+// The 2-D scan quirk (tsne.cpp:1045-1048, see k_center_bounds) acts on the centred, interleaved sequence from flat
+// index 0, i.e. on the head of rank 0's slice -- but the means are only known after the exchange.  Rank 0 therefore
+// ships the raw new positions of its first SHARD_HEAD points and leaves them out of its slice minimum; every rank
+// replays the scan on that head.  Exact unless the strictly ascending prefix is longer than 2*SHARD_HEAD values
+// (probability 1/16! for continuous data); a longer prefix is cut there.
+constexpr int SHARD_HEAD = 8;
+struct ShardStats {              // one per rank, 128 bytes
+    double sum[2];               // column sums of the rank's new (un-centred) positions
+    float mn[2], mx[2];          // per-dimension min (head points excluded on rank 0) / max (all points)
+    float head[2 * SHARD_HEAD];  // rank 0: first points, interleaved; unused elsewhere
+    int nhead;                   // number of valid head VALUES (flat), 0 on ranks > 0 and in 1-D
+    int pad_[7];
+};
+static_assert(sizeof(ShardStats) == 128, "ShardStats is exchanged as 128 raw bytes");
+
+template <int D>
+__global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Ynext, int row_begin, int row_end, int rank,
+                                                     const GridParams *__restrict__ gpp, double *__restrict__ sum_partial,
+                                                     float4 *__restrict__ mm_partial, ShardStats *__restrict__ out,
+                                                     unsigned int *__restrict__ ticket) {
+    if (!gpp->ok) return;
+    __shared__ double smd[32];
+    __shared__ float4 smm[8];
+    const int n = row_end - row_begin;
+    const int nhead_pts = (rank == 0 && D == 2) ? min(SHARD_HEAD, n) : 0;
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int b = blockIdx.x * per, e = min(n, b + per);
+    double s0 = 0, s1 = 0;
+    float4 mm = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);      // (min0, min1, max0, max1)
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+        if (D == 2) {
+            const float2 v = reinterpret_cast<const float2 *>(Ynext)[row_begin + i];
+            s0 += v.x; s1 += v.y;
+            mm.z = fmaxf(mm.z, v.x); mm.w = fmaxf(mm.w, v.y);
+            if (i >= nhead_pts) { mm.x = fminf(mm.x, v.x); mm.y = fminf(mm.y, v.y); }
+        } else {
+            const float v = Ynext[row_begin + i];
+            s0 += v;
+            mm.x = fminf(mm.x, v); mm.z = fmaxf(mm.z, v);
+        }
+    }
+    const double r0 = block_sum(s0, smd);
+    const double r1 = D == 2 ? block_sum(s1, smd) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mm.x = fminf(mm.x, __shfl_xor_sync(0xffffffffu, mm.x, o)); mm.y = fminf(mm.y, __shfl_xor_sync(0xffffffffu, mm.y, o));
+        mm.z = fmaxf(mm.z, __shfl_xor_sync(0xffffffffu, mm.z, o)); mm.w = fmaxf(mm.w, __shfl_xor_sync(0xffffffffu, mm.w, o));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smm[w] = mm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int) (blockDim.x >> 5); i++) {
+            mm.x = fminf(mm.x, smm[i].x); mm.y = fminf(mm.y, smm[i].y); mm.z = fmaxf(mm.z, smm[i].z); mm.w = fmaxf(mm.w, smm[i].w);
+        }
+        sum_partial[blockIdx.x * 2] = r0; sum_partial[blockIdx.x * 2 + 1] = r1;
+        mm_partial[blockIdx.x] = mm;
+    }
+    if (last_block_done(ticket) && threadIdx.x == 0) {       // a few hundred partials: one thread, fixed order
+        double t0 = 0, t1 = 0;
+        float4 a = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+        for (int i = 0; i < (int) gridDim.x; i++) {
+            t0 += __ldcg(sum_partial + 2 * i); t1 += __ldcg(sum_partial + 2 * i + 1);
+            const float4 v = __ldcg(mm_partial + i);
+            a.x = fminf(a.x, v.x); a.y = fminf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w);
+        }
+        out->sum[0] = t0; out->sum[1] = t1;
+        out->mn[0] = a.x; out->mn[1] = a.y; out->mx[0] = a.z; out->mx[1] = a.w;
+        out->nhead = nhead_pts * 2;
+        for (int i = 0; i < 2 * SHARD_HEAD; i++) out->head[i] = i < nhead_pts * 2 ? Ynext[(size_t) row_begin * 2 + i] : 0.f;
+    }
+}
+
+// Every rank: global means and bounds from the all-gathered records (identical bytes => identical results on all
+// ranks), centre the local slice Y[row] = Ynext[row] - mean (tsne.cpp:1851-1876), publish the bounds.
+template <int D>
+__global__ void __launch_bounds__(256) k_center_shard(const float *__restrict__ Ynext, float *__restrict__ Y, int row_begin, int row_end,
+                                                      int N, const ShardStats *__restrict__ all, int world,
+                                                      const GridParams *__restrict__ gpp, Scalars *__restrict__ sc,
+                                                      volatile float *host_bounds) {
+    if (!gpp->ok) return;
+    __shared__ double mean_s[2];
+    if (threadIdx.x == 0) {
+        double t0 = 0, t1 = 0;
+        for (int r = 0; r < world; r++) { t0 += all[r].sum[0]; t1 += all[r].sum[1]; }
+        mean_s[0] = t0 / (double) N; mean_s[1] = t1 / (double) N;
+    }
+    __syncthreads();
+    const double m0 = mean_s[0], m1 = mean_s[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // centring is monotonic per dimension ((float)((double) y - mean)), so the bounds of the centred values are the
+        // centred per-dimension bounds
+        float bmn = INFINITY, bmx = -INFINITY;
+        for (int r = 0; r < world; r++) {
+            for (int d = 0; d < D; d++) {
+                const double m = d ? m1 : m0;
+                bmn = fminf(bmn, (float) ((double) all[r].mn[d] - m));
+                bmx = fmaxf(bmx, (float) ((double) all[r].mx[d] - m));
+            }
+        }
+        const int nh = all[0].nhead;
+        float run = -INFINITY;
+        bool ascending = true;
+        for (int i = 0; i < nh; i++) {            // replay of the `if (>max) .. else if (<min)` scan on the head
+            const float v = (float) ((double) all[0].head[i] - ((i & 1) ? m1 : m0));
+            if (ascending && v > run) run = v;   // still in the strictly ascending prefix: max only
+            else { ascending = false; bmn = fminf(bmn, v); }
+        }
+        sc->mean[0] = m0; sc->mean[1] = m1;
+        sc->bmin = bmn; sc->bmax = bmx;
+        sc->iter_done += 1;
+        if (host_bounds) {
+            host_bounds[0] = bmn; host_bounds[1] = bmx;
+            *reinterpret_cast<volatile unsigned long long *>(host_bounds + 4) = sc->iter_done;
+        }
+    }
+    const int i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row_end) return;
+    if (D == 2) {
+        float2 v = reinterpret_cast<const float2 *>(Ynext)[i];
+        v.x = (float) ((double) v.x - m0);
+        v.y = (float) ((double) v.y - m1);
+        reinterpret_cast<float2 *>(Y)[i] = v;
+    } else {
+        Y[i] = (float) ((double) Ynext[i] - m0);
+    }
+}
 
 // ------------------------------------------------------------- locality re-ordering + tiled attractive term --
 // k_attract over a plain CSR is bound by L1 gather wavefronts (one 128-byte line per random neighbour), not by

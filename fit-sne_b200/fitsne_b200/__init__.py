@@ -66,7 +66,7 @@ def load_library(path=None):
     """dlopen the CUDA library; raises OSError if it has not been built (python __graft_entry__.py build)."""
     global _lib
     if _lib is None:
-        lib = ctypes.CDLL(path or LIB_PATH)
+        lib = ctypes.CDLL(path or os.environ.get("FITSNE_LIB") or LIB_PATH)      # FITSNE_LIB: A/B another build (diagnostics)
         lib.fitsne_last_error.restype = ctypes.c_char_p
         lib.fitsne_last_error.argtypes = [ctypes.c_void_p]
         lib.fitsne_version.restype = ctypes.c_char_p

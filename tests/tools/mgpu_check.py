@@ -29,18 +29,33 @@ def main():
         dist.broadcast(idt, 0)
         return idt.cpu().numpy().tobytes()
 
-    N = 200003   # not divisible by the world size on purpose
+    def mark(msg):
+        if os.environ.get("MGPU_TRACE"):
+            print("[rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
+    N = int(os.environ.get("MGPU_N", "200003"))   # not divisible by the world size on purpose
     row, col, val, labels = bench_util.knn_like_graph(N, 8, seed=3)
     ok = True
-    for dims, df, span in ((2, 1.0, 60.0), (1, 0.5, 120.0)):
+    cases = ((2, 1.0, 60.0), (1, 0.5, 120.0))
+    if os.environ.get("MGPU_CASES"):
+        cases = tuple(cases[int(i)] for i in os.environ["MGPU_CASES"].split(","))
+    for dims, df, span in cases:
         Y0 = bench_util.clustered_embedding(labels, dims, span, seed=5)
+        mark("case dims=%d: create" % dims)
         t = fb.FitSNE(row, col, val, Y0, df=df, device=local, rank=rank, world=world, nccl_id=fresh_id())
+        mark("gradient")
         dC, Z = t.gradient(4.0)
+        mark("kl")
         kl = t.kl(4.0)
         b, e = t.row_begin, t.row_end
         sched = dict(max_iter=60, stop_lying_iter=20, mom_switch_iter=20, learning_rate=500.0, early_exag_coeff=4.0)
+        mark("run")
         Y, costs = t.run(**sched)
+        mark("close")
         t.close()
+        mark("closed; compare: |Y| %.12g costs %s" % (np.linalg.norm(Y), costs[costs != 0]))
+        if os.environ.get("MGPU_SKIP_SINGLE"):
+            continue
         # every rank must hold the same Y after the all-gather
         ty = torch.from_numpy(Y).cuda()
         ref = ty.clone()
@@ -53,6 +68,7 @@ def main():
             full = np.zeros_like(dC)
             for bb, ee, part in parts:
                 full[bb:ee] = part
+            mark("single-GPU reference")
             with fb.FitSNE(row, col, val, Y0, df=df, device=local) as s:
                 dC1, Z1 = s.gradient(4.0)
                 kl1 = s.kl(4.0)
@@ -61,6 +77,7 @@ def main():
             r_y = np.linalg.norm(Y - Y1) / np.linalg.norm(Y1)
             nz = costs1 != 0
             r_c = np.max(np.abs(costs[nz] - costs1[nz]) / np.abs(costs1[nz]))
+            mark("costs sharded %s single %s" % (costs[costs != 0], costs1[nz]))
             print("dims=%d df=%g: grad rel-L2 %.2e, Z rel %.2e, KL rel %.2e, 60-step Y rel-L2 %.2e, costs rel %.2e, ranks agree %s"
                   % (dims, df, r_g, abs(Z - Z1) / Z1, abs(kl - kl1) / abs(kl1), r_y, r_c, same), flush=True)
             ok = ok and r_g < 1e-5 and abs(Z - Z1) / Z1 < 1e-6 and abs(kl - kl1) / abs(kl1) < 1e-6 and r_c < 1e-2 and r_y < 5e-2
