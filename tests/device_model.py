@@ -131,3 +131,61 @@ def device_gradient_rep(Y32, p, ipi, min_int, df, ft=np.float32):
         for a in range(p):
             Fo += L[:,a]*(b[:,a]*v1[node[:,a]]+Bv[node[:,a]])
         return (Fo/ft(Z))[:,None], Z
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Sharded zero-mean + bounds (k_shard_stats / k_center_shard in fitsne_kernels.cuh): per-rank records of the new,
+# un-centred positions -> global mean and the bounds of the CENTRED embedding, including the reference's 2-D scan quirk
+# (tsne.cpp:1045-1048), without any rank ever seeing the whole Y.  tests/test_shard_bounds_model.py checks this model
+# against the literal scan on the centred array.
+SHARD_HEAD = 8
+
+
+def literal_bounds_scan(flat):
+    """tsne.cpp:1045-1048 on the interleaved sequence: `if (v > max) max = v; else if (v < min) min = v;`"""
+    mx, mn = -np.inf, np.inf
+    for v in flat:
+        if v > mx:
+            mx = v
+        elif v < mn:
+            mn = v
+    return mn, mx
+
+
+def centre32(y32, mean64):
+    """(float)((double) y - mean): the device's centring (monotonic in y)"""
+    return (y32.astype(np.float64) - mean64).astype(np.float32)
+
+
+def shard_records(Ynew32, world, head=SHARD_HEAD):
+    """what k_shard_stats leaves on each rank: sums, per-dimension min (head points excluded on rank 0) / max, head values"""
+    N, d = Ynew32.shape
+    per = -(-N // world)
+    recs = []
+    for r in range(world):
+        sl = Ynew32[r * per:min(N, (r + 1) * per)]
+        nhead = min(head, len(sl)) if (r == 0 and d == 2) else 0
+        rest = sl[nhead:]
+        recs.append(dict(sum=sl.astype(np.float64).sum(0), mx=sl.max(0),
+                         mn=rest.min(0) if len(rest) else np.full(d, np.inf, np.float32),
+                         head=sl[:nhead].reshape(-1).copy()))
+    return recs
+
+
+def shard_bounds(recs, N, d):
+    """what k_center_shard derives on every rank from the all-gathered records: (mean, bmin, bmax)"""
+    mean = sum(r["sum"] for r in recs) / N
+    bmn, bmx = np.float32(np.inf), np.float32(-np.inf)
+    for r in recs:
+        for k in range(d):
+            bmn = min(bmn, centre32(np.float32(r["mn"][k]), mean[k]))
+            bmx = max(bmx, centre32(np.float32(r["mx"][k]), mean[k]))
+    run, ascending = -np.inf, True
+    for i, v in enumerate(recs[0]["head"]):
+        c = centre32(np.float32(v), mean[i & 1])
+        if ascending and c > run:
+            run = c
+        else:
+            ascending = False
+            bmn = min(bmn, c)
+    return mean, bmn, bmx
