@@ -281,6 +281,17 @@ static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, int M, const
     if (!gather) {
         const int cpb = std::max(1, 256 / nodes);
         const int nchunks = cdiv(c->nloc, CHUNK);
+        // opt-in second formulation (one thread per chunk, accumulators in registers): P = 2..4 in 2-D, 2..5 in 1-D
+        constexpr bool has2 = P >= 2 && (D == 2 ? P <= 4 : P <= 5);
+        if constexpr (has2) {
+            if (c->cfg.flags & FITSNE_FLAG_SPREAD2) {
+                k_spread_chunks2<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, 0, c->stream>>>(
+                    c->sorted_u, skeys, c->box_start, c->nloc, c->gp, c->slots, c->planes, c->world > 1 ? c->compact : nullptr);
+                LAUNCH_CHECK();
+                c->stats.kernel_launches += 1;
+                return 0;
+            }
+        }
         k_spread_chunks<D, P><<<cdiv(nchunks, cpb), cpb * nodes, 0, c->stream>>>(c->sorted_u, skeys, c->box_start, c->nloc, c->gp, cpb,
                                                                                   c->slots, c->planes,
                                                                                   c->world > 1 ? c->compact : nullptr);

@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(256) k_post_sort(const uint32_t *__restrict__ 
 // --------------------------------------------------------------------------------------------- spread --
 
 template <int P>
-__device__ __forceinline__ float lagrange1(const GridParams &gp, int p, int j, float u) {
+__host__ __device__ __forceinline__ float lagrange1(const GridParams &gp, int p, int j, float u) {
     float v = gp.inv_den[j];
     if (P > 0) {
 #pragma unroll
@@ -703,7 +703,7 @@ __device__ __forceinline__ float lagrange1(const GridParams &gp, int p, int j, f
 //     this chunk, else to slot[c][1]; k_spread_combine adds a box's slots in chunk order.
 //   2-D: node = a*p + b, a = y node, b = x node (grid row = y node, column = x node).  1-D: (L, L*b, L*b^2, 0).
 template <int D>
-__device__ __forceinline__ int key_to_box(uint32_t key, const GridParams &gp) {
+__host__ __device__ __forceinline__ int key_to_box(uint32_t key, const GridParams &gp) {
     return D == 2 ? (int) (key >> gp.xbits) * gp.B + (int) (key & ((1u << gp.xbits) - 1u)) : (int) key;
 }
 
@@ -712,14 +712,14 @@ __device__ __forceinline__ int key_to_box(uint32_t key, const GridParams &gp) {
 // delta and wbb are kept in BOX UNITS (offsets / box width): every plane is then O(w1) whatever the embedding's
 // scale, which is what makes packing two real planes into one fp32 complex transform safe (a 1e-5-scale plane
 // packed beside an O(1) plane would lose 5 digits in the separation).
-__device__ __forceinline__ void store_node(float2 *__restrict__ dst, size_t stride, size_t off, float4 v) {
+__host__ __device__ __forceinline__ void store_node(float2 *__restrict__ dst, size_t stride, size_t off, float4 v) {
     dst[off] = make_float2(v.x, v.y);
     dst[stride + off] = make_float2(v.z, v.w);
 }
 
 // offset of (box, node) inside one plane: padded FFT input (row stride M) or, multi-GPU, the compact G^D layout
 template <int D>
-__device__ __forceinline__ size_t node_offset(int box, int node, const GridParams &gp, int p, bool compact) {
+__host__ __device__ __forceinline__ size_t node_offset(int box, int node, const GridParams &gp, int p, bool compact) {
     if (D == 2) {
         const int by = box / gp.B, bx = box - by * gp.B;
         const int a = node / p, b = node - a * p;
@@ -789,6 +789,144 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
     const bool started_here = (int) box_start[cur] >= kb, ends_here = (int) box_start[cur + 1] <= ke;
     if (started_here && ends_here) store_node(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc);
     else myslots[(started_here ? 1 : 0) * nodes + node] = acc;
+}
+
+// ---- spread, second formulation: ONE THREAD PER CHUNK (all p^D nodes in registers) -------------------------------
+// k_spread_chunks spends one thread per (chunk, node): the key decode, the box-change test, both loads and the Lagrange
+// factors are repeated p^D times per point (SASS: ~45 instructions per point and node, 400 per point at p = 3, issue-
+// and latency-bound: 31 us at N = 1M, 0.4 ms at N = 10M = 4 % of the HBM roofline).  Here a thread owns a chunk and
+// keeps the p^D float4 accumulators in registers: ~95 instructions per point.  A thread walking 32 consecutive points
+// would read with a 256-byte lane stride, so the block first stages its 64 chunks (2048 points: keys + in-box
+// coordinates) in shared memory with coalesced loads; chunk c lives at element offset c*33, which makes the per-thread
+// walk bank-conflict free.  Same segment rules, same per-node summation order (serial over the chunk's points) and the
+// same slot layout as k_spread_chunks, so k_spread_combine is unchanged.
+// Written as two phase functions so that tests/tools/spread_emul.cu can run the very same code on the host (all
+// threads of a block through phase 1, then through phase 2) and check it against a direct spread.
+constexpr int SP2_THREADS = 64;                 // chunks per block
+constexpr int SP2_STRIDE = CHUNK + 1;           // padded chunk stride in shared memory (elements)
+constexpr int SP2_POINTS = SP2_THREADS * CHUNK;
+
+template <int D>
+struct alignas(16) Sp2Smem {
+    uint32_t keys[SP2_THREADS * SP2_STRIDE];
+    float u[SP2_THREADS * SP2_STRIDE * D];
+};
+
+// phase 1: thread t of block `blk` copies its share of the block's points (coalesced) into the padded layout
+template <int D>
+__host__ __device__ __forceinline__ void spread2_load(int t, int blk, const float *__restrict__ sorted_u,
+                                                      const uint32_t *__restrict__ skeys, int n, Sp2Smem<D> &sm) {
+    const int base = blk * SP2_POINTS;
+    for (int i = t; i < SP2_POINTS; i += SP2_THREADS) {
+        const int k = base + i;
+        if (k < n) {
+            const int e = i + (i >> 5);          // CHUNK == 32: one pad element per chunk
+            sm.keys[e] = skeys[k];
+            if (D == 2) reinterpret_cast<float2 *>(sm.u)[e] = reinterpret_cast<const float2 *>(sorted_u)[k];
+            else sm.u[e] = sorted_u[k];
+        }
+    }
+}
+
+// all nodes of one box segment: to the grid (finished box; one box -> base offset computed once) or to a slot
+template <int D, int P, int NODES>
+__host__ __device__ __forceinline__ void spread2_flush(const float4 (&acc)[NODES], bool to_grid, int box, const GridParams &gp,
+                                                       float2 *__restrict__ dst, size_t stride, bool is_compact,
+                                                       float4 *__restrict__ slot) {
+    if (to_grid) {
+        const size_t base = node_offset<D>(box, 0, gp, P, is_compact);
+        const size_t rs = is_compact ? (size_t) gp.G : (size_t) gp.M;
+#pragma unroll
+        for (int j = 0; j < NODES; j++) {
+            const size_t off = D == 2 ? base + (size_t) (j / P) * rs + (size_t) (j % P) : base + (size_t) j;
+            store_node(dst, stride, off, acc[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NODES; j++) slot[j] = acc[j];
+    }
+}
+
+// phase 2: thread t walks chunk c = blk*SP2_THREADS + t
+template <int D, int P>
+__host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const Sp2Smem<D> &sm, const uint32_t *__restrict__ box_start,
+                                                       int n, const GridParams &gp, float4 *__restrict__ slots,
+                                                       float2 *__restrict__ fft_in, float2 *__restrict__ compact) {
+    constexpr int NODES = D == 2 ? P * P : P;
+    const int c = blk * SP2_THREADS + t;
+    const int kb = c * CHUNK;
+    if (kb >= n) return;
+    const int ke = kb + CHUNK < n ? kb + CHUNK : n;
+    float2 *dst = compact ? compact : fft_in;
+    const int Gc = gp.M / 2;
+    const size_t stride = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) gp.M * gp.M : (size_t) gp.M);
+    float4 *myslots = slots + (size_t) c * 2 * NODES;
+    const uint32_t *kp = sm.keys + t * SP2_STRIDE;
+    float4 acc[NODES];
+#pragma unroll
+    for (int j = 0; j < NODES; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur = key_to_box<D>(kp[0], gp);
+    for (int k = kb; k < ke; k++) {
+        const int box = key_to_box<D>(kp[k - kb], gp);
+        if (box != cur) {
+            // segment of `cur` ended inside the chunk: finished box unless it started before the chunk
+            spread2_flush<D, P, NODES>(acc, (int) box_start[cur] >= kb, cur, gp, dst, stride, compact != nullptr, myslots);
+#pragma unroll
+            for (int j = 0; j < NODES; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cur = box;
+        }
+        if (D == 2) {
+            const float2 u = reinterpret_cast<const float2 *>(sm.u)[t * SP2_STRIDE + (k - kb)];
+            float Lx[P], Ly[P], ox[P], oy[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                Lx[j] = lagrange1<P>(gp, P, j, u.x); Ly[j] = lagrange1<P>(gp, P, j, u.y);
+                ox[j] = u.x - gp.s[j]; oy[j] = u.y - gp.s[j];          // offsets in BOX UNITS, as in k_spread_chunks
+            }
+#pragma unroll
+            for (int a = 0; a < P; a++) {
+#pragma unroll
+                for (int b = 0; b < P; b++) {
+                    const float L = Ly[a] * Lx[b];
+                    float4 &q = acc[a * P + b];
+                    q.x += L;
+                    q.y += L * ox[b];
+                    q.z += L * oy[a];
+                    q.w += L * (ox[b] * ox[b] + oy[a] * oy[a]);
+                }
+            }
+        } else {
+            const float u = sm.u[t * SP2_STRIDE + (k - kb)];
+#pragma unroll
+            for (int a = 0; a < P; a++) {
+                const float L = lagrange1<P>(gp, P, a, u);
+                const float o = u - gp.s[a];
+                float4 &q = acc[a];
+                q.x += L;
+                q.y += L * o;
+                q.z += L * o * o;
+            }
+        }
+    }
+    // last segment: finished only if the box both started in this chunk and ends with it
+    const bool started_here = (int) box_start[cur] >= kb, ends_here = (int) box_start[cur + 1] <= ke;
+    spread2_flush<D, P, NODES>(acc, started_here && ends_here, cur, gp, dst, stride, compact != nullptr,
+                               myslots + (started_here ? 1 : 0) * NODES);
+}
+
+template <int D, int P>
+__global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks2(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
+                                                                const uint32_t *__restrict__ box_start, int n,
+                                                                const GridParams *__restrict__ gpp, float4 *__restrict__ slots,
+                                                                float2 *__restrict__ fft_in, float2 *__restrict__ compact) {
+    __shared__ GridParams gps;
+    __shared__ Sp2Smem<D> sm;
+    for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
+        reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
+    spread2_load<D>(threadIdx.x, blockIdx.x, sorted_u, skeys, n, sm);
+    __syncthreads();
+    if (!gps.ok) return;
+    spread2_chunk<D, P>(threadIdx.x, blockIdx.x, sm, box_start, n, gps, slots, fft_in, compact);
 }
 
 // One thread group (LPN lanes, a power of two <= 32) per element of the output plane.  Inside the G^D corner:
