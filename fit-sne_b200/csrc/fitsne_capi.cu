@@ -225,7 +225,8 @@ static int get_plans(fitsne_ctx *c, int M, Plans **out) {
     auto it = c->plans.find(M);
     if (it != c->plans.end()) { *out = &it->second; return 0; }
     Plans pl;
-    if (!fft_make_plan(M, &pl.plan)) return fail(c, FITSNE_EINVAL, "FFT length %d is not of the form 2^a 3^b 5^c", M);
+    if (!fft_make_plan(M, &pl.plan, (c->cfg.flags & FITSNE_FLAG_FFT_WIDE) != 0))
+        return fail(c, FITSNE_EINVAL, "FFT length %d is not of the form 2^a 3^b 5^c", M);
     CK(cudaMalloc((void **) &pl.W, (size_t) M * sizeof(float2)));
     k_fft_twiddles<<<cdiv(M, 256), 256, 0, c->stream>>>(pl.W, M);
     LAUNCH_CHECK();
@@ -448,24 +449,28 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     const unsigned *gskip = &c->gp->fft_skip;
     const int LR = pl->lines_rows, LC = pl->lines_cols;
     const int FT = FFT_THREADS;
+    const bool wide = (c->cfg.flags & FITSNE_FLAG_FFT_WIDE) != 0;
+#define FFT_PASS(COLS, grid, smem, ...) do { if (wide) k_fft_pass<COLS, true><<<grid, FT, smem, st>>>(__VA_ARGS__); \
+                                             else k_fft_pass<COLS, false><<<grid, FT, smem, st>>>(__VA_ARGS__); } while (0)
     if (D == 2) {
         // rows: the charge planes (0,1) are zero beyond row G -> pruned; the kernel planes (2..5) need every row and are
         // skipped altogether (device-side mask) on iterations that re-use the cached kernel spectra
-        k_fft_pass<false><<<dim3(cdiv(M, LR), 6), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
-        k_fft_pass<true><<<dim3(cdiv(M, LC), 6), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
+        FFT_PASS(false, dim3(cdiv(M, LR), 6), pl->smem_rows, c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
+        FFT_PASS(true, dim3(cdiv(M, LC), 6), pl->smem_cols, c->planes, plane, M, LC, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
     } else {
-        k_fft_pass<false><<<dim3(1, 6), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
+        FFT_PASS(false, dim3(1, 6), pl->smem_rows, c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
     }
     k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0);
     if (D == 2) {
         // inverse: columns first (all of them), then only the G rows the gather reads
-        k_fft_pass<true><<<dim3(cdiv(M, LC), 2), FT, pl->smem_cols, st>>>(c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
-        k_fft_pass<false><<<dim3(cdiv(M, LR), 2), FT, pl->smem_rows, st>>>(c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok, nullptr);
+        FFT_PASS(true, dim3(cdiv(M, LC), 2), pl->smem_cols, c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
+        FFT_PASS(false, dim3(cdiv(M, LR), 2), pl->smem_rows, c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok, nullptr);
         c->stats.kernel_launches += 5;
     } else {
-        k_fft_pass<false><<<dim3(1, 1), FT, pl->smem_rows, st>>>(c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
+        FFT_PASS(false, dim3(1, 1), pl->smem_rows, c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
         c->stats.kernel_launches += 3;
     }
+#undef FFT_PASS
     LAUNCH_CHECK();
 
     // ---- gather (+ 1/Z)
@@ -874,6 +879,8 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_fft_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(k_fft_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute((k_fft_pass<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute((k_fft_pass<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 
     const size_t yel = (size_t) c->per * world * no_dims;
     c->y_elems = yel;
