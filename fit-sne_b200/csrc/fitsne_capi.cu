@@ -377,6 +377,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     CKRC(get_plans(c, M, &pl));
     const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
     const bool overlap = !c->timing_this_iter;    // timers mode serialises everything to time each phase
+    const int kpack = (c->cfg.flags & FITSNE_FLAG_KPACK) ? 1 : 0;     // all four kernel planes in one complex transform (opt-in)
 
     // Sharded: after an optimiser step every rank only holds ITS slice of the new Y.  The all-gather that completes Y is
     // issued here, on the SpMV's stream: the SpMV is its only consumer inside the iteration (bin / sort / spread / gather /
@@ -398,7 +399,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
 
     phase_mark(c, FITSNE_PHASE_BOUNDS);
     k_setup_grid<<<1, 256, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
-                                    c->mismatch, c->sort_totals, c->sc, (c->cfg.flags & FITSNE_FLAG_NO_KERNEL_CACHE) ? 0 : 1);
+                                    c->mismatch, c->sort_totals, c->sc, (c->cfg.flags & FITSNE_FLAG_NO_KERNEL_CACHE) ? 0 : 1, kpack);
     c->stats.kernel_launches += 1;
 
     // ---- bin + stable two-pass LSD radix sort by box
@@ -442,7 +443,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
 
     // ---- kernel samples, then the convolution: forward FFTs of the 4 packed planes, Hadamard (+ sum_Q), inverse FFTs
     phase_mark(c, FITSNE_PHASE_KERNEL_SPECTRUM);
-    k_gen_kernels<D><<<cdiv(plane, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->planes);
+    k_gen_kernels<D><<<cdiv(plane, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->planes, kpack);
     LAUNCH_CHECK();
     phase_mark(c, FITSNE_PHASE_FFT);
     const int *gG = &c->gp->G, *gok = &c->gp->ok;
@@ -460,7 +461,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     } else {
         FFT_PASS(false, dim3(1, 6), pl->smem_rows, c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
     }
-    k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0);
+    k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0, kpack);
     if (D == 2) {
         // inverse: columns first (all of them), then only the G rows the gather reads
         FFT_PASS(true, dim3(cdiv(M, LC), 2), pl->smem_cols, c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
@@ -487,6 +488,14 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
                                                            c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         c->stats.kernel_launches += 1;
         phase_mark(c, FITSNE_PHASE_CENTER);
+    } else if (c->world == 1 && (c->cfg.flags & FITSNE_FLAG_SPLIT_COLSUM)) {
+        // A/B variant of the tail: update, then a separate column-sum pass, then centring (three launches, no epilogue in k_update)
+        k_update<D, true><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
+                                                          c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
+        phase_mark(c, FITSNE_PHASE_CENTER);
+        k_colsum<D><<<RED_BLOCKS, 256, 0, st>>>(c->Yb, c->N, c->colsum_partial, c->gp);
+        c->stats.kernel_launches += 2;
+        CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1, 0));
     } else if (c->world == 1) {
         // single GPU: k_update also produces the column means of the new positions (last-block reduction), the
         // centring kernel subtracts them, finds the bounds and publishes them -- two launches for the whole tail

@@ -371,7 +371,7 @@ __host__ __device__ inline int sort_bits_for(int B, int dims) {
 // Fill GridParams for a grid of B boxes/dim (the host's choice; verified against the device's own bounds).
 __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restrict__ sc, const int *__restrict__ B_host, int M, int p, int dims,
                              double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals,
-                             Scalars *__restrict__ scw, int use_kernel_cache) {
+                             Scalars *__restrict__ scw, int use_kernel_cache, int kpack) {
     for (int i = threadIdx.x; i < 2 * (1 << SORT_MAX_BITS); i += blockDim.x) sort_totals[i] = 0;   // both passes
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     // B_host > 0: the host sized the grid after reading the bounds (single-step API); 0: speculative launch, the device
@@ -398,7 +398,9 @@ __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restr
     gp->pad_ = 0;
     gp->nb = dims == 2 ? B * B : B;
     // kernel-spectrum cache decision (only for iterations that will really run)
-    gp->kmode = 0; gp->with_deriv = 0; gp->dh = 0.f; gp->fft_skip = 0x30u;   // planes 4,5 (dK/dh) idle by default
+    // plane roles: 2,3 = kernel spectra, 4,5 = their d/dh; packed layout (kpack): 2 = all four kernels, 3 = d/dh, 4,5 unused
+    const unsigned skip_deriv = kpack ? 0x38u : 0x30u, skip_none = kpack ? 0x30u : 0u;
+    gp->kmode = 0; gp->with_deriv = 0; gp->dh = 0.f; gp->fft_skip = skip_deriv;   // derivative planes idle by default
     if (gp->ok) {
         const double h = gp->h;
         if (use_kernel_cache) {
@@ -411,7 +413,7 @@ __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restr
             } else {
                 const bool slow = !scw->kc_valid || (scw->kc_B == B && fabs(h - scw->kc_hprev) <= KC_SLOW_REL * h);
                 gp->with_deriv = slow ? 1 : 0;
-                gp->fft_skip = slow ? 0u : 0x30u;
+                gp->fft_skip = slow ? skip_none : skip_deriv;
                 scw->kc_h0 = h; scw->kc_B = B; scw->kc_M = M; scw->kc_valid = 1; scw->kc_has_deriv = slow ? 1 : 0;
             }
         } else {
@@ -1028,8 +1030,12 @@ __global__ void __launch_bounds__(256) k_pad_grids(const float2 *__restrict__ co
 //   plane 2 = (Ksq, Kb)   plane 3 = (Kgrad_x, Kgrad_y)  [1-D: (Kgrad, 0)]   planes 4, 5 = d/dh of planes 2, 3 (with_deriv)
 //   Ksq=(1+r2/df)^-(df+1)   Kgrad_k = (R_k/bw)*Ksq  (box units)   Kb=(1+r2/df)^-df      (tsne.cpp:69-94)
 // Values carry the 1/M^D inverse-FFT normalisation (nbodyfft.cpp:202-203).
+// kpack != 0 (opt-in): ALL FOUR kernels in ONE complex plane,  plane 2 = (Kb + Kgrad_x + Kgrad_y) + i*Ksq,  plane 3 = d/dh of it.
+// Ksq and Kb are even in both lattice offsets, Kgrad_x is odd in the column offset only, Kgrad_y in the row offset only, so
+// with Z = FFT(plane 2):  Kb^ = Re Z,  and Im Z = Ksq^ + ax + ay with Kgrad_x^ = i*ax, Kgrad_y^ = i*ay separates by the
+// parities under k2 -> -k2 and k1 -> -k1 (four mirror points, see k_hadamard) -- one kernel transform instead of two.
 template <int D>
-__global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restrict__ gpp, double df, float2 *__restrict__ planes) {
+__global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restrict__ gpp, double df, float2 *__restrict__ planes, int kpack) {
     const GridParams &gp = *gpp;
     if (!gp.ok || gp.kmode == 1) return;          // kmode 1: the cached spectra (planes 2..5) stay as they are
     const int M = gp.M, G = gp.G;
@@ -1068,6 +1074,11 @@ __global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restric
             d2 = make_float2((float) (ux * a), D == 2 ? (float) (uy * a) : 0.f);
         }
     }
+    if (kpack) {
+        planes[2 * plane + id] = make_float2(k1.y + k2.x + k2.y, k1.x);
+        if (gp.with_deriv) planes[3 * plane + id] = make_float2(d1.y + d2.x + d2.y, d1.x);
+        return;
+    }
     planes[2 * plane + id] = k1;
     planes[3 * plane + id] = k2;
     if (gp.with_deriv) {
@@ -1097,7 +1108,7 @@ __device__ __forceinline__ void unpack_pair(float2 zk, float2 zm, float2 &A, flo
 template <int D>
 __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, const GridParams *__restrict__ gpp,
                                                   int df_is_one, double *__restrict__ zpartial, int N, Scalars *__restrict__ sc,
-                                                  unsigned int *__restrict__ ticket) {
+                                                  unsigned int *__restrict__ ticket, int kpack) {
     __shared__ double sm[32];
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
@@ -1120,14 +1131,40 @@ __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, c
         float2 w1, d1, d2, wbb, ksq, kb, kg1, kg2;
         unpack_pair(Z1[e], Z1[em], w1, d1);
         unpack_pair(Z2[e], Z2[em], d2, wbb);        // 1-D: d2 = wbb-plane real part, see below
-        float2 k1e = K1[e], k1m = K1[em], k2e = K2[e], k2m = K2[em];
-        if (taylor) {      // K^(h) = K^(h0) + dh * dK^/dh(h0), on the packed values (the unpacking is linear)
-            const float2 a1 = dK1[e], b1 = dK1[em], a2 = dK2[e], b2 = dK2[em];
-            k1e.x += dh * a1.x; k1e.y += dh * a1.y; k1m.x += dh * b1.x; k1m.y += dh * b1.y;
-            k2e.x += dh * a2.x; k2e.y += dh * a2.y; k2m.x += dh * b2.x; k2m.y += dh * b2.y;
+        if (!kpack) {
+            float2 k1e = K1[e], k1m = K1[em], k2e = K2[e], k2m = K2[em];
+            if (taylor) {      // K^(h) = K^(h0) + dh * dK^/dh(h0), on the packed values (the unpacking is linear)
+                const float2 a1 = dK1[e], b1 = dK1[em], a2 = dK2[e], b2 = dK2[em];
+                k1e.x += dh * a1.x; k1e.y += dh * a1.y; k1m.x += dh * b1.x; k1m.y += dh * b1.y;
+                k2e.x += dh * a2.x; k2e.y += dh * a2.y; k2m.x += dh * b2.x; k2m.y += dh * b2.y;
+            }
+            unpack_pair(k1e, k1m, ksq, kb);
+            unpack_pair(k2e, k2m, kg1, kg2);
+        } else {
+            // packed layout: Z = FFT((Kb + Kgx + Kgy) + i*Ksq) at k and its mirror points (k1,-k2), (-k1,k2), (-k1,-k2);
+            // plane 3 holds dZ/dh for the Taylor step
+            size_t e1 = em, e2 = em;
+            if (D == 2) {
+                const int r1 = (int) (e / M), r2 = (int) (e - (size_t) r1 * M);
+                e1 = (size_t) r1 * M + (size_t) ((M - r2) % M);
+                e2 = (size_t) ((M - r1) % M) * M + (size_t) r2;
+            }
+            float2 ze = K1[e], zm = K1[em], z1 = D == 2 ? K1[e1] : ze, z2 = D == 2 ? K1[e2] : zm;
+            if (taylor) {
+                const float2 de = K2[e], dm = K2[em], d1_ = D == 2 ? K2[e1] : de, d2_ = D == 2 ? K2[e2] : dm;
+                ze.x += dh * de.x; ze.y += dh * de.y; zm.x += dh * dm.x; zm.y += dh * dm.y;
+                z1.x += dh * d1_.x; z1.y += dh * d1_.y; z2.x += dh * d2_.x; z2.y += dh * d2_.y;
+            }
+            // 2-D: Im Z = S + ax + ay at k, S - ax + ay at (k1,-k2), S + ax - ay at (-k1,k2), S - ax - ay at -k
+            // 1-D (z1 = ze, z2 = zm): Im Z = S + a at k, S - a at -k
+            const float S = 0.25f * ((ze.y + z1.y) + (z2.y + zm.y));
+            const float ax = 0.25f * ((ze.y - z1.y) + (z2.y - zm.y));
+            const float ay = 0.25f * ((ze.y + z1.y) - (z2.y + zm.y));
+            ksq = make_float2(S, 0.f);
+            kb = make_float2(0.25f * ((ze.x + z1.x) + (z2.x + zm.x)), 0.f);
+            if (D == 2) { kg1 = make_float2(0.f, ax); kg2 = make_float2(0.f, ay); }
+            else { kg1 = make_float2(0.f, ay); kg2 = make_float2(0.f, 0.f); }     // 1-D: a = (Im Z(k) - Im Z(-k)) / 2 = ay above
         }
-        unpack_pair(k1e, k1m, ksq, kb);
-        unpack_pair(k2e, k2m, kg1, kg2);
         if (D == 1) { wbb = d2; }                   // 1-D plane 1 = (wbb, 0)
         const float2 v1 = cmul(ksq, w1);
         const float2 kgw1 = cmul(kg1, w1), ksd1 = cmul(ksq, d1);

@@ -52,6 +52,8 @@ typedef struct fitsne_config {
 #define FITSNE_FLAG_NO_SPECULATION 32 /* fitsne_run: one host round trip per iteration instead of batches  */
 #define FITSNE_FLAG_NO_KERNEL_CACHE 64 /* re-sample + re-transform the kernel planes every iteration (no Taylor re-use) */
 #define FITSNE_FLAG_FFT_WIDE 256  /* FFT plans with radix-16 / radix-9 stages (3 stages instead of 4-5); opt-in until measured */
+#define FITSNE_FLAG_SPLIT_COLSUM 512 /* A/B: separate column-sum pass instead of the epilogue inside the update kernel   */
+#define FITSNE_FLAG_KPACK 1024    /* all four kernel planes in ONE complex transform (parity separation); opt-in until measured */
 #define FITSNE_FLAG_SPREAD2 128   /* spread with one thread per 32-point chunk (all nodes in registers); opt-in until measured */
 
 /* One optimiser step's parameters: the state TSNE::run carries across iterations (tsne.cpp:437-544). */
