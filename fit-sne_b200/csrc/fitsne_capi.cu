@@ -282,10 +282,11 @@ static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, int M, const
     if (!gather) {
         const int cpb = std::max(1, 256 / nodes);
         const int nchunks = cdiv(c->nloc, CHUNK);
-        // opt-in second formulation (one thread per chunk, accumulators in registers): P = 2..4 in 2-D, 2..5 in 1-D
+        // default: one thread per chunk with all p^D accumulators in registers (P = 2..4 in 2-D, 2..5 in 1-D; bitwise the
+        // same sums as the per-(chunk, node) kernel, which stays for other P and behind FITSNE_FLAG_SPREAD_PER_NODE)
         constexpr bool has2 = P >= 2 && (D == 2 ? P <= 4 : P <= 5);
         if constexpr (has2) {
-            if (c->cfg.flags & FITSNE_FLAG_SPREAD2) {
+            if (!(c->cfg.flags & FITSNE_FLAG_SPREAD_PER_NODE)) {
                 k_spread_chunks2<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, 0, c->stream>>>(
                     c->sorted_u, skeys, c->box_start, c->nloc, c->gp, c->slots, c->planes, c->world > 1 ? c->compact : nullptr);
                 LAUNCH_CHECK();
@@ -488,8 +489,10 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
                                                            c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         c->stats.kernel_launches += 1;
         phase_mark(c, FITSNE_PHASE_CENTER);
-    } else if (c->world == 1 && (c->cfg.flags & FITSNE_FLAG_SPLIT_COLSUM)) {
-        // A/B variant of the tail: update, then a separate column-sum pass, then centring (three launches, no epilogue in k_update)
+    } else if (c->world == 1 && !(c->cfg.flags & FITSNE_FLAG_FUSED_COLSUM)) {
+        // single GPU: update, a separate column-sum pass, centring + bounds.  (The variant below folds the column sums into
+        // k_update as a last-block epilogue: one launch fewer but measured 8 us SLOWER per iteration at N = 1M --
+        // profiles/r1_oneshot_ab.json -- the two fp64 block reductions sit on every CTA's critical path.)
         k_update<D, true><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
                                                           c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         phase_mark(c, FITSNE_PHASE_CENTER);

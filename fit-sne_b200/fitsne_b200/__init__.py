@@ -14,9 +14,9 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfitsne_b200.so")
 
 STEP_MOMENTUM_CLIP, STEP_MOMENTUM, STEP_PLAIN_GD = 0, 1, 2
 FLAG_NO_GRAPH, FLAG_TIMERS, FLAG_NO_REORDER, FLAG_FORCE_TILES, FLAG_NO_TILES, FLAG_NO_SPECULATION, FLAG_NO_KERNEL_CACHE = 1, 2, 4, 8, 16, 32, 64
-FLAG_SPREAD2 = 128
+FLAG_SPREAD_PER_NODE = 128
 FLAG_FFT_WIDE = 256
-FLAG_SPLIT_COLSUM = 512
+FLAG_FUSED_COLSUM = 512
 FLAG_KPACK = 1024
 PHASES = ["bounds", "sort", "spread", "kernel_spectrum", "fft", "gather", "attract_update", "center", "kl",
           "collectives"]

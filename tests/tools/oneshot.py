@@ -1,6 +1,8 @@
-"""One short GPU shot (no torch import; finishes in seconds): A/B of the opt-in kernels against the shipped path.
-  FLAG_SPREAD2  -- k_spread_chunks2 (one thread per chunk)          FLAG_FFT_WIDE -- radix-16/9 FFT plans
-  FLAG_KPACK    -- four kernel planes in one complex transform      FLAG_SPLIT_COLSUM -- separate column-sum pass
+"""One short GPU shot (no torch import; finishes in seconds): A/B of alternative kernels against the shipped path.
+  FLAG_SPREAD_PER_NODE -- first spread formulation (thread per chunk and node)   FLAG_FFT_WIDE -- radix-16/9 FFT plans
+  FLAG_KPACK -- four kernel planes in one complex transform                      FLAG_FUSED_COLSUM -- column sums inside k_update
+(Round 1 ran this with the then-opt-in kernels as variants: profiles/r1_oneshot_ab.json; the per-chunk spread and the
+separate column-sum pass became the defaults as a result, so their flags now select the OLD variants.)
 For each: gradient parity with the shipped kernels (and with the oracle on the small cases) + per-phase device times.
 Writes gpurun_out/oneshot.json incrementally (the call may be cut short)."""
 import json, os, sys, time
@@ -32,8 +34,8 @@ def blobs(N, dims, span, seed, spread=0.03):
 def rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
-ALL = fb.FLAG_SPREAD2 | fb.FLAG_FFT_WIDE | fb.FLAG_KPACK
-VARIANTS = (("spread2", fb.FLAG_SPREAD2), ("fftwide", fb.FLAG_FFT_WIDE), ("kpack", fb.FLAG_KPACK), ("wide+kpack", fb.FLAG_FFT_WIDE | fb.FLAG_KPACK), ("both", ALL))
+ALL = fb.FLAG_FFT_WIDE | fb.FLAG_KPACK
+VARIANTS = (("spread_per_node", fb.FLAG_SPREAD_PER_NODE), ("fftwide", fb.FLAG_FFT_WIDE), ("kpack", fb.FLAG_KPACK), ("both", ALL))
 BASEF = fb.FLAG_NO_REORDER
 
 def grad(row, col, val, Y, flags, **kw):
@@ -66,8 +68,8 @@ try:
         OUT["A"][name] = {"dC_rel": rel(dC, base_dC), "Z_rel": abs(Z - base_Z) / base_Z, "bitwise": bool(np.array_equal(dC, base_dC))}
         say("1M %-8s vs shipped: dC rel %.2e  Z rel %.2e  bitwise %s" % (name, OUT["A"][name]["dC_rel"], OUT["A"][name]["Z_rel"], OUT["A"][name]["bitwise"]))
     OUT["A_ms"] = {}
-    for name, fl in (("shipped", 0), ("spread2", fb.FLAG_SPREAD2), ("fftwide", fb.FLAG_FFT_WIDE), ("kpack", fb.FLAG_KPACK), ("all", ALL),
-                     ("split_colsum", fb.FLAG_SPLIT_COLSUM)):
+    for name, fl in (("shipped", 0), ("spread_per_node", fb.FLAG_SPREAD_PER_NODE), ("fftwide", fb.FLAG_FFT_WIDE), ("kpack", fb.FLAG_KPACK), ("all", ALL),
+                     ("fused_colsum", fb.FLAG_FUSED_COLSUM)):
         ms, M = timed(row, col, val, Y, fl)
         OUT["A_ms"][name] = ms
         say("1M %-8s per-step ms (M=%d): %s" % (name, M, ms))
