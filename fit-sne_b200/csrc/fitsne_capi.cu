@@ -111,6 +111,11 @@ struct fitsne_ctx {
     TileGeom tg{};
     size_t ntiles = 0;
     bool reordered = false, use_tiles = false;
+    // column-sorted edge layout for k_attract_sorted (opt-in, FITSNE_FLAG_SORTED_SPMV)
+    SortedGeom sg{};
+    uint32_t *srt_cnt = nullptr, *srt_start = nullptr, *srt_cur = nullptr;
+    size_t srt_tiles = 0;
+    bool use_sorted = false;
     uint64_t last_reorder_iter = 0, reorder_interval = 50, reorders = 0;
     uint32_t nonempty_tiles = 0;
     unsigned long long kc_hits_base = 0;
@@ -326,6 +331,13 @@ template <int D>
 static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
     const int rows = c->row_end - c->row_begin;
     const float inv_df = (float) (1.0 / c->cfg.df);
+    if (c->use_sorted) {
+        k_attract_sorted<D><<<c->sg.nchunks, SRT_THREADS, sizeof(SrtSmem<D>), st>>>(c->Y, c->N, c->sg, c->srt_start, c->tile_pack, c->tile_val,
+                                                                                    inv_df, c->tile_fix32, c->attr);
+        LAUNCH_CHECK();
+        c->stats.kernel_launches += 1;
+        return 0;
+    }
     if (c->use_tiles) {
         // accumulation: 32-bit fixed point scaled by the largest row sum of P (|attr_i| <= rowsum_i / 2) -- native
         // shared-memory integer atomics, order-independent => bitwise repeatable.  FITSNE_TILE_ACC overrides (experiments).
@@ -653,6 +665,32 @@ static int reorder_points(fitsne_ctx *c) {
     if (c->cfg.flags & FITSNE_FLAG_NO_TILES) c->use_tiles = false;
     TRACE("reorder #%llu: %u of %zu tiles non-empty, est tiles %.0f us vs csr %.0f us -> %s", (unsigned long long) c->reorders,
           c->nonempty_tiles, c->ntiles, est_tiles_us, est_csr_us, c->use_tiles ? "tiles" : "csr");
+    // 6. opt-in: edges of every row chunk regrouped by column block for k_attract_sorted (edge word = 12-bit row | 20-bit column)
+    c->use_sorted = false;
+    if ((c->cfg.flags & FITSNE_FLAG_SORTED_SPMV) && N <= (1 << SRT_COL_BITS)) {
+        static const int shift_env = getenv("FITSNE_SRT_COL_SHIFT") ? atoi(getenv("FITSNE_SRT_COL_SHIFT")) : 6;
+        c->sg.col_shift = std::min(12, std::max(3, shift_env));
+        c->sg.nchunks = cdiv(N, SRT_ROWS);
+        c->sg.ncb = cdiv(N, 1 << c->sg.col_shift);
+        const size_t nt = (size_t) c->sg.nchunks * c->sg.ncb;
+        if (nt != c->srt_tiles) {
+            CKRC(dev_alloc(c, &c->srt_cnt, nt + 1)); CKRC(dev_alloc(c, &c->srt_start, nt + 1)); CKRC(dev_alloc(c, &c->srt_cur, nt + 1));
+            c->srt_tiles = nt;
+            if (D == 2) CK(cudaFuncSetAttribute(k_attract_sorted<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SrtSmem<2>)));
+            else CK(cudaFuncSetAttribute(k_attract_sorted<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SrtSmem<1>)));
+        }
+        CK(cudaMemsetAsync(c->srt_cnt, 0, (nt + 1) * 4, st));
+        CK(cudaMemsetAsync(c->srt_cur, 0, (nt + 1) * 4, st));
+        k_sorted_count<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(c->row_P, c->col_P, N, c->sg, c->srt_cnt);
+        k_scan_excl<<<1, 1024, 0, st>>>(c->srt_cnt, c->srt_start, (int) nt);
+        k_sorted_fill<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(c->row_P, c->col_P, c->val_P, N, c->sg, c->srt_start, c->srt_cur,
+                                                                    c->tile_pack, c->tile_val);
+        LAUNCH_CHECK();
+        CK(cudaStreamSynchronize(st));
+        c->use_sorted = true;
+        c->use_tiles = false;
+        c->kernel_launches_reorder += 3;
+    }
     drop_graphs(c);              // CSR pointers and the attractive kernel changed
     c->kernel_launches_reorder += 20;
     return 0;
@@ -1004,7 +1042,7 @@ int fitsne_destroy(fitsne_ctx *c) {
                     c->compact, c->colsum_partial, c->update_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->col_P2, c->val_P2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
-                    c->nonempty, c->gp_reorder, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial};
+                    c->nonempty, c->gp_reorder, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial, c->srt_cnt, c->srt_start, c->srt_cur};
     for (void *b : bufs) if (b) cudaFree(b);
     if (c->host_bounds) cudaFreeHost(c->host_bounds);
     if (c->host_sc) cudaFreeHost(c->host_sc);

@@ -1811,6 +1811,141 @@ __global__ void __launch_bounds__(1024, 1) k_attract_tiles(const float *__restri
     }
 }
 
+// ------------------------------------------------- attractive term over column-sorted edges (opt-in, experimental) --
+// k_attract is bound by the L1 tag stage: every one of the E random 8-byte neighbour gathers is its own 128-byte-line
+// lookup (ncu: L1/TEX 80 %, one wavefront per lane), the DRAM traffic is only the algorithmic 8 B/edge.  This layout
+// attacks the lookup count instead of the bytes: after a Morton re-ordering the edges of a row chunk (SRT_ROWS
+// consecutive points) are regrouped by COLUMN block (2^col_shift consecutive points, default 64 = four lines), so the
+// 32 edges a warp handles together touch a handful of lines instead of 32.  The price is that edges of one row are no
+// longer adjacent: row sums are accumulated with shared-memory integer atomics in 32-bit fixed point (the same scale
+// as k_attract_tiles; integer addition is associative, so the result is independent of the arrival order and bitwise
+// repeatable).  One CTA per row chunk; shared memory holds the chunk's own positions and accumulators only.
+// Edge word: (row within chunk) << 20 | column, hence N <= 2^20 and SRT_ROWS = 4096.  Built by k_sorted_count /
+// k_scan_excl / k_sorted_fill at re-ordering time.  Phase functions are host-callable for tests/tools/spmv_emul.cu.
+constexpr int SRT_ROWS = 4096;
+constexpr int SRT_COL_BITS = 20;
+constexpr int SRT_THREADS = 512;
+
+struct SortedGeom {
+    int nchunks, ncb, col_shift;     // chunk c = rows [c*SRT_ROWS, ...); column block b = points [b << col_shift, ...)
+};
+
+#ifdef __CUDA_ARCH__
+#define FK_ATOMIC_ADD(ptr, v) atomicAdd((ptr), (v))
+#else
+#define FK_ATOMIC_ADD(ptr, v) fk_host_fetch_add((ptr), (v))
+template <typename T>
+static inline T fk_host_fetch_add(T *p, T v) { const T old = *p; *p = old + v; return old; }
+#endif
+
+// one lane (sub of 8) of one CSR row: count / place the row's edges into (row chunk, column block) groups
+__host__ __device__ __forceinline__ void sorted_count_lane(int row, int sub, const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
+                                                           SortedGeom g, uint32_t *__restrict__ cnt) {
+    const uint32_t rc = (uint32_t) row / SRT_ROWS;
+    for (uint32_t e = row_P[row] + sub; e < row_P[row + 1]; e += 8)
+        FK_ATOMIC_ADD(&cnt[(size_t) rc * g.ncb + (col_P[e] >> g.col_shift)], 1u);
+}
+__host__ __device__ __forceinline__ void sorted_fill_lane(int row, int sub, const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
+                                                          const float *__restrict__ val_P, SortedGeom g, const uint32_t *__restrict__ start,
+                                                          uint32_t *__restrict__ cur, uint32_t *__restrict__ pack, float *__restrict__ val_out) {
+    const uint32_t rc = (uint32_t) row / SRT_ROWS, rl = (uint32_t) row - rc * SRT_ROWS;
+    for (uint32_t e = row_P[row] + sub; e < row_P[row + 1]; e += 8) {
+        const uint32_t c = col_P[e];
+        const size_t t = (size_t) rc * g.ncb + (c >> g.col_shift);
+        const uint32_t pos = start[t] + FK_ATOMIC_ADD(&cur[t], 1u);
+        pack[pos] = (rl << SRT_COL_BITS) | c;
+        val_out[pos] = val_P[e];
+    }
+}
+__global__ void __launch_bounds__(256) k_sorted_count(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P, int n,
+                                                      SortedGeom g, uint32_t *__restrict__ cnt) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((gid >> 3) < n) sorted_count_lane(gid >> 3, gid & 7, row_P, col_P, g, cnt);
+}
+__global__ void __launch_bounds__(256) k_sorted_fill(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
+                                                     const float *__restrict__ val_P, int n, SortedGeom g, const uint32_t *__restrict__ start,
+                                                     uint32_t *__restrict__ cur, uint32_t *__restrict__ pack, float *__restrict__ val_out) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((gid >> 3) < n) sorted_fill_lane(gid >> 3, gid & 7, row_P, col_P, val_P, g, start, cur, pack, val_out);
+}
+
+// shared memory of one CTA: positions of the chunk's rows, then their D fixed-point accumulators
+template <int D>
+struct SrtSmem {
+    float y[SRT_ROWS * D];
+    int acc[SRT_ROWS * D];
+};
+// phase 1 (thread tid of nthreads): stage the chunk's positions, clear the accumulators
+template <int D>
+__host__ __device__ __forceinline__ void attract_sorted_load(int tid, int nthreads, int rc, const float *__restrict__ Y, int n, SrtSmem<D> &sm) {
+    const int r0 = rc * SRT_ROWS, rn = (n - r0) < SRT_ROWS ? (n - r0) : SRT_ROWS;
+    for (int i = tid; i < rn * D; i += nthreads) { sm.y[i] = Y[(size_t) r0 * D + i]; sm.acc[i] = 0; }
+}
+// phase 2: this thread's share of the chunk's edge stream (4 independent edges per trip)
+template <int D>
+__host__ __device__ __forceinline__ void attract_sorted_edges(int tid, int nthreads, int rc, const float *__restrict__ Y, SortedGeom g,
+                                                              const uint32_t *__restrict__ start, const uint32_t *__restrict__ pack,
+                                                              const float *__restrict__ val, float inv_df, float fix32, SrtSmem<D> &sm) {
+    const uint32_t e0 = start[(size_t) rc * g.ncb], e1 = start[(size_t) (rc + 1) * g.ncb];
+    for (uint32_t eb = e0 + tid; eb < e1; eb += 4u * nthreads) {
+        uint32_t pk[4];
+        float pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t e = eb + (uint32_t) u * nthreads;
+            pk[u] = e < e1 ? pack[e] : 0u;
+            pv[u] = e < e1 ? val[e] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (eb + (uint32_t) u * nthreads >= e1) break;
+            const uint32_t rl = pk[u] >> SRT_COL_BITS, c = pk[u] & ((1u << SRT_COL_BITS) - 1u);
+            if (D == 2) {
+                const float2 yj = reinterpret_cast<const float2 *>(Y)[c];
+                const float dx = sm.y[2 * rl] - yj.x, dy = sm.y[2 * rl + 1] - yj.y;
+                const float q = pv[u] / (1.f + (dx * dx + dy * dy) * inv_df);
+#ifdef __CUDA_ARCH__
+                atomicAdd(&sm.acc[2 * rl], __float2int_rn(q * dx * fix32));
+                atomicAdd(&sm.acc[2 * rl + 1], __float2int_rn(q * dy * fix32));
+#else
+                sm.acc[2 * rl] += (int) lrintf(q * dx * fix32);
+                sm.acc[2 * rl + 1] += (int) lrintf(q * dy * fix32);
+#endif
+            } else {
+                const float dx = sm.y[rl] - Y[c];
+                const float q = pv[u] / (1.f + dx * dx * inv_df);
+#ifdef __CUDA_ARCH__
+                atomicAdd(&sm.acc[rl], __float2int_rn(q * dx * fix32));
+#else
+                sm.acc[rl] += (int) lrintf(q * dx * fix32);
+#endif
+            }
+        }
+    }
+}
+// phase 3: fixed point -> float
+template <int D>
+__host__ __device__ __forceinline__ void attract_sorted_store(int tid, int nthreads, int rc, int n, float fix32, const SrtSmem<D> &sm,
+                                                               float *__restrict__ attr) {
+    const int r0 = rc * SRT_ROWS, rn = (n - r0) < SRT_ROWS ? (n - r0) : SRT_ROWS;
+    for (int i = tid; i < rn * D; i += nthreads) attr[(size_t) r0 * D + i] = (float) ((double) sm.acc[i] / (double) fix32);
+}
+
+template <int D>
+__global__ void __launch_bounds__(SRT_THREADS) k_attract_sorted(const float *__restrict__ Y, int n, SortedGeom g,
+                                                                const uint32_t *__restrict__ start, const uint32_t *__restrict__ pack,
+                                                                const float *__restrict__ val, float inv_df, float fix32,
+                                                                float *__restrict__ attr) {
+    extern __shared__ __align__(16) unsigned char srt_raw[];
+    SrtSmem<D> &sm = *reinterpret_cast<SrtSmem<D> *>(srt_raw);
+    const int rc = blockIdx.x;
+    attract_sorted_load<D>(threadIdx.x, blockDim.x, rc, Y, n, sm);
+    __syncthreads();
+    attract_sorted_edges<D>(threadIdx.x, blockDim.x, rc, Y, g, start, pack, val, inv_df, fix32, sm);
+    __syncthreads();
+    attract_sorted_store<D>(threadIdx.x, blockDim.x, rc, n, fix32, sm, attr);
+}
+
 // ------------------------------------------------------------------------------------------------ KL --
 // sum_edges (alpha p) log((alpha p + FLT_MIN) / (q + FLT_MIN)), q = (1+d2/df)^-df / sum_Q  (tsne.cpp:1340-1348);
 // per-row sums in fp64, per-block partials reduced in fixed order by k_finalize_kl.

@@ -18,6 +18,7 @@ FLAG_SPREAD_PER_NODE = 128
 FLAG_FFT_WIDE = 256
 FLAG_FUSED_COLSUM = 512
 FLAG_KPACK = 1024
+FLAG_SORTED_SPMV = 2048
 PHASES = ["bounds", "sort", "spread", "kernel_spectrum", "fft", "gather", "attract_update", "center", "kl",
           "collectives"]
 

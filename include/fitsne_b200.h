@@ -53,6 +53,7 @@ typedef struct fitsne_config {
 #define FITSNE_FLAG_NO_KERNEL_CACHE 64 /* re-sample + re-transform the kernel planes every iteration (no Taylor re-use) */
 #define FITSNE_FLAG_FFT_WIDE 256  /* FFT plans with radix-16 / radix-9 stages (3 stages instead of 4-5); opt-in until measured */
 #define FITSNE_FLAG_FUSED_COLSUM 512 /* column sums as an epilogue of the update kernel instead of a separate pass (measured 8 us slower at N=1M) */
+#define FITSNE_FLAG_SORTED_SPMV 2048 /* attractive term over column-sorted edges + shared-memory integer accumulators (after a re-ordering, N <= 2^20); experimental, not yet measured */
 #define FITSNE_FLAG_KPACK 1024    /* all four kernel planes in ONE complex transform (parity separation); opt-in until measured */
 #define FITSNE_FLAG_SPREAD_PER_NODE 128 /* spread with one thread per (32-point chunk, node) -- the first formulation; the default keeps all nodes of a chunk in one thread's registers */
 

@@ -99,6 +99,27 @@ try:
         b, Zb, _ = grad(row, col, val, Yc, ALL)
         OUT["C"][str(st["fft_side"])] = {"n_boxes": st["n_boxes"], "both_vs_shipped": rel(b, a), "Z_rel": abs(Zb - Za) / Za}
         say("span %-4d B=%-4d M=%-5d both vs shipped: dC rel %.2e  Z rel %.1e" % (span, st["n_boxes"], st["fft_side"], rel(b, a), abs(Zb - Za) / Za))
+    # ---- D: column-sorted SpMV (needs a re-ordered context and a graph with real edges)
+    import bench_util
+    nD = 200000
+    rowD, colD, valD, labD = bench_util.knn_like_graph(nD, 15, seed=0)
+    YD = bench_util.clustered_embedding(labD, 2, 120.0)
+    OUT["D"] = {}
+    res = {}
+    for name, fl in (("csr", 0), ("sorted", fb.FLAG_SORTED_SPMV)):
+        with fb.FitSNE(rowD, colD, valD, YD, flags=fl) as t:          # re-ordering ON (first gradient re-orders)
+            dC, Z = t.gradient(1.0)
+        res[name] = dC
+        with fb.FitSNE(rowD, colD, valD, YD, flags=fl | fb.FLAG_TIMERS) as t:
+            for _ in range(3):
+                t.step(exaggeration=1.0, momentum=0.8, learning_rate=1000.0, max_step_norm=5.0)
+            t.reset_stats()
+            for _ in range(20):
+                t.step(exaggeration=1.0, momentum=0.8, learning_rate=1000.0, max_step_norm=5.0)
+            OUT["D"][name + "_attract_update_ms"] = t.stats()["phase_ms"]["attract_update"] / 20
+    OUT["D"]["sorted_vs_csr"] = rel(res["sorted"], res["csr"])
+    say("200k kNN-like graph: sorted vs CSR gradient rel %.2e; attract+update ms: csr %.4f sorted %.4f" % (
+        OUT["D"]["sorted_vs_csr"], OUT["D"]["csr_attract_update_ms"], OUT["D"]["sorted_attract_update_ms"]))
     say("ONESHOT_DONE")
 except Exception as e:                                       # keep whatever was measured
     say("FAILED: %r" % (e,))
