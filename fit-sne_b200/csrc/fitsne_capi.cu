@@ -84,6 +84,7 @@ struct fitsne_ctx {
     int n_fwd = 0, n_kern = 0, n_inv = 0;
     cudaStream_t stream = nullptr;    // repulsive pipeline + update (high priority)
     cudaStream_t stream2 = nullptr;   // attractive SpMV, concurrent with the repulsive pipeline (low priority)
+    cudaStream_t stream3 = nullptr;   // sharded runs, FITSNE_AG_STREAM=1: the Y all-gather on its own high-priority stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ag = nullptr;
     ncclComm_t comm = nullptr;
     // sharded runs: per-rank reduction records (all-gathered, 128 B each) and whether c->Y currently holds every rank's slice
@@ -400,8 +401,13 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         CK(cudaEventRecord(c->ev_fork, st));
         CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
         if (c->world > 1) {
-            CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, c->stream2));
-            CK(cudaEventRecord(c->ev_ag, c->stream2));
+            // (experiment for the 8-GPU profile: NCCL's CTAs on the low-priority SpMV stream may be scheduled late behind the
+            //  repulsive kernels; FITSNE_AG_STREAM=1 runs the transfer on a high-priority stream of its own instead)
+            cudaStream_t ag = c->stream3 ? c->stream3 : c->stream2;
+            if (c->stream3) CK(cudaStreamWaitEvent(c->stream3, c->ev_fork, 0));
+            CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, ag));
+            CK(cudaEventRecord(c->ev_ag, ag));
+            if (c->stream3) CK(cudaStreamWaitEvent(c->stream2, c->ev_ag, 0));
         }
         CKRC(launch_attract<D>(c, c->stream2));
         CK(cudaEventRecord(c->ev_join, c->stream2));
@@ -918,6 +924,8 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
+    if (world > 1 && getenv("FITSNE_AG_STREAM") && atoi(getenv("FITSNE_AG_STREAM")) != 0)
+        CK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_ag, cudaEventDisableTiming));
@@ -1034,6 +1042,7 @@ int fitsne_destroy(fitsne_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
+    if (c->stream3) cudaStreamSynchronize(c->stream3);
     drop_graphs(c);
     for (auto &p : c->plans) if (p.second.W) cudaFree(p.second.W);
     if (c->comm) g_nccl.CommDestroy(c->comm);
@@ -1051,6 +1060,7 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_ag) cudaEventDestroy(c->ev_ag);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->stream3) cudaStreamDestroy(c->stream3);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
