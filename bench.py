@@ -138,6 +138,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    # watchdog: a wedged collective must not hold the box -- give up loudly after 15 minutes (the default run takes ~1-2)
+    import signal
+
+    def _give_up(signum, frame):
+        sys.stderr.write("bench.py: watchdog expired after 900 s (rank %s); aborting\n" % os.environ.get("RANK", "0"))
+        sys.stderr.flush()
+        os._exit(3)
+    signal.signal(signal.SIGALRM, _give_up)
+    signal.alarm(900)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
