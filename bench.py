@@ -138,15 +138,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    # watchdog: a wedged collective must not hold the box -- give up loudly after 15 minutes (the default run takes ~1-2)
-    import signal
-
-    def _give_up(signum, frame):
+    # watchdog: a wedged collective must not hold the box -- give up loudly after 15 minutes (the default run takes ~1-2).
+    # A thread, not SIGALRM: the main thread may be blocked inside the library (ctypes releases the GIL, Python-level
+    # signal handlers would only run once the call returns).
+    def _give_up():
         sys.stderr.write("bench.py: watchdog expired after 900 s (rank %s); aborting\n" % os.environ.get("RANK", "0"))
         sys.stderr.flush()
         os._exit(3)
-    signal.signal(signal.SIGALRM, _give_up)
-    signal.alarm(900)
+    wd = threading.Timer(900.0, _give_up)
+    wd.daemon = True
+    wd.start()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
