@@ -288,3 +288,42 @@ def test_kernel_spectrum_cache_keeps_reference_parity(fb, oracle, golden_graph):
         out.append((Y, costs[costs != 0]))
     assert np.allclose(out[0][1], out[1][1], rtol=1e-4)
     assert rel(out[0][0], out[1][0]) < 1e-2
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_alternative_kernels_keep_reference_parity(fb, golden_graph, golden_gradients, name):
+    """The kernels kept behind flags -- per-(chunk, node) spread, radix-16/9 FFT plans, packed kernel planes -- against the
+    reference's golden gradients; the two spread formulations must agree bit for bit (same sums in the same order)."""
+    row, col, val, _ = golden_graph
+    g = golden_gradients
+    dims, df, nterms, ipi, min_int, Z, kl = g[name + "__meta"]
+    Y = g[name + "__Y"].astype(np.float64)
+    kw = dict(nterms=int(nterms), intervals_per_integer=ipi, min_num_intervals=int(min_int), df=df)
+    out = {}
+    for label, flags in (("default", 0), ("spread_per_node", fb.FLAG_SPREAD_PER_NODE), ("fft_wide", fb.FLAG_FFT_WIDE),
+                         ("kpack", fb.FLAG_KPACK), ("wide+kpack", fb.FLAG_FFT_WIDE | fb.FLAG_KPACK)):
+        with fb.FitSNE(row, col, val.astype(np.float64), Y, flags=flags | fb.FLAG_NO_REORDER, **kw) as t:
+            dC, z = t.gradient(1.0)
+        assert rel(dC, g[name + "__dC"]) < GRAD_TOL, (label, rel(dC, g[name + "__dC"]))
+        assert abs(z - Z) / Z < 1e-5, (label, abs(z - Z) / Z)
+        out[label] = dC
+    if int(dims) == 2:          # measured bitwise identical on B200 (profiles/r1_oneshot_ab.json)
+        assert np.array_equal(out["default"], out["spread_per_node"])
+    else:
+        assert rel(out["default"], out["spread_per_node"]) < 1e-6
+
+
+def test_fused_and_separate_column_sums_agree(fb, golden_graph):
+    """FLAG_FUSED_COLSUM (column sums as an epilogue of k_update) vs the default separate pass: same trajectory up to the
+    fp64 summation order of the means."""
+    row, col, val, labels = golden_graph
+    import bench_util
+    Y0 = bench_util.clustered_embedding(labels.astype(np.int64), 2, 50.0, seed=6)
+    kw = dict(max_iter=60, stop_lying_iter=20, mom_switch_iter=20, learning_rate=500.0, early_exag_coeff=4.0)
+    res = []
+    for flags in (0, fb.FLAG_FUSED_COLSUM):
+        with fb.FitSNE(row, col, val.astype(np.float64), Y0, flags=flags) as t:
+            Y, costs = t.run(**kw)
+        res.append((Y, costs[costs != 0]))
+    assert rel(res[1][0], res[0][0]) < 1e-4
+    assert np.allclose(res[0][1], res[1][1], rtol=1e-6)
