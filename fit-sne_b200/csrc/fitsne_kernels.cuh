@@ -1871,7 +1871,7 @@ __global__ void __launch_bounds__(256) k_sorted_fill(const uint32_t *__restrict_
 
 // shared memory of one CTA: positions of the chunk's rows, then their D fixed-point accumulators
 template <int D>
-struct SrtSmem {
+struct alignas(16) SrtSmem {
     float y[SRT_ROWS * D];
     int acc[SRT_ROWS * D];
 };
@@ -1902,21 +1902,24 @@ __host__ __device__ __forceinline__ void attract_sorted_edges(int tid, int nthre
             const uint32_t rl = pk[u] >> SRT_COL_BITS, c = pk[u] & ((1u << SRT_COL_BITS) - 1u);
             if (D == 2) {
                 const float2 yj = reinterpret_cast<const float2 *>(Y)[c];
-                const float dx = sm.y[2 * rl] - yj.x, dy = sm.y[2 * rl + 1] - yj.y;
-                const float q = pv[u] / (1.f + (dx * dx + dy * dy) * inv_df);
+                const float2 yi = reinterpret_cast<const float2 *>(sm.y)[rl];
+                const float dx = yi.x - yj.x, dy = yi.y - yj.y;
 #ifdef __CUDA_ARCH__
+                const float q = __fdividef(pv[u], 1.f + (dx * dx + dy * dy) * inv_df);      // as k_attract
                 atomicAdd(&sm.acc[2 * rl], __float2int_rn(q * dx * fix32));
                 atomicAdd(&sm.acc[2 * rl + 1], __float2int_rn(q * dy * fix32));
 #else
+                const float q = pv[u] / (1.f + (dx * dx + dy * dy) * inv_df);
                 sm.acc[2 * rl] += (int) lrintf(q * dx * fix32);
                 sm.acc[2 * rl + 1] += (int) lrintf(q * dy * fix32);
 #endif
             } else {
                 const float dx = sm.y[rl] - Y[c];
-                const float q = pv[u] / (1.f + dx * dx * inv_df);
 #ifdef __CUDA_ARCH__
+                const float q = __fdividef(pv[u], 1.f + dx * dx * inv_df);
                 atomicAdd(&sm.acc[rl], __float2int_rn(q * dx * fix32));
 #else
+                const float q = pv[u] / (1.f + dx * dx * inv_df);
                 sm.acc[rl] += (int) lrintf(q * dx * fix32);
 #endif
             }
