@@ -156,6 +156,14 @@ struct fitsne_ctx {
     fitsne_stats stats{};
     cudaEvent_t ev[FITSNE_PHASE_COUNT + 1] = {};
     bool timing_this_iter = false;
+    // FITSNE_KTIMES=1 + FITSNE_FLAG_TIMERS: one CUDA event after every kernel of the iteration -> warm per-kernel times
+    // (ncu's per-launch times are cold-cache); read back as text with fitsne_debug_copy(ctx, "ktimes", ...)
+    bool ktimes_on = false;
+    std::vector<cudaEvent_t> kt_ev;
+    std::vector<const char *> kt_name;
+    size_t kt_n = 0;
+    std::map<std::string, std::pair<double, uint64_t>> kt_acc;
+    std::string kt_text;
     std::string err;
 };
 
@@ -264,6 +272,18 @@ static int get_plans(fitsne_ctx *c, int M, Plans **out) {
 // ------------------------------------------------------------------------------------- launch sequences --
 static inline void phase_mark(fitsne_ctx *c, int phase) {
     if (c->timing_this_iter) cudaEventRecord(c->ev[phase], c->stream);
+}
+
+static inline void kt(fitsne_ctx *c, const char *name) {
+    if (!c->ktimes_on || !c->timing_this_iter) return;
+    if (c->kt_n == c->kt_ev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c->kt_ev.push_back(e); c->kt_name.push_back(name);
+    }
+    c->kt_name[c->kt_n] = name;
+    cudaEventRecord(c->kt_ev[c->kt_n], c->stream);
+    c->kt_n++;
 }
 
 template <int D>
@@ -417,9 +437,11 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     c->y_whole = true;
 
     phase_mark(c, FITSNE_PHASE_BOUNDS);
+    kt(c, "(start)");
     k_setup_grid<<<1, 256, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
                                     c->mismatch, c->sort_totals, c->sc, (c->cfg.flags & FITSNE_FLAG_NO_KERNEL_CACHE) ? 0 : 1, kpack);
     c->stats.kernel_launches += 1;
+    kt(c, "k_setup_grid");
 
     // ---- bin + stable two-pass LSD radix sort by box
     phase_mark(c, FITSNE_PHASE_SORT);
@@ -429,21 +451,29 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     // (one-pass layout: k_bin writes keys[1] + the pass-1 histogram + in-box coordinates (staged in frep, free until the
     //  gather), the pass-0 kernels return at once, the pass-1 scatter produces keys[0]/perm[0]/sorted_u and box_start)
     k_bin<D><<<tiles, SORT_THREADS, 0, st>>>(c->Y, c->row_begin, nloc, c->gp, c->keys[0], c->keys[1], c->frep, c->hist, tiles, c->sort_totals);
+    kt(c, "k_bin");
     k_radix_offsets<D><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, 0, nloc, nullptr, c->gp);
+    kt(c, "k_radix_offsets#0");
     k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], nloc, 0, c->hist, tiles,
                                                               (uint32_t) c->row_begin, c->gp, nullptr, nullptr, D);
+    kt(c, "k_radix_scatter#0");
     k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[1], nloc, 1, c->hist, tiles, c->sort_totals + max_bins, c->gp);
+    kt(c, "k_radix_hist");
     k_radix_offsets<D><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, 1, nloc, c->box_start, c->gp);
+    kt(c, "k_radix_offsets#1");
     k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], nloc, 1, c->hist, tiles,
                                                               (uint32_t) c->row_begin, c->gp, c->frep, c->sorted_u, D);
     const uint32_t *skeys = c->keys[0], *sperm = c->perm[0];
+    kt(c, "k_radix_scatter#1");
     k_post_sort<D><<<cdiv(nloc, 256), 256, 0, st>>>(skeys, sperm, c->Y, nloc, c->gp, c->box_start, c->sorted_u);
+    kt(c, "k_post_sort");
     c->stats.kernel_launches += 7;
     LAUNCH_CHECK();
 
     // ---- spread
     phase_mark(c, FITSNE_PHASE_SPREAD);
     CKRC(launch_spread_gather<D>(c, false, M, skeys, sperm));
+    kt(c, "k_spread_chunks");
     const int lpn = combine_lanes(c, M);
     const int Gc = M / 2;
     const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
@@ -460,10 +490,12 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         c->stats.kernel_launches += 3;
     }
 
+    kt(c, "k_spread_combine(+collective)");
     // ---- kernel samples, then the convolution: forward FFTs of the 4 packed planes, Hadamard (+ sum_Q), inverse FFTs
     phase_mark(c, FITSNE_PHASE_KERNEL_SPECTRUM);
     k_gen_kernels<D><<<cdiv(plane, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->planes, kpack);
     LAUNCH_CHECK();
+    kt(c, "k_gen_kernels");
     phase_mark(c, FITSNE_PHASE_FFT);
     const int *gG = &c->gp->G, *gok = &c->gp->ok;
     const unsigned *gskip = &c->gp->fft_skip;
@@ -476,14 +508,19 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         // rows: the charge planes (0,1) are zero beyond row G -> pruned; the kernel planes (2..5) need every row and are
         // skipped altogether (device-side mask) on iterations that re-use the cached kernel spectra
         FFT_PASS(false, dim3(cdiv(M, LR), 6), pl->smem_rows, c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
+        kt(c, "k_fft_pass rows fwd");
         FFT_PASS(true, dim3(cdiv(M, LC), 6), pl->smem_cols, c->planes, plane, M, LC, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
+        kt(c, "k_fft_pass cols fwd");
     } else {
         FFT_PASS(false, dim3(1, 6), pl->smem_rows, c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
     }
+    if (D == 1) kt(c, "k_fft_pass fwd");
     k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0, kpack);
+    kt(c, "k_hadamard");
     if (D == 2) {
         // inverse: columns first (all of them), then only the G rows the gather reads
         FFT_PASS(true, dim3(cdiv(M, LC), 2), pl->smem_cols, c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
+        kt(c, "k_fft_pass cols inv");
         FFT_PASS(false, dim3(cdiv(M, LR), 2), pl->smem_rows, c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok, nullptr);
         c->stats.kernel_launches += 5;
     } else {
@@ -492,15 +529,18 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     }
 #undef FFT_PASS
     LAUNCH_CHECK();
+    kt(c, D == 2 ? "k_fft_pass rows inv" : "k_fft_pass inv");
 
     // ---- gather (+ 1/Z)
     phase_mark(c, FITSNE_PHASE_GATHER);
     CKRC(launch_spread_gather<D>(c, true, M, skeys, sperm));
+    kt(c, "k_gather");
 
     // ---- attractive term (joined here) + optimiser step
     phase_mark(c, FITSNE_PHASE_ATTRACT_UPDATE);
     if (overlap) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     else CKRC(launch_attract<D>(c, st));
+    kt(c, "k_attract");
     const int rows = c->row_end - c->row_begin;
     if (!update) {
         k_update<D, false><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
@@ -541,6 +581,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     }
     phase_mark(c, FITSNE_PHASE_COUNT);
     LAUNCH_CHECK();
+    kt(c, "k_update + zero-mean/bounds tail");
     return 0;
 }
 
@@ -845,6 +886,14 @@ static int run_iteration(fitsne_ctx *c, bool update) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, c->ev[seq[i]], c->ev[seq[i + 1]]) == cudaSuccess) c->stats.phase_ms[seq[i]] += ms;
         }
+        for (size_t i = 1; i < c->kt_n; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, c->kt_ev[i - 1], c->kt_ev[i]) == cudaSuccess) {
+                auto &a = c->kt_acc[c->kt_name[i]];
+                a.first += ms; a.second += 1;
+            }
+        }
+        c->kt_n = 0;
         c->timing_this_iter = false;
     }
     c->have_grad = true;
@@ -929,6 +978,7 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_ag, cudaEventDisableTiming));
+    c->ktimes_on = getenv("FITSNE_KTIMES") && atoi(getenv("FITSNE_KTIMES")) != 0;
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_attract<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_attract<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1056,6 +1106,7 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (c->host_bounds) cudaFreeHost(c->host_bounds);
     if (c->host_sc) cudaFreeHost(c->host_sc);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->kt_ev) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_ag) cudaEventDestroy(c->ev_ag);
@@ -1352,6 +1403,19 @@ int fitsne_debug_copy(fitsne_ctx *c, const char *what, void *dst, size_t dst_byt
             CK(cudaStreamSynchronize(c->stream));
             src = c->dC;
         }
+    }
+    else if (!strcmp(what, "ktimes")) {      // text: "<kernel> <total ms> <count>" per line (FITSNE_KTIMES=1 + timers mode)
+        c->kt_text.clear();
+        for (auto &kv : c->kt_acc) {
+            char line[160];
+            snprintf(line, sizeof line, "%s\t%.6f\t%llu\n", kv.first.c_str(), kv.second.first, (unsigned long long) kv.second.second);
+            c->kt_text += line;
+        }
+        if (needed) *needed = c->kt_text.size();
+        if (!dst) return 0;
+        if (dst_bytes < c->kt_text.size()) return fail(c, FITSNE_EINVAL, "buffer too small for 'ktimes'");
+        memcpy(dst, c->kt_text.data(), c->kt_text.size());
+        return 0;
     }
     else if (!strcmp(what, "perm")) { src = c->perm[sorted_buf]; bytes = (size_t) c->nloc * 4; }
     else if (!strcmp(what, "keys")) { src = c->keys[sorted_buf]; bytes = (size_t) c->nloc * 4; }

@@ -232,6 +232,20 @@ class FitSNE:
         return out
 
 
+def _kernel_times(self):
+    """{kernel: (total ms, launches)} of the timers-mode steps so far (needs FITSNE_KTIMES=1 in the environment when the
+    context is created, and FLAG_TIMERS): warm per-kernel device times, one CUDA event after every kernel."""
+    txt = self.debug("ktimes", np.uint8).tobytes().decode()
+    out = {}
+    for line in txt.splitlines():
+        name, ms, n = line.split("\t")
+        out[name] = (float(ms), int(n))
+    return out
+
+
+FitSNE.kernel_times = _kernel_times
+
+
 def run_host(row_P, col_P, val_P, Y0, schedule=None, nterms=3, intervals_per_integer=1.0, min_num_intervals=50,
              df=1.0, device=-1, flags=0, **kw):
     """fitsne_run_host: host CSR P + host Y in, host Y + costs out (the call a patched tsne.cpp makes)."""
