@@ -1,11 +1,11 @@
 // fitsne_kernels.cuh -- hand-written sm_100a kernels for FIt-SNE's per-iteration gradient loop.
 //
 // Everything the reference does per iteration (reference = /root/reference/src/...) in fp32 on the device:
-//   bounds + zero-mean        tsne.cpp:1039-1049, :1851-1876        k_colsum, k_center_bounds, k_setup_grid
+//   bounds + zero-mean        tsne.cpp:1039-1049, :1851-1876        k_colsum, k_center_bounds, k_setup_grid (sharded: k_shard_stats, k_center_shard)
 //   point -> box, sort        nbodyfft.cpp:85-114                    k_bin, k_radix_hist/offsets/scatter, k_post_sort
-//   Lagrange spread           nbodyfft.cpp:123-147, :310-336         k_spread_chunks, k_spread_combine
-//   kernel samples            nbodyfft.cpp:52-61, tsne.cpp:69-94     k_gen_kernels        (+ cuFFT R2C)
-//   Hadamard + sum_Q          nbodyfft.cpp:184-191, tsne.cpp:1101-1110  k_hadamard, k_finalize_z  (+ cuFFT C2R)
+//   Lagrange spread           nbodyfft.cpp:123-147, :310-336         k_spread_chunks2 (k_spread_chunks), k_spread_combine
+//   kernel samples            nbodyfft.cpp:52-61, tsne.cpp:69-94     k_gen_kernels        (+ forward FFTs, fitsne_fft.cuh)
+//   Hadamard + sum_Q          nbodyfft.cpp:184-191, tsne.cpp:1101-1110  k_hadamard           (+ inverse FFTs)
 //   gather + normalise        nbodyfft.cpp:222-239, tsne.cpp:1149-1151  k_gather
 //   attractive + optimiser    tsne.cpp:1121-1137, :479-513           k_attract (2nd stream), k_update
 //   KL                        tsne.cpp:1329-1355                      k_kl
@@ -288,37 +288,6 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
                 host_bounds[0] = bmn; host_bounds[1] = bmx;
                 if (gpp) *reinterpret_cast<volatile unsigned long long *>(host_bounds + 4) = sc->iter_done;
             }
-        }
-    }
-}
-
-// (superseded by the last-block epilogue of k_center_bounds; kept for reference / sharded experiments)
-// Reduce the per-block bounds; publish them to the device scalars and to a host-mapped word pair.
-__global__ void __launch_bounds__(256) k_reduce_bounds(const float2 *__restrict__ bounds_partial, int nparts,
-                                                       Scalars *__restrict__ sc, volatile float *host_bounds,
-                                                       const GridParams *__restrict__ gpp) {
-    __shared__ float smf[64];
-    if (gpp && !gpp->ok) return;
-    float mn = INFINITY, mx = -INFINITY;
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
-        float2 v = bounds_partial[i];
-        mn = fminf(mn, v.x); mx = fmaxf(mx, v.y);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { smf[w] = mn; smf[32 + w] = mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < (int) (blockDim.x >> 5); i++) { mn = fminf(mn, smf[i]); mx = fmaxf(mx, smf[32 + i]); }
-        sc->bmin = mn; sc->bmax = mx;
-        if (gpp) sc->iter_done += 1;      // closing kernel of a full optimiser step
-        if (host_bounds) {
-            host_bounds[0] = mn; host_bounds[1] = mx;
-            if (gpp) *reinterpret_cast<volatile unsigned long long *>(host_bounds + 4) = sc->iter_done;
         }
     }
 }
@@ -1196,20 +1165,6 @@ __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, c
             sc->Z = Z;
             sc->inv_Z = (float) (1.0 / Z);
         }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_finalize_z(const double *__restrict__ zpartial, int nparts, int N,
-                                                    const GridParams *__restrict__ gpp, Scalars *__restrict__ sc) {
-    __shared__ double sm[32];
-    if (!gpp->ok) return;
-    double s = 0;
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += zpartial[i];
-    const double r = block_sum(s, sm);
-    if (threadIdx.x == 0) {
-        const double Z = r - (double) N;      // "- N": the sums include i == j (tsne.cpp:1110)
-        sc->Z = Z;
-        sc->inv_Z = (float) (1.0 / Z);
     }
 }
 
