@@ -1,10 +1,11 @@
 // fitsne_capi.cu -- context, per-iteration launch sequence, CUDA-graph cache and the C ABI
-// (include/fitsne_b200.h) of libfitsne_b200.so.  Kernels live in fitsne_kernels.cuh and fitsne_fft.cuh (no library
-// call is left on the path: the FFTs are our own); NCCL (loaded with dlopen, only for sharded runs) carries the grid
-// all-reduce and the Y all-gather.  There is no CPU fallback anywhere in this file.
+// (include/fitsne_b200.h) of libfitsne_b200.so.  Kernels live in fitsne_kernels.cuh, fitsne_conv.cuh and fitsne_fft.cuh
+// (no library call is left on the path: the FFTs are our own); NCCL (loaded with dlopen, only for sharded runs) carries
+// the grid all-reduce and the Y all-gather.  There is no CPU fallback anywhere in this file.
 #include "../../include/fitsne_b200.h"
 #include "fitsne_kernels.cuh"
 #include "fitsne_fft.cuh"
+#include "fitsne_conv.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -57,12 +58,29 @@ struct NcclApi {
 NcclApi g_nccl;
 std::string g_create_error;
 
-struct Plans {          // per FFT length: radix plan + twiddle table (no library plans, nothing to JIT)
-    FftPlan plan{};
+struct Plans {          // per FFT length: radix plans + twiddle table (no library plans, nothing to JIT)
+    FftPlan plan{};      // Stockham (natural order): row passes, 1-D lines
+    ColPlan cplan{};     // in place (digit-reversed spectra): column passes of the 2-D convolution
     float2 *W = nullptr;
-    int lines_rows = 1, lines_cols = 1;          // rows / columns per CTA tile
-    size_t smem_rows = 0, smem_cols = 0;
+    size_t smem_row2 = 0, smem_row1 = 0, smem_col = 0, smem_line = 0;
+    CUtensorMap tmS;     // 2-D: TMA view of S as [rows = M/2][(M/2+1) * 8 floats], box = 128 rows x 8 floats
+    const void *tm_base = nullptr;   // the S allocation the map was encoded for
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
 
 // The launch sequence depends on the FFT length M only (n_boxes and all grid geometry are read from the
 // device-resident GridParams), so one captured graph serves every iteration whose 2G maps to the same M.
@@ -85,7 +103,8 @@ struct fitsne_ctx {
     cudaStream_t stream = nullptr;    // repulsive pipeline + update (high priority)
     cudaStream_t stream2 = nullptr;   // attractive SpMV, concurrent with the repulsive pipeline (low priority)
     cudaStream_t stream3 = nullptr;   // sharded runs, FITSNE_AG_STREAM=1: the Y all-gather on its own high-priority stream
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ag = nullptr;
+    cudaStream_t stream_k = nullptr;  // 2-D: kernel-spectrum side of the convolution, concurrent with sort + spread
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ag = nullptr, ev_kfork = nullptr, ev_kjoin = nullptr;
     ncclComm_t comm = nullptr;
     // sharded runs: per-rank reduction records (all-gathered, 128 B each) and whether c->Y currently holds every rank's slice
     ShardStats *shard_stats = nullptr;
@@ -119,7 +138,6 @@ struct fitsne_ctx {
     bool use_sorted = false;
     uint64_t last_reorder_iter = 0, reorder_interval = 50, reorders = 0;
     uint32_t nonempty_tiles = 0;
-    unsigned long long kc_hits_base = 0;
     float tile_fix32 = 1.0f;
     uint64_t kernel_launches_reorder = 0;
     // sort / bins
@@ -128,11 +146,13 @@ struct fitsne_ctx {
     uint32_t *box_start = nullptr, *hist = nullptr, *sort_totals = nullptr;
     size_t box_cap = 0, hist_cap = 0;
     float4 *slots = nullptr;          // spread partials: [chunk][2][nodes]
-    // grids
-    float2 *planes = nullptr, *compact = nullptr;   // 4 packed complex planes [M^D]; multi-GPU compact grids
-    size_t plane_cap = 0;                            // capacity in complex elements per plane
+    // grids.  2-D: chg (spread result, float4 per node of the G x G grid), S (x-spectra per row, in place the convolved
+    // half-spectra), KR / KS (kernel spectra after the row / column pass), pot (v1, Bx, By per node); 1-D: four packed lines
+    float4 *chg = nullptr, *pot = nullptr, *KR = nullptr, *KS = nullptr;
+    float2 *S = nullptr, *planes = nullptr;
+    int grid_cap_M = 0;                              // FFT length the grid buffers are sized for
     // small stuff
-    double *colsum_partial = nullptr, *zpartial = nullptr, *kl_partial = nullptr, *update_partial = nullptr;
+    double *colsum_partial = nullptr, *zpartial = nullptr, *kl_partial = nullptr;
     float2 *bounds_partial = nullptr;
     GridParams *gp = nullptr;
     StepParams *sp = nullptr;
@@ -222,13 +242,19 @@ static int ensure_grid_capacity(fitsne_ctx *c, int M) {
         c->box_cap = cap;
         moved = true;
     }
-    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
-    if (plane > c->plane_cap) {
-        const size_t cap = plane + plane / 2;
-        CKRC(dev_alloc(c, &c->planes, cap * 6));      // 2 charge + 2 kernel + 2 kernel-derivative planes
-        CK(cudaMemsetAsync(&c->sc->kc_valid, 0, sizeof(int), c->stream));   // cached spectra are gone
-        if (c->world > 1) CKRC(dev_alloc(c, &c->compact, cap / 2 + 1024));
-        c->plane_cap = cap;
+    if (M > c->grid_cap_M) {
+        const size_t Mc = (size_t) M + M / 4;           // head room: the grid grows through a ladder of lengths
+        const size_t Gc = Mc / 2 + 1, H = Mc / 2 + 2;
+        if (D == 2) {
+            CKRC(dev_alloc(c, &c->chg, Gc * Gc)); CKRC(dev_alloc(c, &c->pot, Gc * Gc));
+            CKRC(dev_alloc(c, &c->S, Gc * H * COL_SLOTS));
+            CKRC(dev_alloc(c, &c->KR, Gc * H)); CKRC(dev_alloc(c, &c->KS, H * Mc));
+            // sharded runs all-reduce (M/2)^2 nodes of chg whatever G is: the tail must hold finite numbers
+            CK(cudaMemsetAsync(c->chg, 0, Gc * Gc * sizeof(float4), c->stream));
+        } else {
+            CKRC(dev_alloc(c, &c->planes, Mc * 4));
+        }
+        c->grid_cap_M = (int) Mc;
         moved = true;
     }
     if (moved) drop_graphs(c);   // captured graphs point at the old buffers
@@ -237,35 +263,39 @@ static int ensure_grid_capacity(fitsne_ctx *c, int M) {
 
 static int get_plans(fitsne_ctx *c, int M, Plans **out) {
     auto it = c->plans.find(M);
-    if (it != c->plans.end()) { *out = &it->second; return 0; }
-    Plans pl;
-    if (!fft_make_plan(M, &pl.plan, (c->cfg.flags & FITSNE_FLAG_FFT_WIDE) != 0))
-        return fail(c, FITSNE_EINVAL, "FFT length %d is not of the form 2^a 3^b 5^c", M);
-    CK(cudaMalloc((void **) &pl.W, (size_t) M * sizeof(float2)));
-    k_fft_twiddles<<<cdiv(M, 256), 256, 0, c->stream>>>(pl.W, M);
-    LAUNCH_CHECK();
-    CK(cudaStreamSynchronize(c->stream));
-    // tiles: column passes take up to 8 adjacent columns per CTA (64-byte segments), row passes up to 4 rows.
-    // Bounds: M * lines <= FFT_EPT * FFT_THREADS (register staging) and the two ping-pong buffers + twiddles in smem.
-    auto fit = [&](int want) {
-        int l = c->D == 2 ? want : 1;
-        while (l > 1 && ((size_t) M * l > (size_t) FFT_EPT * FFT_THREADS ||
-                         ((size_t) 2 * l * fft_buf_len(M, l) + M) * sizeof(float2) > (size_t) 200 * 1024)) l /= 2;
-        return l;
-    };
-    // B200 sweep at M=1280 (tests/tools/fft_sweep.py): 8 columns / 4 rows per 512-thread CTA is the best of a flat
-    // optimum (0.20-0.23 ms for the whole convolution)
-    static const int env_lc = getenv("FITSNE_FFT_LINES_COLS") ? atoi(getenv("FITSNE_FFT_LINES_COLS")) : 8;
-    static const int env_lr = getenv("FITSNE_FFT_LINES_ROWS") ? atoi(getenv("FITSNE_FFT_LINES_ROWS")) : 4;
-    pl.lines_cols = fit(env_lc);
-    pl.lines_rows = fit(env_lr);
-    if ((size_t) M * pl.lines_cols > (size_t) FFT_EPT * FFT_THREADS) return fail(c, FITSNE_EINVAL, "FFT length %d too long", M);
-    pl.smem_cols = ((size_t) 2 * pl.lines_cols * fft_buf_len(M, pl.lines_cols) + M) * sizeof(float2);
-    pl.smem_rows = ((size_t) 2 * pl.lines_rows * fft_buf_len(M, pl.lines_rows) + M) * sizeof(float2);
-    if (pl.smem_rows > (size_t) 220 * 1024 || pl.smem_cols > (size_t) 220 * 1024)
-        return fail(c, FITSNE_EINVAL, "FFT length %d does not fit in shared memory", M);
-    c->plans[M] = pl;
-    *out = &c->plans[M];
+    if (it == c->plans.end()) {
+        Plans pl;
+        if (!fft_make_plan(M, &pl.plan) || !col_make_plan(M, &pl.cplan))
+            return fail(c, FITSNE_EINVAL, "FFT length %d is not of the form 2^a 3^b 5^c", M);
+        CK(cudaMalloc((void **) &pl.W, (size_t) M * sizeof(float2)));
+        k_fft_twiddles<<<cdiv(M, 256), 256, 0, c->stream>>>(pl.W, M);
+        LAUNCH_CHECK();
+        CK(cudaStreamSynchronize(c->stream));
+        pl.smem_row2 = (size_t) 4 * fft_buf_len(M, 2) * sizeof(float2);          // two sequences, ping-pong
+        pl.smem_row1 = (size_t) 2 * fft_buf_len(M, 1) * sizeof(float2);
+        pl.smem_line = ((size_t) 2 * fft_buf_len(M, 1) + M) * sizeof(float2);    // 1-D: + twiddles
+        pl.smem_col = (size_t) M * COL_SLOTS * sizeof(float2);
+        if ((c->D == 2 ? std::max(pl.smem_row2, pl.smem_col) : pl.smem_line) > (size_t) 220 * 1024)
+            return fail(c, FITSNE_EINVAL, "FFT length %d does not fit in shared memory", M);
+        it = c->plans.emplace(M, pl).first;
+    }
+    Plans &pl = it->second;
+    if (c->D == 2 && pl.tm_base != (const void *) c->S) {
+        // S viewed as a 2-D fp32 tensor: inner = (M/2+1) frequencies x 4 slots x (re, im), outer = M/2 rows (>= G);
+        // one box = one kx (8 floats = 32 bytes) x 128 rows.  Out-of-range rows read as zero / are not written.
+        EncodeTiledFn enc = get_encode_tiled();
+        if (!enc) return fail(c, FITSNE_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        const cuuint64_t H = (cuuint64_t) M / 2 + 1;
+        const cuuint64_t dims[2] = {H * 2 * COL_SLOTS, (cuuint64_t) M / 2};
+        const cuuint64_t strides[1] = {H * COL_SLOTS * sizeof(float2)};
+        const cuuint32_t box[2] = {2 * COL_SLOTS, COL_BOX_ROWS};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&pl.tmS, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *) c->S, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(c, FITSNE_ECUDA, "cuTensorMapEncodeTiled failed (%d) for M=%d", (int) r, M);
+        pl.tm_base = c->S;
+    }
+    *out = &pl;
     return 0;
 }
 
@@ -287,14 +317,13 @@ static inline void kt(fitsne_ctx *c, const char *name) {
 }
 
 template <int D>
-static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int do_center, int mean_ready = 0) {
-    // do_center == 1: closing kernel of an optimiser step (skipped, like the rest, when the grid check failed).
-    // The last block to finish combines the per-block bounds and publishes them (no second launch).
+static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int do_center) {
+    // do_center == 1: closing kernel of an optimiser step (skipped, like the rest, when the grid check failed); the means
+    // are in Scalars::mean (k_update).  The last block to finish combines the per-block bounds and publishes them.
     const GridParams *gate = do_center ? c->gp : nullptr;
-    k_center_bounds<D><<<RED_BLOCKS, 256, 0, c->stream>>>(Yin, Yout, c->N, c->colsum_partial, RED_BLOCKS, do_center,
-                                                          c->bounds_partial, c->sc, c->reordered ? c->orig_of : nullptr,
-                                                          c->reordered ? c->pos_of : nullptr, gate, c->host_bounds_dev,
-                                                          c->tickets + 1, mean_ready);
+    k_center_bounds<D><<<RED_BLOCKS, 256, 0, c->stream>>>(Yin, Yout, c->N, do_center, c->bounds_partial, c->sc,
+                                                          c->reordered ? c->orig_of : nullptr, c->reordered ? c->pos_of : nullptr, gate,
+                                                          c->host_bounds_dev, c->tickets + 1);
     LAUNCH_CHECK();
     c->stats.kernel_launches += 1;
     return 0;
@@ -305,27 +334,23 @@ static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, int M, const
     (void) M;
     const int p = c->cfg.nterms;
     const int nodes = D == 2 ? p * p : p;
+    void *grid = D == 2 ? (void *) c->chg : (void *) c->planes;
     if (!gather) {
         const int cpb = std::max(1, 256 / nodes);
         const int nchunks = cdiv(c->nloc, CHUNK);
-        // default: one thread per chunk with all p^D accumulators in registers (P = 2..4 in 2-D, 2..5 in 1-D; bitwise the
-        // same sums as the per-(chunk, node) kernel, which stays for other P and behind FITSNE_FLAG_SPREAD_PER_NODE)
+        // one thread per chunk with all p^D accumulators in registers (P = 2..4 in 2-D, 2..5 in 1-D); other P: one thread per
+        // (chunk, node) -- both produce bitwise identical sums
         constexpr bool has2 = P >= 2 && (D == 2 ? P <= 4 : P <= 5);
         if constexpr (has2) {
-            if (!(c->cfg.flags & FITSNE_FLAG_SPREAD_PER_NODE)) {
-                k_spread_chunks2<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, 0, c->stream>>>(
-                    c->sorted_u, skeys, c->box_start, c->nloc, c->gp, c->slots, c->planes, c->world > 1 ? c->compact : nullptr);
-                LAUNCH_CHECK();
-                c->stats.kernel_launches += 1;
-                return 0;
-            }
+            k_spread_chunks2<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, 0, c->stream>>>(c->sorted_u, skeys, c->box_start, c->nloc, c->gp,
+                                                                                              c->slots, grid);
+        } else {
+            k_spread_chunks<D, P><<<cdiv(nchunks, cpb), cpb * nodes, 0, c->stream>>>(c->sorted_u, skeys, c->box_start, c->nloc, c->gp, cpb,
+                                                                                      c->slots, grid);
         }
-        k_spread_chunks<D, P><<<cdiv(nchunks, cpb), cpb * nodes, 0, c->stream>>>(c->sorted_u, skeys, c->box_start, c->nloc, c->gp, cpb,
-                                                                                  c->slots, c->planes,
-                                                                                  c->world > 1 ? c->compact : nullptr);
     } else {
         k_gather<D, P><<<cdiv(c->nloc, 256), 256, 0, c->stream>>>(c->sorted_u, skeys, sperm, c->nloc, c->gp, c->sc,
-                                                                   c->planes, c->frep);
+                                                                   D == 2 ? (const void *) c->pot : (const void *) c->planes, c->frep);
     }
     LAUNCH_CHECK();
     c->stats.kernel_launches += 1;
@@ -409,9 +434,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     cudaStream_t st = c->stream;
     Plans *pl;
     CKRC(get_plans(c, M, &pl));
-    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
     const bool overlap = !c->timing_this_iter;    // timers mode serialises everything to time each phase
-    const int kpack = (c->cfg.flags & FITSNE_FLAG_KPACK) ? 1 : 0;     // all four kernel planes in one complex transform (opt-in)
 
     // Sharded: after an optimiser step every rank only holds ITS slice of the new Y.  The all-gather that completes Y is
     // issued here, on the SpMV's stream: the SpMV is its only consumer inside the iteration (bin / sort / spread / gather /
@@ -439,9 +462,25 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     phase_mark(c, FITSNE_PHASE_BOUNDS);
     kt(c, "(start)");
     k_setup_grid<<<1, 256, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
-                                    c->mismatch, c->sort_totals, c->sc, (c->cfg.flags & FITSNE_FLAG_NO_KERNEL_CACHE) ? 0 : 1, kpack);
+                                    c->mismatch, c->sort_totals);
     c->stats.kernel_launches += 1;
     kt(c, "k_setup_grid");
+    // 2-D: the kernel spectra depend on the grid geometry only (not on the points): sample + transform them on their own
+    // stream while this one sorts and spreads; joined right before the fused column pass
+    auto launch_kernel_side = [&](cudaStream_t ks) -> int {
+        const int Gc = M / 2, H = M / 2 + 1;
+        k_kspec_rows<<<Gc, ROW_THREADS, pl->smem_row1, ks>>>(c->KR, pl->plan, pl->W, c->gp, c->cfg.df);
+        k_kspec_cols<<<(H + 1) / 2, COL_THREADS, pl->smem_col, ks>>>(c->KR, c->KS, pl->cplan, pl->W, c->gp);
+        LAUNCH_CHECK();
+        c->stats.kernel_launches += 2;
+        return 0;
+    };
+    if (D == 2 && overlap) {
+        CK(cudaEventRecord(c->ev_kfork, st));
+        CK(cudaStreamWaitEvent(c->stream_k, c->ev_kfork, 0));
+        CKRC(launch_kernel_side(c->stream_k));
+        CK(cudaEventRecord(c->ev_kjoin, c->stream_k));
+    }
 
     // ---- bin + stable two-pass LSD radix sort by box
     phase_mark(c, FITSNE_PHASE_SORT);
@@ -476,60 +515,47 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     kt(c, "k_spread_chunks");
     const int lpn = combine_lanes(c, M);
     const int Gc = M / 2;
-    const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
-    if (c->world == 1) {
-        // 2-D: only the (M/2)^2 corner is touched (the zero padding is substituted inside the forward FFT passes)
-        k_spread_combine<D><<<cdiv((D == 2 ? cplane : plane) * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, lpn, c->planes, nullptr);
-        c->stats.kernel_launches += 1;
-    } else {
-        k_spread_combine<D><<<cdiv(cplane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, lpn, c->planes, c->compact);
+    const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) M;            // k_spread_combine's index space
+    k_spread_combine<D><<<cdiv(cplane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, lpn, D == 2 ? (void *) c->chg : (void *) c->planes);
+    c->stats.kernel_launches += 1;
+    if (c->world > 1) {
+        // every rank spread its own points: sum the partial grids (fp32).  2-D: the dense (M/2)^2 float4 region that holds
+        // the G x G grid; 1-D: the two packed charge lines.  The element count depends on M only, like every launch shape.
         phase_mark(c, FITSNE_PHASE_COLLECTIVES);
         if (overlap) CK(cudaStreamWaitEvent(st, c->ev_ag, 0));       // collective order: Y all-gather first (see above)
-        CKNCCL(g_nccl.AllReduce(c->compact, c->compact, cplane * 4, ncclFloat, ncclSum, c->comm, st));   // 2 planes x float2
-        k_pad_grids<D><<<cdiv(D == 2 ? cplane : plane, 256), 256, 0, st>>>(c->compact, c->gp, c->planes);
-        c->stats.kernel_launches += 3;
+        if (D == 2) CKNCCL(g_nccl.AllReduce(c->chg, c->chg, cplane * 4, ncclFloat, ncclSum, c->comm, st));
+        else CKNCCL(g_nccl.AllReduce(c->planes, c->planes, (size_t) M * 4, ncclFloat, ncclSum, c->comm, st));
     }
-
     kt(c, "k_spread_combine(+collective)");
-    // ---- kernel samples, then the convolution: forward FFTs of the 4 packed planes, Hadamard (+ sum_Q), inverse FFTs
+
+    // ---- convolution (+ sum_Q)
     phase_mark(c, FITSNE_PHASE_KERNEL_SPECTRUM);
-    k_gen_kernels<D><<<cdiv(plane, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->planes, kpack);
-    LAUNCH_CHECK();
-    kt(c, "k_gen_kernels");
-    phase_mark(c, FITSNE_PHASE_FFT);
-    const int *gG = &c->gp->G, *gok = &c->gp->ok;
-    const unsigned *gskip = &c->gp->fft_skip;
-    const int LR = pl->lines_rows, LC = pl->lines_cols;
-    const int FT = FFT_THREADS;
-    const bool wide = (c->cfg.flags & FITSNE_FLAG_FFT_WIDE) != 0;
-#define FFT_PASS(COLS, grid, smem, ...) do { if (wide) k_fft_pass<COLS, true><<<grid, FT, smem, st>>>(__VA_ARGS__); \
-                                             else k_fft_pass<COLS, false><<<grid, FT, smem, st>>>(__VA_ARGS__); } while (0)
+    const int *gok = &c->gp->ok;
     if (D == 2) {
-        // rows: the charge planes (0,1) are zero beyond row G -> pruned; the kernel planes (2..5) need every row and are
-        // skipped altogether (device-side mask) on iterations that re-use the cached kernel spectra
-        FFT_PASS(false, dim3(cdiv(M, LR), 6), pl->smem_rows, c->planes, plane, M, LR, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
-        kt(c, "k_fft_pass rows fwd");
-        FFT_PASS(true, dim3(cdiv(M, LC), 6), pl->smem_cols, c->planes, plane, M, LC, pl->plan, pl->W, 0, 0x3u, gG, gok, gskip);
-        kt(c, "k_fft_pass cols fwd");
-    } else {
-        FFT_PASS(false, dim3(1, 6), pl->smem_rows, c->planes, plane, 1, 1, pl->plan, pl->W, 0, 0u, gG, gok, gskip);
-    }
-    if (D == 1) kt(c, "k_fft_pass fwd");
-    k_hadamard<D><<<Z_BLOCKS, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0, kpack);
-    kt(c, "k_hadamard");
-    if (D == 2) {
-        // inverse: columns first (all of them), then only the G rows the gather reads
-        FFT_PASS(true, dim3(cdiv(M, LC), 2), pl->smem_cols, c->planes, plane, M, LC, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
-        kt(c, "k_fft_pass cols inv");
-        FFT_PASS(false, dim3(cdiv(M, LR), 2), pl->smem_rows, c->planes, plane, M, LR, pl->plan, pl->W, 1, 0x3u, gG, gok, nullptr);
-        c->stats.kernel_launches += 5;
-    } else {
-        FFT_PASS(false, dim3(1, 1), pl->smem_rows, c->planes, plane, 1, 1, pl->plan, pl->W, 1, 0u, gG, gok, nullptr);
+        if (!overlap) { CKRC(launch_kernel_side(st)); kt(c, "k_kspec_rows + k_kspec_cols"); }
+        phase_mark(c, FITSNE_PHASE_FFT);
+        const int H = M / 2 + 1;
+        k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp);
+        kt(c, "k_conv_rows_fwd");
+        if (overlap) CK(cudaStreamWaitEvent(st, c->ev_kjoin, 0));
+        k_conv_cols<<<H, COL_THREADS, pl->smem_col, st>>>(pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
+                                                          c->sc, c->tickets + 0);
+        kt(c, "k_conv_cols");
+        k_conv_rows_inv<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->S, c->pot, pl->plan, pl->W, c->gp);
+        kt(c, "k_conv_rows_inv");
         c->stats.kernel_launches += 3;
+    } else {
+        k_gen_kernels_1d<<<cdiv(M, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->planes);
+        kt(c, "k_gen_kernels_1d");
+        phase_mark(c, FITSNE_PHASE_FFT);
+        // lines 0,1 = charges (zero beyond G: substituted while loading), lines 2,3 = kernels
+        k_fft_line<<<4, FFT_THREADS, pl->smem_line, st>>>(c->planes, pl->plan, pl->W, 0, 0x0u, &c->gp->G, gok);
+        k_hadamard_1d<<<Z_BLOCKS_1D, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0);
+        k_fft_line<<<1, FFT_THREADS, pl->smem_line, st>>>(c->planes, pl->plan, pl->W, 1, 0u, &c->gp->G, gok);
+        kt(c, "1-D convolution");
+        c->stats.kernel_launches += 4;
     }
-#undef FFT_PASS
     LAUNCH_CHECK();
-    kt(c, D == 2 ? "k_fft_pass rows inv" : "k_fft_pass inv");
 
     // ---- gather (+ 1/Z)
     phase_mark(c, FITSNE_PHASE_GATHER);
@@ -542,34 +568,25 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     else CKRC(launch_attract<D>(c, st));
     kt(c, "k_attract");
     const int rows = c->row_end - c->row_begin;
+    const int ublocks = std::min(RED_BLOCKS, cdiv(rows, 256));
     if (!update) {
-        k_update<D, false><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
-                                                           c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
+        k_update<D, false><<<ublocks, 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
+                                                   c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         c->stats.kernel_launches += 1;
         phase_mark(c, FITSNE_PHASE_CENTER);
-    } else if (c->world == 1 && !(c->cfg.flags & FITSNE_FLAG_FUSED_COLSUM)) {
-        // single GPU: update, a separate column-sum pass, centring + bounds.  (The variant below folds the column sums into
-        // k_update as a last-block epilogue: one launch fewer but measured 8 us SLOWER per iteration at N = 1M --
-        // profiles/r1_oneshot_ab.json -- the two fp64 block reductions sit on every CTA's critical path.)
-        k_update<D, true><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
-                                                          c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
-        phase_mark(c, FITSNE_PHASE_CENTER);
-        k_colsum<D><<<RED_BLOCKS, 256, 0, st>>>(c->Yb, c->N, c->colsum_partial, c->gp);
-        c->stats.kernel_launches += 2;
-        CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1, 0));
     } else if (c->world == 1) {
-        // single GPU: k_update also produces the column means of the new positions (last-block reduction), the
-        // centring kernel subtracts them, finds the bounds and publishes them -- two launches for the whole tail
-        k_update<D, true><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
-                                                          c->uY, c->gains, c->Yb, c->update_partial, c->N, c->sc, c->tickets + 2);
+        // single GPU: k_update also produces the column means of the new positions (per-CTA register sums, last-block
+        // reduction), the centring kernel subtracts them, finds the bounds and publishes them -- two launches for the tail
+        k_update<D, true><<<ublocks, 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
+                                                  c->uY, c->gains, c->Yb, c->colsum_partial, c->N, c->sc, c->tickets + 2);
         c->stats.kernel_launches += 1;
         phase_mark(c, FITSNE_PHASE_CENTER);
-        CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1, 1));
+        CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1));
     } else {
         // sharded tail: local update -> local sums / bounds -> 128-byte records all-gathered -> every rank centres its own
         // slice with the global mean and publishes the (identical) global bounds.  Y itself is gathered next iteration.
-        k_update<D, true><<<cdiv(rows, 256), 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
-                                                          c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
+        k_update<D, true><<<ublocks, 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
+                                                  c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         phase_mark(c, FITSNE_PHASE_CENTER);
         k_shard_stats<D><<<SHARD_BLOCKS, 256, 0, st>>>(c->Yb, c->row_begin, c->row_end, c->rank, c->gp, c->shard_sum_partial,
                                                       c->shard_mm_partial, c->shard_stats + c->rank, c->tickets + 3);
@@ -978,6 +995,9 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_ag, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithPriority(&c->stream_k, cudaStreamNonBlocking, prio_hi));
+    CK(cudaEventCreateWithFlags(&c->ev_kfork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_kjoin, cudaEventDisableTiming));
     c->ktimes_on = getenv("FITSNE_KTIMES") && atoi(getenv("FITSNE_KTIMES")) != 0;
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_attract<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -985,10 +1005,12 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaFuncSetAttribute(k_attract<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_attract<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CK(cudaFuncSetAttribute(k_fft_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CK(cudaFuncSetAttribute(k_fft_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CK(cudaFuncSetAttribute((k_fft_pass<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CK(cudaFuncSetAttribute((k_fft_pass<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_fft_line, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_conv_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_conv_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_kspec_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_kspec_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_conv_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 
     const size_t yel = (size_t) c->per * world * no_dims;
     c->y_elems = yel;
@@ -1034,9 +1056,8 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
         CKRC(dev_alloc(c, &c->slots, (size_t) cdiv(c->nloc, CHUNK) * 2 * nodes));
     }
     CKRC(dev_alloc(c, &c->colsum_partial, (size_t) RED_BLOCKS * 2));
-    CKRC(dev_alloc(c, &c->update_partial, (size_t) cdiv(c->nloc, 256) * 2 + 2));
     CKRC(dev_alloc(c, &c->bounds_partial, (size_t) RED_BLOCKS));
-    CKRC(dev_alloc(c, &c->zpartial, (size_t) Z_BLOCKS));
+    CKRC(dev_alloc(c, &c->zpartial, (size_t) 4096));     // per-column (2-D, <= M/2+1) or per-block (1-D) Parseval partials
     CKRC(dev_alloc(c, &c->kl_partial, (size_t) 4096));
     CKRC(dev_alloc(c, &c->gp, (size_t) 1)); CKRC(dev_alloc(c, &c->sp, (size_t) 1)); CKRC(dev_alloc(c, &c->sc, (size_t) 1));
     CKRC(dev_alloc(c, &c->mismatch, (size_t) 1));
@@ -1093,12 +1114,13 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->stream3) cudaStreamSynchronize(c->stream3);
+    if (c->stream_k) cudaStreamSynchronize(c->stream_k);
     drop_graphs(c);
     for (auto &p : c->plans) if (p.second.W) cudaFree(p.second.W);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->col_P, c->val_P, c->keys[0], c->keys[1],
                     c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->hist, c->sort_totals, c->slots, c->attr, c->planes,
-                    c->compact, c->colsum_partial, c->update_partial, c->zpartial, c->kl_partial, c->bounds_partial,
+                    c->chg, c->pot, c->S, c->KR, c->KS, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->col_P2, c->val_P2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
                     c->nonempty, c->gp_reorder, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial, c->srt_cnt, c->srt_start, c->srt_cur};
@@ -1110,6 +1132,9 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_ag) cudaEventDestroy(c->ev_ag);
+    if (c->ev_kfork) cudaEventDestroy(c->ev_kfork);
+    if (c->ev_kjoin) cudaEventDestroy(c->ev_kjoin);
+    if (c->stream_k) cudaStreamDestroy(c->stream_k);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream3) cudaStreamDestroy(c->stream3);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1371,8 +1396,6 @@ int fitsne_last_run_ms(fitsne_ctx *c, double *ms) {
 int fitsne_get_stats(fitsne_ctx *c, fitsne_stats *out) {
     if (!c || !out) return FITSNE_EINVAL;
     CK(cudaStreamSynchronize(c->stream));
-    CKRC(read_scalars(c));
-    c->stats.spectrum_cache_hits = c->host_sc->kc_hits - c->kc_hits_base;
     c->stats.reorders = c->reorders;
     *out = c->stats;
     return 0;
@@ -1381,7 +1404,6 @@ int fitsne_get_stats(fitsne_ctx *c, fitsne_stats *out) {
 int fitsne_reset_stats(fitsne_ctx *c) {
     if (!c) return FITSNE_EINVAL;
     const fitsne_stats old = c->stats;
-    if (read_scalars(c) == 0) c->kc_hits_base = c->host_sc->kc_hits;
     c->stats = fitsne_stats{};
     c->stats.n_boxes = old.n_boxes; c->stats.grid_side = old.grid_side; c->stats.fft_side = old.fft_side;
     c->stats.min_coord = old.min_coord; c->stats.max_coord = old.max_coord;
@@ -1420,7 +1442,8 @@ int fitsne_debug_copy(fitsne_ctx *c, const char *what, void *dst, size_t dst_byt
     else if (!strcmp(what, "perm")) { src = c->perm[sorted_buf]; bytes = (size_t) c->nloc * 4; }
     else if (!strcmp(what, "keys")) { src = c->keys[sorted_buf]; bytes = (size_t) c->nloc * 4; }
     else if (!strcmp(what, "box_start")) { src = c->box_start; bytes = ((c->D == 2 ? (size_t) c->cur_B * c->cur_B : (size_t) c->cur_B) + 1) * 4; }
-    else if (!strcmp(what, "planes")) { src = c->planes; bytes = (c->D == 2 ? (size_t) c->cur_M * c->cur_M : (size_t) c->cur_M) * 4 * sizeof(float2); }
+    else if (!strcmp(what, "grid") && c->D == 2) { src = c->chg; bytes = (size_t) c->stats.grid_side * c->stats.grid_side * sizeof(float4); }
+    else if (!strcmp(what, "pot") && c->D == 2) { src = c->pot; bytes = (size_t) c->stats.grid_side * c->stats.grid_side * sizeof(float4); }
     else return fail(c, FITSNE_EINVAL, "unknown debug array '%s'", what);
     if (needed) *needed = bytes;
     if (!dst) return 0;

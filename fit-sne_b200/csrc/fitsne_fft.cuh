@@ -1,17 +1,15 @@
-// fitsne_fft.cuh -- hand-written shared-memory FFTs for the circulant kernel convolution (nbodyfft.cpp:150-217).
+// fitsne_fft.cuh -- hand-written shared-memory FFT building blocks for the circulant kernel convolution
+// (nbodyfft.cpp:150-217, :401-433).
 //
 // Why not cuFFT: on sm_100 cuFFT finalises (JIT-compiles) kernels at plan-creation time -- 1-3 s per new FFT
 // length on a machine that has not seen it -- and the grid size of a t-SNE run drifts through a dozen lengths,
 // so plan creation cost more wall-clock than the whole optimisation.  These kernels
-// need no plans, work for every length 2^a 3^b 5^c <= 4096 (8192 in 1-D), and let the convolution use:
-//   * two real planes per complex transform (w1 + i*delta_x, ...), separated inside the Hadamard kernel;
-//   * pruning: only the G non-zero rows of the zero-padded input are row-transformed, and only the G rows of the
-//     output that the gather reads are inverse row-transformed;
-//   * in-place passes: rows (contiguous) then columns (tiles of FFT_TC adjacent columns, 32-byte segments).
+// need no plans and work for every length 2^a 3^b 5^c <= 4096 (8192 in 1-D).
 // Algorithm: Stockham autosort, decimation in frequency, mixed radix 8/4/2/3/5, ping-pong in shared memory, one
-// __syncthreads per stage; twiddles from a per-length fp32 table computed in fp64.  The inverse transform is
-// conj(FFT(conj(x))) (conjugation folded into the global loads/stores); normalisation is folded into the kernel
-// samples (k_gen_kernels), as before.
+// __syncthreads per stage, natural order in and out; twiddles from a per-length fp32 table computed in fp64.  The
+// inverse transform is conj(FFT(conj(x))); normalisation is folded into the kernel samples.
+// Users: the row passes of the 2-D convolution (fitsne_conv.cuh; its column pass has its own in-place transform) and the
+// 1-D convolution (k_fft_line below).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,7 +17,6 @@
 namespace fk {
 
 constexpr int FFT_MAX_STAGES = 14;
-constexpr int FFT_THREADS = 512;
 
 // shared-memory index skew: one pad slot every 8 elements turns the stride-R / stride-8R writes of the first Stockham
 // stages (which would hit 2 of the 16 eight-byte bank pairs) into conflict-free or 2-way patterns
@@ -60,28 +57,18 @@ struct FftPlan {
     int tpl_log2[FFT_MAX_STAGES];      // per stage: log2(butterfly slots per line group), see fft_stage
 };
 
-// wide == false: radices 8/4/2/3/5 (the round-1 plan).  wide == true: also 16 and 9, which turns the 4-5 stages of the
-// lengths a t-SNE grid produces (1152 = 8*8*2*3*3, 1280 = 8*8*4*5, 1024 = 8*8*8*2) into 3 (16*8*9, 16*16*5, 16*16*4):
-// every stage is a full pass over shared memory plus a barrier, so fewer, wider stages is less of everything but FMAs.
-__host__ inline bool fft_make_plan(int n, FftPlan *p, bool wide = false) {
+__host__ inline bool fft_make_plan(int n, FftPlan *p) {
     p->n = n; p->nstages = 0;
     int m = n;
     auto take = [&](int r) { while (m % r == 0 && p->nstages < FFT_MAX_STAGES) { p->radix[p->nstages++] = r; m /= r; } };
-    if (wide) {
-        take(16);
-        // leftover power of two next (8, 4 or 2), then nines, threes, fives
-        take(8); take(4); take(2); take(9); take(3); take(5);
-    } else {
-        take(8); take(4); take(2); take(3); take(5);
-    }
+    take(8); take(4); take(2); take(3); take(5);
     if (m != 1) return false;
     int sacc = 1;
     for (int st = 0; st < p->nstages; st++) {
         p->div_s[st] = make_fastdiv((uint32_t) sacc);
         sacc *= p->radix[st];
-        // butterfly slots per line group: the power of two >= the stage's butterflies per line (n / radix), 32..256
-        // (narrow plans keep the round-1 value: the power of two >= n/8 for every stage)
-        const int per = wide ? n / p->radix[st] : n / 8;
+        // butterfly slots per line group: the power of two >= n/8, 32..256
+        const int per = n / 8;
         int l2 = 5;
         while ((1 << l2) < per && l2 < 8) l2++;
         p->tpl_log2[st] = l2;
@@ -152,61 +139,6 @@ __host__ __device__ __forceinline__ void dft_small<5>(float2 (&a)[5]) {
     a[1] = cadd(p1, q1); a[4] = csub(p1, q1); a[2] = cadd(p2, q2); a[3] = csub(p2, q2);
 }
 
-// Wide radices as one Cooley-Tukey step in registers: N = N1*N2, input n = N2*n1 + n2, output k = k1 + N1*k2,
-//   X[k1 + N1*k2] = sum_n2 w_N^(n2*k1) * (sum_n1 x[N2*n1 + n2] w_N1^(n1*k1)) * w_N2^(n2*k2).
-// The inner twiddles w_N^(n2*k1) are literals (multiplying by a literal complex number).
-__host__ __device__ __forceinline__ float2 cmulc(float2 a, float c, float s) {      // a * (c - i*s), i.e. times exp(-i*theta)
-    return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
-}
-template <>
-__host__ __device__ __forceinline__ void dft_small<16>(float2 (&a)[16]) {
-    // 16 = 4 x 4.  cos/sin of k*pi/8
-    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
-    float2 y[4][4];
-#pragma unroll
-    for (int n2 = 0; n2 < 4; n2++) {
-        float2 t[4] = {a[n2], a[4 + n2], a[8 + n2], a[12 + n2]};
-        dft_small<4>(t);
-#pragma unroll
-        for (int k1 = 0; k1 < 4; k1++) y[n2][k1] = t[k1];
-    }
-    // twiddles w16^(n2*k1): exponents 1,2,3 / 2,4,6 / 3,6,9
-    y[1][1] = cmulc(y[1][1], c1, s1); y[1][2] = cmulc(y[1][2], h, h);     y[1][3] = cmulc(y[1][3], s1, c1);
-    y[2][1] = cmulc(y[2][1], h, h);   y[2][2] = mul_mi(y[2][2]);          y[2][3] = cmulc(y[2][3], -h, h);
-    y[3][1] = cmulc(y[3][1], s1, c1); y[3][2] = cmulc(y[3][2], -h, h);    y[3][3] = cmulc(y[3][3], -c1, -s1);
-#pragma unroll
-    for (int k1 = 0; k1 < 4; k1++) {
-        float2 t[4] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1]};
-        dft_small<4>(t);
-#pragma unroll
-        for (int k2 = 0; k2 < 4; k2++) a[k1 + 4 * k2] = t[k2];
-    }
-}
-template <>
-__host__ __device__ __forceinline__ void dft_small<9>(float2 (&a)[9]) {
-    // 9 = 3 x 3.  cos/sin of 40, 80 and 160 degrees
-    const float c1 = 0.76604444311897803520f, s1 = 0.64278760968653932632f;
-    const float c2 = 0.17364817766693034885f, s2 = 0.98480775301220805937f;
-    const float c4 = -0.93969262078590838405f, s4 = 0.34202014332566873304f;
-    float2 y[3][3];
-#pragma unroll
-    for (int n2 = 0; n2 < 3; n2++) {
-        float2 t[3] = {a[n2], a[3 + n2], a[6 + n2]};
-        dft_small<3>(t);
-#pragma unroll
-        for (int k1 = 0; k1 < 3; k1++) y[n2][k1] = t[k1];
-    }
-    y[1][1] = cmulc(y[1][1], c1, s1); y[1][2] = cmulc(y[1][2], c2, s2);
-    y[2][1] = cmulc(y[2][1], c2, s2); y[2][2] = cmulc(y[2][2], c4, s4);
-#pragma unroll
-    for (int k1 = 0; k1 < 3; k1++) {
-        float2 t[3] = {y[0][k1], y[1][k1], y[2][k1]};
-        dft_small<3>(t);
-#pragma unroll
-        for (int k2 = 0; k2 < 3; k2++) a[k1 + 3 * k2] = t[k2];
-    }
-}
-
 // One Stockham stage of radix R for `batch` independent length-N sequences stored at x + b*NS, written to y + b*NS.
 // Sub-problem (n_cur, s): butterflies t in [0, N/R): p = t / s, q = t % s, m = n_cur / R,
 //   a_k = x[q + s*(p + k*m)],  y[q + s*(R*p + j)] = (sum_k a_k w_R^{jk}) * W_N[p*j*s].   W lives in shared memory.
@@ -256,7 +188,6 @@ __host__ __device__ __forceinline__ void fft_stage(const float2 *__restrict__ x,
 
 // One thread's share of stage `st` (x -> y).  Host-callable: tests/tools/fft_emul.cu runs every thread of a CTA through a
 // stage, then the next stage -- what the barrier in fft_smem enforces -- and compares with a direct DFT.
-template <bool WIDE>
 __host__ __device__ __forceinline__ void fft_run_stage(const float2 *x, float2 *y, int NS, int batch, const FftPlan &plan, int st,
                                                        int n_cur, int s, const float2 *__restrict__ W, int tid, int nthreads) {
     const int N = plan.n;
@@ -264,21 +195,20 @@ __host__ __device__ __forceinline__ void fft_run_stage(const float2 *x, float2 *
     const FastDiv ds = plan.div_s[st];
     const int tl = plan.tpl_log2[st];
     if (r == 8) fft_stage<8>(x, y, N, NS, batch, n_cur, s, ds, tl, W, tid, nthreads);
-    else if (WIDE && r == 16) fft_stage<16>(x, y, N, NS, batch, n_cur, s, ds, tl, W, tid, nthreads);
     else if (r == 4) fft_stage<4>(x, y, N, NS, batch, n_cur, s, ds, tl, W, tid, nthreads);
     else if (r == 2) fft_stage<2>(x, y, N, NS, batch, n_cur, s, ds, tl, W, tid, nthreads);
-    else if (WIDE && r == 9) fft_stage<9>(x, y, N, NS, batch, n_cur, s, ds, tl, W, tid, nthreads);
     else if (r == 3) fft_stage<3>(x, y, N, NS, batch, n_cur, s, ds, tl, W, tid, nthreads);
     else fft_stage<5>(x, y, N, NS, batch, n_cur, s, ds, tl, W, tid, nthreads);
 }
 
-// Runs all stages (ping-pong between a and b); returns the buffer holding the result.
-template <bool WIDE>
+#ifdef __CUDACC__
+// Runs all stages (ping-pong between a and b); returns the buffer holding the result.  W may live in shared or global
+// memory.  Every stage ends with a barrier.
 __device__ __forceinline__ float2 *fft_smem(float2 *a, float2 *b, int NS, int batch, const FftPlan &plan, const float2 *__restrict__ W) {
     int n_cur = plan.n, s = 1;
     float2 *x = a, *y = b;
     for (int st = 0; st < plan.nstages; st++) {
-        fft_run_stage<WIDE>(x, y, NS, batch, plan, st, n_cur, s, W, (int) threadIdx.x, (int) blockDim.x);
+        fft_run_stage(x, y, NS, batch, plan, st, n_cur, s, W, (int) threadIdx.x, (int) blockDim.x);
         __syncthreads();
         n_cur /= plan.radix[st]; s *= plan.radix[st];
         float2 *t = x; x = y; y = t;
@@ -286,99 +216,35 @@ __device__ __forceinline__ float2 *fft_smem(float2 *a, float2 *b, int NS, int ba
     return x;
 }
 
-// In-place FFT of `lines` rows (COLS=false: contiguous) or columns (COLS=true: `lines` adjacent columns, row pitch M)
-// per CTA: one large CTA per SM, all of its global loads issued before the first use (FFT_EPT independent loads per
-// thread, 64-byte column segments), Stockham stages in shared memory, store back.
-//   rows: grid = (ceil(rows_total / lines), nplanes); prune_mask bit i set => plane i only needs rows < *g_rows
-//         (g_rows points at GridParams::G on the device)
-//   cols: grid = (ceil(M / lines), nplanes)
-//   forward passes (inverse == 0): prune_mask bit i also says "plane i is a zero-padded G x G corner": everything outside
-//   the corner is taken as zero WITHOUT being read (rows pass: columns >= G; columns pass: rows >= G), so the padding never
-//   has to be written to memory and whatever an earlier iteration left there is ignored.
-// Dynamic smem: (2 * lines * fft_buf_len(M, lines) + M) float2.  Requires M * lines <= FFT_EPT * FFT_THREADS.
-constexpr int FFT_EPT = 24;
-
-// WIDE: the plan may contain radix-16 / radix-9 stages (separate instantiation: the wide butterflies need ~2x the
-// registers, which must not cost the narrow kernel its occupancy at small M)
-template <bool COLS, bool WIDE = false>
-__global__ void __launch_bounds__(FFT_THREADS) k_fft_pass(float2 *__restrict__ data, size_t plane, int rows_total, int lines,
-                                                             FftPlan plan, const float2 *__restrict__ W, int inverse, unsigned prune_mask,
-                                                             const int *__restrict__ g_rows, const int *__restrict__ ok,
-                                                             const unsigned *__restrict__ skip_mask) {
+// 1-D embeddings: in-place FFT of one length-M line per CTA (grid = number of lines, line l at data + l*M).
+//   zero_from != nullptr (forward passes of the charge lines): elements >= *zero_from are taken as zero without being read.
+// Dynamic smem: (2 * fft_buf_len(M, 1) + M) float2.
+constexpr int FFT_THREADS = 512;
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_line(float2 *__restrict__ data, FftPlan plan, const float2 *__restrict__ W, int inverse,
+                                                          unsigned zero_mask, const int *__restrict__ zero_from, const int *__restrict__ ok) {
     if (ok && !*ok) return;
-    if (skip_mask && ((*skip_mask >> blockIdx.y) & 1u)) return;      // plane keeps its (cached) contents this iteration
     extern __shared__ float2 fft_sm[];
-    // the stage loop indexes the plan dynamically: keep it in shared memory, not in the (slow to index) parameter bank
     __shared__ FftPlan plan_s;
     for (int i = threadIdx.x; i < (int) (sizeof(FftPlan) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&plan_s)[i] = reinterpret_cast<const int *>(&plan)[i];
-    const int M = plan.n, NS = fft_buf_len(M, lines);
-    const int l0 = blockIdx.x * lines;
-    int limit = COLS ? M : rows_total;
-    if (!COLS && ((prune_mask >> blockIdx.y) & 1u)) limit = min(limit, *g_rows);
-    if (l0 >= limit) return;
-    const int nl = min(lines, limit - l0);
-    const bool zpad = !inverse && ((prune_mask >> blockIdx.y) & 1u);
-    const int gz = zpad ? *g_rows : M;                                 // data extent along the transformed axis
-    float2 *bufa = fft_sm, *bufb = fft_sm + (size_t) lines * NS, *Ws = fft_sm + (size_t) 2 * lines * NS;
+    const int M = plan.n, NS = fft_buf_len(M, 1);
+    const int gz = ((zero_mask >> blockIdx.x) & 1u) ? *zero_from : M;
+    float2 *bufa = fft_sm, *bufb = fft_sm + NS, *Ws = fft_sm + 2 * NS;
     for (int i = threadIdx.x; i < M; i += blockDim.x) Ws[i] = W[i];
-    float2 *base = data + (size_t) blockIdx.y * plane + (COLS ? (size_t) l0 : (size_t) l0 * M);
-    // staging without integer divisions: rows line by line (contiguous); columns with `lines` a power of two
-    // (i -> pos = i >> lg, line = i & (lines-1); full tiles only, M is a multiple of 16)
-    int lg = 0;
-    while ((1 << lg) < lines) lg++;
-    if (COLS) {
-        const int total = M << lg;
-        float2 v[FFT_EPT];
-#pragma unroll
-        for (int u = 0; u < FFT_EPT; u++) {
-            const int i = threadIdx.x + u * blockDim.x;
-            if (i < total) v[u] = (i >> lg) < gz ? base[(size_t) (i >> lg) * M + (i & (lines - 1))] : make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < FFT_EPT; u++) {
-            const int i = threadIdx.x + u * blockDim.x;
-            if (i < total) {
-                if (inverse) v[u].y = -v[u].y;
-                bufa[(i & (lines - 1)) * NS + fft_phys(i >> lg)] = v[u];
-            }
-        }
-    } else {
-        for (int ln = 0; ln < nl; ln++) {
-            const float2 *src = base + (size_t) ln * M;
-            float2 *dst = bufa + ln * NS;
-#pragma unroll 2
-            for (int pos = threadIdx.x; pos < M; pos += blockDim.x) {
-                float2 v = pos < gz ? src[pos] : make_float2(0.f, 0.f);
-                if (inverse) v.y = -v.y;
-                dst[fft_phys(pos)] = v;
-            }
-        }
+    float2 *line = data + (size_t) blockIdx.x * M;
+    for (int pos = threadIdx.x; pos < M; pos += blockDim.x) {
+        float2 v = pos < gz ? line[pos] : make_float2(0.f, 0.f);
+        if (inverse) v.y = -v.y;
+        bufa[fft_phys(pos)] = v;
     }
     __syncthreads();
-    const float2 *res = fft_smem<WIDE>(bufa, bufb, NS, nl, plan_s, Ws);
-    if (COLS) {
-        const int total = M << lg;
-#pragma unroll 4
-        for (int u = 0; u < FFT_EPT; u++) {
-            const int i = threadIdx.x + u * blockDim.x;
-            if (i < total) {
-                float2 v = res[(i & (lines - 1)) * NS + fft_phys(i >> lg)];
-                if (inverse) v.y = -v.y;
-                base[(size_t) (i >> lg) * M + (i & (lines - 1))] = v;
-            }
-        }
-    } else {
-        for (int ln = 0; ln < nl; ln++) {
-            float2 *dstg = base + (size_t) ln * M;
-            const float2 *srcs = res + ln * NS;
-            for (int pos = threadIdx.x; pos < M; pos += blockDim.x) {
-                float2 v = srcs[fft_phys(pos)];
-                if (inverse) v.y = -v.y;
-                dstg[pos] = v;
-            }
-        }
+    const float2 *res = fft_smem(bufa, bufb, NS, 1, plan_s, Ws);
+    for (int pos = threadIdx.x; pos < M; pos += blockDim.x) {
+        float2 v = res[fft_phys(pos)];
+        if (inverse) v.y = -v.y;
+        line[pos] = v;
     }
 }
+#endif  // __CUDACC__
 
 }  // namespace fk

@@ -30,7 +30,7 @@ constexpr int SORT_MAX_BITS = 11;     // widest radix digit
 constexpr int SORT_ONE_PASS_BITS = 8; // keys this short sort in ONE pass.  (Measured on B200: a single 12-bit pass -- 4096 bins --
                                       // is slower than two 6-bit passes: 84 vs 70 us at N=1M; so only short 1-D keys qualify.)
 constexpr int RED_BLOCKS = 592;   // 4 x 148 SMs: partial-reduction width for bounds / column sums
-constexpr int Z_BLOCKS = 592;
+constexpr int Z_BLOCKS_1D = 32;      // Parseval partials of the 1-D Hadamard kernel
 constexpr int SHARD_BLOCKS = 148;  // one CTA per SM: per-rank sums / bounds of the local slice (sharded runs)
 
 // Device-resident description of this iteration's interpolation grid.  Rewritten every iteration by
@@ -46,11 +46,7 @@ struct GridParams {
     int B, G, M, p, xbits, nb, ok;
     int sort_bits;        // radix digit width
     int sort_passes;      // 1: the whole key is one digit (<= SORT_MAX_BITS bits); 2: two LSD passes of sort_bits each
-    int kmode;            // kernel spectra this iteration: 0 = sample + transform at h, 1 = first-order Taylor from the cache
-    int with_deriv;       // kmode 0 only: also sample + transform dK/dh (so that later iterations can use kmode 1)
-    unsigned fft_skip;    // bit i set: forward FFT passes leave plane i alone this iteration
-    float dh;             // h - h0 of the cached spectra (kmode 1)
-    int pad_;
+    int pad_[3];
     float s[PMAX];        // in-box node positions (k+1/2)/p, accumulated like nbodyfft.cpp:30-34
     float inv_den[PMAX];  // 1/prod_{j!=i}(s_i-s_j)          nbodyfft.cpp:313-321
 };
@@ -70,22 +66,7 @@ struct Scalars {          // small device-resident results
     float bmin, bmax;     // bounds of the current Y (with the 2-D scan quirk)
     double kl;
     unsigned long long iter_done;   // optimiser steps that really executed (speculative launches that found a grid mismatch do not count)
-    // kernel-spectrum cache (planes 2..5 hold K^(h0) and dK^/dh(h0)): see k_setup_grid
-    double kc_h0, kc_hprev;
-    int kc_B, kc_M, kc_valid, kc_has_deriv;
-    unsigned long long kc_hits;     // iterations served from the cache
 };
-
-// Kernel-spectrum cache.  The kernel samples depend on the grid only through the node spacing h (and n_boxes / M), and
-// h drifts by ~1e-4 per iteration late in a run.  Instead of re-sampling and re-transforming the four kernel planes
-// every iteration (~45 % of the convolution), iterations whose h is within KC_MAX_REL of the cached h0 use
-//   K^(h) = K^(h0) + (h - h0) * dK^/dh (h0)
-// (second-order term <= 10 (dh/h)^2 relative = 1e-5 at the limit: two decades inside the 1e-4 gradient tolerance).
-// dK/dh planes are only built when h moved slowly since the previous iteration, so the fast-drift early phase pays
-// nothing extra.  Exactness is restored at every refresh; reference parity is kept (tests/test_gpu_parity.py).
-constexpr double KC_MAX_REL = 1.0e-3;    // |h - h0| / h0 beyond which the spectra are refreshed
-constexpr double KC_SLOW_REL = 2.5e-4;   // |h - h_prev| / h below which a refresh also builds dK/dh
-
 
 // ------------------------------------------------------------------------------------------ helpers --
 
@@ -153,62 +134,22 @@ __device__ __forceinline__ int box_of(float y, const GridParams &gp, float &u) {
 
 // ------------------------------------------------------------------------- column sums, centring, bounds --
 
-// partial[b*D+d] = sum of Y[:,d] over block b's contiguous slice (fixed order -> deterministic)
-template <int D>
-__global__ void __launch_bounds__(256) k_colsum(const float *__restrict__ Y, int N, double *__restrict__ partial,
-                                                const GridParams *__restrict__ gpp) {
-    __shared__ double sm[32];
-    if (gpp && !gpp->ok) return;
-    const int per = (N + gridDim.x - 1) / gridDim.x;
-    const int b = blockIdx.x * per, e = min(N, b + per);
-    double s0 = 0, s1 = 0;
-    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
-        if (D == 2) {
-            float2 v = reinterpret_cast<const float2 *>(Y)[i];
-            s0 += v.x; s1 += v.y;
-        } else s0 += Y[i];
-    }
-    double r0 = block_sum(s0, sm);
-    if (threadIdx.x == 0) partial[blockIdx.x * D] = r0;
-    if (D == 2) {
-        double r1 = block_sum(s1, sm);
-        if (threadIdx.x == 0) partial[blockIdx.x * D + 1] = r1;
-    }
-}
-
 // Yout = Yin - mean (tsne.cpp:1851-1876) and per-block (min,max) of the centred values.
 // 2-D min follows the reference's `if (>max) .. else if (<min)` scan (tsne.cpp:1045-1048): values in the
 // strictly ascending prefix of the interleaved sequence x0,y0,x1,y1,... only ever update max, so the min is
 // taken over flat indices >= t, t = length of that prefix.  1-D uses plain min/max (tsne.cpp:769-772).
 template <int D>
 __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__ Yin, float *__restrict__ Yout, int N,
-                                                       const double *__restrict__ colsum_partial, int nparts,
                                                        int do_center, float2 *__restrict__ bounds_partial,
                                                        Scalars *__restrict__ sc, const uint32_t *__restrict__ orig_of,
                                                        const uint32_t *__restrict__ pos_of, const GridParams *__restrict__ gpp,
-                                                       volatile float *host_bounds, unsigned int *__restrict__ ticket,
-                                                       int mean_ready) {
-    __shared__ double smd[32];
+                                                       volatile float *host_bounds, unsigned int *__restrict__ ticket) {
     if (gpp && !gpp->ok) return;
     __shared__ float smf[64];
-    __shared__ double mean_s[2];
     __shared__ int t_s;
     double mean[2] = {0, 0};
-    if (do_center) {
-        if (mean_ready) {            // k_update's last block already reduced the column sums (single-GPU path)
-            for (int d = 0; d < D; d++) mean[d] = sc->mean[d];
-        } else {
-            // every block re-reduces the (few hundred) partials in the same fixed order
-            for (int d = 0; d < D; d++) {
-                double s = 0;
-                for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += colsum_partial[i * D + d];
-                double r = block_sum(s, smd);
-                if (threadIdx.x == 0) mean_s[d] = r / (double) N;
-            }
-            __syncthreads();
-            for (int d = 0; d < D; d++) mean[d] = mean_s[d];
-            if (blockIdx.x == 0 && threadIdx.x == 0) { sc->mean[0] = mean[0]; sc->mean[1] = mean[1]; }
-        }
+    if (do_center) {                 // k_update's last block reduced the column sums of the new positions
+        for (int d = 0; d < D; d++) mean[d] = sc->mean[d];
     }
     const int nflat = N * D;
     if (threadIdx.x == 0) {
@@ -339,8 +280,7 @@ __host__ __device__ inline int sort_bits_for(int B, int dims) {
 
 // Fill GridParams for a grid of B boxes/dim (the host's choice; verified against the device's own bounds).
 __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restrict__ sc, const int *__restrict__ B_host, int M, int p, int dims,
-                             double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals,
-                             Scalars *__restrict__ scw, int use_kernel_cache, int kpack) {
+                             double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals) {
     for (int i = threadIdx.x; i < 2 * (1 << SORT_MAX_BITS); i += blockDim.x) sort_totals[i] = 0;   // both passes
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     // B_host > 0: the host sized the grid after reading the bounds (single-step API); 0: speculative launch, the device
@@ -364,32 +304,8 @@ __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restr
     while ((1 << xb) < B) xb++;
     gp->xbits = xb;
     sort_layout(B, dims, &gp->sort_bits, &gp->sort_passes);
-    gp->pad_ = 0;
+    gp->pad_[0] = gp->pad_[1] = gp->pad_[2] = 0;
     gp->nb = dims == 2 ? B * B : B;
-    // kernel-spectrum cache decision (only for iterations that will really run)
-    // plane roles: 2,3 = kernel spectra, 4,5 = their d/dh; packed layout (kpack): 2 = all four kernels, 3 = d/dh, 4,5 unused
-    const unsigned skip_deriv = kpack ? 0x38u : 0x30u, skip_none = kpack ? 0x30u : 0u;
-    gp->kmode = 0; gp->with_deriv = 0; gp->dh = 0.f; gp->fft_skip = skip_deriv;   // derivative planes idle by default
-    if (gp->ok) {
-        const double h = gp->h;
-        if (use_kernel_cache) {
-            const bool same = scw->kc_valid && scw->kc_B == B && scw->kc_M == M;
-            if (same && scw->kc_has_deriv && fabs(h - scw->kc_h0) <= KC_MAX_REL * scw->kc_h0) {
-                gp->kmode = 1;
-                scw->kc_hits += 1;
-                gp->dh = (float) (h - scw->kc_h0);
-                gp->fft_skip = 0x3cu;                    // kernel planes 2..5 keep the cached spectra
-            } else {
-                const bool slow = !scw->kc_valid || (scw->kc_B == B && fabs(h - scw->kc_hprev) <= KC_SLOW_REL * h);
-                gp->with_deriv = slow ? 1 : 0;
-                gp->fft_skip = slow ? skip_none : skip_deriv;
-                scw->kc_h0 = h; scw->kc_B = B; scw->kc_M = M; scw->kc_valid = 1; scw->kc_has_deriv = slow ? 1 : 0;
-            }
-        } else {
-            scw->kc_valid = 0;
-        }
-        scw->kc_hprev = h;
-    }
     double s[PMAX];
     const double hh = 1.0 / (double) p;
     s[0] = hh / 2;
@@ -678,24 +594,30 @@ __host__ __device__ __forceinline__ int key_to_box(uint32_t key, const GridParam
     return D == 2 ? (int) (key >> gp.xbits) * gp.B + (int) (key & ((1u << gp.xbits) - 1u)) : (int) key;
 }
 
-// Spread results live in two packed complex planes (two real grids per complex transform, see fitsne_fft.cuh):
-//   plane 0 = (w1, delta_x)   plane 1 = (delta_y, wbb)        [1-D: (w1, delta), (wbb, 0)]
-// delta and wbb are kept in BOX UNITS (offsets / box width): every plane is then O(w1) whatever the embedding's
-// scale, which is what makes packing two real planes into one fp32 complex transform safe (a 1e-5-scale plane
-// packed beside an O(1) plane would lose 5 digits in the separation).
-__host__ __device__ __forceinline__ void store_node(float2 *__restrict__ dst, size_t stride, size_t off, float4 v) {
-    dst[off] = make_float2(v.x, v.y);
-    dst[stride + off] = make_float2(v.z, v.w);
+// Spread results.  delta and wbb are kept in BOX UNITS (offsets / box width): every component is then O(w1) whatever the
+// embedding's scale, which is what makes packing two real grids into one fp32 complex transform safe (a 1e-5-scale grid
+// packed beside an O(1) grid would lose 5 digits in the separation).
+//   2-D: one float4 per node, chg[(y node) * G + (x node)] = (w1, delta_x, delta_y, wbb): the dense G x G grid that
+//        k_conv_rows_fwd reads row by row (and that sharded runs all-reduce as it is);
+//   1-D: two packed complex lines of length M, plane 0 = (w1, delta), plane 1 = (wbb, 0), the FFT input itself.
+template <int D>
+__host__ __device__ __forceinline__ void store_node(void *__restrict__ grid, size_t stride, size_t off, float4 v) {
+    if (D == 2) {
+        reinterpret_cast<float4 *>(grid)[off] = v;
+    } else {
+        float2 *dst = reinterpret_cast<float2 *>(grid);
+        dst[off] = make_float2(v.x, v.y);
+        dst[stride + off] = make_float2(v.z, v.w);
+    }
 }
 
-// offset of (box, node) inside one plane: padded FFT input (row stride M) or, multi-GPU, the compact G^D layout
+// offset of (box, node) in the spread grid
 template <int D>
-__host__ __device__ __forceinline__ size_t node_offset(int box, int node, const GridParams &gp, int p, bool compact) {
+__host__ __device__ __forceinline__ size_t node_offset(int box, int node, const GridParams &gp, int p) {
     if (D == 2) {
         const int by = box / gp.B, bx = box - by * gp.B;
         const int a = node / p, b = node - a * p;
-        const size_t rs = compact ? (size_t) gp.G : (size_t) gp.M;
-        return (size_t) (by * p + a) * rs + (size_t) (bx * p + b);
+        return (size_t) (by * p + a) * (size_t) gp.G + (size_t) (bx * p + b);
     }
     return (size_t) box * p + node;
 }
@@ -704,8 +626,7 @@ template <int D, int P>
 __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
                                                        const uint32_t *__restrict__ box_start, int n,
                                                        const GridParams *__restrict__ gpp, int chunks_per_block,
-                                                       float4 *__restrict__ slots, float2 *__restrict__ fft_in,
-                                                       float2 *__restrict__ compact) {
+                                                       float4 *__restrict__ slots, void *__restrict__ grid) {
     __shared__ GridParams gps;
     for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
@@ -723,9 +644,7 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
     const int ke = min(kb + CHUNK, n);
     const int a = D == 2 ? node / p : node, b = D == 2 ? node - a * p : 0;
     const float sa = gp.s[a], sb = gp.s[b];
-    float2 *dst = compact ? compact : fft_in;
-    const int Gc = gp.M / 2;
-    const size_t stride = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) gp.M * gp.M : (size_t) gp.M);
+    const size_t stride = (size_t) gp.M;              // 1-D: plane 0 -> plane 1
     float4 *myslots = slots + (size_t) c * 2 * nodes;
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -734,7 +653,7 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
         const int box = key_to_box<D>(skeys[k], gp);
         if (box != cur) {
             // segment of `cur` ended inside the chunk: finished box unless it started before the chunk
-            if ((int) box_start[cur] >= kb) store_node(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc);
+            if ((int) box_start[cur] >= kb) store_node<D>(grid, stride, node_offset<D>(cur, node, gp, p), acc);
             else myslots[node] = acc;
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
             cur = box;
@@ -758,7 +677,7 @@ __global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__
     }
     // last segment: finished only if the box both started in this chunk and ends with it
     const bool started_here = (int) box_start[cur] >= kb, ends_here = (int) box_start[cur + 1] <= ke;
-    if (started_here && ends_here) store_node(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc);
+    if (started_here && ends_here) store_node<D>(grid, stride, node_offset<D>(cur, node, gp, p), acc);
     else myslots[(started_here ? 1 : 0) * nodes + node] = acc;
 }
 
@@ -802,15 +721,14 @@ __host__ __device__ __forceinline__ void spread2_load(int t, int blk, const floa
 // all nodes of one box segment: to the grid (finished box; one box -> base offset computed once) or to a slot
 template <int D, int P, int NODES>
 __host__ __device__ __forceinline__ void spread2_flush(const float4 (&acc)[NODES], bool to_grid, int box, const GridParams &gp,
-                                                       float2 *__restrict__ dst, size_t stride, bool is_compact,
-                                                       float4 *__restrict__ slot) {
+                                                       void *__restrict__ grid, size_t stride, float4 *__restrict__ slot) {
     if (to_grid) {
-        const size_t base = node_offset<D>(box, 0, gp, P, is_compact);
-        const size_t rs = is_compact ? (size_t) gp.G : (size_t) gp.M;
+        const size_t base = node_offset<D>(box, 0, gp, P);
+        const size_t rs = (size_t) gp.G;
 #pragma unroll
         for (int j = 0; j < NODES; j++) {
             const size_t off = D == 2 ? base + (size_t) (j / P) * rs + (size_t) (j % P) : base + (size_t) j;
-            store_node(dst, stride, off, acc[j]);
+            store_node<D>(grid, stride, off, acc[j]);
         }
     } else {
 #pragma unroll
@@ -822,15 +740,13 @@ __host__ __device__ __forceinline__ void spread2_flush(const float4 (&acc)[NODES
 template <int D, int P>
 __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const Sp2Smem<D> &sm, const uint32_t *__restrict__ box_start,
                                                        int n, const GridParams &gp, float4 *__restrict__ slots,
-                                                       float2 *__restrict__ fft_in, float2 *__restrict__ compact) {
+                                                       void *__restrict__ grid) {
     constexpr int NODES = D == 2 ? P * P : P;
     const int c = blk * SP2_THREADS + t;
     const int kb = c * CHUNK;
     if (kb >= n) return;
     const int ke = kb + CHUNK < n ? kb + CHUNK : n;
-    float2 *dst = compact ? compact : fft_in;
-    const int Gc = gp.M / 2;
-    const size_t stride = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) gp.M * gp.M : (size_t) gp.M);
+    const size_t stride = (size_t) gp.M;              // 1-D: plane 0 -> plane 1
     float4 *myslots = slots + (size_t) c * 2 * NODES;
     const uint32_t *kp = sm.keys + t * SP2_STRIDE;
     float4 acc[NODES];
@@ -841,7 +757,7 @@ __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const Sp2
         const int box = key_to_box<D>(kp[k - kb], gp);
         if (box != cur) {
             // segment of `cur` ended inside the chunk: finished box unless it started before the chunk
-            spread2_flush<D, P, NODES>(acc, (int) box_start[cur] >= kb, cur, gp, dst, stride, compact != nullptr, myslots);
+            spread2_flush<D, P, NODES>(acc, (int) box_start[cur] >= kb, cur, gp, grid, stride, myslots);
 #pragma unroll
             for (int j = 0; j < NODES; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             cur = box;
@@ -881,15 +797,14 @@ __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const Sp2
     }
     // last segment: finished only if the box both started in this chunk and ends with it
     const bool started_here = (int) box_start[cur] >= kb, ends_here = (int) box_start[cur + 1] <= ke;
-    spread2_flush<D, P, NODES>(acc, started_here && ends_here, cur, gp, dst, stride, compact != nullptr,
-                               myslots + (started_here ? 1 : 0) * NODES);
+    spread2_flush<D, P, NODES>(acc, started_here && ends_here, cur, gp, grid, stride, myslots + (started_here ? 1 : 0) * NODES);
 }
 
 template <int D, int P>
 __global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks2(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
                                                                 const uint32_t *__restrict__ box_start, int n,
                                                                 const GridParams *__restrict__ gpp, float4 *__restrict__ slots,
-                                                                float2 *__restrict__ fft_in, float2 *__restrict__ compact) {
+                                                                void *__restrict__ grid) {
     __shared__ GridParams gps;
     __shared__ Sp2Smem<D> sm;
     for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
@@ -897,46 +812,35 @@ __global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks2(const float *__r
     spread2_load<D>(threadIdx.x, blockIdx.x, sorted_u, skeys, n, sm);
     __syncthreads();
     if (!gps.ok) return;
-    spread2_chunk<D, P>(threadIdx.x, blockIdx.x, sm, box_start, n, gps, slots, fft_in, compact);
+    spread2_chunk<D, P>(threadIdx.x, blockIdx.x, sm, box_start, n, gps, slots, grid);
 }
 
-// One thread group (LPN lanes, a power of two <= 32) per element of the output plane.  Inside the G^D corner:
-// empty box -> 0; box finished by a single chunk -> already written by k_spread_chunks; otherwise add the box's
-// slot partials in chunk order (lane-strided, then a fixed shuffle tree: deterministic for a given LPN).
-// 2-D: the index space is the (M/2)^2 corner that can hold data (G <= M/2); elements of it outside G^2 are left alone
-// and the zero padding of the FFT input is never materialised -- the forward FFT passes substitute zeros for everything
-// outside the G^2 corner while loading (k_fft_pass, prune_mask), so the launch shape still depends on M only.
-// 1-D: the whole length-M line, zeros included (tiny).  Multi-GPU (compact != nullptr): the plane is the dense Gcap^D
-// buffer (G^D values then zeros) that is all-reduced and then copied into the corner by k_pad_grids.
+// One thread group (LPN lanes, a power of two <= 32) per node of the spread grid: empty box -> 0; box finished by a
+// single chunk -> already written by the chunk kernel; otherwise add the box's slot partials in chunk order (lane-strided,
+// then a fixed shuffle tree: deterministic for a given LPN).
+// 2-D: the launch covers (M/2)^2 >= G^2 ids (its shape depends on M only); ids >= G^2 do nothing -- the zero padding of the
+// FFT input is never materialised (k_conv_rows_fwd substitutes zeros for columns >= G, k_conv_cols for rows >= G).
+// 1-D: the whole length-M line, zeros included (tiny).
 template <int D>
 __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ slots, const uint32_t *__restrict__ box_start,
-                                                        const GridParams *__restrict__ gpp, int lpn,
-                                                        float2 *__restrict__ fft_in, float2 *__restrict__ compact) {
+                                                        const GridParams *__restrict__ gpp, int lpn, void *__restrict__ grid) {
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
     const int G = gp.G, p = gp.p, M = gp.M;
     const size_t gid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     const size_t id = gid / lpn;
     const int sub = (int) (gid - id * lpn);
-    const int Gc = M / 2;
-    const size_t space = D == 2 ? (size_t) Gc * Gc : (compact ? (size_t) Gc : (size_t) M);      // index space of this launch
-    const size_t stride = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) M * M : (size_t) M);   // plane 0 -> plane 1
+    const size_t space = D == 2 ? (size_t) G * G : (size_t) M;
     const bool live = id < space;
     int row = 0, col = 0;
     bool inside = false;
     if (live) {
-        if (!compact) {
-            if (D == 2) { row = (int) (id / Gc); col = (int) (id - (size_t) row * Gc); } else col = (int) id;
-            inside = col < G && row < G;
-        } else {
-            const size_t GG = D == 2 ? (size_t) G * G : (size_t) G;
-            inside = id < GG;
-            if (D == 2) { row = (int) (id / G); col = (int) (id - (size_t) row * G); } else col = (int) id;
-        }
+        if (D == 2) { row = (int) (id / G); col = (int) (id - (size_t) row * G); inside = true; }
+        else { col = (int) id; inside = col < G; }
     }
-    // what to do with this element: 0 = leave (finished by k_spread_chunks), 1 = write acc (zero or the slot sum)
+    // what to do with this element: leave it (finished by the chunk kernel) or write acc (zero or the slot sum)
     int node = 0, nodes = 1, c0 = 0, c1 = -1;
-    bool write = live && (inside || compact != nullptr || D == 1);
+    bool write = live;
     if (inside) {
         int box;
         if (D == 2) {
@@ -963,108 +867,40 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
         acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
         acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
-    const size_t off = (compact || D == 1) ? id : (size_t) row * M + col;
-    if (write && sub == 0) store_node(compact ? compact : fft_in, stride, off, acc);
+    if (write && sub == 0) store_node<D>(grid, (size_t) M, id, acc);
 }
 
-// multi-GPU: expand the all-reduced compact grids into the zero-padded FFT input planes
-template <int D>
-__global__ void __launch_bounds__(256) k_pad_grids(const float2 *__restrict__ compact, const GridParams *__restrict__ gpp,
-                                                   float2 *__restrict__ fft_in) {
+// ------------------------------------------------------------------------- kernel samples (1-D embeddings) --
+// 2-D embeddings sample and transform their kernels inside fitsne_conv.cuh (k_kspec_rows / k_kspec_cols).  1-D: real
+// kernels on the wrap-around node-offset line, offsets d in (-G, G) stored at index d mod M (the reference's 2G
+// circulant embedding, nbodyfft.cpp:280-300, with M >= 2G), packed two per complex line:
+//   plane 2 = (Ksq, Kb)   plane 3 = (Kgrad, 0)
+//   Ksq=(1+r2/df)^-(df+1)   Kgrad = (R/bw)*Ksq  (box units)   Kb=(1+r2/df)^-df      (tsne.cpp:69-94)
+// Values carry the 1/M inverse-FFT normalisation (nbodyfft.cpp:427-430).
+__global__ void __launch_bounds__(256) k_gen_kernels_1d(const GridParams *__restrict__ gpp, double df, float2 *__restrict__ planes) {
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
-    const int G = gp.G, M = gp.M, Gc = M / 2;
-    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
-    const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) Gc;
-    const size_t id = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (D == 2) {           // copy the G^2 corner; the padding is substituted by the FFT passes (see k_spread_combine)
-        if (id >= cplane) return;
-        const int row = (int) (id / Gc), col = (int) (id - (size_t) row * Gc);
-        if (row >= G || col >= G) return;
-        const size_t src = (size_t) row * G + col, dst = (size_t) row * M + col;
-        fft_in[dst] = compact[src];
-        fft_in[plane + dst] = compact[cplane + src];
-    } else {
-        if (id >= plane) return;
-        const bool inside = (int) id < G;
-        const float2 z = make_float2(0.f, 0.f);
-        fft_in[id] = inside ? compact[id] : z;
-        fft_in[plane + id] = inside ? compact[cplane + id] : z;
-    }
-}
-
-// ------------------------------------------------------------------------------------ kernel samples --
-// Real kernels on the wrap-around node-offset lattice, offsets d in (-G, G) stored at index d mod M
-// (the reference's 2G circulant embedding, nbodyfft.cpp:52-61, with M >= 2G), packed two per complex plane:
-//   plane 2 = (Ksq, Kb)   plane 3 = (Kgrad_x, Kgrad_y)  [1-D: (Kgrad, 0)]   planes 4, 5 = d/dh of planes 2, 3 (with_deriv)
-//   Ksq=(1+r2/df)^-(df+1)   Kgrad_k = (R_k/bw)*Ksq  (box units)   Kb=(1+r2/df)^-df      (tsne.cpp:69-94)
-// Values carry the 1/M^D inverse-FFT normalisation (nbodyfft.cpp:202-203).
-// kpack != 0 (opt-in): ALL FOUR kernels in ONE complex plane,  plane 2 = (Kb + Kgrad_x + Kgrad_y) + i*Ksq,  plane 3 = d/dh of it.
-// Ksq and Kb are even in both lattice offsets, Kgrad_x is odd in the column offset only, Kgrad_y in the row offset only, so
-// with Z = FFT(plane 2):  Kb^ = Re Z,  and Im Z = Ksq^ + ax + ay with Kgrad_x^ = i*ax, Kgrad_y^ = i*ay separates by the
-// parities under k2 -> -k2 and k1 -> -k1 (four mirror points, see k_hadamard) -- one kernel transform instead of two.
-template <int D>
-__global__ void __launch_bounds__(256) k_gen_kernels(const GridParams *__restrict__ gpp, double df, float2 *__restrict__ planes, int kpack) {
-    const GridParams &gp = *gpp;
-    if (!gp.ok || gp.kmode == 1) return;          // kmode 1: the cached spectra (planes 2..5) stay as they are
     const int M = gp.M, G = gp.G;
-    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
-    const size_t id = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= plane) return;
-    int r = 0, c;
-    if (D == 2) { r = (int) (id / M); c = (int) (id - (size_t) r * M); } else c = (int) id;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= M) return;
     const int dc = c < G ? c : (c > M - G ? c - M : 0);
-    const int dr = r < G ? r : (r > M - G ? r - M : 0);
-    const bool valid = (c < G || c > M - G) && (D == 1 || r < G || r > M - G);
-    float2 k1 = make_float2(0.f, 0.f), k2 = make_float2(0.f, 0.f), d1 = k1, d2 = k1;
-    if (valid) {
-        const double d2l = (double) dc * (double) dc + (D == 2 ? (double) dr * (double) dr : 0.0);   // lattice distance^2
-        const double r2 = gp.h * gp.h * d2l;
-        double kb, ksq, dksq;
-        if (df == 1.0) {
-            kb = 1.0 / (1.0 + r2);
-            ksq = kb * kb;
-            dksq = -4.0 * gp.h * d2l * ksq * kb;                       // d/dh (1+h^2 d2)^-2
-        } else {
-            const double t = 1.0 + r2 / df;
-            kb = pow(t, -df);
-            ksq = pow(t, -(df + 1.0));
-            dksq = -(df + 1.0) * (2.0 * gp.h * d2l / df) * ksq / t;   // d/dh (1+h^2 d2/df)^-(df+1)
-        }
-        const double dkb = -2.0 * gp.h * d2l * ksq;                    // d/dh (1+h^2 d2/df)^-df
+    float2 k1 = make_float2(0.f, 0.f), k2 = k1;
+    if (c < G || c > M - G) {
+        const double r2 = gp.h * gp.h * (double) dc * (double) dc;
+        double kb, ksq;
+        if (df == 1.0) { kb = 1.0 / (1.0 + r2); ksq = kb * kb; }
+        else { const double t = 1.0 + r2 / df; kb = pow(t, -df); ksq = pow(t, -(df + 1.0)); }
         kb *= gp.inv_norm; ksq *= gp.inv_norm;
         k1 = make_float2((float) ksq, (float) kb);
-        // gradient kernels in box units as well: R_k / bw = (lattice offset) / p
-        const double ux = (double) dc / (double) gp.p, uy = (double) dr / (double) gp.p;
-        k2 = make_float2((float) (ux * ksq), D == 2 ? (float) (uy * ksq) : 0.f);
-        if (gp.with_deriv) {
-            const double a = dksq * gp.inv_norm, bb = dkb * gp.inv_norm;
-            d1 = make_float2((float) a, (float) bb);
-            d2 = make_float2((float) (ux * a), D == 2 ? (float) (uy * a) : 0.f);
-        }
+        k2 = make_float2((float) ((double) dc / (double) gp.p * ksq), 0.f);   // gradient kernel in box units: R / bw = offset / p
     }
-    if (kpack) {
-        planes[2 * plane + id] = make_float2(k1.y + k2.x + k2.y, k1.x);
-        if (gp.with_deriv) planes[3 * plane + id] = make_float2(d1.y + d2.x + d2.y, d1.x);
-        return;
-    }
-    planes[2 * plane + id] = k1;
-    planes[3 * plane + id] = k2;
-    if (gp.with_deriv) {
-        planes[4 * plane + id] = d1;
-        planes[5 * plane + id] = d2;
-    }
+    planes[2 * (size_t) M + c] = k1;
+    planes[3 * (size_t) M + c] = k2;
 }
 
 // ------------------------------------------------------------------------------ Hadamard + sum_Q terms --
-// Input: the (full, M^D) spectra of the four packed planes.  A packed spectrum Z = FFT(A + iB) of two REAL arrays
-// separates as  A^[k] = (Z[k] + conj(Z[-k]))/2,  B^[k] = (Z[k] - conj(Z[-k]))/(2i);  one thread owns the frequency
-// pair (k, -k), so everything is done in place:
-//   plane 0 <- V1 = v1^ + i*B1^      v1 = Ksq*w1,  B_k = Kgrad_k*w1 - Ksq*delta_k     (nbodyfft.cpp:184-191)
-//   plane 1 <- V2 = B2^              (2-D only)
-// and, by Parseval in fp64, the sum_Q terms
-//   df==1: <w1,Kb*w1> + 2<wbb,v1> + sum_k (4<delta_k,Kgrad_k*w1> - 2<delta_k,Ksq*delta_k>)   (tsne.cpp:1101-1110)
-//   df!=1: <w1,Kb*w1>                                                                          (tsne.cpp:950-955)
+// A packed spectrum Z = FFT(A + iB) of two REAL arrays separates as  A^[k] = (Z[k] + conj(Z[-k]))/2,
+// B^[k] = (Z[k] - conj(Z[-k]))/(2i).
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 __device__ __forceinline__ double re_conj_mul(float2 a, float2 b) { return (double) a.x * (double) b.x + (double) a.y * (double) b.y; }
@@ -1074,67 +910,32 @@ __device__ __forceinline__ void unpack_pair(float2 zk, float2 zm, float2 &A, flo
     B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
 }
 
-template <int D>
-__global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, const GridParams *__restrict__ gpp,
-                                                  int df_is_one, double *__restrict__ zpartial, int N, Scalars *__restrict__ sc,
-                                                  unsigned int *__restrict__ ticket, int kpack) {
+// 1-D embeddings.  Input: the length-M spectra of the four packed lines; one thread owns the frequency pair (k, -k), so
+// everything is done in place:
+//   plane 0 <- V1 = v1^ + i*B^      v1 = Ksq*w1,  B = Kgrad*w1 - Ksq*delta     (nbodyfft.cpp:410-420)
+// and, by Parseval in fp64, the sum_Q terms
+//   df==1: <w1,Kb*w1> + 2<wbb,v1> + 4<delta,Kgrad*w1> - 2<delta,Ksq*delta>   (tsne.cpp:809-818)
+//   df!=1: <w1,Kb*w1>                                                        (tsne.cpp:700-706)
+__global__ void __launch_bounds__(256) k_hadamard_1d(float2 *__restrict__ planes, const GridParams *__restrict__ gpp,
+                                                     int df_is_one, double *__restrict__ zpartial, int N, Scalars *__restrict__ sc,
+                                                     unsigned int *__restrict__ ticket) {
     __shared__ double sm[32];
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
     const int M = gp.M;
-    const size_t plane = D == 2 ? (size_t) M * M : (size_t) M;
-    float2 *Z1 = planes, *Z2 = planes + plane;
-    const float2 *K1 = planes + 2 * plane, *K2 = planes + 3 * plane, *dK1 = planes + 4 * plane, *dK2 = planes + 5 * plane;
-    const bool taylor = gp.kmode == 1;
-    const float dh = gp.dh;
+    float2 *Z1 = planes, *Z2 = planes + M;
+    const float2 *K1 = planes + 2 * (size_t) M, *K2 = planes + 3 * (size_t) M;
     const double bw2 = gp.bw * gp.bw;
     double zacc = 0;
-    for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < plane; e += (size_t) gridDim.x * blockDim.x) {
-        size_t em;
-        if (D == 2) {
-            const int k1 = (int) (e / M), k2 = (int) (e - (size_t) k1 * M);
-            em = (size_t) ((M - k1) % M) * M + (size_t) ((M - k2) % M);
-        } else em = (size_t) ((M - (int) e) % M);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M; e += gridDim.x * blockDim.x) {
+        const int em = (M - e) % M;
         if (em < e) continue;                       // the partner thread owns this pair
         const double wt = em == e ? 1.0 : 2.0;
-        float2 w1, d1, d2, wbb, ksq, kb, kg1, kg2;
+        float2 w1, d1, wbb, unused, ksq, kb, kg1, kg2;
         unpack_pair(Z1[e], Z1[em], w1, d1);
-        unpack_pair(Z2[e], Z2[em], d2, wbb);        // 1-D: d2 = wbb-plane real part, see below
-        if (!kpack) {
-            float2 k1e = K1[e], k1m = K1[em], k2e = K2[e], k2m = K2[em];
-            if (taylor) {      // K^(h) = K^(h0) + dh * dK^/dh(h0), on the packed values (the unpacking is linear)
-                const float2 a1 = dK1[e], b1 = dK1[em], a2 = dK2[e], b2 = dK2[em];
-                k1e.x += dh * a1.x; k1e.y += dh * a1.y; k1m.x += dh * b1.x; k1m.y += dh * b1.y;
-                k2e.x += dh * a2.x; k2e.y += dh * a2.y; k2m.x += dh * b2.x; k2m.y += dh * b2.y;
-            }
-            unpack_pair(k1e, k1m, ksq, kb);
-            unpack_pair(k2e, k2m, kg1, kg2);
-        } else {
-            // packed layout: Z = FFT((Kb + Kgx + Kgy) + i*Ksq) at k and its mirror points (k1,-k2), (-k1,k2), (-k1,-k2);
-            // plane 3 holds dZ/dh for the Taylor step
-            size_t e1 = em, e2 = em;
-            if (D == 2) {
-                const int r1 = (int) (e / M), r2 = (int) (e - (size_t) r1 * M);
-                e1 = (size_t) r1 * M + (size_t) ((M - r2) % M);
-                e2 = (size_t) ((M - r1) % M) * M + (size_t) r2;
-            }
-            float2 ze = K1[e], zm = K1[em], z1 = D == 2 ? K1[e1] : ze, z2 = D == 2 ? K1[e2] : zm;
-            if (taylor) {
-                const float2 de = K2[e], dm = K2[em], d1_ = D == 2 ? K2[e1] : de, d2_ = D == 2 ? K2[e2] : dm;
-                ze.x += dh * de.x; ze.y += dh * de.y; zm.x += dh * dm.x; zm.y += dh * dm.y;
-                z1.x += dh * d1_.x; z1.y += dh * d1_.y; z2.x += dh * d2_.x; z2.y += dh * d2_.y;
-            }
-            // 2-D: Im Z = S + ax + ay at k, S - ax + ay at (k1,-k2), S + ax - ay at (-k1,k2), S - ax - ay at -k
-            // 1-D (z1 = ze, z2 = zm): Im Z = S + a at k, S - a at -k
-            const float S = 0.25f * ((ze.y + z1.y) + (z2.y + zm.y));
-            const float ax = 0.25f * ((ze.y - z1.y) + (z2.y - zm.y));
-            const float ay = 0.25f * ((ze.y + z1.y) - (z2.y + zm.y));
-            ksq = make_float2(S, 0.f);
-            kb = make_float2(0.25f * ((ze.x + z1.x) + (z2.x + zm.x)), 0.f);
-            if (D == 2) { kg1 = make_float2(0.f, ax); kg2 = make_float2(0.f, ay); }
-            else { kg1 = make_float2(0.f, ay); kg2 = make_float2(0.f, 0.f); }     // 1-D: a = (Im Z(k) - Im Z(-k)) / 2 = ay above
-        }
-        if (D == 1) { wbb = d2; }                   // 1-D plane 1 = (wbb, 0)
+        unpack_pair(Z2[e], Z2[em], wbb, unused);
+        unpack_pair(K1[e], K1[em], ksq, kb);
+        unpack_pair(K2[e], K2[em], kg1, kg2);
         const float2 v1 = cmul(ksq, w1);
         const float2 kgw1 = cmul(kg1, w1), ksd1 = cmul(ksq, d1);
         const float2 B1 = make_float2(kgw1.x - ksd1.x, kgw1.y - ksd1.y);
@@ -1145,18 +946,11 @@ __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, c
         // V1 = v1 + i*B1 at k; at -k both spectra are conjugated (real arrays): V1[-k] = conj(v1) + i*conj(B1)
         Z1[e] = make_float2(v1.x - B1.y, v1.y + B1.x);
         if (em != e) Z1[em] = make_float2(v1.x + B1.y, -v1.y + B1.x);
-        if (D == 2) {
-            const float2 kgw2 = cmul(kg2, w1), ksd2 = cmul(ksq, d2);
-            const float2 B2 = make_float2(kgw2.x - ksd2.x, kgw2.y - ksd2.y);
-            if (df_is_one) zb += 4.0 * re_conj_mul(d2, kgw2) - 2.0 * re_conj_mul(d2, ksd2);
-            Z2[e] = B2;
-            if (em != e) Z2[em] = cconj(B2);
-        }
         zacc += wt * (z + bw2 * zb);
     }
     const double r = block_sum(zacc, sm);
     if (threadIdx.x == 0) zpartial[blockIdx.x] = r;
-    if (last_block_done(ticket)) {           // sum_Q = (sum of the partials, in index order) - N   (tsne.cpp:1110)
+    if (last_block_done(ticket)) {           // sum_Q = (sum of the partials, in index order) - N   (tsne.cpp:818)
         double s2 = 0;
         for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) s2 += ld_partial(zpartial + i);
         const double tot = block_sum(s2, sm);
@@ -1171,11 +965,12 @@ __global__ void __launch_bounds__(256) k_hadamard(float2 *__restrict__ planes, c
 // --------------------------------------------------------------------------------------------- gather --
 // One thread per box-sorted point: F_rep/Z = (1/Z) sum_nodes L * (a_k * v1 + B_k) with a = y - X_node;
 // written to the point's ORIGINAL index (frep[perm[k]]), so the update runs coalesced in point order.
+// 2-D: `field` = pot, one float4 (v1, Bx, By, 0) per node of the G x G grid; 1-D: packed line (v1, B).
 template <int D, int P>
 __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
                                                 const uint32_t *__restrict__ perm, int n,
                                                 const GridParams *__restrict__ gpp, const Scalars *__restrict__ sc,
-                                                const float2 *__restrict__ planes, float *__restrict__ frep) {
+                                                const void *__restrict__ field, float *__restrict__ frep) {
     __shared__ GridParams gps;
     for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
@@ -1185,11 +980,10 @@ __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int p = P > 0 ? P : gp.p;
-    const int M = gp.M;
     const float bw = gp.bwf, inv_Z = sc->inv_Z;
     const uint32_t key = skeys[k];
     if (D == 2) {
-        const size_t plane = (size_t) M * M;
+        const int G = gp.G;
         const int by = (int) (key >> gp.xbits), bx = (int) (key & ((1u << gp.xbits) - 1u));
         const float2 u = reinterpret_cast<const float2 *>(sorted_u)[k];
         float Lx[P > 0 ? P : PMAX], ox[P > 0 ? P : PMAX];
@@ -1198,21 +992,20 @@ __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted
             if (b < p) { Lx[b] = lagrange1<P>(gp, p, b, u.x); ox[b] = u.x - gp.s[b]; }
         }
         float fx = 0.f, fy = 0.f;
-        const float2 *g0 = planes + (size_t) (by * p) * M + bx * p;   // plane 0 = (v1, Bx), plane 1 = (By, .)
+        const float4 *g0 = reinterpret_cast<const float4 *>(field) + (size_t) (by * p) * G + bx * p;
 #pragma unroll(P > 0 ? P : 1)
         for (int a = 0; a < (P > 0 ? P : PMAX); a++) {
             if (a < p) {
                 const float Ly = lagrange1<P>(gp, p, a, u.y);
                 const float oy = u.y - gp.s[a];
-                const float2 *row = g0 + (size_t) a * M;
+                const float4 *row = g0 + (size_t) a * G;
 #pragma unroll(P > 0 ? P : 1)
                 for (int b = 0; b < (P > 0 ? P : PMAX); b++) {
                     if (b < p) {
                         const float L = Ly * Lx[b];
-                        const float2 vb = __ldg(row + b);
-                        const float By = __ldg(reinterpret_cast<const float *>(row + plane + b));
+                        const float4 vb = __ldg(row + b);
                         fx += L * (ox[b] * vb.x + vb.y);
-                        fy += L * (oy * vb.x + By);
+                        fy += L * (oy * vb.x + vb.z);
                     }
                 }
             }
@@ -1221,7 +1014,7 @@ __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted
         reinterpret_cast<float2 *>(frep)[perm[k]] = make_float2(fx * bw * inv_Z, fy * bw * inv_Z);
     } else {
         const float u = sorted_u[k];
-        const float2 *g0 = planes + (size_t) key * p;                  // plane 0 = (v1, B)
+        const float2 *g0 = reinterpret_cast<const float2 *>(field) + (size_t) key * p;                  // plane 0 = (v1, B)
         float f = 0.f;
         for (int a = 0; a < p; a++) {
             const float L = lagrange1<P>(gp, p, a, u);
@@ -1343,6 +1136,11 @@ __device__ __forceinline__ void update_row(int row, const float *__restrict__ Y,
     }
 }
 
+// Persistent form: gridDim.x CTAs, each walking a contiguous slice of the rows, so that the column sums of the new
+// positions (for the zero-mean step, tsne.cpp:1851-1876) ride along in registers and cost ONE block reduction per CTA at
+// the very end; the last CTA to finish adds the per-CTA partials in index order and publishes the means.  (A first
+// attempt with one 256-row CTA per block reduction was 8 us slower than a separate column-sum pass; this one has the
+// separate pass's summation order -- slice per CTA, thread-strided, fixed tree -- without its second read of Ynext.)
 template <int D, bool UPDATE>
 __global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, const float *__restrict__ attr,
                                                 const float *__restrict__ frep, int row_begin, int row_end,
@@ -1352,18 +1150,21 @@ __global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, con
                                                 Scalars *__restrict__ sc, unsigned int *__restrict__ ticket) {
     if (!gpp->ok) return;
     const StepParams sp = *spp;
-    const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    float new0 = 0.f, new1 = 0.f;           // this thread's new (un-centred) position, 0 beyond the slice
-    if (row < row_end) update_row<D, UPDATE>(row, Y, attr, frep, sp, dC_out, uY, gains, Ynext, new0, new1);
+    const int per = (row_end - row_begin + gridDim.x - 1) / gridDim.x;
+    const int b = row_begin + blockIdx.x * per, e = min(row_end, b + per);
+    double s0 = 0, s1 = 0;
+    for (int row = b + threadIdx.x; row < e; row += blockDim.x) {
+        float new0 = 0.f, new1 = 0.f;           // this row's new (un-centred) position
+        update_row<D, UPDATE>(row, Y, attr, frep, sp, dC_out, uY, gains, Ynext, new0, new1);
+        s0 += new0; s1 += new1;
+    }
     if (!UPDATE || colsum_partial == nullptr) return;
-    // column sums of Ynext for the zero-mean step (tsne.cpp:1851-1876): per-block partials in a fixed tree, then the
-    // last block adds the partials in index order -- no separate reduction pass over Ynext
     __shared__ double smu[32];
-    const double s0 = block_sum((double) new0, smu);
-    if (threadIdx.x == 0) colsum_partial[blockIdx.x * D] = s0;
+    const double r0 = block_sum(s0, smu);
+    if (threadIdx.x == 0) colsum_partial[blockIdx.x * D] = r0;
     if (D == 2) {
-        const double s1 = block_sum((double) new1, smu);
-        if (threadIdx.x == 0) colsum_partial[blockIdx.x * D + 1] = s1;
+        const double r1 = block_sum(s1, smu);
+        if (threadIdx.x == 0) colsum_partial[blockIdx.x * D + 1] = r1;
     }
     if (last_block_done(ticket)) {
         for (int d = 0; d < D; d++) {

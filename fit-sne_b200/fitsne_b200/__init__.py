@@ -13,11 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfitsne_b200.so")
 
 STEP_MOMENTUM_CLIP, STEP_MOMENTUM, STEP_PLAIN_GD = 0, 1, 2
-FLAG_NO_GRAPH, FLAG_TIMERS, FLAG_NO_REORDER, FLAG_FORCE_TILES, FLAG_NO_TILES, FLAG_NO_SPECULATION, FLAG_NO_KERNEL_CACHE = 1, 2, 4, 8, 16, 32, 64
-FLAG_SPREAD_PER_NODE = 128
-FLAG_FFT_WIDE = 256
-FLAG_FUSED_COLSUM = 512
-FLAG_KPACK = 1024
+FLAG_NO_GRAPH, FLAG_TIMERS, FLAG_NO_REORDER, FLAG_FORCE_TILES, FLAG_NO_TILES, FLAG_NO_SPECULATION = 1, 2, 4, 8, 16, 32
 FLAG_SORTED_SPMV = 2048
 PHASES = ["bounds", "sort", "spread", "kernel_spectrum", "fft", "gather", "attract_update", "center", "kl",
           "collectives"]
@@ -54,8 +50,7 @@ class Stats(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
                 ("graph_launches", ctypes.c_uint64), ("regrids", ctypes.c_uint64), ("n_boxes", ctypes.c_int),
                 ("grid_side", ctypes.c_int), ("fft_side", ctypes.c_int), ("min_coord", ctypes.c_double),
-                ("max_coord", ctypes.c_double), ("phase_ms", ctypes.c_double * 16),
-                ("spectrum_cache_hits", ctypes.c_uint64), ("reorders", ctypes.c_uint64)]
+                ("max_coord", ctypes.c_double), ("phase_ms", ctypes.c_double * 16), ("reorders", ctypes.c_uint64)]
 
 
 class FitsneError(RuntimeError):
@@ -202,7 +197,7 @@ class FitSNE:
         return Y, costs
 
     def prewarm(self, n_boxes_lo, n_boxes_hi):
-        """Create the cuFFT plans for grids of n_boxes_lo..n_boxes_hi boxes per dimension ahead of the loop."""
+        """Prepare twiddle tables / buffers for grids of n_boxes_lo..n_boxes_hi boxes per dimension ahead of the loop."""
         self._ck(self._lib.fitsne_prewarm(self._h, int(n_boxes_lo), int(n_boxes_hi)))
 
     def synchronize(self):

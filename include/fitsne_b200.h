@@ -26,7 +26,7 @@ extern "C" {
 #define FITSNE_OK 0
 #define FITSNE_EINVAL (-1)    /* bad argument (no_dims not 1/2, nterms out of range, ...)        */
 #define FITSNE_ENODEV (-2)    /* no usable CUDA device / wrong architecture                      */
-#define FITSNE_ECUDA (-3)     /* a CUDA / cuFFT call failed                                      */
+#define FITSNE_ECUDA (-3)     /* a CUDA call failed                                              */
 #define FITSNE_ENOMEM (-4)    /* device or host allocation failed                                */
 #define FITSNE_ENCCL (-5)     /* NCCL could not be loaded or a collective failed                 */
 #define FITSNE_ESTATE (-6)    /* call sequence error (e.g. KL before any gradient)               */
@@ -50,12 +50,7 @@ typedef struct fitsne_config {
 #define FITSNE_FLAG_FORCE_TILES 8 /* always use the tiled attractive kernel after a re-ordering            */
 #define FITSNE_FLAG_NO_TILES 16   /* re-order for locality but keep the CSR attractive kernel              */
 #define FITSNE_FLAG_NO_SPECULATION 32 /* fitsne_run: one host round trip per iteration instead of batches  */
-#define FITSNE_FLAG_NO_KERNEL_CACHE 64 /* re-sample + re-transform the kernel planes every iteration (no Taylor re-use) */
-#define FITSNE_FLAG_FFT_WIDE 256  /* FFT plans with radix-16 / radix-9 stages (3 stages instead of 4-5); opt-in until measured */
-#define FITSNE_FLAG_FUSED_COLSUM 512 /* column sums as an epilogue of the update kernel instead of a separate pass (measured 8 us slower at N=1M) */
-#define FITSNE_FLAG_SORTED_SPMV 2048 /* attractive term over column-sorted edges + shared-memory integer accumulators (after a re-ordering, N <= 2^20); experimental, not yet measured */
-#define FITSNE_FLAG_KPACK 1024    /* all four kernel planes in ONE complex transform (parity separation); opt-in until measured */
-#define FITSNE_FLAG_SPREAD_PER_NODE 128 /* spread with one thread per (32-point chunk, node) -- the first formulation; the default keeps all nodes of a chunk in one thread's registers */
+#define FITSNE_FLAG_SORTED_SPMV 2048 /* attractive term over column-sorted edges + shared-memory integer accumulators (after a re-ordering, N <= 2^20) */
 
 /* One optimiser step's parameters: the state TSNE::run carries across iterations (tsne.cpp:437-544). */
 typedef struct fitsne_step_params {
@@ -89,7 +84,7 @@ typedef struct fitsne_schedule {
 /* Timers / counters filled by fitsne_get_stats (all times in milliseconds of device time). */
 typedef struct fitsne_stats {
     uint64_t iterations;          /* optimiser steps executed                                   */
-    uint64_t kernel_launches;     /* our kernels + cuFFT executions launched (graph nodes count) */
+    uint64_t kernel_launches;     /* our kernels launched (graph nodes count)                    */
     uint64_t graph_launches;
     uint64_t regrids;             /* iterations whose grid (n_boxes) differed from the previous  */
     int n_boxes;                  /* last grid: boxes per dimension                              */
@@ -97,7 +92,6 @@ typedef struct fitsne_stats {
     int fft_side;                 /* last FFT length per dimension                               */
     double min_coord, max_coord;  /* last bounds used for the grid                               */
     double phase_ms[16];          /* FITSNE_PHASE_* accumulators (only with FITSNE_FLAG_TIMERS)  */
-    uint64_t spectrum_cache_hits; /* iterations that re-used the cached kernel spectra (Taylor step in h) */
     uint64_t reorders;            /* device-side Morton re-orderings of the points                */
 } fitsne_stats;
 
@@ -175,7 +169,8 @@ int fitsne_reset_stats(fitsne_ctx *ctx);
 /* Device time of the last fitsne_run in ms (CUDA events around the loop, KL included). */
 int fitsne_last_run_ms(fitsne_ctx *ctx, double *ms);
 /* Copy internal device arrays to the host for tests: what = "frep" (N*no_dims floats, F_rep/Z of the last
- * gradient), "perm" (N u32, box-sorted order), "keys" (N u32), "grid" (n_fwd*G^d floats, spread result). */
+ * gradient), "perm" (N u32, box-sorted order), "keys" (N u32), "box_start", and in 2-D "grid" (G*G float4: the spread
+ * result w1, delta_x, delta_y, wbb) and "pot" (G*G float4: v1, Bx, By, 0 at the nodes). */
 int fitsne_debug_copy(fitsne_ctx *ctx, const char *what, void *dst, size_t dst_bytes, size_t *needed_bytes);
 const char *fitsne_version(void);
 

@@ -252,78 +252,3 @@ def test_speculative_batches_equal_stepwise_run(fb, golden_graph):
     assert np.array_equal(res["batched"][1], res["stepwise"][1])
     assert np.array_equal(res["batched"][0], res["stepwise"][0])
     assert res["batched"][2]["graph_launches"] >= 130
-
-
-def test_kernel_spectrum_cache_keeps_reference_parity(fb, oracle, golden_graph):
-    """Iterations whose node spacing h is within 1e-3 of the cached one re-use the kernel spectra through a first-order
-    Taylor step in h instead of re-sampling + re-transforming them.  Parity with the reference must survive."""
-    row, col, val, labels = golden_graph
-    import bench_util
-    val64 = val.astype(np.float64)
-    for dims, df in ((2, 1.0), (2, 0.5), (1, 1.0)):
-        Y = bench_util.clustered_embedding(labels.astype(np.int64), dims, 120.0, seed=9)
-        with fb.FitSNE(row, col, val64, Y, df=df) as t, fb.FitSNE(row, col, val64, Y, df=df, flags=fb.FLAG_NO_KERNEL_CACHE) as tn:
-            t.gradient(1.0)                                     # builds K^(h0) and dK^/dh(h0)
-            for scale in (1.0 + 4e-4, 1.0 - 7e-4, 1.0 + 9.5e-4):     # inside the Taylor window
-                Y2 = (Y * scale).astype(np.float32).astype(np.float64)
-                t.set_Y(Y2); tn.set_Y(Y2)
-                dC, z = t.gradient(1.0)
-                dCn, zn = tn.gradient(1.0)
-                ref, zr = oracle.gradient(Y2, row, col, val64, df=df)
-                assert rel(dCn, ref) < 5e-6
-                assert rel(dC, ref) < GRAD_TOL / 4, (dims, df, scale, rel(dC, ref))      # measured ~1e-5 at the window's edge
-                assert abs(z - zr) / zr < 2e-5
-            Y3 = (Y * 1.01).astype(np.float32).astype(np.float64)   # outside the window: spectra are refreshed, exact again
-            t.set_Y(Y3)
-            dC, z = t.gradient(1.0)
-            ref, zr = oracle.gradient(Y3, row, col, val64, df=df)
-            assert rel(dC, ref) < 5e-6
-    # whole runs: same final KL with and without the cache
-    Y0 = bench_util.clustered_embedding(labels.astype(np.int64), 2, 60.0, seed=5)
-    kw = dict(max_iter=150, stop_lying_iter=-1, mom_switch_iter=-1, momentum=0.8, learning_rate=300.0, early_exag_coeff=1.0)
-    out = []
-    for flags in (0, fb.FLAG_NO_KERNEL_CACHE):
-        with fb.FitSNE(row, col, val64, Y0, flags=flags) as t:
-            Y, costs = t.run(**kw)
-        out.append((Y, costs[costs != 0]))
-    assert np.allclose(out[0][1], out[1][1], rtol=1e-4)
-    assert rel(out[0][0], out[1][0]) < 1e-2
-
-
-@pytest.mark.parametrize("name", GRAD_CASES)
-def test_alternative_kernels_keep_reference_parity(fb, golden_graph, golden_gradients, name):
-    """The kernels kept behind flags -- per-(chunk, node) spread, radix-16/9 FFT plans, packed kernel planes -- against the
-    reference's golden gradients; the two spread formulations must agree bit for bit (same sums in the same order)."""
-    row, col, val, _ = golden_graph
-    g = golden_gradients
-    dims, df, nterms, ipi, min_int, Z, kl = g[name + "__meta"]
-    Y = g[name + "__Y"].astype(np.float64)
-    kw = dict(nterms=int(nterms), intervals_per_integer=ipi, min_num_intervals=int(min_int), df=df)
-    out = {}
-    for label, flags in (("default", 0), ("spread_per_node", fb.FLAG_SPREAD_PER_NODE), ("fft_wide", fb.FLAG_FFT_WIDE),
-                         ("kpack", fb.FLAG_KPACK), ("wide+kpack", fb.FLAG_FFT_WIDE | fb.FLAG_KPACK)):
-        with fb.FitSNE(row, col, val.astype(np.float64), Y, flags=flags | fb.FLAG_NO_REORDER, **kw) as t:
-            dC, z = t.gradient(1.0)
-        assert rel(dC, g[name + "__dC"]) < GRAD_TOL, (label, rel(dC, g[name + "__dC"]))
-        assert abs(z - Z) / Z < 1e-5, (label, abs(z - Z) / Z)
-        out[label] = dC
-    if int(dims) == 2:          # measured bitwise identical on B200 (profiles/r1_oneshot_ab.json)
-        assert np.array_equal(out["default"], out["spread_per_node"])
-    else:
-        assert rel(out["default"], out["spread_per_node"]) < 1e-6
-
-
-def test_fused_and_separate_column_sums_agree(fb, golden_graph):
-    """FLAG_FUSED_COLSUM (column sums as an epilogue of k_update) vs the default separate pass: same trajectory up to the
-    fp64 summation order of the means."""
-    row, col, val, labels = golden_graph
-    import bench_util
-    Y0 = bench_util.clustered_embedding(labels.astype(np.int64), 2, 50.0, seed=6)
-    kw = dict(max_iter=60, stop_lying_iter=20, mom_switch_iter=20, learning_rate=500.0, early_exag_coeff=4.0)
-    res = []
-    for flags in (0, fb.FLAG_FUSED_COLSUM):
-        with fb.FitSNE(row, col, val.astype(np.float64), Y0, flags=flags) as t:
-            Y, costs = t.run(**kw)
-        res.append((Y, costs[costs != 0]))
-    assert rel(res[1][0], res[0][0]) < 1e-4
-    assert np.allclose(res[0][1], res[1][1], rtol=1e-6)
