@@ -116,15 +116,15 @@ struct fitsne_ctx {
     float *Y = nullptr, *Yb = nullptr, *uY = nullptr, *gains = nullptr, *frep = nullptr, *dC = nullptr, *attr = nullptr;
     size_t y_elems = 0;   // allocated elements per Y buffer (padded to per*world*D)
     // CSR
-    uint32_t *row_P = nullptr, *col_P = nullptr;
-    float *val_P = nullptr;
+    uint32_t *row_P = nullptr;
+    uint2 *edges = nullptr;           // (column, fp32 weight bits) per edge of this rank's rows
     uint32_t edge_base = 0;
     size_t E = 0;
     int lpr = 32;
     // locality re-ordering + tiled attractive term (single-GPU contexts)
     uint32_t *orig_of = nullptr, *orig_tmp = nullptr, *pos_of = nullptr, *rank_map = nullptr;   // u32[N]
-    uint32_t *row_P2 = nullptr, *col_P2 = nullptr;   // second CSR buffer (re-labelled copy is built here, then swapped)
-    float *val_P2 = nullptr;
+    uint32_t *row_P2 = nullptr;       // second CSR buffer (re-labelled copy is built here, then swapped)
+    uint2 *edges2 = nullptr;
     uint32_t *tile_cnt = nullptr, *tile_start = nullptr, *tile_cur = nullptr, *tile_pack = nullptr, *nonempty = nullptr;
     float *tile_val = nullptr;
     GridParams *gp_reorder = nullptr;
@@ -136,6 +136,7 @@ struct fitsne_ctx {
     uint32_t *srt_cnt = nullptr, *srt_start = nullptr, *srt_cur = nullptr;
     size_t srt_tiles = 0;
     bool use_sorted = false;
+    uint64_t steps_total = 0;         // optimiser steps since creation (fitsne_reset_stats does not touch it: re-order scheduling)
     uint64_t last_reorder_iter = 0, reorder_interval = 50, reorders = 0;
     uint32_t nonempty_tiles = 0;
     float tile_fix32 = 1.0f;
@@ -143,9 +144,11 @@ struct fitsne_ctx {
     // sort / bins
     uint32_t *keys[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
     float *sorted_u = nullptr;
-    uint32_t *box_start = nullptr, *hist = nullptr, *sort_totals = nullptr;
+    uint32_t *box_start = nullptr, *hist = nullptr, *sort_totals = nullptr, *sort_bases = nullptr, *sweep_state = nullptr;
+    uint32_t *work = nullptr;         // spread work list: [0] = count, [1..] = boxes that span several chunks
     size_t box_cap = 0, hist_cap = 0;
-    float4 *slots = nullptr;          // spread partials: [chunk][2][nodes]
+    float4 *slots = nullptr;          // spread partials of boxes that cross a CTA boundary: [CTA][2][nodes]
+    float4 *gpart = nullptr;          // run-time-nterms fallback only: per-chunk partials [chunk][2][nodes]
     // grids.  2-D: chg (spread result, float4 per node of the G x G grid), S (x-spectra per row, in place the convolved
     // half-spectra), KR / KS (kernel spectra after the row / column pass), pot (v1, Bx, By per node); 1-D: four packed lines
     float4 *chg = nullptr, *pot = nullptr, *KR = nullptr, *KS = nullptr;
@@ -330,24 +333,12 @@ static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int 
 }
 
 template <int D, int P>
-static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, int M, const uint32_t *skeys, const uint32_t *sperm) {
-    (void) M;
-    const int p = c->cfg.nterms;
-    const int nodes = D == 2 ? p * p : p;
+static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, const uint32_t *skeys, const uint32_t *sperm) {
     void *grid = D == 2 ? (void *) c->chg : (void *) c->planes;
     if (!gather) {
-        const int cpb = std::max(1, 256 / nodes);
         const int nchunks = cdiv(c->nloc, CHUNK);
-        // one thread per chunk with all p^D accumulators in registers (P = 2..4 in 2-D, 2..5 in 1-D); other P: one thread per
-        // (chunk, node) -- both produce bitwise identical sums
-        constexpr bool has2 = P >= 2 && (D == 2 ? P <= 4 : P <= 5);
-        if constexpr (has2) {
-            k_spread_chunks2<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, 0, c->stream>>>(c->sorted_u, skeys, c->box_start, c->nloc, c->gp,
-                                                                                              c->slots, grid);
-        } else {
-            k_spread_chunks<D, P><<<cdiv(nchunks, cpb), cpb * nodes, 0, c->stream>>>(c->sorted_u, skeys, c->box_start, c->nloc, c->gp, cpb,
-                                                                                      c->slots, grid);
-        }
+        k_spread_chunks<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, spread_smem_bytes<D, P>(), c->stream>>>(
+            c->sorted_u, skeys, c->nloc, c->gp, c->slots, c->gpart, grid, c->box_start, c->work);
     } else {
         k_gather<D, P><<<cdiv(c->nloc, 256), 256, 0, c->stream>>>(c->sorted_u, skeys, sperm, c->nloc, c->gp, c->sc,
                                                                    D == 2 ? (const void *) c->pot : (const void *) c->planes, c->frep);
@@ -357,14 +348,16 @@ static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, int M, const
     return 0;
 }
 
+// compile-time node counts for nterms 2..4 (2-D) / 2..5 (1-D): accumulators in registers; anything else: run-time loops
 template <int D>
-static int launch_spread_gather(fitsne_ctx *c, bool gather, int M, const uint32_t *skeys, const uint32_t *sperm) {
+static int launch_spread_gather(fitsne_ctx *c, bool gather, const uint32_t *skeys, const uint32_t *sperm) {
     switch (c->cfg.nterms) {
-        case 2: return launch_spread_gather_variant<D, 2>(c, gather, M, skeys, sperm);
-        case 3: return launch_spread_gather_variant<D, 3>(c, gather, M, skeys, sperm);
-        case 4: return launch_spread_gather_variant<D, 4>(c, gather, M, skeys, sperm);
-        case 5: return launch_spread_gather_variant<D, 5>(c, gather, M, skeys, sperm);
-        default: return launch_spread_gather_variant<D, 0>(c, gather, M, skeys, sperm);
+        case 2: return launch_spread_gather_variant<D, 2>(c, gather, skeys, sperm);
+        case 3: return launch_spread_gather_variant<D, 3>(c, gather, skeys, sperm);
+        case 4: return launch_spread_gather_variant<D, 4>(c, gather, skeys, sperm);
+        case 5: if constexpr (D == 1) return launch_spread_gather_variant<D, 5>(c, gather, skeys, sperm);
+        // fall through
+        default: return launch_spread_gather_variant<D, 0>(c, gather, skeys, sperm);
     }
 }
 
@@ -402,7 +395,7 @@ static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
     static const int lpr_env = getenv("FITSNE_LPR") ? atoi(getenv("FITSNE_LPR")) : 0;
     static const int dummy_smem = getenv("FITSNE_SPMV_SMEM_KB") ? atoi(getenv("FITSNE_SPMV_SMEM_KB")) * 1024 : 0;
 #define ATT(L) k_attract<D, L><<<std::min(cdiv((long long) rows * L, 256), 148 * per_sm), 256, dummy_smem, st>>>( \
-        c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->row_begin, c->row_end, inv_df, c->attr)
+        c->row_P, c->edges, c->edge_base, c->Y, c->row_begin, c->row_end, inv_df, c->attr)
     switch (lpr_env ? lpr_env : c->lpr) {
         case 4: ATT(4); break;
         case 8: ATT(8); break;
@@ -413,14 +406,6 @@ static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
     LAUNCH_CHECK();
     c->stats.kernel_launches += 1;
     return 0;
-}
-
-// lanes per output node in k_spread_combine: more lanes when the grid is small (few, heavy boxes)
-static inline int combine_lanes(const fitsne_ctx *c, int M) {
-    const size_t space = c->D == 2 ? (size_t) (M / 2) * (M / 2) : (size_t) M;      // k_spread_combine's index space
-    int lpn = 1;
-    while (lpn < 32 && space * (size_t) (lpn * 2) <= (size_t) 3 << 20) lpn *= 2;   // up to ~3M threads: cheap, and heavy boxes (early exaggeration) get a full warp per node
-    return lpn;
 }
 
 // Everything from "bounds are known" to either dC (update=false) or the centred new Y and its bounds
@@ -434,7 +419,8 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     cudaStream_t st = c->stream;
     Plans *pl;
     CKRC(get_plans(c, M, &pl));
-    const bool overlap = !c->timing_this_iter;    // timers mode serialises everything to time each phase
+    static const bool serial_env = getenv("FITSNE_SERIAL") && atoi(getenv("FITSNE_SERIAL")) != 0;     // diagnostics: no second / third stream
+    const bool overlap = !c->timing_this_iter && !serial_env;    // timers mode serialises everything to time each phase
 
     // Sharded: after an optimiser step every rank only holds ITS slice of the new Y.  The all-gather that completes Y is
     // issued here, on the SpMV's stream: the SpMV is its only consumer inside the iteration (bin / sort / spread / gather /
@@ -462,7 +448,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     phase_mark(c, FITSNE_PHASE_BOUNDS);
     kt(c, "(start)");
     k_setup_grid<<<1, 256, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
-                                    c->mismatch, c->sort_totals);
+                                    c->mismatch, c->sort_totals, c->work, c->tickets + 5);
     c->stats.kernel_launches += 1;
     kt(c, "k_setup_grid");
     // 2-D: the kernel spectra depend on the grid geometry only (not on the points): sample + transform them on their own
@@ -482,41 +468,37 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         CK(cudaEventRecord(c->ev_kjoin, c->stream_k));
     }
 
-    // ---- bin + stable two-pass LSD radix sort by box
+    // ---- bin + stable two-pass LSD radix sort by box (three launches; see fitsne_kernels.cuh)
     phase_mark(c, FITSNE_PHASE_SORT);
     const int tiles = cdiv(nloc, SORT_TILE);
     const int max_bins = 1 << SORT_MAX_BITS;
-    const size_t scatter_smem = (size_t) max_bins * 4 + (size_t) (SORT_THREADS / 32) * max_bins * 2;
-    // (one-pass layout: k_bin writes keys[1] + the pass-1 histogram + in-box coordinates (staged in frep, free until the
-    //  gather), the pass-0 kernels return at once, the pass-1 scatter produces keys[0]/perm[0]/sorted_u and box_start)
-    k_bin<D><<<tiles, SORT_THREADS, 0, st>>>(c->Y, c->row_begin, nloc, c->gp, c->keys[0], c->keys[1], c->frep, c->hist, tiles, c->sort_totals);
+    const size_t sweep_smem = (size_t) max_bins * 4 + (size_t) (SWEEP_THREADS / 32) * max_bins * 2;
+    // in-box coordinates travel with the keys: k_bin -> frep (free until the gather) -> sweep#0 -> dC (free until the
+    // update) -> sweep#1 -> sorted_u.  One-pass layout: k_bin writes keys[1] and the coordinates straight to dC, sweep#0
+    // returns at once.
+    float *u0 = c->frep, *u1 = c->dC;
+    k_bin<D><<<tiles, BIN_THREADS, 0, st>>>(c->Y, c->row_begin, nloc, c->gp, c->keys[0], c->keys[1], u0, u1, c->sort_totals, c->sort_bases,
+                                           c->sweep_state, tiles, c->tickets + 4);
     kt(c, "k_bin");
-    k_radix_offsets<D><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, 0, nloc, nullptr, c->gp);
-    kt(c, "k_radix_offsets#0");
-    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], nloc, 0, c->hist, tiles,
-                                                              (uint32_t) c->row_begin, c->gp, nullptr, nullptr, D);
-    kt(c, "k_radix_scatter#0");
-    k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[1], nloc, 1, c->hist, tiles, c->sort_totals + max_bins, c->gp);
-    kt(c, "k_radix_hist");
-    k_radix_offsets<D><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, 1, nloc, c->box_start, c->gp);
-    kt(c, "k_radix_offsets#1");
-    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], nloc, 1, c->hist, tiles,
-                                                              (uint32_t) c->row_begin, c->gp, c->frep, c->sorted_u, D);
+    k_radix_sweep<<<tiles, SWEEP_THREADS, sweep_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], nloc, 0, c->sort_bases, c->sweep_state,
+                                                           tiles, c->tickets + 5, (uint32_t) c->row_begin, c->gp, u0, u1, D);
+    kt(c, "k_radix_sweep#0");
+    k_radix_sweep<<<tiles, SWEEP_THREADS, sweep_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], nloc, 1, c->sort_bases, c->sweep_state,
+                                                           tiles, c->tickets + 6, (uint32_t) c->row_begin, c->gp, u1, c->sorted_u, D);
     const uint32_t *skeys = c->keys[0], *sperm = c->perm[0];
-    kt(c, "k_radix_scatter#1");
-    k_post_sort<D><<<cdiv(nloc, 256), 256, 0, st>>>(skeys, sperm, c->Y, nloc, c->gp, c->box_start, c->sorted_u);
-    kt(c, "k_post_sort");
-    c->stats.kernel_launches += 7;
+    kt(c, "k_radix_sweep#1");
+    c->stats.kernel_launches += 3;
     LAUNCH_CHECK();
 
-    // ---- spread
+    // ---- spread: the grid is cleared, chunks write finished boxes + partial slots, the listed multi-chunk boxes are combined
     phase_mark(c, FITSNE_PHASE_SPREAD);
-    CKRC(launch_spread_gather<D>(c, false, M, skeys, sperm));
-    kt(c, "k_spread_chunks");
-    const int lpn = combine_lanes(c, M);
     const int Gc = M / 2;
-    const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) M;            // k_spread_combine's index space
-    k_spread_combine<D><<<cdiv(cplane * lpn, 256), 256, 0, st>>>(c->slots, c->box_start, c->gp, lpn, D == 2 ? (void *) c->chg : (void *) c->planes);
+    const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) M;            // grid elements a length-M FFT can hold
+    if (D == 2) CK(cudaMemsetAsync(c->chg, 0, cplane * sizeof(float4), st));
+    else CK(cudaMemsetAsync(c->planes, 0, (size_t) 2 * M * sizeof(float2), st));
+    CKRC(launch_spread_gather<D>(c, false, skeys, sperm));
+    kt(c, "k_spread_chunks");
+    k_spread_combine<D><<<148 * 8, 256, 0, st>>>(c->slots, c->box_start, c->gp, c->work, D == 2 ? (void *) c->chg : (void *) c->planes);
     c->stats.kernel_launches += 1;
     if (c->world > 1) {
         // every rank spread its own points: sum the partial grids (fp32).  2-D: the dense (M/2)^2 float4 region that holds
@@ -559,7 +541,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
 
     // ---- gather (+ 1/Z)
     phase_mark(c, FITSNE_PHASE_GATHER);
-    CKRC(launch_spread_gather<D>(c, true, M, skeys, sperm));
+    CKRC(launch_spread_gather<D>(c, true, skeys, sperm));
     kt(c, "k_gather");
 
     // ---- attractive term (joined here) + optimiser step
@@ -646,7 +628,7 @@ static int reorder_points(fitsne_ctx *c) {
     if (!c->orig_of) {
         CKRC(dev_alloc(c, &c->orig_of, (size_t) N)); CKRC(dev_alloc(c, &c->orig_tmp, (size_t) N));
         CKRC(dev_alloc(c, &c->pos_of, (size_t) N)); CKRC(dev_alloc(c, &c->rank_map, (size_t) N));
-        CKRC(dev_alloc(c, &c->row_P2, (size_t) N + 1)); CKRC(dev_alloc(c, &c->col_P2, E + 1)); CKRC(dev_alloc(c, &c->val_P2, E + 1));
+        CKRC(dev_alloc(c, &c->row_P2, (size_t) N + 1)); CKRC(dev_alloc(c, &c->edges2, E + 1));
         CKRC(dev_alloc(c, &c->tile_pack, E + 1)); CKRC(dev_alloc(c, &c->tile_val, E + 1));
         const int w = std::max(1, cdiv(N, 148 * TILE_ROWS));            // waves of 148 row chunks
         c->tg.rows_per_chunk = std::min(TILE_ROWS, std::max(64, cdiv(N, 148 * w)));
@@ -663,13 +645,14 @@ static int reorder_points(fitsne_ctx *c) {
         CK(cudaStreamSynchronize(st));
         {   // fixed-point scale of the tiled kernel: 2^30 / max row sum
             const int blocks = 1024;
-            k_row_sum_max<<<blocks, 256, 0, st>>>(c->row_P, c->val_P, c->edge_base, c->row_begin, c->row_end, c->kl_partial);
+            k_row_sum_max<<<blocks, 256, 0, st>>>(c->row_P, c->edges, c->edge_base, c->row_begin, c->row_end, c->kl_partial);
             std::vector<double> h(blocks);
             CK(cudaMemcpyAsync(h.data(), c->kl_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             double mx = 0;
             for (double v : h) mx = std::max(mx, v);
-            c->tile_fix32 = (float) (1073741824.0 / std::max(mx, 1e-300));
+            // |q dx| / p <= sqrt(df) / 2 for the kernel (1 + d^2/df)^-1, so a row sum stays below rowsum * max(1, sqrt(df)) / 2
+            c->tile_fix32 = (float) (1073741824.0 / (std::max(mx, 1e-300) * std::max(1.0, std::sqrt(c->cfg.df))));
         }
 #define SETSM(DD, A) CK(cudaFuncSetAttribute(k_attract_tiles<DD, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tiles_smem_bytes(DD)))
         if (D == 2) { SETSM(2, 0); SETSM(2, 1); SETSM(2, 2); SETSM(2, 3); } else { SETSM(1, 0); SETSM(1, 1); SETSM(1, 2); SETSM(1, 3); }
@@ -684,11 +667,11 @@ static int reorder_points(fitsne_ctx *c) {
     else k_morton_keys<1><<<cdiv(N, 256), 256, 0, st>>>(c->Y, N, c->sc, c->keys[0]);
     CK(cudaMemsetAsync(c->sort_totals, 0, sizeof(uint32_t) * 2 * max_bins, st));
     k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[0], N, 0, c->hist, tiles, c->sort_totals, c->gp_reorder);
-    k_radix_offsets<2><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, 0, N, nullptr, c->gp_reorder);
-    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], N, 0, c->hist, tiles, 0u, c->gp_reorder, nullptr, nullptr, D);
+    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, 0, c->gp_reorder);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], N, 0, c->hist, tiles, 0u, c->gp_reorder);
     k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[1], N, 1, c->hist, tiles, c->sort_totals + max_bins, c->gp_reorder);
-    k_radix_offsets<2><<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, 1, N, nullptr, c->gp_reorder);
-    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], N, 1, c->hist, tiles, 0u, c->gp_reorder, nullptr, nullptr, D);
+    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, 1, c->gp_reorder);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], N, 1, c->hist, tiles, 0u, c->gp_reorder);
     LAUNCH_CHECK();
     // 2. maps
     k_reorder_maps<<<cdiv(N, 256), 256, 0, st>>>(c->perm[0], N, c->rank_map, c->reordered ? c->orig_of : nullptr, c->orig_tmp, c->pos_of);
@@ -706,17 +689,17 @@ static int reorder_points(fitsne_ctx *c) {
     CK(cudaMemsetAsync(c->tile_cnt, 0, (c->ntiles + 1) * 4, st));
     CK(cudaMemsetAsync(c->tile_cur, 0, (c->ntiles + 1) * 4, st));
     CK(cudaMemsetAsync(c->nonempty, 0, 4, st));
-    k_relabel_csr<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(0, c->row_P, c->col_P, c->val_P, c->rank_map, N, c->tg, new_len, c->tile_cnt,
-                                                                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_relabel_csr<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(0, c->row_P, c->edges, c->rank_map, N, c->tg, new_len, c->tile_cnt,
+                                                                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     k_scan_excl<<<1, 1024, 0, st>>>(new_len, c->row_P2, N);
     k_scan_excl<<<1, 1024, 0, st>>>(c->tile_cnt, c->tile_start, (int) c->ntiles);
-    k_relabel_csr<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(1, c->row_P, c->col_P, c->val_P, c->rank_map, N, c->tg, new_len, c->tile_cnt,
-                                                                 c->row_P2, c->col_P2, c->val_P2, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val);
+    k_relabel_csr<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(1, c->row_P, c->edges, c->rank_map, N, c->tg, new_len, c->tile_cnt,
+                                                                 c->row_P2, c->edges2, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val);
     k_count_nonempty<<<cdiv(c->ntiles, 256), 256, 0, st>>>(c->tile_cnt, c->ntiles, c->nonempty);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(&c->nonempty_tiles, c->nonempty, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    std::swap(c->row_P, c->row_P2); std::swap(c->col_P, c->col_P2); std::swap(c->val_P, c->val_P2);
+    std::swap(c->row_P, c->row_P2); std::swap(c->edges, c->edges2);
     c->reordered = true;
     c->reorders++;
     // 5. which attractive kernel: modelled cost of the tiled path (column-block fills from L2 + the edge stream) vs
@@ -745,9 +728,9 @@ static int reorder_points(fitsne_ctx *c) {
         }
         CK(cudaMemsetAsync(c->srt_cnt, 0, (nt + 1) * 4, st));
         CK(cudaMemsetAsync(c->srt_cur, 0, (nt + 1) * 4, st));
-        k_sorted_count<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(c->row_P, c->col_P, N, c->sg, c->srt_cnt);
+        k_sorted_count<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(c->row_P, c->edges, N, c->sg, c->srt_cnt);
         k_scan_excl<<<1, 1024, 0, st>>>(c->srt_cnt, c->srt_start, (int) nt);
-        k_sorted_fill<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(c->row_P, c->col_P, c->val_P, N, c->sg, c->srt_start, c->srt_cur,
+        k_sorted_fill<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(c->row_P, c->edges, N, c->sg, c->srt_start, c->srt_cur,
                                                                     c->tile_pack, c->tile_val);
         LAUNCH_CHECK();
         CK(cudaStreamSynchronize(st));
@@ -762,9 +745,9 @@ static int reorder_points(fitsne_ctx *c) {
 
 static int maybe_reorder(fitsne_ctx *c) {
     if (c->world > 1 || (c->cfg.flags & FITSNE_FLAG_NO_REORDER) || c->E == 0) return 0;
-    if (c->reordered && c->stats.iterations - c->last_reorder_iter < c->reorder_interval) return 0;
+    if (c->reordered && c->steps_total - c->last_reorder_iter < c->reorder_interval) return 0;
     if (c->reordered) c->reorder_interval = std::min<uint64_t>(c->reorder_interval * 2, 400);
-    c->last_reorder_iter = c->stats.iterations;
+    c->last_reorder_iter = c->steps_total;
     return reorder_points(c);
 }
 
@@ -776,12 +759,12 @@ static int get_graph(fitsne_ctx *c, int M, bool update, fitsne_ctx::GraphEntry *
         Plans *pl;
         TRACE("new graph for M=%d kind=%d", M, update ? 1 : 0);
         CKRC(get_plans(c, M, &pl));   // twiddle tables are computed outside the capture
-        cudaGraph_t graph;
         const uint64_t launches_before = c->stats.kernel_launches;
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         const int rc = enqueue_iteration_d(c, M, update);
+        cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
-        if (rc != 0) return rc;
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return fail(c, FITSNE_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
         cudaGraphExec_t exec;
         CK(cudaGraphInstantiate(&exec, graph, 0));
@@ -852,6 +835,7 @@ static int run_batch(fitsne_ctx *c, int n, int *done) {
         c->stats.kernel_launches = l0 + per_iter * (uint64_t) ran;
     }
     c->stats.iterations += ran;
+    c->steps_total += ran;
     c->have_grad = c->have_grad || ran > 0;
     c->bounds_valid = true;
     TRACE("batch of %d at M=%d: %d ran", n, M, ran);
@@ -914,7 +898,7 @@ static int run_iteration(fitsne_ctx *c, bool update) {
         c->timing_this_iter = false;
     }
     c->have_grad = true;
-    if (update) { c->stats.iterations++; c->bounds_valid = true; }
+    if (update) { c->stats.iterations++; c->steps_total++; c->bounds_valid = true; }
     return 0;
 }
 
@@ -1005,6 +989,8 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaFuncSetAttribute(k_attract<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_attract<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_radix_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute((k_spread_chunks<2, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) spread_smem_bytes<2, 4>()));
     CK(cudaFuncSetAttribute(k_fft_line, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(k_conv_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(k_conv_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1028,19 +1014,22 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     c->E = (size_t) row_P[row_end] - (size_t) row_P[row_begin];
     CKRC(dev_alloc(c, &c->row_P, (size_t) N + 1));
     CK(cudaMemcpyAsync(c->row_P, row_P, ((size_t) N + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-    CKRC(dev_alloc(c, &c->col_P, c->E + 1)); CKRC(dev_alloc(c, &c->val_P, c->E + 1));
+    CKRC(dev_alloc(c, &c->edges, c->E + 1));
     if (c->E) {
         if (!col_P || !val_P) return fail(c, FITSNE_EINVAL, "col_P/val_P are NULL but the graph has edges");
-        CK(cudaMemcpyAsync(c->col_P, col_P, c->E * 4, cudaMemcpyHostToDevice, c->stream));
-        // val_P: double -> float in bounded chunks
+        // (col u32, val f64) -> one 8-byte edge word (col, fp32 weight), in bounded chunks through two staging buffers
         const size_t chunk = 1u << 24;
         CKRC(dev_alloc(c, &c->staging, chunk)); c->staging_elems = chunk;
+        uint32_t *col_stage = nullptr;
+        CKRC(dev_alloc(c, &col_stage, chunk));
         for (size_t off = 0; off < c->E; off += chunk) {
             const size_t n = std::min(chunk, c->E - off);
+            CK(cudaMemcpyAsync(col_stage, col_P + off, n * 4, cudaMemcpyHostToDevice, c->stream));
             CK(cudaMemcpyAsync(c->staging, val_P + off, n * 8, cudaMemcpyHostToDevice, c->stream));
-            k_d2f<<<cdiv(n, 256), 256, 0, c->stream>>>(c->staging, c->val_P + off, n);
+            k_pack_edges<<<cdiv(n, 256), 256, 0, c->stream>>>(col_stage, c->staging, c->edges + off, n);
             CK(cudaStreamSynchronize(c->stream));
         }
+        cudaFree(col_stage);
     }
     const double avg = (double) c->E / (double) std::max(1, c->nloc);
     c->lpr = avg > 96 ? 32 : avg > 40 ? 16 : avg > 6 ? 8 : 4;   // lanes per CSR row (B200 sweep at 30 nnz/row: 8 lanes best)
@@ -1049,11 +1038,15 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CKRC(dev_alloc(c, &c->perm[0], (size_t) c->nloc)); CKRC(dev_alloc(c, &c->perm[1], (size_t) c->nloc));
     CKRC(dev_alloc(c, &c->sorted_u, (size_t) c->nloc * no_dims));
     c->hist_cap = (size_t) cdiv(c->nloc, SORT_TILE) * (1 << SORT_MAX_BITS);
-    CKRC(dev_alloc(c, &c->hist, c->hist_cap));
+    CKRC(dev_alloc(c, &c->hist, c->hist_cap)); CKRC(dev_alloc(c, &c->sweep_state, 2 * c->hist_cap));
+    CKRC(dev_alloc(c, &c->sort_bases, (size_t) 2 * (1 << SORT_MAX_BITS)));
+    CKRC(dev_alloc(c, &c->work, (size_t) cdiv(c->nloc, CHUNK) + 2));
     CKRC(dev_alloc(c, &c->sort_totals, (size_t) 2 * (1 << SORT_MAX_BITS)));
     {
         const size_t nodes = no_dims == 2 ? (size_t) cfg->nterms * cfg->nterms : (size_t) cfg->nterms;
-        CKRC(dev_alloc(c, &c->slots, (size_t) cdiv(c->nloc, CHUNK) * 2 * nodes));
+        CKRC(dev_alloc(c, &c->slots, (size_t) cdiv(c->nloc, SP2_POINTS) * 2 * nodes));
+        const bool generic = cfg->nterms < 2 || cfg->nterms > (no_dims == 2 ? 4 : 5);      // launch_spread_gather's fallback
+        if (generic) CKRC(dev_alloc(c, &c->gpart, (size_t) cdiv(c->nloc, SP2_POINTS) * SP2_THREADS * 2 * nodes));
     }
     CKRC(dev_alloc(c, &c->colsum_partial, (size_t) RED_BLOCKS * 2));
     CKRC(dev_alloc(c, &c->bounds_partial, (size_t) RED_BLOCKS));
@@ -1118,11 +1111,11 @@ int fitsne_destroy(fitsne_ctx *c) {
     drop_graphs(c);
     for (auto &p : c->plans) if (p.second.W) cudaFree(p.second.W);
     if (c->comm) g_nccl.CommDestroy(c->comm);
-    void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->col_P, c->val_P, c->keys[0], c->keys[1],
-                    c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->hist, c->sort_totals, c->slots, c->attr, c->planes,
+    void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->edges, c->keys[0], c->keys[1],
+                    c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->gpart, c->hist, c->sweep_state, c->sort_bases, c->work, c->sort_totals, c->slots, c->attr, c->planes,
                     c->chg, c->pot, c->S, c->KR, c->KS, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
-                    c->row_P2, c->col_P2, c->val_P2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
+                    c->row_P2, c->edges2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
                     c->nonempty, c->gp_reorder, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial, c->srt_cnt, c->srt_start, c->srt_cur};
     for (void *b : bufs) if (b) cudaFree(b);
     if (c->host_bounds) cudaFreeHost(c->host_bounds);
@@ -1240,10 +1233,10 @@ static int kl_impl(fitsne_ctx *c, double exaggeration, double *C_out) {
     CKRC(ensure_whole_Y(c));
     const int blocks = std::min(4096, std::max(1, cdiv((long long) (c->row_end - c->row_begin) * 32, 256)));
     if (c->D == 2)
-        k_kl<2><<<blocks, 256, 0, c->stream>>>(c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->row_begin, c->row_end,
+        k_kl<2><<<blocks, 256, 0, c->stream>>>(c->row_P, c->edges, c->edge_base, c->Y, c->row_begin, c->row_end,
                                               exaggeration, c->cfg.df, c->sc, c->kl_partial);
     else
-        k_kl<1><<<blocks, 256, 0, c->stream>>>(c->row_P, c->col_P, c->val_P, c->edge_base, c->Y, c->row_begin, c->row_end,
+        k_kl<1><<<blocks, 256, 0, c->stream>>>(c->row_P, c->edges, c->edge_base, c->Y, c->row_begin, c->row_end,
                                               exaggeration, c->cfg.df, c->sc, c->kl_partial);
     k_finalize_kl<<<1, 256, 0, c->stream>>>(c->kl_partial, blocks, c->sc);
     LAUNCH_CHECK();
@@ -1265,7 +1258,7 @@ int fitsne_kl(fitsne_ctx *c, double exaggeration, double *C_out) {
 
 static int auto_exaggeration(fitsne_ctx *c, double learning_rate, double *coeff) {
     const int blocks = 1024;
-    k_row_sum_max<<<blocks, 256, 0, c->stream>>>(c->row_P, c->val_P, c->edge_base, c->row_begin, c->row_end, c->kl_partial);
+    k_row_sum_max<<<blocks, 256, 0, c->stream>>>(c->row_P, c->edges, c->edge_base, c->row_begin, c->row_end, c->kl_partial);
     LAUNCH_CHECK();
     std::vector<double> h(blocks);
     CK(cudaMemcpyAsync(h.data(), c->kl_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1314,7 +1307,7 @@ int fitsne_run(fitsne_ctx *c, const fitsne_schedule *s, double *costs, double *Y
         clip(s->stop_lying_iter); clip(s->start_late_exag_iter); clip(s->mom_switch_iter);
         clip((long long) (iter / 50 + 1) * 50 - 1);
         if (c->world == 1 && !(c->cfg.flags & FITSNE_FLAG_NO_REORDER) && c->reordered)
-            clip((long long) iter + (long long) (c->last_reorder_iter + c->reorder_interval - c->stats.iterations) - 1);
+            clip((long long) iter + (long long) (c->last_reorder_iter + c->reorder_interval - c->steps_total) - 1);
         int ran = 1;
         if (batched) CKRC(run_batch(c, end - iter + 1, &ran));
         else { CKRC(run_iteration(c, true)); end = iter; }

@@ -2,8 +2,8 @@
 //
 // Everything the reference does per iteration (reference = /root/reference/src/...) in fp32 on the device:
 //   bounds + zero-mean        tsne.cpp:1039-1049, :1851-1876        k_colsum, k_center_bounds, k_setup_grid (sharded: k_shard_stats, k_center_shard)
-//   point -> box, sort        nbodyfft.cpp:85-114                    k_bin, k_radix_hist/offsets/scatter, k_post_sort
-//   Lagrange spread           nbodyfft.cpp:123-147, :310-336         k_spread_chunks2 (k_spread_chunks), k_spread_combine
+//   point -> box, sort        nbodyfft.cpp:85-114                    k_bin, k_radix_offsets, k_radix_scatter
+//   Lagrange spread           nbodyfft.cpp:123-147, :310-336         k_spread_chunks, k_spread_combine
 //   kernel samples            nbodyfft.cpp:52-61, tsne.cpp:69-94     k_gen_kernels        (+ forward FFTs, fitsne_fft.cuh)
 //   Hadamard + sum_Q          nbodyfft.cpp:184-191, tsne.cpp:1101-1110  k_hadamard           (+ inverse FFTs)
 //   gather + normalise        nbodyfft.cpp:222-239, tsne.cpp:1149-1151  k_gather
@@ -16,13 +16,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include <float.h>
 #include <type_traits>
 
 namespace fk {
 
 constexpr int PMAX = 16;          // max interpolation points per box and axis
-constexpr int CHUNK = 32;         // points per spread work item
+constexpr int CHUNK = 16;         // points per spread work item
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
@@ -280,9 +281,12 @@ __host__ __device__ inline int sort_bits_for(int B, int dims) {
 
 // Fill GridParams for a grid of B boxes/dim (the host's choice; verified against the device's own bounds).
 __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restrict__ sc, const int *__restrict__ B_host, int M, int p, int dims,
-                             double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals) {
+                             double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals,
+                             uint32_t *__restrict__ work, unsigned int *__restrict__ sweep_tickets) {
     for (int i = threadIdx.x; i < 2 * (1 << SORT_MAX_BITS); i += blockDim.x) sort_totals[i] = 0;   // both passes
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    work[0] = 0;                                     // spread work list (boxes that span several chunks) starts empty
+    sweep_tickets[0] = 0; sweep_tickets[1] = 0;      // tile tickets of the two sort passes
     // B_host > 0: the host sized the grid after reading the bounds (single-step API); 0: speculative launch, the device
     // sizes the grid itself and the whole iteration becomes a no-op if that grid does not belong to this graph's M
     const int hostB = *reinterpret_cast<const volatile int *>(B_host);
@@ -319,47 +323,95 @@ __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restr
 }
 
 // -------------------------------------------------------------------------------------------- binning --
-// Stable LSD radix sort of (box key, point index): one pass when the key has <= SORT_ONE_PASS_BITS bits, else two
-// passes of `sort_bits` bits each:
-//   k_bin            keys + per-tile histogram of digit 0 (fused)      k_radix_hist   per-tile histogram of digit 1
-//   k_radix_offsets  per-digit tile offsets (one CTA per digit value)  k_radix_scatter stable scatter
-// Stability (ties keep point-index order) makes the box-sorted order, hence the spread's summation order,
-// bitwise repeatable.  key = (by << xbits) | bx.
-// hist layout: [digit][tile];  totals[pass][digit] = sum over tiles (integer atomics: order-independent).
+// Stable LSD radix sort of (box key, point index, in-box coordinates) in THREE launches (one pass when the key has
+// <= SORT_ONE_PASS_BITS bits, else two passes of `sort_bits` bits each):
+//   k_bin            box id + in-box coordinate (fp64, reference order); global totals of BOTH digits (shared-memory
+//                    histograms, one integer atomic per digit and CTA); the last CTA turns the totals into exclusive digit
+//                    bases; every CTA clears its tile's look-back words
+//   k_radix_sweep#0  one CTA per tile of SORT_TILE keys: warp-level stable ranks, tile totals per digit published as ONE
+//   k_radix_sweep#1  word (ready bit | count), exclusive prefix over the earlier tiles by summing their words as they
+//                    appear, stable scatter.  Tiles take their index from an atomic ticket, so a tile's predecessors are
+//                    always running or done: no deadlock, no separate histogram / offset kernels, no host involvement.
+// The in-box coordinates ride through both scatters (8 bytes per point) instead of being recomputed from Y[perm] in fp64
+// after the sort.  Counts are integers, so the result does not depend on timing: stability (ties keep point-index order)
+// makes the box-sorted order, hence the spread's summation order, bitwise repeatable.  key = (by << xbits) | bx.
+// (The point re-ordering every few hundred iterations sorts 22-bit Morton keys with the older four-kernel pass below.)
+
+#ifdef __CUDA_ARCH__
+#define FK_ATOMIC_ADD(ptr, v) atomicAdd((ptr), (v))
+#else
+#define FK_ATOMIC_ADD(ptr, v) fk_host_fetch_add((ptr), (v))
+template <typename T>
+static inline T fk_host_fetch_add(T *p, T v) { const T old = *p; *p = old + v; return old; }
+#endif
+
+constexpr int BIN_THREADS = 1024;                       // k_bin: SORT_TILE / 1024 = 4 points per thread
+constexpr int SWEEP_THREADS = 512;                      // k_radix_sweep: 16 warps x 8 keys per lane
+constexpr int SWEEP_IPT = SORT_TILE / SWEEP_THREADS;
+constexpr uint32_t SWEEP_READY = 0x80000000u;
 
 __device__ __forceinline__ void tile_hist_flush(const uint32_t *cnt, int nb, uint32_t *hist, int tiles, uint32_t *totals) {
-    for (int i = threadIdx.x; i < nb; i += SORT_THREADS) {
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
         const uint32_t v = cnt[i];
-        hist[(size_t) i * tiles + blockIdx.x] = v;
+        if (hist) hist[(size_t) i * tiles + blockIdx.x] = v;
         if (v) atomicAdd(&totals[i], v);
     }
 }
 
+// exclusive scan of totals[0..nb) into bases[0..nb) by one CTA (nb <= 2048)
+__device__ __forceinline__ void block_excl_scan(const uint32_t *__restrict__ totals, uint32_t *__restrict__ bases, int nb, uint32_t *sm /*[33]*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t carry = 0;
+    for (int base = 0; base < nb; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const uint32_t x = i < nb ? __ldcg(totals + i) : 0u;
+        uint32_t inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        __syncthreads();
+        if (lane == 31) sm[w] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int i2 = 0; i2 < w; i2++) wbase += sm[i2];
+        if (i < nb) bases[i] = carry + wbase + inc - x;
+        uint32_t tot = 0;
+        for (int i2 = 0; i2 < nw; i2++) tot += sm[i2];
+        carry += tot;
+    }
+}
+
 template <int D>
-__global__ void __launch_bounds__(SORT_THREADS) k_bin(const float *__restrict__ Y, int first, int n,
-                                                      const GridParams *__restrict__ gpp, uint32_t *__restrict__ keys_two_pass,
-                                                      uint32_t *__restrict__ keys_one_pass, float *__restrict__ ubuf,
-                                                      uint32_t *__restrict__ hist, int tiles, uint32_t *__restrict__ totals) {
-    __shared__ uint32_t cnt[1 << SORT_MAX_BITS];
+__global__ void __launch_bounds__(BIN_THREADS) k_bin(const float *__restrict__ Y, int first, int n,
+                                                     const GridParams *__restrict__ gpp, uint32_t *__restrict__ keys_two_pass,
+                                                     uint32_t *__restrict__ keys_one_pass, float *__restrict__ ubuf_two_pass,
+                                                     float *__restrict__ ubuf_one_pass, uint32_t *__restrict__ totals,
+                                                     uint32_t *__restrict__ bases, uint32_t *__restrict__ state, int tiles,
+                                                     unsigned int *__restrict__ ticket) {
+    __shared__ uint32_t cnt[2 << SORT_MAX_BITS];       // digit 0 | digit 1
     __shared__ GridParams gps;
+    __shared__ uint32_t scan_sm[33];
     for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
     __syncthreads();
     const GridParams &gp = gps;
     if (!gp.ok) return;
-    // one-pass layout: this histogram (whole key) is the one the single scatter uses -> it goes to the pass-1 totals,
-    // the keys go to the scatter's input buffer, and the in-box coordinates ride along (no k_post_sort needed)
     const bool one = gp.sort_passes == 1;
-    uint32_t *keys = one ? keys_one_pass : keys_two_pass;
-    uint32_t *tot = one ? totals + (1 << SORT_MAX_BITS) : totals;
-    const int nb = 1 << gp.sort_bits;
+    uint32_t *keys = one ? keys_one_pass : keys_two_pass;      // whatever feeds the first sweep that really runs
+    float *ubuf = one ? ubuf_one_pass : ubuf_two_pass;
+    const int bits = gp.sort_bits, nb = 1 << bits;
     const uint32_t mask = (uint32_t) nb - 1;
-    for (int i = threadIdx.x; i < nb; i += SORT_THREADS) cnt[i] = 0;
+    constexpr int NBMAX = 1 << SORT_MAX_BITS;
+    uint32_t *cnt1 = cnt + NBMAX;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        cnt[i] = 0; cnt1[i] = 0;
+        state[((size_t) blockIdx.x) * NBMAX + i] = 0;                          // look-back words of this tile, pass 0
+        state[((size_t) tiles + blockIdx.x) * NBMAX + i] = 0;                  // ... pass 1
+    }
     __syncthreads();
     const int base = blockIdx.x * SORT_TILE;
-#pragma unroll 4
-    for (int r = 0; r < SORT_IPT; r++) {
-        const int k = base + r * SORT_THREADS + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < SORT_TILE / BIN_THREADS; r++) {
+        const int k = base + r * BIN_THREADS + threadIdx.x;
         if (k < n) {
             uint32_t key;
             if (D == 2) {
@@ -368,24 +420,137 @@ __global__ void __launch_bounds__(SORT_THREADS) k_bin(const float *__restrict__ 
                 const int bx = box_of<true>(y.x, gp, u.x);
                 const int by = box_of<true>(y.y, gp, u.y);
                 key = ((uint32_t) by << gp.xbits) | (uint32_t) bx;
-                if (one) reinterpret_cast<float2 *>(ubuf)[k] = u;
+                reinterpret_cast<float2 *>(ubuf)[k] = u;
             } else {
                 float u;
                 key = (uint32_t) box_of<false>(Y[first + k], gp, u);
-                if (one) ubuf[k] = u;
+                ubuf[k] = u;
             }
             keys[k] = key;
             atomicAdd(&cnt[key & mask], 1u);
+            if (!one) atomicAdd(&cnt1[(key >> bits) & mask], 1u);
         }
     }
     __syncthreads();
-    tile_hist_flush(cnt, nb, hist, tiles, tot);
+    // one-pass layout: this histogram (whole key) is the one the single sweep uses -> pass-1 slot
+    if (one) tile_hist_flush(cnt, nb, nullptr, tiles, totals + NBMAX);
+    else {
+        tile_hist_flush(cnt, nb, nullptr, tiles, totals);
+        tile_hist_flush(cnt1, nb, nullptr, tiles, totals + NBMAX);
+    }
+    __threadfence();
+    __syncthreads();                              // all of this CTA's atomics are performed before thread 0 takes the ticket
+    if (last_block_done(ticket)) {                // digit totals -> exclusive digit bases, both passes
+        if (!one) block_excl_scan(totals, bases, nb, scan_sm);
+        __syncthreads();
+        block_excl_scan(totals + NBMAX, bases + NBMAX, nb, scan_sm);
+    }
 }
 
+// One pass of the per-iteration sort; see the section comment.  vals_in == nullptr or first executed pass: values are the
+// identity (+ val_base).  u_in/u_out: `dims` floats per element that travel with it.
+__global__ void __launch_bounds__(SWEEP_THREADS) k_radix_sweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                               uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int n,
+                                                               int pass, const uint32_t *__restrict__ bases, uint32_t *state, int tiles,
+                                                               unsigned int *__restrict__ ticket, uint32_t val_base,
+                                                               const GridParams *__restrict__ gpp, const float *__restrict__ u_in,
+                                                               float *__restrict__ u_out, int dims) {
+    if (!gpp->ok) return;
+    const bool one = gpp->sort_passes == 1;
+    if (one && pass == 0) return;
+    if (one || pass == 0) vals_in = nullptr;
+    extern __shared__ uint32_t smem[];
+    __shared__ int tile_s;
+    const int bits = gpp->sort_bits, shift = one ? 0 : pass * bits;
+    const int nb = 1 << bits;
+    constexpr int NW = SWEEP_THREADS / 32, NBMAX = 1 << SORT_MAX_BITS;
+    uint32_t *gbase = smem;                                          // [nb]
+    uint16_t *cnt = reinterpret_cast<uint16_t *>(smem + nb);         // [NW][nb]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) tile_s = (int) atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < NW * nb; i += SWEEP_THREADS) cnt[i] = 0;
+    __syncthreads();
+    const int tile = tile_s;
+    const uint32_t mask = (uint32_t) nb - 1;
+    const int base = tile * SORT_TILE + w * (SWEEP_IPT * 32);
+    uint32_t key[SWEEP_IPT], rank[SWEEP_IPT];
+    uint16_t *mycnt = cnt + w * nb;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < SWEEP_IPT; r++) {
+        const int i = base + r * 32 + lane;
+        key[r] = i < n ? keys_in[i] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < SWEEP_IPT; r++) {
+        const int i = base + r * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((key[r] >> shift) & mask) : (uint32_t) nb;   // sentinel digit groups the tail
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader && valid) {
+            old = mycnt[d];
+            mycnt[d] = (uint16_t) (old + __popc(peers));
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over this tile's warps, publish the tile total, sum the earlier tiles' totals
+    uint32_t *mystate = state + ((size_t) pass * tiles + tile) * NBMAX;
+    const uint32_t *prev = state + (size_t) pass * tiles * NBMAX;
+    for (int d = threadIdx.x; d < nb; d += SWEEP_THREADS) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++) {
+            const uint32_t t = cnt[ww * nb + d];
+            cnt[ww * nb + d] = (uint16_t) run;
+            run += t;
+        }
+        *reinterpret_cast<volatile uint32_t *>(mystate + d) = SWEEP_READY | run;
+        uint32_t excl = 0;
+        int t = 0;
+        for (; t + 8 <= tile; t += 8) {           // eight words in flight; re-read until all eight are published
+            uint32_t v[8];
+            bool all;
+            do {
+                all = true;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { v[j] = *reinterpret_cast<const volatile uint32_t *>(prev + (size_t) (t + j) * NBMAX + d); all = all && (v[j] & SWEEP_READY); }
+            } while (!all);
+#pragma unroll
+            for (int j = 0; j < 8; j++) excl += v[j] & ~SWEEP_READY;
+        }
+        for (; t < tile; t++) {
+            uint32_t v;
+            do { v = *reinterpret_cast<const volatile uint32_t *>(prev + (size_t) t * NBMAX + d); } while (!(v & SWEEP_READY));
+            excl += v & ~SWEEP_READY;
+        }
+        gbase[d] = bases[(size_t) pass * NBMAX + d] + excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SWEEP_IPT; r++) {
+        const int i = base + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (key[r] >> shift) & mask;
+            const uint32_t pos = gbase[d] + mycnt[d] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = vals_in ? vals_in[i] : (val_base + (uint32_t) i);
+            if (dims == 2) reinterpret_cast<float2 *>(u_out)[pos] = reinterpret_cast<const float2 *>(u_in)[i];
+            else u_out[pos] = u_in[i];
+        }
+    }
+}
+
+// per-tile histogram of digit `pass` of already computed keys (point re-ordering only: the per-iteration box sort gets
+// its histograms from k_bin and k_radix_scatter)
 __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint32_t *__restrict__ keys, int n, int pass,
                                                              uint32_t *__restrict__ hist, int tiles, uint32_t *__restrict__ totals,
                                                              const GridParams *__restrict__ gpp) {
-    if (!gpp->ok || gpp->sort_passes == 1) return;      // one-pass layout: k_bin already produced the histogram
+    if (!gpp->ok || gpp->sort_passes == 1) return;
     __shared__ uint32_t cnt[1 << SORT_MAX_BITS];
     const int bits = gpp->sort_bits, shift = pass * bits;
     const int nb = 1 << bits;
@@ -403,10 +568,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint32_t *__r
 }
 
 // One CTA per digit value d: hist[d][t] <- (sum of totals[d' < d]) + (exclusive prefix over tiles t' < t), in place.
-template <int D>
 __global__ void __launch_bounds__(256) k_radix_offsets(uint32_t *__restrict__ hist, int tiles, const uint32_t *__restrict__ totals,
-                                                       int pass, int n, uint32_t *__restrict__ box_start,
-                                                       const GridParams *__restrict__ gpp) {
+                                                       int pass, const GridParams *__restrict__ gpp) {
     if (!gpp->ok) return;
     const bool one = gpp->sort_passes == 1;
     if (one && pass == 0) return;
@@ -427,15 +590,6 @@ __global__ void __launch_bounds__(256) k_radix_offsets(uint32_t *__restrict__ hi
         uint32_t t = 0;
         for (int i = 0; i < 8; i++) t += wsum[i];
         carry_s = t;
-        if (one && box_start) {
-            // the digit IS the box key: its global base is the box's first sorted position (keys are ordered like boxes)
-            const int B = gpp->B;
-            if (D == 2) {
-                const int by = d >> gpp->xbits, bx = d & ((1 << gpp->xbits) - 1);
-                if (bx < B && by < B) box_start[by * B + bx] = t;
-            } else if (d < B) box_start[d] = t;
-            if (d == 0) box_start[gpp->nb] = (uint32_t) n;
-        }
     }
     __syncthreads();
     uint32_t *rowp = hist + (size_t) d * tiles;
@@ -461,17 +615,17 @@ __global__ void __launch_bounds__(256) k_radix_offsets(uint32_t *__restrict__ hi
     }
 }
 
+// Stable scatter by digit `pass` from precomputed offsets.  vals_in == nullptr: values are the identity (+ val_base).
 __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t *__restrict__ keys_in,
                                                                 const uint32_t *__restrict__ vals_in,
                                                                 uint32_t *__restrict__ keys_out,
                                                                 uint32_t *__restrict__ vals_out, int n, int pass,
                                                                 const uint32_t *__restrict__ hist, int tiles,
-                                                                uint32_t val_base, const GridParams *__restrict__ gpp,
-                                                                const float *__restrict__ ubuf, float *__restrict__ sorted_u, int dims) {
+                                                                uint32_t val_base, const GridParams *__restrict__ gpp) {
     if (!gpp->ok) return;
     const bool one = gpp->sort_passes == 1;
     if (one && pass == 0) return;
-    if (one) vals_in = nullptr;                           // single pass: values are the identity (+ val_base)
+    if (one || pass == 0) vals_in = nullptr;              // first scatter of the sort: values are the identity (+ val_base)
     extern __shared__ uint32_t smem[];
     const int bits = gpp->sort_bits, shift = one ? 0 : pass * bits;
     const int nb = 1 << bits;
@@ -524,47 +678,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t *
             const uint32_t pos = gbase[d] + mycnt[d] + rank[r];
             keys_out[pos] = key[r];
             vals_out[pos] = vals_in ? vals_in[i] : (val_base + (uint32_t) i);
-            if (one && ubuf) {                            // in-box coordinates computed by k_bin ride along
-                if (dims == 2) reinterpret_cast<float2 *>(sorted_u)[pos] = reinterpret_cast<const float2 *>(ubuf)[i];
-                else sorted_u[pos] = ubuf[i];
-            }
         }
-    }
-}
-
-// After the sort: box_start[] by boundary detection (no atomics, empty boxes included) and the in-box
-// coordinates in sorted order.  box id = by*B + bx.
-template <int D>
-__global__ void __launch_bounds__(256) k_post_sort(const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ perm,
-                                                   const float *__restrict__ Y, int n,
-                                                   const GridParams *__restrict__ gpp, uint32_t *__restrict__ box_start,
-                                                   float *__restrict__ sorted_u) {
-    const GridParams &gp = *gpp;
-    if (!gp.ok || gp.sort_passes == 1) return;           // one-pass layout: box_start and sorted_u are already there
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const uint32_t key = skeys[k];
-    const uint32_t xmask = (1u << gp.xbits) - 1u;
-    const int box = D == 2 ? (int) (key >> gp.xbits) * gp.B + (int) (key & xmask) : (int) key;
-    int lo;   // boxes (lo, box] start at k
-    if (k == 0) lo = -1;
-    else {
-        const uint32_t pk = skeys[k - 1];
-        lo = D == 2 ? (int) (pk >> gp.xbits) * gp.B + (int) (pk & xmask) : (int) pk;
-    }
-    for (int b = lo + 1; b <= box; b++) box_start[b] = (uint32_t) k;
-    if (k == n - 1) for (int b = box + 1; b <= gp.nb; b++) box_start[b] = (uint32_t) n;
-    const uint32_t pi = perm[k];
-    if (D == 2) {
-        const float2 y = reinterpret_cast<const float2 *>(Y)[pi];
-        float2 u;
-        box_of<true>(y.x, gp, u.x);
-        box_of<true>(y.y, gp, u.y);
-        reinterpret_cast<float2 *>(sorted_u)[k] = u;
-    } else {
-        float u;
-        box_of<false>(Y[pi], gp, u);
-        sorted_u[k] = u;
     }
 }
 
@@ -582,13 +696,25 @@ __host__ __device__ __forceinline__ float lagrange1(const GridParams &gp, int p,
     return v;
 }
 
-// Spread, deterministic and atomic-free.  The box-sorted points are cut into fixed chunks of CHUNK consecutive
-// points (chunk c = sorted positions [c*CHUNK, (c+1)*CHUNK)); one thread per (chunk, interpolation node) walks its
-// points in order and accumulates (L, L*bx, L*by, L*|b|^2) per box segment:
-//   * a box that lies entirely inside the chunk is finished here and written straight to the grid;
-//   * a segment of a box that continues into a neighbouring chunk goes to slot[c][0] when the box started before
-//     this chunk, else to slot[c][1]; k_spread_combine adds a box's slots in chunk order.
+// Spread (nbodyfft.cpp:123-147), deterministic and free of float atomics.  The box-sorted points are cut into fixed
+// chunks of CHUNK consecutive points; ONE THREAD per chunk walks its points in order with all p^D node accumulators
+// (L, L*bx, L*by, L*|b|^2) in registers (phase 2), then the chunks of a CTA (SP2_THREADS chunks = SP2_POINTS points) are
+// stitched together in shared memory (phase 3):
+//   * a box that lies entirely inside a chunk is finished in phase 2 and written straight to the (pre-zeroed) grid;
+//   * the first / last segment of a chunk that continues from / into the neighbouring chunk is parked in shared memory
+//     (H / T partial of the chunk); in phase 3 the thread of the chunk where such a box starts adds the partials of the
+//     following chunks in chunk order and writes the box -- no round trip through global memory;
+//   * only a box that crosses a CTA boundary leaves a partial in a global slot (two per CTA) and is appended to a work
+//     list by the CTA that holds its head; k_spread_combine adds those few slots in CTA order.
+//   * box boundaries are detected on the way (one look at the key before and after the chunk): box_start[] -- which only
+//     the combine step needs -- is a by-product, not a separate pass.
+// Everything else in the grid is zero (empty box), so nothing ever iterates over the grid's nodes.  Every sum has a fixed
+// order given the sorted order, which the stable sort makes unique: bitwise repeatable.
 //   2-D: node = a*p + b, a = y node, b = x node (grid row = y node, column = x node).  1-D: (L, L*b, L*b^2, 0).
+// A chunk's keys are 64 contiguous bytes and its in-box coordinates 128 (2-D): the walk reads them straight from global
+// memory -- one cache line per thread, L1 hits after the first touch -- so shared memory holds nothing but the partials.
+// Written as phase functions so that tests/tools/spread_emul.cu can run the very same code on the host (all threads of a
+// block through phase 2, then phase 3) and check it against a direct spread.
 template <int D>
 __host__ __device__ __forceinline__ int key_to_box(uint32_t key, const GridParams &gp) {
     return D == 2 ? (int) (key >> gp.xbits) * gp.B + (int) (key & ((1u << gp.xbits) - 1u)) : (int) key;
@@ -622,160 +748,96 @@ __host__ __device__ __forceinline__ size_t node_offset(int box, int node, const 
     return (size_t) box * p + node;
 }
 
-template <int D, int P>
-__global__ void __launch_bounds__(256) k_spread_chunks(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
-                                                       const uint32_t *__restrict__ box_start, int n,
-                                                       const GridParams *__restrict__ gpp, int chunks_per_block,
-                                                       float4 *__restrict__ slots, void *__restrict__ grid) {
-    __shared__ GridParams gps;
-    for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
-        reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
-    __syncthreads();
-    const GridParams &gp = gps;
-    if (!gp.ok) return;
-    const int p = P > 0 ? P : gp.p;
-    const int nodes = D == 2 ? p * p : p;
-    const int cl = threadIdx.x / nodes;
-    if (cl >= chunks_per_block) return;
-    const int node = threadIdx.x - cl * nodes;
-    const int c = blockIdx.x * chunks_per_block + cl;
-    const int kb = c * CHUNK;
-    if (kb >= n) return;
-    const int ke = min(kb + CHUNK, n);
-    const int a = D == 2 ? node / p : node, b = D == 2 ? node - a * p : 0;
-    const float sa = gp.s[a], sb = gp.s[b];
-    const size_t stride = (size_t) gp.M;              // 1-D: plane 0 -> plane 1
-    float4 *myslots = slots + (size_t) c * 2 * nodes;
-
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cur = key_to_box<D>(skeys[kb], gp);
-    for (int k = kb; k < ke; k++) {
-        const int box = key_to_box<D>(skeys[k], gp);
-        if (box != cur) {
-            // segment of `cur` ended inside the chunk: finished box unless it started before the chunk
-            if ((int) box_start[cur] >= kb) store_node<D>(grid, stride, node_offset<D>(cur, node, gp, p), acc);
-            else myslots[node] = acc;
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            cur = box;
-        }
-        if (D == 2) {
-            const float2 u = reinterpret_cast<const float2 *>(sorted_u)[k];
-            const float L = lagrange1<P>(gp, p, a, u.y) * lagrange1<P>(gp, p, b, u.x);
-            const float ox = u.x - sb, oy = u.y - sa;      // offsets in BOX UNITS (x bw later): keeps the packed planes O(w1)
-            acc.x += L;
-            acc.y += L * ox;
-            acc.z += L * oy;
-            acc.w += L * (ox * ox + oy * oy);
-        } else {
-            const float u = sorted_u[k];
-            const float L = lagrange1<P>(gp, p, a, u);
-            const float o = u - sa;                         // box units
-            acc.x += L;
-            acc.y += L * o;
-            acc.z += L * o * o;
-        }
-    }
-    // last segment: finished only if the box both started in this chunk and ends with it
-    const bool started_here = (int) box_start[cur] >= kb, ends_here = (int) box_start[cur + 1] <= ke;
-    if (started_here && ends_here) store_node<D>(grid, stride, node_offset<D>(cur, node, gp, p), acc);
-    else myslots[(started_here ? 1 : 0) * nodes + node] = acc;
-}
-
-// ---- spread, second formulation: ONE THREAD PER CHUNK (all p^D nodes in registers) -------------------------------
-// k_spread_chunks spends one thread per (chunk, node): the key decode, the box-change test, both loads and the Lagrange
-// factors are repeated p^D times per point (SASS: ~45 instructions per point and node, 400 per point at p = 3, issue-
-// and latency-bound: 31 us at N = 1M, 0.4 ms at N = 10M = 4 % of the HBM roofline).  Here a thread owns a chunk and
-// keeps the p^D float4 accumulators in registers: ~95 instructions per point.  A thread walking 32 consecutive points
-// would read with a 256-byte lane stride, so the block first stages its 64 chunks (2048 points: keys + in-box
-// coordinates) in shared memory with coalesced loads; chunk c lives at element offset c*33, which makes the per-thread
-// walk bank-conflict free.  Same segment rules, same per-node summation order (serial over the chunk's points) and the
-// same slot layout as k_spread_chunks, so k_spread_combine is unchanged.
-// Written as two phase functions so that tests/tools/spread_emul.cu can run the very same code on the host (all
-// threads of a block through phase 1, then through phase 2) and check it against a direct spread.
-constexpr int SP2_THREADS = 64;                 // chunks per block
-constexpr int SP2_STRIDE = CHUNK + 1;           // padded chunk stride in shared memory (elements)
+constexpr int SP2_THREADS = 128;                // chunks per block
 constexpr int SP2_POINTS = SP2_THREADS * CHUNK;
 
-template <int D>
-struct alignas(16) Sp2Smem {
-    uint32_t keys[SP2_THREADS * SP2_STRIDE];
-    float u[SP2_THREADS * SP2_STRIDE * D];
-};
-
-// phase 1: thread t of block `blk` copies its share of the block's points (coalesced) into the padded layout
-template <int D>
-__host__ __device__ __forceinline__ void spread2_load(int t, int blk, const float *__restrict__ sorted_u,
-                                                      const uint32_t *__restrict__ skeys, int n, Sp2Smem<D> &sm) {
-    const int base = blk * SP2_POINTS;
-    for (int i = t; i < SP2_POINTS; i += SP2_THREADS) {
-        const int k = base + i;
-        if (k < n) {
-            const int e = i + (i >> 5);          // CHUNK == 32: one pad element per chunk
-            sm.keys[e] = skeys[k];
-            if (D == 2) reinterpret_cast<float2 *>(sm.u)[e] = reinterpret_cast<const float2 *>(sorted_u)[k];
-            else sm.u[e] = sorted_u[k];
-        }
-    }
-}
-
-// all nodes of one box segment: to the grid (finished box; one box -> base offset computed once) or to a slot
-template <int D, int P, int NODES>
-__host__ __device__ __forceinline__ void spread2_flush(const float4 (&acc)[NODES], bool to_grid, int box, const GridParams &gp,
+// all nodes of one box segment: to the grid (finished box; one box -> base offset computed once) or to a partial slot.
+// P > 0: compile-time node count (registers); P == 0: run-time p (nterms > 4 in 2-D, > 5 in 1-D; local-memory accumulators)
+template <int D, int P, int MAXN>
+__host__ __device__ __forceinline__ void spread2_flush(const float4 (&acc)[MAXN], int p, bool to_grid, int box, const GridParams &gp,
                                                        void *__restrict__ grid, size_t stride, float4 *__restrict__ slot) {
+    const int nodes = D == 2 ? p * p : p;
     if (to_grid) {
-        const size_t base = node_offset<D>(box, 0, gp, P);
+        const size_t base = node_offset<D>(box, 0, gp, p);
         const size_t rs = (size_t) gp.G;
 #pragma unroll
-        for (int j = 0; j < NODES; j++) {
-            const size_t off = D == 2 ? base + (size_t) (j / P) * rs + (size_t) (j % P) : base + (size_t) j;
+        for (int j = 0; j < MAXN; j++) {
+            if (P == 0 && j >= nodes) break;
+            const size_t off = D == 2 ? base + (size_t) (j / p) * rs + (size_t) (j % p) : base + (size_t) j;
             store_node<D>(grid, stride, off, acc[j]);
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < NODES; j++) slot[j] = acc[j];
+        for (int j = 0; j < MAXN; j++) {
+            if (P == 0 && j >= nodes) break;
+            slot[j] = acc[j];
+        }
     }
 }
 
-// phase 2: thread t walks chunk c = blk*SP2_THREADS + t
+// per-chunk bookkeeping between phase 2 and phase 3
+constexpr int SP2_HVALID = 1;     // the chunk's first segment continues a box from the previous chunk: partial H
+constexpr int SP2_TVALID = 2;     // the chunk's last segment continues into the next chunk (and is not the H segment): partial T
+constexpr int SP2_THROUGH = 4;    // the H segment is the whole chunk AND continues into the next chunk
+struct Sp2Meta {
+    int first_box[SP2_THREADS], last_box[SP2_THREADS];
+    int flags[SP2_THREADS];
+};
+
+// phase 2: thread t walks chunk c = blk*SP2_THREADS + t.  part = this CTA's partials, [chunk][H|T][node].
 template <int D, int P>
-__host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const Sp2Smem<D> &sm, const uint32_t *__restrict__ box_start,
-                                                       int n, const GridParams &gp, float4 *__restrict__ slots,
-                                                       void *__restrict__ grid) {
-    constexpr int NODES = D == 2 ? P * P : P;
+__host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
+                                                       int n, const GridParams &gp, float4 *__restrict__ part, Sp2Meta &meta,
+                                                       void *__restrict__ grid, uint32_t *__restrict__ box_start) {
+    constexpr int PP = P > 0 ? P : PMAX;
+    constexpr int MAXN = D == 2 ? PP * PP : PP;
+    const int p = P > 0 ? P : gp.p;
+    const int nodes = D == 2 ? p * p : p;
     const int c = blk * SP2_THREADS + t;
     const int kb = c * CHUNK;
+    meta.flags[t] = 0;
     if (kb >= n) return;
     const int ke = kb + CHUNK < n ? kb + CHUNK : n;
     const size_t stride = (size_t) gp.M;              // 1-D: plane 0 -> plane 1
-    float4 *myslots = slots + (size_t) c * 2 * NODES;
-    const uint32_t *kp = sm.keys + t * SP2_STRIDE;
-    float4 acc[NODES];
+    float4 *myH = part + (size_t) t * 2 * nodes, *myT = myH + nodes;
+    const uint32_t *kp = skeys + kb;
+    float4 acc[MAXN];
 #pragma unroll
-    for (int j = 0; j < NODES; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < MAXN; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur = key_to_box<D>(kp[0], gp);
+    const int prev = kb > 0 ? key_to_box<D>(skeys[kb - 1], gp) : -1;
+    const bool head_cont = prev == cur;               // the first segment continues a box from the previous chunk
+    bool started = !head_cont;                        // the segment being accumulated started inside this chunk
+    if (started) for (int b = prev + 1; b <= cur; b++) box_start[b] = (uint32_t) kb;
+    meta.first_box[t] = cur;
     for (int k = kb; k < ke; k++) {
         const int box = key_to_box<D>(kp[k - kb], gp);
         if (box != cur) {
-            // segment of `cur` ended inside the chunk: finished box unless it started before the chunk
-            spread2_flush<D, P, NODES>(acc, (int) box_start[cur] >= kb, cur, gp, grid, stride, myslots);
+            // segment of `cur` ended inside the chunk: finished box unless it started before the chunk (-> H partial)
+            spread2_flush<D, P, MAXN>(acc, p, started, cur, gp, grid, stride, myH);
+            for (int b = cur + 1; b <= box; b++) box_start[b] = (uint32_t) k;
 #pragma unroll
-            for (int j = 0; j < NODES; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < MAXN; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             cur = box;
+            started = true;
         }
         if (D == 2) {
-            const float2 u = reinterpret_cast<const float2 *>(sm.u)[t * SP2_STRIDE + (k - kb)];
-            float Lx[P], Ly[P], ox[P], oy[P];
+            const float2 u = reinterpret_cast<const float2 *>(sorted_u)[k];
+            float Lx[PP], Ly[PP], ox[PP], oy[PP];
 #pragma unroll
-            for (int j = 0; j < P; j++) {
-                Lx[j] = lagrange1<P>(gp, P, j, u.x); Ly[j] = lagrange1<P>(gp, P, j, u.y);
-                ox[j] = u.x - gp.s[j]; oy[j] = u.y - gp.s[j];          // offsets in BOX UNITS, as in k_spread_chunks
+            for (int j = 0; j < PP; j++) {
+                if (P == 0 && j >= p) break;
+                Lx[j] = lagrange1<P>(gp, p, j, u.x); Ly[j] = lagrange1<P>(gp, p, j, u.y);
+                ox[j] = u.x - gp.s[j]; oy[j] = u.y - gp.s[j];          // offsets in BOX UNITS (x bw later)
             }
 #pragma unroll
-            for (int a = 0; a < P; a++) {
+            for (int a = 0; a < PP; a++) {
+                if (P == 0 && a >= p) break;
 #pragma unroll
-                for (int b = 0; b < P; b++) {
+                for (int b = 0; b < PP; b++) {
+                    if (P == 0 && b >= p) break;
                     const float L = Ly[a] * Lx[b];
-                    float4 &q = acc[a * P + b];
+                    float4 &q = acc[a * p + b];
                     q.x += L;
                     q.y += L * ox[b];
                     q.z += L * oy[a];
@@ -783,10 +845,11 @@ __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const Sp2
                 }
             }
         } else {
-            const float u = sm.u[t * SP2_STRIDE + (k - kb)];
+            const float u = sorted_u[k];
 #pragma unroll
-            for (int a = 0; a < P; a++) {
-                const float L = lagrange1<P>(gp, P, a, u);
+            for (int a = 0; a < PP; a++) {
+                if (P == 0 && a >= p) break;
+                const float L = lagrange1<P>(gp, p, a, u);
                 const float o = u - gp.s[a];
                 float4 &q = acc[a];
                 q.x += L;
@@ -795,80 +858,164 @@ __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const Sp2
             }
         }
     }
-    // last segment: finished only if the box both started in this chunk and ends with it
-    const bool started_here = (int) box_start[cur] >= kb, ends_here = (int) box_start[cur + 1] <= ke;
-    spread2_flush<D, P, NODES>(acc, started_here && ends_here, cur, gp, grid, stride, myslots + (started_here ? 1 : 0) * NODES);
+    // last segment
+    const int next = ke < n ? key_to_box<D>(skeys[ke], gp) : gp.nb;
+    const bool ends = next != cur;
+    if (ke == n) for (int b = cur + 1; b <= gp.nb; b++) box_start[b] = (uint32_t) n;
+    meta.last_box[t] = cur;
+    int fl = head_cont ? SP2_HVALID : 0;
+    if (started) {                                    // started in this chunk: finished, or the head (T) of a longer box
+        spread2_flush<D, P, MAXN>(acc, p, ends, cur, gp, grid, stride, myT);
+        if (!ends) fl |= SP2_TVALID;
+    } else {                                          // the whole chunk is one segment of a box that started earlier (H)
+        spread2_flush<D, P, MAXN>(acc, p, false, cur, gp, grid, stride, myH);
+        if (!ends) fl |= SP2_THROUGH;
+    }
+    meta.flags[t] = fl;
 }
 
+// phase 3: thread t finishes the boxes whose in-CTA run of partials starts at chunk t (T of chunk t, or -- thread 0 -- the
+// H run the CTA inherits from its predecessor).  A run that stays inside the CTA is final -> grid; one that crosses a CTA
+// boundary goes to the CTA's global slot (0: continues from the previous CTA, 1: continues into the next) and, if its head
+// is here, onto the work list.
 template <int D, int P>
-__global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks2(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
-                                                                const uint32_t *__restrict__ box_start, int n,
-                                                                const GridParams *__restrict__ gpp, float4 *__restrict__ slots,
-                                                                void *__restrict__ grid) {
+__host__ __device__ __forceinline__ void spread2_stitch(int t, int blk, int n, const GridParams &gp, const float4 *__restrict__ part,
+                                                        const Sp2Meta &meta, void *__restrict__ grid, float4 *__restrict__ cslots,
+                                                        uint32_t *__restrict__ work) {
+    constexpr int PP = P > 0 ? P : PMAX;
+    constexpr int MAXN = D == 2 ? PP * PP : PP;
+    const int p = P > 0 ? P : gp.p;
+    const int nodes = D == 2 ? p * p : p;
+    const int nch = min(SP2_THREADS, (n - blk * SP2_POINTS + CHUNK - 1) / CHUNK);       // chunks of this CTA
+    if (t >= nch) return;
+    const size_t stride = (size_t) gp.M;
+    float4 *myc = cslots + (size_t) blk * 2 * nodes;
+    for (int which = (t == 0 ? 0 : 1); which < 2; which++) {
+        // which == 0 (thread 0 only): the run that starts with H[0]; which == 1: the run that starts with T[t]
+        const int fl = meta.flags[t];
+        if (which == 0 ? !(fl & SP2_HVALID) : !(fl & SP2_TVALID)) continue;
+        float4 acc[MAXN];
+#pragma unroll
+        for (int j = 0; j < MAXN; j++) {
+            if (P == 0 && j >= nodes) break;
+            acc[j] = part[((size_t) t * 2 + which) * nodes + j];
+        }
+        // follow the H partials of the next chunks while the box goes on
+        bool open = which == 0 ? (fl & SP2_THROUGH) != 0 : true;      // the box continues beyond the chunk just added
+        int tt = t;
+        while (open && tt + 1 < nch) {
+            tt++;
+            const float4 *h = part + (size_t) tt * 2 * nodes;
+#pragma unroll
+            for (int j = 0; j < MAXN; j++) {
+                if (P == 0 && j >= nodes) break;
+                const float4 v = h[j];
+                acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+            }
+            open = (meta.flags[tt] & SP2_THROUGH) != 0;
+        }
+        const int box = which == 0 ? meta.first_box[0] : meta.last_box[t];
+        if (which == 1 && !open) {
+            spread2_flush<D, P, MAXN>(acc, p, true, box, gp, grid, stride, nullptr);      // started and ended inside the CTA
+        } else {
+            spread2_flush<D, P, MAXN>(acc, p, false, box, gp, grid, stride, myc + (size_t) which * nodes);
+            if (which == 1) {                         // head of a box that crosses into the next CTA
+                const uint32_t e = FK_ATOMIC_ADD(work, 1u);
+                work[1 + e] = (uint32_t) box;
+            }
+        }
+    }
+}
+
+// dynamic shared memory of k_spread_chunks: the partials of the CTA's chunks (compile-time node counts only; the run-time-p
+// fallback keeps them in a global scratch area)
+template <int D, int P>
+__host__ __device__ constexpr size_t spread_smem_bytes() {
+    return (size_t) SP2_THREADS * 2 * (P > 0 ? (D == 2 ? P * P : P) : 0) * sizeof(float4);
+}
+
+#ifdef __CUDACC__
+template <int D, int P>
+__global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys, int n,
+                                                               const GridParams *__restrict__ gpp, float4 *__restrict__ cslots,
+                                                               float4 *__restrict__ gpart, void *__restrict__ grid,
+                                                               uint32_t *__restrict__ box_start, uint32_t *__restrict__ work) {
+    extern __shared__ __align__(16) unsigned char sp_raw[];
     __shared__ GridParams gps;
-    __shared__ Sp2Smem<D> sm;
+    __shared__ Sp2Meta meta;
     for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
-    spread2_load<D>(threadIdx.x, blockIdx.x, sorted_u, skeys, n, sm);
     __syncthreads();
     if (!gps.ok) return;
-    spread2_chunk<D, P>(threadIdx.x, blockIdx.x, sm, box_start, n, gps, slots, grid);
+    const int p = P > 0 ? P : gps.p;
+    const int nodes = D == 2 ? p * p : p;
+    float4 *part = P > 0 ? reinterpret_cast<float4 *>(sp_raw) : gpart + (size_t) blockIdx.x * SP2_THREADS * 2 * nodes;
+    spread2_chunk<D, P>(threadIdx.x, blockIdx.x, sorted_u, skeys, n, gps, part, meta, grid, box_start);
+    __syncthreads();                                  // (block-scope barrier also orders the global-memory partials of P == 0)
+    spread2_stitch<D, P>(threadIdx.x, blockIdx.x, n, gps, part, meta, grid, cslots, work);
 }
 
-// One thread group (LPN lanes, a power of two <= 32) per node of the spread grid: empty box -> 0; box finished by a
-// single chunk -> already written by the chunk kernel; otherwise add the box's slot partials in chunk order (lane-strided,
-// then a fixed shuffle tree: deterministic for a given LPN).
-// 2-D: the launch covers (M/2)^2 >= G^2 ids (its shape depends on M only); ids >= G^2 do nothing -- the zero padding of the
-// FFT input is never materialised (k_conv_rows_fwd substitutes zeros for columns >= G, k_conv_cols for rows >= G).
-// 1-D: the whole length-M line, zeros included (tiny).
+// Combine the boxes that cross CTA boundaries of k_spread_chunks: work[0] = number of listed boxes, work[1..] = the boxes
+// (in arrival order, which does not matter: every box is summed on its own).  One thread per (box, node) adds the CTA slots
+// in CTA order; a box that spans COMBINE_COOP CTAs or more is summed by the whole warp (lane-strided + fixed shuffle tree).
+// The summation order depends only on the number of CTAs the box spans: deterministic.  Persistent grid.
+constexpr int COMBINE_COOP = 32;
+#endif
+
+// Host-callable core: lane `lane` of `lanes` of one (box, node); CTA b0 holds the box's head in slot 1, later CTAs use slot 0
 template <int D>
-__global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ slots, const uint32_t *__restrict__ box_start,
-                                                        const GridParams *__restrict__ gpp, int lpn, void *__restrict__ grid) {
-    const GridParams &gp = *gpp;
-    if (!gp.ok) return;
-    const int G = gp.G, p = gp.p, M = gp.M;
-    const size_t gid = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t id = gid / lpn;
-    const int sub = (int) (gid - id * lpn);
-    const size_t space = D == 2 ? (size_t) G * G : (size_t) M;
-    const bool live = id < space;
-    int row = 0, col = 0;
-    bool inside = false;
-    if (live) {
-        if (D == 2) { row = (int) (id / G); col = (int) (id - (size_t) row * G); inside = true; }
-        else { col = (int) id; inside = col < G; }
-    }
-    // what to do with this element: leave it (finished by the chunk kernel) or write acc (zero or the slot sum)
-    int node = 0, nodes = 1, c0 = 0, c1 = -1;
-    bool write = live;
-    if (inside) {
-        int box;
-        if (D == 2) {
-            const int by = row / p, a = row - by * p, bx = col / p, b = col - bx * p;
-            box = by * gp.B + bx; node = a * p + b; nodes = p * p;
-        } else {
-            box = col / p; node = col - box * p; nodes = p;
-        }
-        const int s = (int) box_start[box], e = (int) box_start[box + 1];
-        if (e > s) {
-            c0 = s / CHUNK; c1 = (e - 1) / CHUNK;
-            if (c0 == c1) { write = false; c1 = c0 - 1; }   // single chunk: already written
-        }
-    }
+__host__ __device__ __forceinline__ float4 combine_node_lane(const float4 *__restrict__ cslots, int b0, int b1, int nodes, int node, int lane, int lanes) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // chunk c0 holds the box's head in slot 1 (the box starts inside or at the start of c0); later chunks use slot 0
-    for (int c = c0 + sub; c <= c1; c += lpn) {
-        const float4 v = slots[((size_t) c * 2 + (c == c0 ? 1 : 0)) * nodes + node];
+    for (int b = b0 + lane; b <= b1; b += lanes) {
+        const float4 v = cslots[((size_t) b * 2 + (b == b0 ? 1 : 0)) * nodes + node];
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    for (int o = lpn >> 1; o > 0; o >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if (write && sub == 0) store_node<D>(grid, (size_t) M, id, acc);
+    return acc;
 }
+
+#ifdef __CUDACC__
+template <int D>
+__global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ cslots, const uint32_t *__restrict__ box_start,
+                                                        const GridParams *__restrict__ gpp, const uint32_t *__restrict__ work,
+                                                        void *__restrict__ grid) {
+    const GridParams &gp = *gpp;
+    if (!gp.ok) return;
+    const int p = gp.p, nodes = D == 2 ? p * p : p;
+    const int lane = threadIdx.x & 31;
+    const int ntask = (int) work[0] * nodes;
+    const int stride = gridDim.x * blockDim.x;
+    for (int t0 = blockIdx.x * blockDim.x + threadIdx.x - lane; t0 < ntask; t0 += stride) {
+        const int task = t0 + lane;
+        int box = 0, node = 0, b0 = 0, b1 = -1;
+        if (task < ntask) {
+            const int e = task / nodes;
+            node = task - e * nodes;
+            box = (int) work[1 + e];
+            b0 = (int) box_start[box] / SP2_POINTS; b1 = ((int) box_start[box + 1] - 1) / SP2_POINTS;
+        }
+        const bool coop = b1 - b0 + 1 >= COMBINE_COOP;
+        if (task < ntask && !coop)
+            store_node<D>(grid, (size_t) gp.M, node_offset<D>(box, node, gp, p), combine_node_lane<D>(cslots, b0, b1, nodes, node, 0, 1));
+        // very long boxes (most points in one box): the whole warp takes them one after the other
+        unsigned todo = __ballot_sync(0xffffffffu, coop);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int bbox = __shfl_sync(0xffffffffu, box, src), bnode = __shfl_sync(0xffffffffu, node, src);
+            const int c0 = __shfl_sync(0xffffffffu, b0, src), c1 = __shfl_sync(0xffffffffu, b1, src);
+            float4 acc = combine_node_lane<D>(cslots, c0, c1, nodes, bnode, lane, 32);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            }
+            if (lane == 0) store_node<D>(grid, (size_t) gp.M, node_offset<D>(bbox, bnode, gp, p), acc);
+        }
+    }
+}
+#endif
 
 // ------------------------------------------------------------------------- kernel samples (1-D embeddings) --
 // 2-D embeddings sample and transform their kernels inside fitsne_conv.cuh (k_kspec_rows / k_kspec_cols).  1-D: real
@@ -1034,8 +1181,7 @@ __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted
 // Persistent form: a fixed grid (a few CTAs per SM, set by the host) strides over the row groups, so the kernel
 // never occupies more than its share of each SM and the repulsive pipeline's kernels co-run beside it.
 template <int D, int LPR>
-__global__ void __launch_bounds__(256) k_attract(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
-                                                 const float *__restrict__ val_P, uint32_t edge_base,
+__global__ void __launch_bounds__(256) k_attract(const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges, uint32_t edge_base,
                                                  const float *__restrict__ Y, int row_begin, int row_end, float inv_df,
                                                  float *__restrict__ attr) {
     constexpr int RPB = 256 / LPR;                       // rows per CTA per trip
@@ -1052,8 +1198,9 @@ __global__ void __launch_bounds__(256) k_attract(const uint32_t *__restrict__ ro
             const uint32_t e0 = row_P[row] - edge_base, e1 = row_P[row + 1] - edge_base;
 #pragma unroll 4
             for (uint32_t e = e0 + sub; e < e1; e += LPR) {
-                const uint32_t j = col_P[e];
-                const float pv = val_P[e];
+                const uint2 ed = __ldg(edges + e);                  // one 8-byte load per edge: (column, weight)
+                const uint32_t j = ed.x;
+                const float pv = __uint_as_float(ed.y);
                 if (D == 2) {
                     const float2 yj = __ldg(reinterpret_cast<const float2 *>(Y) + j);
                     const float dx = yix - yj.x, dy = yiy - yj.y;
@@ -1448,11 +1595,11 @@ __global__ void __launch_bounds__(1024) k_scan_excl(const uint32_t *__restrict__
 // Relabel the CSR into the new point order.  One 8-lane group per OLD row i (new row r = rank[i]).
 //   PASS 0: new_len[r] = len(i); tile_cnt[tile(r, rank[col])]++
 //   PASS 1: copy the row's edges to new_row_P[r] (relabelled columns) and scatter them into their tiles
-__global__ void __launch_bounds__(256) k_relabel_csr(int pass, const uint32_t *__restrict__ row_old, const uint32_t *__restrict__ col_old,
-                                                     const float *__restrict__ val_old, const uint32_t *__restrict__ rank, int n,
+__global__ void __launch_bounds__(256) k_relabel_csr(int pass, const uint32_t *__restrict__ row_old, const uint2 *__restrict__ edges_old,
+                                                     const uint32_t *__restrict__ rank, int n,
                                                      TileGeom tg, uint32_t *__restrict__ new_len, uint32_t *__restrict__ tile_cnt,
-                                                     const uint32_t *__restrict__ row_new, uint32_t *__restrict__ col_new,
-                                                     float *__restrict__ val_new, const uint32_t *__restrict__ tile_start,
+                                                     const uint32_t *__restrict__ row_new, uint2 *__restrict__ edges_new,
+                                                     const uint32_t *__restrict__ tile_start,
                                                      uint32_t *__restrict__ tile_cur, uint32_t *__restrict__ tile_pack,
                                                      float *__restrict__ tile_val) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1464,16 +1611,16 @@ __global__ void __launch_bounds__(256) k_relabel_csr(int pass, const uint32_t *_
     if (pass == 0) {
         if (sub == 0) new_len[r] = e1 - e0;
         for (uint32_t e = e0 + sub; e < e1; e += 8) {
-            const uint32_t c = rank[col_old[e]];
+            const uint32_t c = rank[edges_old[e].x];
             atomicAdd(&tile_cnt[(size_t) rc * tg.ncb + c / TILE_COLS], 1u);
         }
     } else {
         const uint32_t nb = row_new[r];
         for (uint32_t e = e0 + sub; e < e1; e += 8) {
-            const uint32_t c = rank[col_old[e]];
-            const float v = val_old[e];
-            col_new[nb + (e - e0)] = c;
-            val_new[nb + (e - e0)] = v;
+            const uint2 ed = edges_old[e];
+            const uint32_t c = rank[ed.x];
+            const float v = __uint_as_float(ed.y);
+            edges_new[nb + (e - e0)] = make_uint2(c, ed.y);
             const uint32_t cb = c / TILE_COLS;
             const size_t t = (size_t) rc * tg.ncb + cb;
             const uint32_t pos = tile_start[t] + atomicAdd(&tile_cur[t], 1u);
@@ -1586,43 +1733,41 @@ struct SortedGeom {
     int nchunks, ncb, col_shift;     // chunk c = rows [c*SRT_ROWS, ...); column block b = points [b << col_shift, ...)
 };
 
-#ifdef __CUDA_ARCH__
-#define FK_ATOMIC_ADD(ptr, v) atomicAdd((ptr), (v))
-#else
-#define FK_ATOMIC_ADD(ptr, v) fk_host_fetch_add((ptr), (v))
-template <typename T>
-static inline T fk_host_fetch_add(T *p, T v) { const T old = *p; *p = old + v; return old; }
-#endif
 
 // one lane (sub of 8) of one CSR row: count / place the row's edges into (row chunk, column block) groups
-__host__ __device__ __forceinline__ void sorted_count_lane(int row, int sub, const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
+__host__ __device__ __forceinline__ void sorted_count_lane(int row, int sub, const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges,
                                                            SortedGeom g, uint32_t *__restrict__ cnt) {
     const uint32_t rc = (uint32_t) row / SRT_ROWS;
     for (uint32_t e = row_P[row] + sub; e < row_P[row + 1]; e += 8)
-        FK_ATOMIC_ADD(&cnt[(size_t) rc * g.ncb + (col_P[e] >> g.col_shift)], 1u);
+        FK_ATOMIC_ADD(&cnt[(size_t) rc * g.ncb + (edges[e].x >> g.col_shift)], 1u);
 }
-__host__ __device__ __forceinline__ void sorted_fill_lane(int row, int sub, const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
-                                                          const float *__restrict__ val_P, SortedGeom g, const uint32_t *__restrict__ start,
+__host__ __device__ __forceinline__ void sorted_fill_lane(int row, int sub, const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges,
+                                                          SortedGeom g, const uint32_t *__restrict__ start,
                                                           uint32_t *__restrict__ cur, uint32_t *__restrict__ pack, float *__restrict__ val_out) {
     const uint32_t rc = (uint32_t) row / SRT_ROWS, rl = (uint32_t) row - rc * SRT_ROWS;
     for (uint32_t e = row_P[row] + sub; e < row_P[row + 1]; e += 8) {
-        const uint32_t c = col_P[e];
+        const uint2 ed = edges[e];
+        const uint32_t c = ed.x;
         const size_t t = (size_t) rc * g.ncb + (c >> g.col_shift);
         const uint32_t pos = start[t] + FK_ATOMIC_ADD(&cur[t], 1u);
         pack[pos] = (rl << SRT_COL_BITS) | c;
-        val_out[pos] = val_P[e];
+#ifdef __CUDA_ARCH__
+        val_out[pos] = __uint_as_float(ed.y);
+#else
+        { float f; memcpy(&f, &ed.y, 4); val_out[pos] = f; }
+#endif
     }
 }
-__global__ void __launch_bounds__(256) k_sorted_count(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P, int n,
+__global__ void __launch_bounds__(256) k_sorted_count(const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges, int n,
                                                       SortedGeom g, uint32_t *__restrict__ cnt) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((gid >> 3) < n) sorted_count_lane(gid >> 3, gid & 7, row_P, col_P, g, cnt);
+    if ((gid >> 3) < n) sorted_count_lane(gid >> 3, gid & 7, row_P, edges, g, cnt);
 }
-__global__ void __launch_bounds__(256) k_sorted_fill(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
-                                                     const float *__restrict__ val_P, int n, SortedGeom g, const uint32_t *__restrict__ start,
+__global__ void __launch_bounds__(256) k_sorted_fill(const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges,
+                                                     int n, SortedGeom g, const uint32_t *__restrict__ start,
                                                      uint32_t *__restrict__ cur, uint32_t *__restrict__ pack, float *__restrict__ val_out) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((gid >> 3) < n) sorted_fill_lane(gid >> 3, gid & 7, row_P, col_P, val_P, g, start, cur, pack, val_out);
+    if ((gid >> 3) < n) sorted_fill_lane(gid >> 3, gid & 7, row_P, edges, g, start, cur, pack, val_out);
 }
 
 // shared memory of one CTA: positions of the chunk's rows, then their D fixed-point accumulators
@@ -1709,8 +1854,8 @@ __global__ void __launch_bounds__(SRT_THREADS) k_attract_sorted(const float *__r
 // sum_edges (alpha p) log((alpha p + FLT_MIN) / (q + FLT_MIN)), q = (1+d2/df)^-df / sum_Q  (tsne.cpp:1340-1348);
 // per-row sums in fp64, per-block partials reduced in fixed order by k_finalize_kl.
 template <int D>
-__global__ void __launch_bounds__(256) k_kl(const uint32_t *__restrict__ row_P, const uint32_t *__restrict__ col_P,
-                                            const float *__restrict__ val_P, uint32_t edge_base, const float *__restrict__ Y,
+__global__ void __launch_bounds__(256) k_kl(const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges,
+                                            uint32_t edge_base, const float *__restrict__ Y,
                                             int row_begin, int row_end, double alpha, double df,
                                             const Scalars *__restrict__ sc, double *__restrict__ partial) {
     __shared__ double sm[32];
@@ -1724,8 +1869,9 @@ __global__ void __launch_bounds__(256) k_kl(const uint32_t *__restrict__ row_P, 
         else yix = Y[row];
         const uint32_t e0 = row_P[row] - edge_base, e1 = row_P[row + 1] - edge_base;
         for (uint32_t e = e0 + lane; e < e1; e += 32) {
-            const uint32_t j = col_P[e];
-            const double pv = alpha * (double) val_P[e];
+            const uint2 ed = __ldg(edges + e);
+            const uint32_t j = ed.x;
+            const double pv = alpha * (double) __uint_as_float(ed.y);
             double d2;
             if (D == 2) {
                 const float2 yj = reinterpret_cast<const float2 *>(Y)[j];
@@ -1754,14 +1900,14 @@ __global__ void __launch_bounds__(256) k_finalize_kl(const double *__restrict__ 
 }
 
 // max row sum of P for the automatic exaggeration coefficient (tsne.cpp:392-399)
-__global__ void __launch_bounds__(256) k_row_sum_max(const uint32_t *__restrict__ row_P, const float *__restrict__ val_P,
+__global__ void __launch_bounds__(256) k_row_sum_max(const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges,
                                                      uint32_t edge_base, int row_begin, int row_end,
                                                      double *__restrict__ partial) {
     __shared__ double sm[32];
     double mx = 0;
     for (int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x; row < row_end; row += gridDim.x * blockDim.x) {
         double s = 0;
-        for (uint32_t e = row_P[row] - edge_base; e < row_P[row + 1] - edge_base; e++) s += (double) val_P[e];
+        for (uint32_t e = row_P[row] - edge_base; e < row_P[row + 1] - edge_base; e++) s += (double) __uint_as_float(edges[e].y);
         mx = fmax(mx, s);
     }
 #pragma unroll
@@ -1772,6 +1918,12 @@ __global__ void __launch_bounds__(256) k_row_sum_max(const uint32_t *__restrict_
         for (int i = 1; i < (int) (blockDim.x >> 5); i++) mx = fmax(mx, sm[i]);
         partial[blockIdx.x] = mx;
     }
+}
+
+// device CSR edge word: (column u32, weight f32 bits) -- one 8-byte load per edge in the SpMV / KL kernels
+__global__ void k_pack_edges(const uint32_t *__restrict__ col, const double *__restrict__ val, uint2 *__restrict__ edges, size_t n) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) edges[i] = make_uint2(col[i], __float_as_uint((float) val[i]));
 }
 
 // fp64 host data <-> fp32 device data

@@ -1,9 +1,14 @@
-// Host emulation of the shared-memory Stockham FFT (fitsne_fft.cuh): for every FFT length the grid ladder can produce
-// and for both plan kinds (narrow: radices 8/4/2/3/5; wide: + 16 and 9) run all 512 "threads" of a CTA through stage 0,
-// then stage 1, ... -- what the barrier between stages enforces -- on `lines` interleaved sequences in the padded /
-// skewed shared-memory layout, and compare with a direct fp64 DFT.  Test infrastructure; prints FFT_EMUL_OK.
+// Host emulation of the shared-memory FFTs (fitsne_fft.cuh, fitsne_conv.cuh), CPU only, test infrastructure.
+//  (1) Stockham (natural order; row passes, 1-D lines): for every FFT length the grid ladder can produce, run all
+//      "threads" of a CTA through stage 0, then stage 1, ... -- what the barrier between stages enforces -- on interleaved
+//      sequences in the padded / skewed shared-memory layout, and compare with a direct fp64 DFT.
+//  (2) In-place column transform (2-D lengths): the [pos][4 slots] tile, forward decimation-in-frequency stages with the
+//      zero-substituting first stage, checked against a direct DFT THROUGH THE DIGIT-REVERSAL the plan implies, then the
+//      conjugate trick + inverse decimation-in-time stages, which must give back M x the input in natural order.
+// Prints FFT_EMUL_OK.
 #include "../../fit-sne_b200/csrc/fitsne_kernels.cuh"
 #include "../../fit-sne_b200/csrc/fitsne_fft.cuh"
+#include "../../fit-sne_b200/csrc/fitsne_conv.cuh"
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -12,10 +17,9 @@
 #include <vector>
 using namespace fk;
 
-template <bool WIDE>
 static double run_len(int M, int lines, bool *plan_ok, int *nstages) {
     FftPlan plan;
-    *plan_ok = fft_make_plan(M, &plan, WIDE);
+    *plan_ok = fft_make_plan(M, &plan);
     if (!*plan_ok) return 0;
     *nstages = plan.nstages;
     const int NS = fft_buf_len(M, lines);
@@ -31,9 +35,9 @@ static double run_len(int M, int lines, bool *plan_ok, int *nstages) {
     }
     float2 *x = bufa.data(), *y = bufb.data();
     int n_cur = M, s = 1;
-    const int nthreads = FFT_THREADS;
+    const int nthreads = lines == 1 ? 512 : 256;      // k_fft_line / the row kernels of fitsne_conv.cuh
     for (int st = 0; st < plan.nstages; st++) {
-        for (int tid = 0; tid < nthreads; tid++) fft_run_stage<WIDE>(x, y, NS, lines, plan, st, n_cur, s, W.data(), tid, nthreads);
+        for (int tid = 0; tid < nthreads; tid++) fft_run_stage(x, y, NS, lines, plan, st, n_cur, s, W.data(), tid, nthreads);
         n_cur /= plan.radix[st]; s *= plan.radix[st];
         std::swap(x, y);
     }
@@ -55,28 +59,84 @@ static double run_len(int M, int lines, bool *plan_ok, int *nstages) {
     return max_err / max_ref;
 }
 
+// in-place column transform: returns the worse of (forward vs DFT, round trip vs M * input), relative
+static double run_col(int M, int nz, bool *plan_ok) {
+    ColPlan pl;
+    *plan_ok = col_make_plan(M, &pl);
+    if (!*plan_ok) return 0;
+    std::vector<float2> W(M), x((size_t) M * COL_SLOTS, make_float2(NAN, NAN));
+    for (int k = 0; k < M; k++) { const double a = -2.0 * M_PI * (double) k / (double) M; W[k] = make_float2((float) cos(a), (float) sin(a)); }
+    std::mt19937 rng(M * 13 + nz);
+    std::uniform_real_distribution<float> U(-1.f, 1.f);
+    std::vector<std::complex<double>> in((size_t) COL_SLOTS * M, 0.0);
+    for (int sl = 0; sl < COL_SLOTS; sl++) for (int i = 0; i < nz; i++) {      // positions >= nz stay poisoned: they must not be read
+        const float2 v = make_float2(U(rng), U(rng));
+        in[(size_t) sl * M + i] = {v.x, v.y};
+        x[(size_t) i * COL_SLOTS + sl] = v;
+    }
+    const int nthreads = COL_THREADS;
+    for (int tid = 0; tid < nthreads; tid++) col_run_fwd_stage<true>(x.data(), pl, 0, nz, W.data(), tid, nthreads);
+    for (int st = 1; st < pl.nstages; st++)
+        for (int tid = 0; tid < nthreads; tid++) col_run_fwd_stage<false>(x.data(), pl, st, nz, W.data(), tid, nthreads);
+    // frequency held by position pos: digit d_st = (pos / m_st) % radix_st contributes d_st * tws_st
+    auto freq = [&](int pos) { int k = 0; for (int st = 0; st < pl.nstages; st++) k += ((pos / pl.m[st]) % pl.radix[st]) * pl.tws[st]; return k; };
+    double max_err = 0, max_ref = 0;
+    std::vector<char> seen(M, 0);
+    for (int pos = 0; pos < M; pos++) { const int k = freq(pos); if (k < 0 || k >= M || seen[k]) return 1.0; seen[k] = 1; }   // a permutation
+    const int step = M > 512 ? M / 53 : 1;
+    for (int sl : {0, COL_SLOTS - 1}) for (int pos = 0; pos < M; pos += step) {
+        const int k = freq(pos);
+        std::complex<double> acc = 0;
+        for (int i = 0; i < nz; i++) {
+            const double a = -2.0 * M_PI * (double) (((long long) i * k) % M) / (double) M;
+            acc += in[(size_t) sl * M + i] * std::complex<double>(cos(a), sin(a));
+        }
+        const float2 got = x[(size_t) pos * COL_SLOTS + sl];
+        max_err = std::max(max_err, std::abs(acc - std::complex<double>(got.x, got.y)));
+        max_ref = std::max(max_ref, std::abs(acc));
+    }
+    double e1 = max_err / max_ref;
+    // conjugate (what the Hadamard step does while storing), inverse stages, compare with M * input
+    for (auto &v : x) v.y = -v.y;
+    for (int st = pl.nstages - 1; st > 0; st--)
+        for (int tid = 0; tid < nthreads; tid++) col_run_inv_stage<false>(x.data(), pl, st, W.data(), tid, nthreads);
+    for (int tid = 0; tid < nthreads; tid++) col_run_inv_stage<true>(x.data(), pl, 0, W.data(), tid, nthreads);
+    max_err = 0; max_ref = 0;
+    for (int sl = 0; sl < COL_SLOTS; sl++) for (int i = 0; i < M; i++) {
+        const std::complex<double> want = in[(size_t) sl * M + i] * (double) M;
+        const float2 got = x[(size_t) i * COL_SLOTS + sl];
+        max_err = std::max(max_err, std::abs(want - std::complex<double>(got.x, got.y)));
+        max_ref = std::max(max_ref, std::abs(want));
+    }
+    return std::max(e1, max_err / max_ref);
+}
+
 int main() {
     std::set<int> lens;
     for (int n = 32; n <= 8192; n += 2) { const int m = nice_fft_size(n); if (m <= 8192) lens.insert(m); }
     bool ok = true;
-    int count = 0, fewer = 0;
-    double worst_n = 0, worst_w = 0;
+    int count = 0, ccount = 0;
+    double worst = 0, worst_col = 0;
     for (int M : lens) {
-        // lines as get_plans picks them: columns up to 8, rows up to 4 (2-D, M <= 4096); a single line in 1-D
-        for (int lines : {1, 4, 8}) {
+        for (int lines : {1, 2}) {
             if (lines > 1 && M > 4096) continue;
-            if ((size_t) M * lines > (size_t) FFT_EPT * FFT_THREADS) continue;
-            bool pn, pw; int sn = 0, sw = 0;
-            const double en = run_len<false>(M, lines, &pn, &sn), ew = run_len<true>(M, lines, &pw, &sw);
-            if (!pn || !pw || !(en < 3e-6) || !(ew < 3e-6)) { printf("M=%d lines=%d: narrow %d stages err %.2e, wide %d stages err %.2e  FAILED\n", M, lines, sn, en, sw, ew); ok = false; }
-            worst_n = std::max(worst_n, en); worst_w = std::max(worst_w, ew);
-            if (lines == 1) { count++; if (sw < sn) fewer++; }
+            bool pn; int sn = 0;
+            const double en = run_len(M, lines, &pn, &sn);
+            if (!pn || !(en < 3e-6)) { printf("M=%d lines=%d: %d stages err %.2e  FAILED\n", M, lines, sn, en); ok = false; }
+            worst = std::max(worst, en);
+            if (lines == 1) count++;
+        }
+        if (M <= 4096) {
+            for (int nz : {M / 2, M / 2 - M / 7, M}) {
+                bool pc;
+                const double ec = run_col(M, nz, &pc);
+                if (!pc || !(ec < 4e-6)) { printf("M=%d nz=%d: in-place column transform err %.2e  FAILED\n", M, nz, ec); ok = false; }
+                worst_col = std::max(worst_col, ec);
+            }
+            ccount++;
         }
     }
-    FftPlan a, b;
-    fft_make_plan(1152, &a, false); fft_make_plan(1152, &b, true);
-    printf("%d lengths (32..8192); wide plans have fewer stages for %d of them (1152: %d -> %d); worst rel. error narrow %.2e, wide %.2e\n",
-           count, fewer, a.nstages, b.nstages, worst_n, worst_w);
+    printf("%d lengths (32..8192) Stockham, worst rel. error %.2e; %d lengths in-place column transform, worst %.2e\n", count, worst, ccount, worst_col);
     if (ok) printf("FFT_EMUL_OK\n");
     return ok ? 0 : 1;
 }

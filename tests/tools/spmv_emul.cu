@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <random>
 #include <vector>
 using namespace fk;
@@ -33,12 +34,14 @@ static bool run_case(const char *name, int n, int deg, int col_shift, double df,
     const size_t nt = (size_t) g.nchunks * g.ncb;
     std::vector<uint32_t> cnt(nt + 1, 0), start(nt + 1, 0), cur(nt + 1, 0), pack(E + 1, 0xffffffffu);
     std::vector<float> val2(E + 1, NAN);
-    for (int r = 0; r < n; r++) for (int sub = 0; sub < 8; sub++) sorted_count_lane(r, sub, row.data(), col.data(), g, cnt.data());
+    std::vector<uint2> edges(E + 1);                                   // the device's edge words: (column, fp32 weight bits)
+    for (size_t e = 0; e < E; e++) { uint32_t bits; memcpy(&bits, &val[e], 4); edges[e] = make_uint2(col[e], bits); }
+    for (int r = 0; r < n; r++) for (int sub = 0; sub < 8; sub++) sorted_count_lane(r, sub, row.data(), edges.data(), g, cnt.data());
     uint32_t run = 0;
     for (size_t t = 0; t < nt; t++) { start[t] = run; run += cnt[t]; }
     start[nt] = run;
     bool ok = run == E;
-    for (int r = 0; r < n; r++) for (int sub = 0; sub < 8; sub++) sorted_fill_lane(r, sub, row.data(), col.data(), val.data(), g, start.data(), cur.data(), pack.data(), val2.data());
+    for (int r = 0; r < n; r++) for (int sub = 0; sub < 8; sub++) sorted_fill_lane(r, sub, row.data(), edges.data(), g, start.data(), cur.data(), pack.data(), val2.data());
     for (size_t t = 0; t < nt; t++) ok = ok && cur[t] == cnt[t];
     // layout: inside a chunk the column blocks never decrease; rows belong to the chunk
     for (int rc = 0; rc < g.nchunks; rc++) {

@@ -1,10 +1,10 @@
-// Host emulation of k_spread_chunks2 (tests/test_spread_emul.py builds and runs this with nvcc, no GPU needed).
-// The kernel is written as two phase functions (fitsne_kernels.cuh: spread2_load / spread2_chunk); here every thread of a
-// block runs phase 1, then every thread runs phase 2 -- exactly what the __syncthreads() in the kernel enforces -- and the
-// results (slots + directly written grid nodes) are compared
-//   (a) bit for bit with a host transcription of the per-(chunk, node) thread of k_spread_chunks (same segment rules,
-//       same summation order), and
-//   (b) after a transcription of k_spread_combine, with a direct fp64 spread of the same points.
+// Host emulation of the spread (tests/test_kernel_emulation.py builds and runs this with nvcc, no GPU needed).
+// k_spread_chunks is written as two phase functions (fitsne_kernels.cuh: spread2_chunk / spread2_stitch); here every thread
+// of a block runs the walk, then every thread runs the stitch -- exactly what the __syncthreads() in the kernel enforces --
+// onto a pre-zeroed grid; then the work list is combined with k_spread_combine's own per-lane function and tree order.
+// Checked: the grid against a direct fp64 spread of the same points; box_start[] (a by-product of the chunk walk) against
+// plain boundary detection; the work list against "boxes that span more than one chunk"; compile-time and run-time node
+// counts (P > 0 / P == 0) bit for bit against each other.
 // Test infrastructure only; prints "SPREAD_EMUL_OK" when every configuration passes.
 #include "../../fit-sne_b200/csrc/fitsne_kernels.cuh"
 #include <algorithm>
@@ -30,62 +30,49 @@ static GridParams make_gp(int D, int B, int p, int M) {
     return gp;
 }
 
-// transcription of the body of k_spread_chunks for one (chunk, node) thread
-template <int D, int P>
-static void old_thread(int c, int node, const float *sorted_u, const uint32_t *skeys, const uint32_t *box_start, int n,
-                       const GridParams &gp, float4 *slots, float2 *fft_in, float2 *compact) {
-    const int p = P, nodes = D == 2 ? p * p : p;
-    const int kb = c * CHUNK; if (kb >= n) return;
-    const int ke = std::min(kb + CHUNK, n);
-    const int a = D == 2 ? node / p : node, b = D == 2 ? node - a * p : 0;
-    const float sa = gp.s[a], sb = gp.s[b];
-    float2 *dst = compact ? compact : fft_in;
-    const int Gc = gp.M / 2;
-    const size_t stride = compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) gp.M * gp.M : (size_t) gp.M);
-    float4 *myslots = slots + (size_t) c * 2 * nodes;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cur = key_to_box<D>(skeys[kb], gp);
-    for (int k = kb; k < ke; k++) {
-        const int box = key_to_box<D>(skeys[k], gp);
-        if (box != cur) {
-            if ((int) box_start[cur] >= kb) store_node(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc);
-            else myslots[node] = acc;
-            acc = make_float4(0.f, 0.f, 0.f, 0.f); cur = box;
-        }
-        if (D == 2) {
-            const float2 u = reinterpret_cast<const float2 *>(sorted_u)[k];
-            const float L = lagrange1<P>(gp, p, a, u.y) * lagrange1<P>(gp, p, b, u.x);
-            const float ox = u.x - sb, oy = u.y - sa;
-            acc.x += L; acc.y += L * ox; acc.z += L * oy; acc.w += L * (ox * ox + oy * oy);
-        } else {
-            const float u = sorted_u[k];
-            const float L = lagrange1<P>(gp, p, a, u);
-            const float o = u - sa;
-            acc.x += L; acc.y += L * o; acc.z += L * o * o;
-        }
-    }
-    const bool started_here = (int) box_start[cur] >= kb, ends_here = (int) box_start[cur + 1] <= ke;
-    if (started_here && ends_here) store_node(dst, stride, node_offset<D>(cur, node, gp, p, compact != nullptr), acc);
-    else myslots[(started_here ? 1 : 0) * nodes + node] = acc;
-}
 
-// transcription of k_spread_combine's arithmetic for one node of one box (lpn = 1: plain chunk order)
-static float4 combine_node(const float4 *slots, int nodes, int node, int s, int e, bool *single) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    *single = false;
-    if (e <= s) return acc;
-    const int c0 = s / CHUNK, c1 = (e - 1) / CHUNK;
-    if (c0 == c1) { *single = true; return acc; }
-    for (int c = c0; c <= c1; c++) {
-        const float4 v = slots[((size_t) c * 2 + (c == c0 ? 1 : 0)) * nodes + node];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+template <int D, int P>
+static void run_spread(int n, const GridParams &gp, const std::vector<uint32_t> &skeys, const std::vector<float> &su,
+                       std::vector<float> &grid, std::vector<uint32_t> &box_start, std::vector<uint32_t> &work, size_t gsize) {
+    const int p = gp.p, nodes = D == 2 ? p * p : p;
+    const int nchunks = (n + CHUNK - 1) / CHUNK;
+    const int nblocks = (nchunks + SP2_THREADS - 1) / SP2_THREADS;
+    std::vector<float4> cslots((size_t) nblocks * 2 * nodes, make_float4(NAN, NAN, NAN, NAN));
+    std::vector<float4> part((size_t) SP2_THREADS * 2 * nodes);
+    grid.assign(gsize, 0.f);                                             // the memset node of the iteration
+    box_start.assign(gp.nb + 2, 0xdeadbeefu);
+    work.assign((size_t) nblocks + 2, 0u);
+    static Sp2Meta meta;
+    for (int blk = 0; blk < nblocks; blk++) {
+        std::fill(part.begin(), part.end(), make_float4(NAN, NAN, NAN, NAN));   // poison: only parked partials may be read
+        for (int t = 0; t < SP2_THREADS; t++) spread2_chunk<D, P>(t, blk, su.data(), skeys.data(), n, gp, part.data(), meta, grid.data(), box_start.data());
+        for (int t = 0; t < SP2_THREADS; t++) spread2_stitch<D, P>(t, blk, n, gp, part.data(), meta, grid.data(), cslots.data(), work.data());
     }
-    return acc;
+    // k_spread_combine: one lane per (box, node) in plain CTA order; COMBINE_COOP CTAs or more: 32 lanes + xor-shuffle tree
+    for (uint32_t e = 0; e < work[0]; e++) {
+        const int box = (int) work[1 + e];
+        const int s = (int) box_start[box], en = (int) box_start[box + 1];
+        const int c0 = s / SP2_POINTS, c1 = (en - 1) / SP2_POINTS;
+        for (int node = 0; node < nodes; node++) {
+            if (c1 - c0 + 1 < 32) {
+                store_node<D>(grid.data(), (size_t) gp.M, node_offset<D>(box, node, gp, p), combine_node_lane<D>(cslots.data(), c0, c1, nodes, node, 0, 1));
+                continue;
+            }
+            float4 lane[32];
+            for (int l = 0; l < 32; l++) lane[l] = combine_node_lane<D>(cslots.data(), c0, c1, nodes, node, l, 32);
+            for (int o = 16; o > 0; o >>= 1) {
+                float4 nxt[32];
+                for (int l = 0; l < 32; l++) nxt[l] = make_float4(lane[l].x + lane[l ^ o].x, lane[l].y + lane[l ^ o].y, lane[l].z + lane[l ^ o].z, lane[l].w + lane[l ^ o].w);
+                for (int l = 0; l < 32; l++) lane[l] = nxt[l];
+            }
+            store_node<D>(grid.data(), (size_t) gp.M, node_offset<D>(box, node, gp, p), lane[0]);
+        }
+    }
 }
 
 template <int D, int P>
-static bool run_case(const char *name, int n, int B, int M, double heavy_frac, bool use_compact, unsigned seed) {
-    const int p = P, nodes = D == 2 ? p * p : p;
+static bool run_case(const char *name, int n, int B, int M, double heavy_frac, unsigned seed, int p_runtime = 0) {
+    const int p = P > 0 ? P : p_runtime, nodes = D == 2 ? p * p : p;
     GridParams gp = make_gp(D, B, p, M);
     std::mt19937 rng(seed);
     std::uniform_real_distribution<float> U(0.f, 1.f);
@@ -104,35 +91,29 @@ static bool run_case(const char *name, int n, int B, int M, double heavy_frac, b
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return keys[x] < keys[y]; });
     std::vector<uint32_t> skeys(n); std::vector<float> su((size_t) n * D);
     for (int k = 0; k < n; k++) { skeys[k] = keys[order[k]]; for (int d = 0; d < D; d++) su[(size_t) k * D + d] = u[(size_t) order[k] * D + d]; }
-    std::vector<uint32_t> box_start(gp.nb + 2, 0);
-    {   // boundary detection like k_post_sort
+    std::vector<uint32_t> bs_ref(gp.nb + 2, 0);
+    {   // plain boundary detection
         int prev = -1;
-        for (int k = 0; k < n; k++) { const int box = key_to_box<D>(skeys[k], gp); for (int b = prev + 1; b <= box; b++) box_start[b] = k; prev = box; }
-        for (int b = prev + 1; b <= gp.nb; b++) box_start[b] = n;
+        for (int k = 0; k < n; k++) { const int box = key_to_box<D>(skeys[k], gp); for (int b = prev + 1; b <= box; b++) bs_ref[b] = k; prev = box; }
+        for (int b = prev + 1; b <= gp.nb; b++) bs_ref[b] = n;
     }
-    const int nchunks = (n + CHUNK - 1) / CHUNK;
-    const int Gc = M / 2;
-    const size_t plane = use_compact ? (D == 2 ? (size_t) Gc * Gc : (size_t) Gc) : (D == 2 ? (size_t) M * M : (size_t) M);
-    const float4 sentinel4 = make_float4(-7.f, -7.f, -7.f, -7.f);
-    std::vector<float4> slotsA((size_t) nchunks * 2 * nodes, sentinel4), slotsB(slotsA);
-    std::vector<float2> gridA(2 * plane, make_float2(-9.f, -9.f)), gridB(gridA);
-    float2 *fa = use_compact ? nullptr : gridA.data(), *ca = use_compact ? gridA.data() : nullptr;
-    float2 *fb = use_compact ? nullptr : gridB.data(), *cb = use_compact ? gridB.data() : nullptr;
-    // A: the new kernel, block by block, phase by phase
-    const int nblocks = (nchunks + SP2_THREADS - 1) / SP2_THREADS;
-    static Sp2Smem<D> sm;
-    for (int blk = 0; blk < nblocks; blk++) {
-        memset(&sm, 0xff, sizeof sm);                                   // poison: nothing may be read before it is staged
-        for (int t = 0; t < SP2_THREADS; t++) spread2_load<D>(t, blk, su.data(), skeys.data(), n, sm);
-        for (int t = 0; t < SP2_THREADS; t++) spread2_chunk<D, P>(t, blk, sm, box_start.data(), n, gp, slotsA.data(), fa, ca);
-    }
-    // B: the old kernel's threads
-    for (int c = 0; c < nchunks; c++) for (int node = 0; node < nodes; node++)
-        old_thread<D, P>(c, node, su.data(), skeys.data(), box_start.data(), n, gp, slotsB.data(), fb, cb);
+    const size_t gsize = D == 2 ? (size_t) gp.G * gp.G * 4 : (size_t) M * 4;     // floats: G^2 float4 / two packed complex lines
+    std::vector<float> grid, grid0;
+    std::vector<uint32_t> box_start, work, bs0, work0;
+    run_spread<D, P>(n, gp, skeys, su, grid, box_start, work, gsize);
     bool ok = true;
-    if (memcmp(slotsA.data(), slotsB.data(), slotsA.size() * sizeof(float4)) != 0) { printf("%s: slots differ\n", name); ok = false; }
-    if (memcmp(gridA.data(), gridB.data(), gridA.size() * sizeof(float2)) != 0) { printf("%s: direct grid writes differ\n", name); ok = false; }
-    // combine + direct fp64 reference
+    for (int b = 0; b <= gp.nb; b++) if (box_start[b] != bs_ref[b]) { printf("%s: box_start[%d] = %u, expected %u\n", name, b, box_start[b], bs_ref[b]); ok = false; break; }
+    {   // work list == boxes crossing a CTA boundary (one CTA = SP2_POINTS sorted points)
+        std::vector<uint32_t> want, got(work.begin() + 1, work.begin() + 1 + work[0]);
+        for (int b = 0; b < gp.nb; b++) if (bs_ref[b + 1] > bs_ref[b] && bs_ref[b] / SP2_POINTS != (bs_ref[b + 1] - 1) / SP2_POINTS) want.push_back(b);
+        std::sort(got.begin(), got.end());
+        if (got != want) { printf("%s: work list has %zu boxes, expected %zu\n", name, got.size(), want.size()); ok = false; }
+    }
+    if (P > 0) {   // the run-time-p instantiation must give the same bits
+        run_spread<D, 0>(n, gp, skeys, su, grid0, bs0, work0, gsize);
+        if (memcmp(grid.data(), grid0.data(), grid.size() * sizeof(float)) != 0) { printf("%s: P=%d and run-time p differ\n", name, P); ok = false; }
+    }
+    // direct fp64 reference
     double max_err = 0, max_ref = 0;
     std::vector<double> ref((size_t) gp.nb * nodes * 4, 0.0);
     for (int k = 0; k < n; k++) {
@@ -149,37 +130,35 @@ static bool run_case(const char *name, int n, int B, int M, double heavy_frac, b
         }
     }
     for (int box = 0; box < gp.nb; box++) for (int node = 0; node < nodes; node++) {
-        bool single;
-        float4 v = combine_node(slotsA.data(), nodes, node, (int) box_start[box], (int) box_start[box + 1], &single);
-        if (single) {
-            const size_t off = node_offset<D>(box, node, gp, p, use_compact);
-            const float2 p0 = gridA[off], p1 = gridA[plane + off];
-            v = make_float4(p0.x, p0.y, p1.x, p1.y);
-        }
+        const size_t off = node_offset<D>(box, node, gp, p);
+        double got[4];
+        if (D == 2) for (int q = 0; q < 4; q++) got[q] = grid[off * 4 + q];
+        else { got[0] = grid[off * 2]; got[1] = grid[off * 2 + 1]; got[2] = grid[((size_t) M + off) * 2]; got[3] = grid[((size_t) M + off) * 2 + 1]; }
         const double *r = &ref[((size_t) box * nodes + node) * 4];
-        const double got[4] = {v.x, v.y, v.z, v.w};
         for (int q = 0; q < 4; q++) { max_err = std::max(max_err, std::fabs(got[q] - r[q])); max_ref = std::max(max_ref, std::fabs(r[q])); }
     }
     const double rel = max_err / std::max(max_ref, 1e-30);
-    if (!(rel < 2e-5)) { printf("%s: combined grid vs fp64 reference: max err %.3e of %.3e\n", name, max_err, max_ref); ok = false; }
-    printf("%-34s n=%7d B=%4d M=%5d heavy=%.2f compact=%d : %s (vs fp64 %.1e)\n", name, n, B, M, heavy_frac, (int) use_compact, ok ? "ok" : "FAILED", rel);
+    if (!(rel < 2e-5)) { printf("%s: grid vs fp64 reference: max err %.3e of %.3e\n", name, max_err, max_ref); ok = false; }
+    printf("%-34s n=%7d B=%4d M=%5d heavy=%.2f : %s (vs fp64 %.1e, %u boxes cross a CTA boundary)\n", name, n, B, M, heavy_frac, ok ? "ok" : "FAILED", rel, work[0]);
     return ok;
 }
 
 int main() {
     bool ok = true;
-    ok &= run_case<2, 3>("2-D p=3 late (small boxes)", 50000, 50, 320, 0.0, false, 1);
-    ok &= run_case<2, 3>("2-D p=3 ragged tail", 50000 + 17, 36, 224, 0.0, false, 2);
-    ok &= run_case<2, 3>("2-D p=3 heavy box", 40000, 25, 160, 0.6, false, 3);
-    ok &= run_case<2, 3>("2-D p=3 one box", 5000, 25, 160, 1.0, false, 4);
-    ok &= run_case<2, 3>("2-D p=3 compact (sharded)", 30011, 50, 320, 0.1, true, 5);
-    ok &= run_case<2, 2>("2-D p=2", 20000, 60, 256, 0.0, false, 6);
-    ok &= run_case<2, 4>("2-D p=4", 20000, 30, 256, 0.2, false, 7);
-    ok &= run_case<1, 3>("1-D p=3", 60000, 138, 864, 0.0, false, 8);
-    ok &= run_case<1, 5>("1-D p=5 heavy", 33333, 50, 512, 0.5, false, 9);
-    ok &= run_case<1, 3>("1-D p=3 compact", 60000, 138, 864, 0.0, true, 10);
-    ok &= run_case<2, 3>("2-D p=3 tiny n", 7, 25, 160, 0.0, false, 11);
-    ok &= run_case<2, 3>("2-D p=3 n = 1 block + 1", SP2_POINTS + 1, 50, 320, 0.0, false, 12);
+    ok &= run_case<2, 3>("2-D p=3 late (small boxes)", 50000, 50, 320, 0.0, 1);
+    ok &= run_case<2, 3>("2-D p=3 ragged tail", 50000 + 17, 36, 224, 0.0, 2);
+    ok &= run_case<2, 3>("2-D p=3 heavy box", 40000, 25, 160, 0.6, 3);
+    ok &= run_case<2, 3>("2-D p=3 very heavy box (coop)", 150000, 25, 160, 0.9, 14);
+    ok &= run_case<2, 3>("2-D p=3 one box", 5000, 25, 160, 1.0, 4);
+    ok &= run_case<2, 3>("2-D p=3 sparse (empty boxes)", 3011, 200, 1280, 0.1, 5);
+    ok &= run_case<2, 2>("2-D p=2", 20000, 60, 256, 0.0, 6);
+    ok &= run_case<2, 4>("2-D p=4", 20000, 30, 256, 0.2, 7);
+    ok &= run_case<2, 0>("2-D p=5 (run-time p)", 9000, 30, 320, 0.2, 13, 5);
+    ok &= run_case<1, 3>("1-D p=3", 60000, 138, 864, 0.0, 8);
+    ok &= run_case<1, 5>("1-D p=5 heavy", 33333, 50, 512, 0.5, 9);
+    ok &= run_case<1, 0>("1-D p=7 (run-time p)", 20000, 60, 864, 0.0, 10, 7);
+    ok &= run_case<2, 3>("2-D p=3 tiny n", 7, 25, 160, 0.0, 11);
+    ok &= run_case<2, 3>("2-D p=3 n = 1 block + 1", SP2_POINTS + 1, 50, 320, 0.0, 12);
     if (ok) printf("SPREAD_EMUL_OK\n");
     return ok ? 0 : 1;
 }
