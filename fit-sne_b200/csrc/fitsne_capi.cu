@@ -144,7 +144,8 @@ struct fitsne_ctx {
     // sort / bins
     uint32_t *keys[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
     float *sorted_u = nullptr;
-    uint32_t *box_start = nullptr, *hist = nullptr, *sort_totals = nullptr, *sort_bases = nullptr, *sweep_state = nullptr;
+    uint2 *box_range = nullptr;       // [first, end) sorted positions of every non-empty box (by-product of the spread walk)
+    uint32_t *hist = nullptr, *sort_totals = nullptr, *sort_bases = nullptr, *sweep_state = nullptr;
     uint32_t *work = nullptr;         // spread work list: [0] = count, [1..] = boxes that span several chunks
     size_t box_cap = 0, hist_cap = 0;
     float4 *slots = nullptr;          // spread partials of boxes that cross a CTA boundary: [CTA][2][nodes]
@@ -241,7 +242,7 @@ static int ensure_grid_capacity(fitsne_ctx *c, int M) {
     bool moved = false;
     if (nb + 2 > c->box_cap) {
         const size_t cap = nb + nb / 2 + 1024;
-        CKRC(dev_alloc(c, &c->box_start, cap));
+        CKRC(dev_alloc(c, &c->box_range, cap));
         c->box_cap = cap;
         moved = true;
     }
@@ -338,7 +339,7 @@ static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, const uint32
     if (!gather) {
         const int nchunks = cdiv(c->nloc, CHUNK);
         k_spread_chunks<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, spread_smem_bytes<D, P>(), c->stream>>>(
-            c->sorted_u, skeys, c->nloc, c->gp, c->slots, c->gpart, grid, c->box_start, c->work);
+            c->sorted_u, skeys, c->nloc, c->gp, c->slots, c->gpart, grid, c->box_range, c->work);
     } else {
         k_gather<D, P><<<cdiv(c->nloc, 256), 256, 0, c->stream>>>(c->sorted_u, skeys, sperm, c->nloc, c->gp, c->sc,
                                                                    D == 2 ? (const void *) c->pot : (const void *) c->planes, c->frep);
@@ -498,7 +499,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     else CK(cudaMemsetAsync(c->planes, 0, (size_t) 2 * M * sizeof(float2), st));
     CKRC(launch_spread_gather<D>(c, false, skeys, sperm));
     kt(c, "k_spread_chunks");
-    k_spread_combine<D><<<148 * 8, 256, 0, st>>>(c->slots, c->box_start, c->gp, c->work, D == 2 ? (void *) c->chg : (void *) c->planes);
+    k_spread_combine<D><<<148 * 8, 256, 0, st>>>(c->slots, c->box_range, c->gp, c->work, D == 2 ? (void *) c->chg : (void *) c->planes);
     c->stats.kernel_launches += 1;
     if (c->world > 1) {
         // every rank spread its own points: sum the partial grids (fp32).  2-D: the dense (M/2)^2 float4 region that holds
@@ -1112,7 +1113,7 @@ int fitsne_destroy(fitsne_ctx *c) {
     for (auto &p : c->plans) if (p.second.W) cudaFree(p.second.W);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->edges, c->keys[0], c->keys[1],
-                    c->perm[0], c->perm[1], c->sorted_u, c->box_start, c->gpart, c->hist, c->sweep_state, c->sort_bases, c->work, c->sort_totals, c->slots, c->attr, c->planes,
+                    c->perm[0], c->perm[1], c->sorted_u, c->box_range, c->gpart, c->hist, c->sweep_state, c->sort_bases, c->work, c->sort_totals, c->slots, c->attr, c->planes,
                     c->chg, c->pot, c->S, c->KR, c->KS, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->edges2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
@@ -1434,7 +1435,9 @@ int fitsne_debug_copy(fitsne_ctx *c, const char *what, void *dst, size_t dst_byt
     }
     else if (!strcmp(what, "perm")) { src = c->perm[sorted_buf]; bytes = (size_t) c->nloc * 4; }
     else if (!strcmp(what, "keys")) { src = c->keys[sorted_buf]; bytes = (size_t) c->nloc * 4; }
-    else if (!strcmp(what, "box_start")) { src = c->box_start; bytes = ((c->D == 2 ? (size_t) c->cur_B * c->cur_B : (size_t) c->cur_B) + 1) * 4; }
+    else if (!strcmp(what, "box_range")) {      // (first, end) per box; entries of empty boxes are stale
+        src = c->box_range; bytes = (c->D == 2 ? (size_t) c->cur_B * c->cur_B : (size_t) c->cur_B) * sizeof(uint2);
+    }
     else if (!strcmp(what, "grid") && c->D == 2) { src = c->chg; bytes = (size_t) c->stats.grid_side * c->stats.grid_side * sizeof(float4); }
     else if (!strcmp(what, "pot") && c->D == 2) { src = c->pot; bytes = (size_t) c->stats.grid_side * c->stats.grid_side * sizeof(float4); }
     else return fail(c, FITSNE_EINVAL, "unknown debug array '%s'", what);

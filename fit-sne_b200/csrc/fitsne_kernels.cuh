@@ -23,7 +23,7 @@
 namespace fk {
 
 constexpr int PMAX = 16;          // max interpolation points per box and axis
-constexpr int CHUNK = 16;         // points per spread work item
+constexpr int CHUNK = 8;          // points per spread work item (one thread walks a chunk; 8 keeps ~26 warps per SM busy at N = 1M)
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
@@ -706,8 +706,8 @@ __host__ __device__ __forceinline__ float lagrange1(const GridParams &gp, int p,
 //     following chunks in chunk order and writes the box -- no round trip through global memory;
 //   * only a box that crosses a CTA boundary leaves a partial in a global slot (two per CTA) and is appended to a work
 //     list by the CTA that holds its head; k_spread_combine adds those few slots in CTA order.
-//   * box boundaries are detected on the way (one look at the key before and after the chunk): box_start[] -- which only
-//     the combine step needs -- is a by-product, not a separate pass.
+//   * box boundaries are detected on the way (one look at the key before and after the chunk): box_range[] = [first, end)
+//     of every non-empty box -- which only the combine step needs -- is a by-product, not a separate pass.
 // Everything else in the grid is zero (empty box), so nothing ever iterates over the grid's nodes.  Every sum has a fixed
 // order given the sorted order, which the stable sort makes unique: bitwise repeatable.
 //   2-D: node = a*p + b, a = y node, b = x node (grid row = y node, column = x node).  1-D: (L, L*b, L*b^2, 0).
@@ -788,7 +788,7 @@ struct Sp2Meta {
 template <int D, int P>
 __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
                                                        int n, const GridParams &gp, float4 *__restrict__ part, Sp2Meta &meta,
-                                                       void *__restrict__ grid, uint32_t *__restrict__ box_start) {
+                                                       void *__restrict__ grid, uint2 *__restrict__ box_range) {
     constexpr int PP = P > 0 ? P : PMAX;
     constexpr int MAXN = D == 2 ? PP * PP : PP;
     const int p = P > 0 ? P : gp.p;
@@ -808,21 +808,32 @@ __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const flo
     const int prev = kb > 0 ? key_to_box<D>(skeys[kb - 1], gp) : -1;
     const bool head_cont = prev == cur;               // the first segment continues a box from the previous chunk
     bool started = !head_cont;                        // the segment being accumulated started inside this chunk
-    if (started) for (int b = prev + 1; b <= cur; b++) box_start[b] = (uint32_t) kb;
+    if (started) box_range[cur].x = (uint32_t) kb;
     meta.first_box[t] = cur;
+    // software pipeline: the next point's key and coordinates are requested before this point's ~100 instructions
+    uint32_t key_next = kp[0];
+    float2 u_next = make_float2(0.f, 0.f);
+    if (D == 2) u_next = reinterpret_cast<const float2 *>(sorted_u)[kb]; else u_next.x = sorted_u[kb];
     for (int k = kb; k < ke; k++) {
-        const int box = key_to_box<D>(kp[k - kb], gp);
+        const uint32_t key_k = key_next;
+        const float2 u_k = u_next;
+        if (k + 1 < ke) {
+            key_next = kp[k + 1 - kb];
+            if (D == 2) u_next = reinterpret_cast<const float2 *>(sorted_u)[k + 1]; else u_next.x = sorted_u[k + 1];
+        }
+        const int box = key_to_box<D>(key_k, gp);
         if (box != cur) {
             // segment of `cur` ended inside the chunk: finished box unless it started before the chunk (-> H partial)
             spread2_flush<D, P, MAXN>(acc, p, started, cur, gp, grid, stride, myH);
-            for (int b = cur + 1; b <= box; b++) box_start[b] = (uint32_t) k;
+            box_range[cur].y = (uint32_t) k;              // [first, end) of every non-empty box: written where the change is seen,
+            box_range[box].x = (uint32_t) k;              // so empty boxes cost nothing (their entries are never read)
 #pragma unroll
             for (int j = 0; j < MAXN; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             cur = box;
             started = true;
         }
         if (D == 2) {
-            const float2 u = reinterpret_cast<const float2 *>(sorted_u)[k];
+            const float2 u = u_k;
             float Lx[PP], Ly[PP], ox[PP], oy[PP];
 #pragma unroll
             for (int j = 0; j < PP; j++) {
@@ -845,7 +856,7 @@ __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const flo
                 }
             }
         } else {
-            const float u = sorted_u[k];
+            const float u = u_k.x;
 #pragma unroll
             for (int a = 0; a < PP; a++) {
                 if (P == 0 && a >= p) break;
@@ -861,7 +872,7 @@ __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const flo
     // last segment
     const int next = ke < n ? key_to_box<D>(skeys[ke], gp) : gp.nb;
     const bool ends = next != cur;
-    if (ke == n) for (int b = cur + 1; b <= gp.nb; b++) box_start[b] = (uint32_t) n;
+    if (ends) box_range[cur].y = (uint32_t) ke;
     meta.last_box[t] = cur;
     int fl = head_cont ? SP2_HVALID : 0;
     if (started) {                                    // started in this chunk: finished, or the head (T) of a longer box
@@ -939,7 +950,7 @@ template <int D, int P>
 __global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys, int n,
                                                                const GridParams *__restrict__ gpp, float4 *__restrict__ cslots,
                                                                float4 *__restrict__ gpart, void *__restrict__ grid,
-                                                               uint32_t *__restrict__ box_start, uint32_t *__restrict__ work) {
+                                                               uint2 *__restrict__ box_range, uint32_t *__restrict__ work) {
     extern __shared__ __align__(16) unsigned char sp_raw[];
     __shared__ GridParams gps;
     __shared__ Sp2Meta meta;
@@ -950,7 +961,7 @@ __global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks(const float *__re
     const int p = P > 0 ? P : gps.p;
     const int nodes = D == 2 ? p * p : p;
     float4 *part = P > 0 ? reinterpret_cast<float4 *>(sp_raw) : gpart + (size_t) blockIdx.x * SP2_THREADS * 2 * nodes;
-    spread2_chunk<D, P>(threadIdx.x, blockIdx.x, sorted_u, skeys, n, gps, part, meta, grid, box_start);
+    spread2_chunk<D, P>(threadIdx.x, blockIdx.x, sorted_u, skeys, n, gps, part, meta, grid, box_range);
     __syncthreads();                                  // (block-scope barrier also orders the global-memory partials of P == 0)
     spread2_stitch<D, P>(threadIdx.x, blockIdx.x, n, gps, part, meta, grid, cslots, work);
 }
@@ -975,7 +986,7 @@ __host__ __device__ __forceinline__ float4 combine_node_lane(const float4 *__res
 
 #ifdef __CUDACC__
 template <int D>
-__global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ cslots, const uint32_t *__restrict__ box_start,
+__global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ cslots, const uint2 *__restrict__ box_range,
                                                         const GridParams *__restrict__ gpp, const uint32_t *__restrict__ work,
                                                         void *__restrict__ grid) {
     const GridParams &gp = *gpp;
@@ -991,7 +1002,8 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
             const int e = task / nodes;
             node = task - e * nodes;
             box = (int) work[1 + e];
-            b0 = (int) box_start[box] / SP2_POINTS; b1 = ((int) box_start[box + 1] - 1) / SP2_POINTS;
+            const uint2 r = box_range[box];
+            b0 = (int) r.x / SP2_POINTS; b1 = ((int) r.y - 1) / SP2_POINTS;
         }
         const bool coop = b1 - b0 + 1 >= COMBINE_COOP;
         if (task < ntask && !coop)

@@ -169,7 +169,7 @@ int fitsne_reset_stats(fitsne_ctx *ctx);
 /* Device time of the last fitsne_run in ms (CUDA events around the loop, KL included). */
 int fitsne_last_run_ms(fitsne_ctx *ctx, double *ms);
 /* Copy internal device arrays to the host for tests: what = "frep" (N*no_dims floats, F_rep/Z of the last
- * gradient), "perm" (N u32, box-sorted order), "keys" (N u32), "box_start", and in 2-D "grid" (G*G float4: the spread
+ * gradient), "perm" (N u32, box-sorted order), "keys" (N u32), "box_range" (first, end per non-empty box), and in 2-D "grid" (G*G float4: the spread
  * result w1, delta_x, delta_y, wbb) and "pot" (G*G float4: v1, Bx, By, 0 at the nodes). */
 int fitsne_debug_copy(fitsne_ctx *ctx, const char *what, void *dst, size_t dst_bytes, size_t *needed_bytes);
 const char *fitsne_version(void);

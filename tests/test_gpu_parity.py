@@ -123,7 +123,7 @@ def test_sort_is_stable_and_complete(fb, golden_graph):
         perm = t.debug("perm", np.uint32)
         keys = t.debug("keys", np.uint32)
         B = t.stats()["n_boxes"]
-        start = t.debug("box_start", np.uint32)
+        rng_ = t.debug("box_range", np.uint32).reshape(-1, 2)
     assert np.array_equal(np.sort(perm), np.arange(N, dtype=np.uint32))
     assert np.all(np.diff(keys.astype(np.int64)) >= 0)
     same = np.diff(keys.astype(np.int64)) == 0
@@ -131,7 +131,9 @@ def test_sort_is_stable_and_complete(fb, golden_graph):
     xbits = int(np.ceil(np.log2(B)))
     box = (keys >> xbits) * B + (keys & ((1 << xbits) - 1))
     counts = np.bincount(box, minlength=B * B)
-    assert np.array_equal(np.diff(start.astype(np.int64)), counts)
+    ne = counts > 0                                                 # (first, end) is defined for non-empty boxes only
+    assert np.array_equal(rng_[ne, 1].astype(np.int64) - rng_[ne, 0], counts[ne])
+    assert np.array_equal(rng_[ne, 0].astype(np.int64), np.concatenate([[0], np.cumsum(counts)])[:-1][ne])
 
 
 def test_errors_are_loud(fb, golden_graph):

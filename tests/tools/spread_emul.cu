@@ -2,7 +2,7 @@
 // k_spread_chunks is written as two phase functions (fitsne_kernels.cuh: spread2_chunk / spread2_stitch); here every thread
 // of a block runs the walk, then every thread runs the stitch -- exactly what the __syncthreads() in the kernel enforces --
 // onto a pre-zeroed grid; then the work list is combined with k_spread_combine's own per-lane function and tree order.
-// Checked: the grid against a direct fp64 spread of the same points; box_start[] (a by-product of the chunk walk) against
+// Checked: the grid against a direct fp64 spread of the same points; box_range[] (a by-product of the chunk walk) against
 // plain boundary detection; the work list against "boxes that span more than one chunk"; compile-time and run-time node
 // counts (P > 0 / P == 0) bit for bit against each other.
 // Test infrastructure only; prints "SPREAD_EMUL_OK" when every configuration passes.
@@ -33,25 +33,25 @@ static GridParams make_gp(int D, int B, int p, int M) {
 
 template <int D, int P>
 static void run_spread(int n, const GridParams &gp, const std::vector<uint32_t> &skeys, const std::vector<float> &su,
-                       std::vector<float> &grid, std::vector<uint32_t> &box_start, std::vector<uint32_t> &work, size_t gsize) {
+                       std::vector<float> &grid, std::vector<uint2> &box_range, std::vector<uint32_t> &work, size_t gsize) {
     const int p = gp.p, nodes = D == 2 ? p * p : p;
     const int nchunks = (n + CHUNK - 1) / CHUNK;
     const int nblocks = (nchunks + SP2_THREADS - 1) / SP2_THREADS;
     std::vector<float4> cslots((size_t) nblocks * 2 * nodes, make_float4(NAN, NAN, NAN, NAN));
     std::vector<float4> part((size_t) SP2_THREADS * 2 * nodes);
     grid.assign(gsize, 0.f);                                             // the memset node of the iteration
-    box_start.assign(gp.nb + 2, 0xdeadbeefu);
+    box_range.assign(gp.nb + 2, make_uint2(0xdeadbeefu, 0xdeadbeefu));
     work.assign((size_t) nblocks + 2, 0u);
     static Sp2Meta meta;
     for (int blk = 0; blk < nblocks; blk++) {
         std::fill(part.begin(), part.end(), make_float4(NAN, NAN, NAN, NAN));   // poison: only parked partials may be read
-        for (int t = 0; t < SP2_THREADS; t++) spread2_chunk<D, P>(t, blk, su.data(), skeys.data(), n, gp, part.data(), meta, grid.data(), box_start.data());
+        for (int t = 0; t < SP2_THREADS; t++) spread2_chunk<D, P>(t, blk, su.data(), skeys.data(), n, gp, part.data(), meta, grid.data(), box_range.data());
         for (int t = 0; t < SP2_THREADS; t++) spread2_stitch<D, P>(t, blk, n, gp, part.data(), meta, grid.data(), cslots.data(), work.data());
     }
     // k_spread_combine: one lane per (box, node) in plain CTA order; COMBINE_COOP CTAs or more: 32 lanes + xor-shuffle tree
     for (uint32_t e = 0; e < work[0]; e++) {
         const int box = (int) work[1 + e];
-        const int s = (int) box_start[box], en = (int) box_start[box + 1];
+        const int s = (int) box_range[box].x, en = (int) box_range[box].y;
         const int c0 = s / SP2_POINTS, c1 = (en - 1) / SP2_POINTS;
         for (int node = 0; node < nodes; node++) {
             if (c1 - c0 + 1 < 32) {
@@ -99,10 +99,12 @@ static bool run_case(const char *name, int n, int B, int M, double heavy_frac, u
     }
     const size_t gsize = D == 2 ? (size_t) gp.G * gp.G * 4 : (size_t) M * 4;     // floats: G^2 float4 / two packed complex lines
     std::vector<float> grid, grid0;
-    std::vector<uint32_t> box_start, work, bs0, work0;
-    run_spread<D, P>(n, gp, skeys, su, grid, box_start, work, gsize);
+    std::vector<uint2> box_range, bs0;
+    std::vector<uint32_t> work, work0;
+    run_spread<D, P>(n, gp, skeys, su, grid, box_range, work, gsize);
     bool ok = true;
-    for (int b = 0; b <= gp.nb; b++) if (box_start[b] != bs_ref[b]) { printf("%s: box_start[%d] = %u, expected %u\n", name, b, box_start[b], bs_ref[b]); ok = false; break; }
+    for (int b = 0; b < gp.nb; b++) if (bs_ref[b + 1] > bs_ref[b] && (box_range[b].x != bs_ref[b] || box_range[b].y != bs_ref[b + 1])) {
+        printf("%s: box_range[%d] = [%u, %u), expected [%u, %u)\n", name, b, box_range[b].x, box_range[b].y, bs_ref[b], bs_ref[b + 1]); ok = false; break; }
     {   // work list == boxes crossing a CTA boundary (one CTA = SP2_POINTS sorted points)
         std::vector<uint32_t> want, got(work.begin() + 1, work.begin() + 1 + work[0]);
         for (int b = 0; b < gp.nb; b++) if (bs_ref[b + 1] > bs_ref[b] && bs_ref[b] / SP2_POINTS != (bs_ref[b + 1] - 1) / SP2_POINTS) want.push_back(b);
