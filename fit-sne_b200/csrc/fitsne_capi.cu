@@ -164,7 +164,7 @@ struct fitsne_ctx {
     int *mismatch = nullptr;
     unsigned int *tickets = nullptr;   // last-block-done counters: [0] hadamard, [1] centre/bounds, [2] update, [3] shard stats
     float *host_bounds = nullptr, *host_bounds_dev = nullptr;   // mapped pinned
-    int *host_B = nullptr, *host_B_dev = nullptr;               // mapped pinned: the host's n_boxes for this iteration
+    int *host_B = nullptr, *host_B_dev = nullptr;               // pinned word + its device-memory copy: the host's n_boxes for this iteration (0 = the device decides)
     Scalars *host_sc = nullptr;                                 // pinned staging for scalar read-back
     StepParams sp_host{};
     bool sp_valid = false;
@@ -454,10 +454,11 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     kt(c, "k_setup_grid");
     // 2-D: the kernel spectra depend on the grid geometry only (not on the points): sample + transform them on their own
     // stream while this one sorts and spreads; joined right before the fused column pass
+    static const int col_threads = getenv("FITSNE_COL_THREADS") ? std::min(COL_THREADS, std::max(64, atoi(getenv("FITSNE_COL_THREADS")))) : 256;
     auto launch_kernel_side = [&](cudaStream_t ks) -> int {
         const int Gc = M / 2, H = M / 2 + 1;
         k_kspec_rows<<<Gc, ROW_THREADS, pl->smem_row1, ks>>>(c->KR, pl->plan, pl->W, c->gp, c->cfg.df);
-        k_kspec_cols<<<(H + 1) / 2, COL_THREADS, pl->smem_col, ks>>>(c->KR, c->KS, pl->cplan, pl->W, c->gp);
+        k_kspec_cols<<<(H + 1) / 2, col_threads, pl->smem_col, ks>>>(c->KR, c->KS, pl->cplan, pl->W, c->gp);
         LAUNCH_CHECK();
         c->stats.kernel_launches += 2;
         return 0;
@@ -521,7 +522,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp);
         kt(c, "k_conv_rows_fwd");
         if (overlap) CK(cudaStreamWaitEvent(st, c->ev_kjoin, 0));
-        k_conv_cols<<<H, COL_THREADS, pl->smem_col, st>>>(pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
+        k_conv_cols<<<H, col_threads, pl->smem_col, st>>>(pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
                                                           c->sc, c->tickets + 0);
         kt(c, "k_conv_cols");
         k_conv_rows_inv<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->S, c->pot, pl->plan, pl->W, c->gp);
@@ -809,6 +810,7 @@ static int run_batch(fitsne_ctx *c, int n, int *done) {
     int B, M;
     CKRC(choose_grid(c, &B, &M));
     *c->host_B = 0;                                           // let the device choose n_boxes
+    CK(cudaMemcpyAsync(c->host_B_dev, c->host_B, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     volatile unsigned long long *host_iter = reinterpret_cast<volatile unsigned long long *>(c->host_bounds + 4);
     const unsigned long long before = *host_iter;
     int ran = 0;
@@ -861,6 +863,7 @@ static int run_iteration(fitsne_ctx *c, bool update) {
     int B, M;
     CKRC(choose_grid(c, &B, &M));
     *c->host_B = B;
+    CK(cudaMemcpyAsync(c->host_B_dev, c->host_B, sizeof(int), cudaMemcpyHostToDevice, c->stream));
 
     const bool timers = (c->cfg.flags & FITSNE_FLAG_TIMERS) != 0;
     const bool use_graph = !(c->cfg.flags & FITSNE_FLAG_NO_GRAPH) && !timers && c->world == 1;   // sharded: plain launches
@@ -1073,7 +1076,8 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     memset(c->host_bounds, 0, 64);
     CK(cudaHostGetDevicePointer((void **) &c->host_bounds_dev, c->host_bounds, 0));
     c->host_B = reinterpret_cast<int *>(c->host_bounds + 8);
-    c->host_B_dev = reinterpret_cast<int *>(c->host_bounds_dev + 8);
+    CKRC(dev_alloc(c, &c->host_B_dev, (size_t) 1));      // read by k_setup_grid: device memory, not a PCIe round trip per iteration
+    CK(cudaMemsetAsync(c->host_B_dev, 0, sizeof(int), c->stream));
     CK(cudaHostAlloc((void **) &c->host_sc, sizeof(Scalars), cudaHostAllocDefault));
     memset(c->host_sc, 0, sizeof(Scalars));
     if (Y0) CKRC(upload_as_float(c, Y0, c->Y, (size_t) N * no_dims));
@@ -1115,7 +1119,7 @@ int fitsne_destroy(fitsne_ctx *c) {
     void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->edges, c->keys[0], c->keys[1],
                     c->perm[0], c->perm[1], c->sorted_u, c->box_range, c->gpart, c->hist, c->sweep_state, c->sort_bases, c->work, c->sort_totals, c->slots, c->attr, c->planes,
                     c->chg, c->pot, c->S, c->KR, c->KS, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
-                    c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
+                    c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->host_B_dev, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->edges2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
                     c->nonempty, c->gp_reorder, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial, c->srt_cnt, c->srt_start, c->srt_cur};
     for (void *b : bufs) if (b) cudaFree(b);

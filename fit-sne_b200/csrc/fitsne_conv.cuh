@@ -40,7 +40,7 @@
 namespace fk {
 
 constexpr int COL_SLOTS = 4;          // sequences per column tile
-constexpr int COL_THREADS = 128;
+constexpr int COL_THREADS = 256;      // upper bound (launch bounds); the launch picks 128..256
 constexpr int COL_BOX_ROWS = 128;     // rows per TMA box (box = 128 rows x 32 bytes)
 constexpr int ROW_THREADS = 256;
 
@@ -109,13 +109,16 @@ __host__ __device__ __forceinline__ void col_fwd_stage(float2 *x, int M, int m, 
 
 // Inverse stage (decimation in time) on CONJUGATED data, in place: conj(inverse butterfly) = forward butterfly of the
 // conjugated, twiddled inputs.  CONJ_OUT (last stage executed = plan stage 0): un-conjugate while storing.
+// nslots (3 or 4): only the first nslots sequences of the tile are transformed (the convolution's inverse needs three).
 template <int R, bool CONJ_OUT>
 __host__ __device__ __forceinline__ void col_inv_stage(float2 *x, int M, int m, int tws, FastDiv div_m,
-                                                       const float2 *__restrict__ W, int tid, int nthreads) {
-    const int ntask = (M / R) * COL_SLOTS;
+                                                       const float2 *__restrict__ W, int tid, int nthreads, int nslots) {
+    const int ntask = (M / R) * nslots;
     const int n_cur = m * R;
     for (int task = tid; task < ntask; task += nthreads) {
-        const int slot = task & (COL_SLOTS - 1), t = task >> 2;
+        int slot, t;
+        if (nslots == COL_SLOTS) { slot = task & (COL_SLOTS - 1); t = task >> 2; }
+        else { t = (int) (((unsigned) task * 43691u) >> 17); slot = task - 3 * t; }      // task / 3, exact for task < 2^16
         const int b = fastdiv_hd(t, div_m), q = t - b * m;
         const int base = b * n_cur + q;
         float2 a[R];
@@ -152,15 +155,15 @@ __host__ __device__ __forceinline__ void col_run_fwd_stage(float2 *x, const ColP
 }
 template <bool CONJ_OUT>
 __host__ __device__ __forceinline__ void col_run_inv_stage(float2 *x, const ColPlan &pl, int st, const float2 *__restrict__ W,
-                                                           int tid, int nthreads) {
+                                                           int tid, int nthreads, int nslots = COL_SLOTS) {
     const int M = pl.n, m = pl.m[st], tws = pl.tws[st];
     const FastDiv dm = pl.div_m[st];
     switch (pl.radix[st]) {
-        case 8: col_inv_stage<8, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads); break;
-        case 4: col_inv_stage<4, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads); break;
-        case 2: col_inv_stage<2, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads); break;
-        case 3: col_inv_stage<3, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads); break;
-        default: col_inv_stage<5, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads); break;
+        case 8: col_inv_stage<8, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
+        case 4: col_inv_stage<4, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
+        case 2: col_inv_stage<2, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
+        case 3: col_inv_stage<3, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
+        default: col_inv_stage<5, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
     }
 }
 
@@ -175,12 +178,12 @@ __device__ __forceinline__ void col_fft_forward(float2 *x, const ColPlan &pl, in
     }
 }
 // inverse (unnormalised) of CONJUGATED digit-reversed spectra: natural order, un-conjugated, out.  Ends with a barrier.
-__device__ __forceinline__ void col_fft_inverse_conj(float2 *x, const ColPlan &pl, const float2 *__restrict__ W) {
+__device__ __forceinline__ void col_fft_inverse_conj(float2 *x, const ColPlan &pl, const float2 *__restrict__ W, int nslots) {
     for (int st = pl.nstages - 1; st > 0; st--) {
-        col_run_inv_stage<false>(x, pl, st, W, (int) threadIdx.x, (int) blockDim.x);
+        col_run_inv_stage<false>(x, pl, st, W, (int) threadIdx.x, (int) blockDim.x, nslots);
         __syncthreads();
     }
-    col_run_inv_stage<true>(x, pl, 0, W, (int) threadIdx.x, (int) blockDim.x);
+    col_run_inv_stage<true>(x, pl, 0, W, (int) threadIdx.x, (int) blockDim.x, nslots);
     __syncthreads();
 }
 
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_conv_cols(const __grid_constant
         s[1] = make_float4(By.x, -By.y, 0.f, 0.f);
     }
     __syncthreads();
-    col_fft_inverse_conj(x, plan_s, W);
+    col_fft_inverse_conj(x, plan_s, W, 3);             // v1, Bx, By: the fourth slot is not transformed (nobody reads it)
     fence_proxy_async_smem();
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -30,7 +30,7 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
 constexpr int SORT_MAX_BITS = 11;     // widest radix digit
 constexpr int SORT_ONE_PASS_BITS = 8; // keys this short sort in ONE pass.  (Measured on B200: a single 12-bit pass -- 4096 bins --
                                       // is slower than two 6-bit passes: 84 vs 70 us at N=1M; so only short 1-D keys qualify.)
-constexpr int RED_BLOCKS = 592;   // 4 x 148 SMs: partial-reduction width for bounds / column sums
+constexpr int RED_BLOCKS = 1184;  // 8 x 148 SMs: partial-reduction width for bounds / column sums
 constexpr int Z_BLOCKS_1D = 32;      // Parseval partials of the 1-D Hadamard kernel
 constexpr int SHARD_BLOCKS = 148;  // one CTA per SM: per-rank sums / bounds of the local slice (sharded runs)
 
@@ -135,10 +135,14 @@ __device__ __forceinline__ int box_of(float y, const GridParams &gp, float &u) {
 
 // ------------------------------------------------------------------------- column sums, centring, bounds --
 
-// Yout = Yin - mean (tsne.cpp:1851-1876) and per-block (min,max) of the centred values.
-// 2-D min follows the reference's `if (>max) .. else if (<min)` scan (tsne.cpp:1045-1048): values in the
-// strictly ascending prefix of the interleaved sequence x0,y0,x1,y1,... only ever update max, so the min is
-// taken over flat indices >= t, t = length of that prefix.  1-D uses plain min/max (tsne.cpp:769-772).
+// Yout = Yin - mean (tsne.cpp:1851-1876) and the bounds of the centred values.
+// 2-D min follows the reference's `if (>max) .. else if (<min)` scan (tsne.cpp:1045-1048): values in the strictly
+// ascending prefix of the interleaved sequence x0,y0,x1,y1,... (ORIGINAL point order) only ever update max, so they are
+// never considered for the min.  The prefix is a handful of values long (k values with probability 1/k!), so: every CTA
+// leaves the first BOUNDS_HEAD points (original order) out of its minimum, and the last CTA to finish replays the scan on
+// exactly those points.  Exact unless the prefix is longer than 2*BOUNDS_HEAD = 64 values (probability 1/64!).
+// 1-D uses plain min/max (tsne.cpp:769-772).
+constexpr int BOUNDS_HEAD = 32;
 template <int D>
 __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__ Yin, float *__restrict__ Yout, int N,
                                                        int do_center, float2 *__restrict__ bounds_partial,
@@ -147,26 +151,11 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
                                                        volatile float *host_bounds, unsigned int *__restrict__ ticket) {
     if (gpp && !gpp->ok) return;
     __shared__ float smf[64];
-    __shared__ int t_s;
     double mean[2] = {0, 0};
     if (do_center) {                 // k_update's last block reduced the column sums of the new positions
         for (int d = 0; d < D; d++) mean[d] = sc->mean[d];
     }
-    const int nflat = N * D;
-    if (threadIdx.x == 0) {
-        int t = 0;
-        if (D == 2) {
-            float run = -INFINITY;
-            while (t < nflat) {   // walk the points in ORIGINAL order (the device may have re-ordered them)
-                const size_t pos = pos_of ? (size_t) pos_of[t >> 1] : (size_t) (t >> 1);
-                float v = (float) ((double) Yin[pos * 2 + (t & 1)] - mean[t & 1]);
-                if (v > run) { run = v; t++; } else break;
-            }
-        }
-        t_s = t;
-    }
-    __syncthreads();
-    const int t0 = t_s;
+    const long long head = D == 2 ? BOUNDS_HEAD : 0;
     float mn = INFINITY, mx = -INFINITY;
     const int per = (N + gridDim.x - 1) / gridDim.x;
     const int b = blockIdx.x * per, e = min(N, b + per);
@@ -177,9 +166,8 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
             v.y = (float) ((double) v.y - mean[1]);
             if (do_center) reinterpret_cast<float2 *>(Yout)[i] = v;
             mx = fmaxf(mx, fmaxf(v.x, v.y));
-            const long long fo = orig_of ? 2ll * (long long) orig_of[i] : 2ll * i;   // flat index in original order
-            if (fo >= t0) mn = fminf(mn, v.x);
-            if (fo + 1 >= t0) mn = fminf(mn, v.y);
+            const long long o = orig_of ? (long long) orig_of[i] : (long long) i;      // original index of this point
+            if (o >= head) mn = fminf(mn, fminf(v.x, v.y));
         } else {
             float v = (float) ((double) Yin[i] - mean[0]);
             if (do_center) Yout[i] = v;
@@ -206,9 +194,16 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
         }
         if (lane == 0) bounds_partial[blockIdx.x] = make_float2(mn, mx);
     }
-    // last block: combine the per-block bounds and publish them (device scalars + host-mapped words); closing a full
-    // optimiser step (gpp != nullptr) also bumps the executed-iterations counter
+    // last block: combine the per-block bounds, replay the scan on the head points, publish (device scalars + host-mapped
+    // words); closing a full optimiser step (gpp != nullptr) also bumps the executed-iterations counter
     if (last_block_done(ticket)) {
+        __shared__ float headv[2 * BOUNDS_HEAD];
+        const int nhead = D == 2 ? min(2 * BOUNDS_HEAD, 2 * N) : 0;
+        if ((int) threadIdx.x < nhead) {      // centred values of the head points, recomputed from the input (same arithmetic)
+            const int j = threadIdx.x;
+            const size_t pos = pos_of ? (size_t) pos_of[j >> 1] : (size_t) (j >> 1);
+            headv[j] = (float) ((double) Yin[pos * 2 + (j & 1)] - mean[j & 1]);
+        }
         float bmn = INFINITY, bmx = -INFINITY;
         for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) {
             const float2 v = ld_partial(bounds_partial + i);
@@ -224,6 +219,13 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int i = 1; i < (int) (blockDim.x >> 5); i++) { bmn = fminf(bmn, smf[i]); bmx = fmaxf(bmx, smf[32 + i]); }
+            float run = -INFINITY;
+            bool ascending = true;
+            for (int j = 0; j < nhead; j++) {          // the reference's scan on the head: max only while strictly ascending
+                const float v = headv[j];
+                if (ascending && v > run) run = v;
+                else { ascending = false; bmn = fminf(bmn, v); }
+            }
             sc->bmin = bmn; sc->bmax = bmx;
             if (gpp) sc->iter_done += 1;
             if (host_bounds) {
@@ -345,7 +347,7 @@ template <typename T>
 static inline T fk_host_fetch_add(T *p, T v) { const T old = *p; *p = old + v; return old; }
 #endif
 
-constexpr int BIN_THREADS = 1024;                       // k_bin: SORT_TILE / 1024 = 4 points per thread
+constexpr int BIN_THREADS = 512;                        // k_bin: SORT_TILE / 512 = 8 points per thread; every tile's CTA is resident at once
 constexpr int SWEEP_THREADS = 512;                      // k_radix_sweep: 16 warps x 8 keys per lane
 constexpr int SWEEP_IPT = SORT_TILE / SWEEP_THREADS;
 constexpr uint32_t SWEEP_READY = 0x80000000u;
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_radix_sweep(const uint32_t *_
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive prefix over this tile's warps, publish the tile total, sum the earlier tiles' totals
+    // per digit: exclusive prefix over this tile's warps, publish the tile total ...
     uint32_t *mystate = state + ((size_t) pass * tiles + tile) * NBMAX;
     const uint32_t *prev = state + (size_t) pass * tiles * NBMAX;
     for (int d = threadIdx.x; d < nb; d += SWEEP_THREADS) {
@@ -510,25 +512,34 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_radix_sweep(const uint32_t *_
             run += t;
         }
         *reinterpret_cast<volatile uint32_t *>(mystate + d) = SWEEP_READY | run;
-        uint32_t excl = 0;
-        int t = 0;
-        for (; t + 8 <= tile; t += 8) {           // eight words in flight; re-read until all eight are published
-            uint32_t v[8];
-            bool all;
-            do {
-                all = true;
+        gbase[d] = bases[(size_t) pass * NBMAX + d];
+    }
+    __syncthreads();
+    // ... and add the totals of the earlier tiles as they appear.  All threads take part: `parts` threads per digit, each
+    // summing every parts-th predecessor with sixteen words in flight; integer adds into shared memory (order-independent).
+    {
+        const int parts = nb < SWEEP_THREADS ? SWEEP_THREADS / nb : 1;
+        for (int task = threadIdx.x; task < nb * parts; task += SWEEP_THREADS) {
+            const int d = task & (nb - 1), part = task / nb;
+            uint32_t excl = 0;
+            int t = part;
+            while (t < tile) {
+                uint32_t v[16];
 #pragma unroll
-                for (int j = 0; j < 8; j++) { v[j] = *reinterpret_cast<const volatile uint32_t *>(prev + (size_t) (t + j) * NBMAX + d); all = all && (v[j] & SWEEP_READY); }
-            } while (!all);
+                for (int j = 0; j < 16; j++) {
+                    const int tt = t + j * parts;
+                    v[j] = tt < tile ? *reinterpret_cast<const volatile uint32_t *>(prev + (size_t) tt * NBMAX + d) : SWEEP_READY;
+                }
+                bool all = true;
 #pragma unroll
-            for (int j = 0; j < 8; j++) excl += v[j] & ~SWEEP_READY;
+                for (int j = 0; j < 16; j++) all = all && (v[j] & SWEEP_READY);
+                if (!all) continue;                   // some predecessor has not published yet: read the batch again
+#pragma unroll
+                for (int j = 0; j < 16; j++) excl += v[j] & ~SWEEP_READY;
+                t += 16 * parts;
+            }
+            if (excl) atomicAdd(&gbase[d], excl);
         }
-        for (; t < tile; t++) {
-            uint32_t v;
-            do { v = *reinterpret_cast<const volatile uint32_t *>(prev + (size_t) t * NBMAX + d); } while (!(v & SWEEP_READY));
-            excl += v & ~SWEEP_READY;
-        }
-        gbase[d] = bases[(size_t) pass * NBMAX + d] + excl;
     }
     __syncthreads();
 #pragma unroll

@@ -60,7 +60,7 @@ static double run_len(int M, int lines, bool *plan_ok, int *nstages) {
 }
 
 // in-place column transform: returns the worse of (forward vs DFT, round trip vs M * input), relative
-static double run_col(int M, int nz, bool *plan_ok) {
+static double run_col(int M, int nz, bool *plan_ok, int inv_slots = COL_SLOTS) {
     ColPlan pl;
     *plan_ok = col_make_plan(M, &pl);
     if (!*plan_ok) return 0;
@@ -99,10 +99,10 @@ static double run_col(int M, int nz, bool *plan_ok) {
     // conjugate (what the Hadamard step does while storing), inverse stages, compare with M * input
     for (auto &v : x) v.y = -v.y;
     for (int st = pl.nstages - 1; st > 0; st--)
-        for (int tid = 0; tid < nthreads; tid++) col_run_inv_stage<false>(x.data(), pl, st, W.data(), tid, nthreads);
-    for (int tid = 0; tid < nthreads; tid++) col_run_inv_stage<true>(x.data(), pl, 0, W.data(), tid, nthreads);
+        for (int tid = 0; tid < nthreads; tid++) col_run_inv_stage<false>(x.data(), pl, st, W.data(), tid, nthreads, inv_slots);
+    for (int tid = 0; tid < nthreads; tid++) col_run_inv_stage<true>(x.data(), pl, 0, W.data(), tid, nthreads, inv_slots);
     max_err = 0; max_ref = 0;
-    for (int sl = 0; sl < COL_SLOTS; sl++) for (int i = 0; i < M; i++) {
+    for (int sl = 0; sl < inv_slots; sl++) for (int i = 0; i < M; i++) {
         const std::complex<double> want = in[(size_t) sl * M + i] * (double) M;
         const float2 got = x[(size_t) i * COL_SLOTS + sl];
         max_err = std::max(max_err, std::abs(want - std::complex<double>(got.x, got.y)));
@@ -129,7 +129,7 @@ int main() {
         if (M <= 4096) {
             for (int nz : {M / 2, M / 2 - M / 7, M}) {
                 bool pc;
-                const double ec = run_col(M, nz, &pc);
+                const double ec = std::max(run_col(M, nz, &pc), run_col(M, nz, &pc, 3));
                 if (!pc || !(ec < 4e-6)) { printf("M=%d nz=%d: in-place column transform err %.2e  FAILED\n", M, nz, ec); ok = false; }
                 worst_col = std::max(worst_col, ec);
             }
