@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- t-SNE gradient-loop iterations/sec (BASELINE.json's metric) on 1..8 B200s, with roofline and CPU baseline.
+"""bench.py -- t-SNE gradient-loop iterations/sec (BASELINE.json's metric) on 1..8 B200s, with roofline, parity and CPU baseline.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--points 1000000] [--phase late|early]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one full iteration of TSNE::run's loop (gradient + gains/momentum update + zero-mean; the KL
-evaluation runs every 50th step inside the timed region, as in the reference) on BASELINE.json's config 3:
-synthetic N=1M points, 2-D, learning_rate=N/12, fixed kNN-style graph injected like load_affinities=1
-(E ~ 30 N).  `value` times device-resident state with CUDA events on the library's stream (fitsne_run);
-`e2e` times fitsne_run_host (host CSR P + host Y in, host Y + costs out) with a host clock.
-`--impl reference` times the UNMODIFIED reference binary (oracle/_ref/fast_tsne_ref) on the host cores.
+evaluation runs every 50th step inside the timed region, as in the reference).  The headline (`value`) is
+BASELINE.json's config 3: synthetic N=1M points, 2-D, learning_rate=N/12, fixed kNN-style graph injected like
+load_affinities=1 (E ~ 30 N), late phase.  `value` times device-resident state with CUDA events on the library's
+stream (fitsne_run); `e2e` times create + run + download through the C ABI with host buffers and a host clock.
+The same line also carries: `roofline` (the phase that takes longest, live CUDA-event times), `roofline_total`,
+`kernels` (every phase), `parity` (our gradient vs the oracle on this very workload, outside the timed region),
+`cpu_baseline` (the unmodified reference on the host cores) and `other_configs` (BASELINE configs 1, 2, 4, 5 and
+the early phase of config 3, short runs).  `--impl reference` times the UNMODIFIED reference binary
+(oracle/_ref/fast_tsne_ref) on the host cores.
 """
 import argparse
 import json
@@ -25,6 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "fit-sne_b200"))
+os.environ.setdefault("FITSNE_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "fitsne_bench_cache"))
 import bench_util  # noqa: E402
 
 METRIC = "tsne_iterations_per_sec"
@@ -39,21 +44,27 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def workload(points, phase, K_nn=15, dims=2):
+def workload(points, phase, K_nn=15, dims=2, span=170.0):
+    """config 3 / 4: (row, col, val, Y0, schedule) -- the kNN-like graph + an early or late looking embedding."""
     row, col, val, labels = bench_util.knn_like_graph(points, K_nn, seed=0)
+    return (row, col, val) + embedding_and_schedule(points, labels, phase, dims, span)
+
+
+def embedding_and_schedule(points, labels, phase, dims, span, late_exag=None):
     if phase == "early":
         Y0 = bench_util.early_embedding(points, dims)
         sched = dict(early_exag_coeff=12.0, stop_lying_iter=10 ** 9, mom_switch_iter=10 ** 9, momentum=0.5, final_momentum=0.8)
     else:
-        Y0 = bench_util.clustered_embedding(labels, dims, 170.0)
-        # late phase: exaggeration off (coefficient 1 from the start), final momentum
-        sched = dict(early_exag_coeff=1.0, stop_lying_iter=-1, mom_switch_iter=-1, momentum=0.8, final_momentum=0.8)
+        Y0 = bench_util.clustered_embedding(labels, dims, span)
+        # late phase: exaggeration off (coefficient 1 from the start) or the late-exaggeration coefficient, final momentum
+        sched = dict(early_exag_coeff=late_exag or 1.0, stop_lying_iter=10 ** 9 if late_exag else -1, mom_switch_iter=-1, momentum=0.8,
+                     final_momentum=0.8)
     sched.update(learning_rate=points / 12.0, max_step_norm=5.0, start_late_exag_iter=-1, late_exag_coeff=-1.0)
-    return row, col, val, Y0, sched
+    return Y0, sched
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -125,6 +136,123 @@ def run_reference(points, phase, steps, threads, keep_dir=None, dims=2, df=1.0):
     return {"loop_seconds": secs, "wall_seconds": wall, "iterations": steps, "it_per_s": steps / secs, "n_edges": int(len(col))}, None
 
 
+# ------------------------------------------------------------------------------------------ our arm --
+class Launcher:
+    """torch.distributed plumbing: rank / world, barrier, max over ranks, ncclUniqueId distribution."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_array(self, a):
+        if not self.dist:
+            return a
+        t = self.torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def nccl_id(self, fb):
+        if self.world == 1:
+            return None
+        import ctypes
+        idt = self.torch.zeros(128, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            buf = (ctypes.c_char * 128)()
+            rc = fb.load_library().fitsne_nccl_unique_id(buf)
+            assert rc == 0, "fitsne_nccl_unique_id failed"
+            idt.copy_(self.torch.frombuffer(bytearray(buf.raw), dtype=self.torch.uint8))
+        self.dist.broadcast(idt, 0)
+        return bytes(idt.cpu().numpy().tobytes())
+
+    def graph(self, maker):
+        """rank 0 builds (and caches) the graph first, then everybody loads it: one generation per box, not one per rank"""
+        if self.dist:
+            if self.rank == 0:
+                out = maker()
+            self.dist.barrier()
+            if self.rank != 0:
+                out = maker()
+            return out
+        return maker()
+
+
+def timed_run(L, fb, row, col, val, Y0, sched, steps, warmup, dims=2, df=1.0, keep=False):
+    """W untimed + K timed steps on device-resident state; returns (it/s, ms total, stats, costs[, context])."""
+    t = fb.FitSNE(row, col, val, Y0, df=df, device=L.local_rank, rank=L.rank, world=L.world, nccl_id=L.nccl_id(fb))
+    t.run(fetch_Y=False, max_iter=max(warmup, 3), **sched)          # graph capture, clocks, first re-ordering
+    b0 = t.stats()["n_boxes"]
+    t.prewarm(max(25, b0 - 60), b0 + 90)     # twiddle tables for the FFT lengths the run can drift through (milliseconds)
+    L.barrier()
+    t.reset_stats()
+    L.barrier()
+    _, costs = t.run(fetch_Y=False, max_iter=steps, **sched)   # CUDA events around the loop, on the library's stream
+    L.barrier()
+    ms = L.max(t.last_run_ms())
+    st = t.stats()
+    if keep:
+        return steps / (ms * 1e-3), ms, st, costs, t
+    t.close()
+    return steps / (ms * 1e-3), ms, st, costs, None
+
+
+def phase_times(L, fb, row, col, val, Y, uY, gains, sched, nsteps, dims, df):
+    """Per-phase device times, live, with CUDA events on the launching stream (timers mode = plain launches, serialised)."""
+    tt = fb.FitSNE(row, col, val, Y, df=df, device=L.local_rank, flags=fb.FLAG_TIMERS, rank=L.rank, world=L.world, nccl_id=L.nccl_id(fb))
+    tt.set_optimizer_state(uY, gains)
+    kw = dict(exaggeration=sched["early_exag_coeff"], momentum=sched["momentum"], learning_rate=sched["learning_rate"], max_step_norm=5.0)
+    for _ in range(3):
+        tt.step(**kw)
+    b0 = tt.stats()["n_boxes"]
+    tt.prewarm(max(25, b0 - 30), b0 + 30)
+    tt.reset_stats()
+    for _ in range(nsteps):
+        tt.step(**kw)
+    sst = tt.stats()
+    tt.close()
+    return sst
+
+
+def short_config(L, fb, name, desc, maker, phase, dims, df, span, steps, late_exag=None):
+    """One of the other BASELINE configs: a short device-resident run, same timing rules."""
+    t0 = time.perf_counter()
+    try:
+        row, col, val, labels = L.graph(maker)
+        N = len(row) - 1
+        Y0, sched = embedding_and_schedule(N, labels, phase, dims, span, late_exag)
+        gen_s = time.perf_counter() - t0
+        value, ms, st, costs, _ = timed_run(L, fb, row, col, val, Y0, sched, steps, 5, dims=dims, df=df)
+        kls = [float(c) for c in costs if c != 0]
+        return {"workload": desc, "points": N, "n_edges": int(len(col)), "phase": phase, "dims": dims, "df": df, "steps": steps,
+                "value": round(value, 1), "unit": UNIT, "ms_per_step": round(ms / steps, 5),
+                "grid": {"n_boxes": st["n_boxes"], "grid_side": st["grid_side"], "fft_side": st["fft_side"]},
+                "kl_last": kls[-1] if kls else None, "gpu_launches": int(st["kernel_launches"]), "setup_seconds": round(gen_s, 1)}
+    except Exception as e:            # a failing extra must not take the headline down with it
+        return {"workload": desc, "error": repr(e)[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,25 +265,25 @@ def main():
     ap.add_argument("--df", type=float, default=1.0, help="t-kernel degrees of freedom (config 5 uses 0.5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (1, 2, 4, 5, early phase)")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
-    # watchdog: a wedged collective must not hold the box -- give up loudly after 15 minutes (the default run takes ~1-2).
-    # A thread, not SIGALRM: the main thread may be blocked inside the library (ctypes releases the GIL, Python-level
-    # signal handlers would only run once the call returns).
+
+    # watchdog: a wedged collective must not hold the box -- give up loudly after 20 minutes (the default run takes ~3-4).
     def _give_up():
-        sys.stderr.write("bench.py: watchdog expired after 900 s (rank %s); aborting\n" % os.environ.get("RANK", "0"))
+        sys.stderr.write("bench.py: watchdog expired after 1200 s (rank %s); aborting\n" % os.environ.get("RANK", "0"))
         sys.stderr.flush()
         os._exit(3)
-    wd = threading.Timer(900.0, _give_up)
+    wd = threading.Timer(1200.0, _give_up)
     wd.daemon = True
     wd.start()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     threads = os.cpu_count() or 1
     config = {"workload": "BASELINE config 3: synthetic N=%d, 2-D, lr=N/12, fixed kNN-style graph (K=15 same-cluster neighbours, "
                           "symmetrised, ~30 nnz/row) injected as load_affinities=1; %s phase" % (args.points, args.phase),
               "points": args.points, "phase": args.phase, "dims": args.dims, "df": args.df, "nterms": 3, "intervals_per_integer": 1, "min_num_intervals": 50,
-              "l2": "inputs larger than L2: the CSR P (~8 B/edge, ~240 MB at 1M points) is streamed from HBM every step",
+              "l2": "inputs larger than L2: the CSR P (8 B/edge, ~240 MB at 1M points) is streamed from HBM every step",
               "sharding": "points/rows sharded across %d rank(s); NCCL grid all-reduce + Y all-gather" % max(world, 1)}
 
     if args.impl == "reference":
@@ -175,112 +303,122 @@ def main():
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
-    import torch
     import fitsne_b200 as fb
     fb.load_library()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    nccl_id = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    L = Launcher()
+
+    row, col, val, Y0, sched = L.graph(lambda: workload(args.points, args.phase, dims=args.dims))
+    N, E, d = args.points, int(len(col)), args.dims
+
+    # ---- parity, outside the timed region: our gradient vs the oracle on this very workload (rank 0 runs the oracle)
+    parity = None
+    if not args.no_parity:
+        with fb.FitSNE(row, col, val, Y0, df=args.df, device=L.local_rank, rank=L.rank, world=L.world, nccl_id=L.nccl_id(fb)) as tp:
+            dC, Z = tp.gradient(sched["early_exag_coeff"])
+            kl = tp.kl(sched["early_exag_coeff"])
+        dC = L.sum_array(dC)                   # sharded: every rank holds its own rows, zeros elsewhere
         if rank == 0:
-            import ctypes
-            buf = (ctypes.c_char * 128)()
-            rc = fb.load_library().fitsne_nccl_unique_id(buf)
-            assert rc == 0, "fitsne_nccl_unique_id failed"
-            idt.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().numpy().tobytes())
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            try:
+                from pyoracle import Oracle
+                O = Oracle()
+                a = sched["early_exag_coeff"]
+                ref, Zr = O.gradient(Y0, row, col, a * val, df=args.df)
+                klr = O.kl(Y0, row, col, a * val, Zr, df=args.df)
+                parity = {"checker": "oracle/fitsne_oracle.c (fp64 restatement, pinned to the compiled reference's golden vectors)",
+                          "gradient_rel_l2": float(np.linalg.norm(dC - ref) / np.linalg.norm(ref)), "tolerance": 1e-4,
+                          "sum_Q_rel": abs(Z - Zr) / Zr, "kl_rel": abs(kl - klr) / abs(klr), "kl": kl,
+                          "ok": bool(np.linalg.norm(dC - ref) / np.linalg.norm(ref) < 1e-4 and abs(Z - Zr) / Zr < 1e-5)}
+            except Exception as e:
+                parity = {"error": repr(e)[:200]}
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    row, col, val, Y0, sched = workload(args.points, args.phase, dims=args.dims)
-    N, E = args.points, int(len(col))
-    t = fb.FitSNE(row, col, val, Y0, df=args.df, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
-    # warm-up: W untimed steps (graph capture, clocks)
-    t.run(fetch_Y=False, max_iter=max(args.warmup, 3), **sched)
-    b0 = t.stats()["n_boxes"]
-    t.prewarm(max(25, b0 - 60), b0 + 90)     # twiddle tables for the FFT lengths the run can drift through (milliseconds)
-    barrier()
-    sampler = ClockSampler(local_rank)
+    # ---- headline: W warm-up + K timed steps, device-resident
+    L.barrier()
+    sampler = ClockSampler(L.local_rank)
     if rank == 0:
         sampler.start()
-    t.reset_stats()
-    barrier()
-    _, costs = t.run(fetch_Y=False, max_iter=args.steps, **sched)   # CUDA events around the loop, on the library's stream
-    barrier()
-    ms = t.last_run_ms()
-    st = t.stats()
+    value, ms, st, costs, t = timed_run(L, fb, row, col, val, Y0, sched, args.steps, args.warmup, dims=d, df=args.df, keep=True)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        import torch.distributed as dist
-        mt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(mt, op=dist.ReduceOp.MAX)
-        ms = float(mt.item())
-    value = args.steps / (ms * 1e-3)
 
-    # per-kernel durations, live, with CUDA events on the launching stream (timers mode = plain launches)
-    kern = {}
-    roofline = None
+    # ---- per-phase durations + roofline (every rank runs the timers context: it is sharded like the run)
+    Ynow = t.get_Y()
+    uY, gains = t.get_optimizer_state()
+    t.close()
+    nsteps_t = 30
+    sst = phase_times(L, fb, row, col, val, Ynow, uY, gains, sched, nsteps_t, d, args.df)
+    kern, roofline, roofline_total = {}, None, None
     if rank == 0:
         peak, peak_src = load_peaks()
-        nsteps_t = 30
-        tt = fb.FitSNE(row, col, val, t.get_Y(), df=args.df, device=local_rank, flags=fb.FLAG_TIMERS) if world == 1 else None
-        if tt is not None:
-            tt.prewarm(max(25, st["n_boxes"] - 30), st["n_boxes"] + 30)
-        if tt is not None:
-            uY, gains = t.get_optimizer_state()
-            tt.set_optimizer_state(uY, gains)
-            alpha = sched["early_exag_coeff"]
-            for _ in range(3):
-                tt.step(exaggeration=alpha, momentum=sched["momentum"], learning_rate=sched["learning_rate"], max_step_norm=5.0)
-            tt.reset_stats()
-            for _ in range(nsteps_t):
-                tt.step(exaggeration=alpha, momentum=sched["momentum"], learning_rate=sched["learning_rate"], max_step_norm=5.0)
-            sst = tt.stats()
-            G, M = sst["grid_side"], sst["fft_side"]
-            # algorithmic bytes per launch
-            d = args.dims
-            algo = {"attract_update": 8 * E + 30 * d * N, "spread": (4 + 4 * d) * N + 16 * G ** d, "gather": (12 + 4 * d) * N + 16 * G ** d,
-                    "sort": 16 * N + 2 * 16 * N, "fft": 4 * 28 * M ** d + 12 * M ** d, "center": 12 * d * N}
-            for k, b in algo.items():
-                dur = sst["phase_ms"][k] / nsteps_t
-                if k == "fft":
-                    dur += sst["phase_ms"]["kernel_spectrum"] / nsteps_t
-                if dur > 0:
-                    kern[k] = {"ms": round(dur, 5), "algorithmic_bytes": int(b), "gbs": round(b / dur / 1e6, 1), "frac": round(b / dur / 1e6 / peak, 4)}
-            tt.close()
-            dom = "attract_update"
-            # traffic: dram__bytes_read+write of k_attract from the committed ncu --set full capture of this exact workload
-            # (profiles/r1_ncu_full_top_kernels.txt: 252.4 MB + 9.9 MB per launch); null for any other workload
-            traffic = 262.3e6 if (N == 1000000 and d == 2 and args.phase == "late") else None
-            roofline = {"kernel": "k_attract + k_update (CSR SpMV on its own stream, then exaggeration/gains/momentum/clip/Y update)", "bound": "hbm",
-                        "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
-                        "traffic": traffic, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"], "avg_launch_ms": kern[dom]["ms"]}
+        G, M = sst["grid_side"], sst["fft_side"]
+        Nl, El = N / world, E / world                      # per-rank points / edges (replicated: the convolution)
+        # algorithmic bytes per launch group, per rank
+        algo = {"attract_update": 8 * El + 30 * d * Nl, "spread": (4 + 4 * d) * Nl + 16 * G ** d, "gather": (12 + 4 * d) * Nl + 16 * G ** d,
+                "sort": 16 * Nl + 2 * 16 * Nl, "fft": 4 * 28 * M ** d + 12 * M ** d, "center": 12 * d * Nl}
+        names = {"attract_update": "k_attract + k_update (CSR SpMV over 8-byte edge words, then exaggeration/gains/momentum/clip/Y update + column sums)",
+                 "fft": "convolution: k_kspec_rows/cols (kernel spectra) + k_conv_rows_fwd + k_conv_cols (TMA tiles, in-place column FFTs, Hadamard, sum_Q) + k_conv_rows_inv",
+                 "sort": "k_bin + 2 x k_radix_sweep (box keys, stable LSD radix sort with look-back)",
+                 "spread": "k_spread_chunks + k_spread_combine (Lagrange spread, stitched in shared memory)",
+                 "gather": "k_gather", "center": "k_center_bounds (zero-mean + bounds)"}
+        for k, b in algo.items():
+            dur = sst["phase_ms"][k] / nsteps_t
+            if k == "fft":
+                dur += sst["phase_ms"]["kernel_spectrum"] / nsteps_t
+            if dur > 0:
+                kern[k] = {"ms": round(dur, 5), "algorithmic_bytes": int(b), "gbs": round(b / dur / 1e6, 1), "frac": round(b / dur / 1e6 / peak, 4)}
+        if world > 1 and sst["phase_ms"].get("collectives", 0) > 0:
+            kern["collectives"] = {"ms": round(sst["phase_ms"]["collectives"] / nsteps_t, 5), "what": "NCCL all-reduce of the spread grid (the Y all-gather overlaps the sort)"}
+        dom = max((k for k in kern if k in algo), key=lambda k: kern[k]["ms"])
+        roofline = {"kernel": names[dom], "phase": dom, "dominant_by": "time (live CUDA events, serialised phases)", "bound": "hbm",
+                    "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": None,
+                    "traffic_note": "not measured in this run; ncu dram__bytes of the same kernels are in profiles/",
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"], "avg_launch_ms": kern[dom]["ms"]}
+        total_bytes = 8 * El + 140 * Nl + 32 * G ** d + 124 * M ** d          # whole iteration
+        roofline_total = {"algorithmic_bytes_per_step": int(total_bytes), "ms_per_step": round(ms / args.steps, 5),
+                          "achieved": round(total_bytes / (ms / args.steps) / 1e6, 1), "peak": peak, "unit": "GB/s",
+                          "frac": round(total_bytes / (ms / args.steps) / 1e6 / peak, 4)}
 
-    # end to end through the C ABI with host buffers: upload P + Y0, run K iterations, download Y + costs
+    # ---- end to end through the C ABI with host buffers: upload P + Y0, run K iterations, download Y + costs
     e2e = None
-    if rank == 0 and world == 1 and not args.no_e2e:
-        pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (row, col, val, Y0)]   # keep the owners alive
+    if not args.no_e2e:
+        torch = L.torch
+        b, e = fb.shard_range(N, L.rank, L.world)
+        lc, lv = (col, val) if world == 1 else (np.ascontiguousarray(col[row[b]:row[e]]), np.ascontiguousarray(val[row[b]:row[e]]))
+        pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (row, lc, lv, Y0)]   # keep the owners alive
         prow, pcol, pval, pY = [p_.numpy() for p_ in pinned]
-        t.close()
-        torch.cuda.synchronize()
+        nid = L.nccl_id(fb)
+        L.barrier()
         t0 = time.perf_counter()
-        Yout, costs2 = fb.run_host(prow, pcol, pval, pY, max_iter=args.steps, device=local_rank, df=args.df, **sched)
-        dt = time.perf_counter() - t0
+        if world == 1:
+            Yout, costs2 = fb.run_host(prow, pcol, pval, pY, max_iter=args.steps, device=L.local_rank, df=args.df, **sched)
+        else:
+            with fb.FitSNE(prow, pcol, pval, pY, df=args.df, device=L.local_rank, rank=L.rank, world=L.world, nccl_id=nid) as te:
+                Yout, costs2 = te.run(max_iter=args.steps, **sched)
+        L.barrier()
+        dt = L.max(time.perf_counter() - t0)
         h2d = prow.nbytes + pcol.nbytes + pval.nbytes + pY.nbytes
         d2h = Yout.nbytes + costs2.nbytes
         e2e = {"value": args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-               "call": "fitsne_run_host (create + %d iterations + download), host wall clock" % args.steps}
+               "call": ("fitsne_run_host" if world == 1 else "fitsne_create_sharded + fitsne_run + download, per rank") +
+                       " (create + %d iterations + download), host wall clock, max over ranks" % args.steps}
         del prow, pcol, pval, pY, pinned       # release the pinned buffers while the CUDA context is still alive
+
+    # ---- the other BASELINE configs, short runs (every rank takes part: the contexts are sharded like the headline)
+    extras = None
+    if not args.no_extras:
+        extras = {}
+        if args.phase == "late":
+            v2, ms2, st2, _, _ = timed_run(L, fb, row, col, val, *embedding_and_schedule(N, None, "early", d, 0), 100, 5, dims=d, df=args.df)
+            extras["config3_early_phase"] = {"value": round(v2, 1), "unit": UNIT, "ms_per_step": round(ms2 / 100, 5), "steps": 100,
+                                             "grid": {"n_boxes": st2["n_boxes"], "fft_side": st2["fft_side"]}}
+        del row, col, val
+        extras["config1_10k"] = short_config(L, fb, "c1", "config 1: N=10k, perplexity-30-like graph (~137 nnz/row), 2-D, late phase",
+                                             lambda: bench_util.knn_like_graph(10000, 69, seed=0), "late", 2, 1.0, 60.0, 200)
+        extras["config2_70k_late_exag"] = short_config(L, fb, "c2", "config 2: N=70k, ~137 nnz/row, 2-D, late exaggeration 4",
+                                                       lambda: bench_util.knn_like_graph(70000, 69, seed=0), "late", 2, 1.0, 110.0, 200, late_exag=4.0)
+        extras["config5_1d_df05_K300"] = short_config(L, fb, "c5", "config 5: N=1M, 1-D, df=0.5, 300 neighbours per point (perplexity list [10,100] -> K=300)",
+                                                      lambda: bench_util.ring_cluster_graph(1000000, 300, seed=0), "late", 1, 0.5, 900.0, 50)
+        extras["config4_10M"] = short_config(L, fb, "c4", "config 4: N=10M, same generator as config 3 (K=15, ~30 nnz/row), 2-D, late phase",
+                                             lambda: bench_util.knn_like_graph(10000000, 15, seed=0), "late", 2, 1.0, 170.0, 50)
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -299,13 +437,12 @@ def main():
                 "data": "synthetic", "config": config, "impl": "ours", "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(st["kernel_launches"]), "graph_launches": int(st["graph_launches"]), "regrids": int(st["regrids"]),
                 "grid": {"n_boxes": st["n_boxes"], "grid_side": st["grid_side"], "fft_side": st["fft_side"]},
-                "n_edges": E, "kl_last": kls[-1] if kls else None, "roofline": roofline, "kernels": kern, "cpu_baseline": cpu_baseline}
+                "n_edges": E, "kl_last": kls[-1] if kls else None, "parity": parity, "roofline": roofline, "roofline_total": roofline_total,
+                "kernels": kern, "cpu_baseline": cpu_baseline, "other_configs": extras}
         print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        t.close()
-        dist.destroy_process_group()
+    if L.dist:
+        L.dist.barrier()
+        L.dist.destroy_process_group()
     return 0
 
 

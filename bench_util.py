@@ -33,6 +33,7 @@ def knn_like_graph(N, K, seed=0, n_clusters=10):
 
 
 def _knn_like_graph(N, K, seed=0, n_clusters=10):
+    import scipy.sparse as sp
     rng = np.random.default_rng(seed)
     labels = rng.integers(0, n_clusters, N).astype(np.int32)
     order = np.argsort(labels, kind="stable")
@@ -41,29 +42,46 @@ def _knn_like_graph(N, K, seed=0, n_clusters=10):
     pos_in_cluster = rng.random((N, K))
     sizes = (starts[1:] - starts[:-1])[labels]
     nb = order[starts[labels][:, None] + np.minimum((pos_in_cluster * sizes[:, None]).astype(np.int64), sizes[:, None] - 1)]
-    rows = np.repeat(np.arange(N, dtype=np.int64), K)
-    cols = nb.reshape(-1).astype(np.int64)
+    rows = np.repeat(np.arange(N, dtype=np.int32), K)
+    cols = nb.reshape(-1).astype(np.int32)
     w = (rng.random(N * K) + 0.1)
     keep = rows != cols
-    rows, cols, w = rows[keep], cols[keep], w[keep]
-    # symmetrise: concatenate both directions, sort by (row, col), merge duplicates
-    r2 = np.concatenate([rows, cols])
-    c2 = np.concatenate([cols, rows])
-    w2 = np.concatenate([w, w])
-    key = r2 * N + c2
-    o = np.argsort(key, kind="stable")
-    key, w2 = key[o], w2[o]
-    first = np.ones(len(key), bool)
-    first[1:] = key[1:] != key[:-1]
-    idx = np.nonzero(first)[0]
-    wsum = np.add.reduceat(w2, idx)
-    ukey = key[idx]
-    rr = (ukey // N).astype(np.int64)
-    cc = (ukey % N).astype(np.uint32)
-    val = (wsum / wsum.sum()).astype(np.float32).astype(np.float64)
-    row = np.zeros(N + 1, np.uint32)
-    row[1:] = np.cumsum(np.bincount(rr, minlength=N)).astype(np.uint32)
-    return row, cc, val, labels
+    # symmetrise: A + A^T with duplicates merged (scipy's O(nnz) counting-sort routines: 3x faster than sorting keys)
+    A = sp.csr_matrix((w[keep], (rows[keep], cols[keep])), shape=(N, N))
+    S = (A + A.T).tocsr()
+    S.sort_indices()
+    val = (S.data / S.data.sum()).astype(np.float32).astype(np.float64)
+    return S.indptr.astype(np.uint32), S.indices.astype(np.uint32), val, labels
+
+
+def ring_cluster_graph(N, K, seed=0, n_clusters=10):
+    """Symmetric K-regular graph for LARGE K (config 5: perplexity list [10, 100] -> 300 neighbours per point), built without
+    any sort: every cluster's members are put in a random cyclic order and each is linked to its K/2 successors and K/2
+    predecessors.  Random in index space (like a kNN graph before any re-ordering), symmetric by construction, weight a
+    symmetric hash of the pair, normalised to sum 1.  Returns (row u32, col u32, val f64-of-f32, labels)."""
+    rng = np.random.default_rng(seed)
+    labels = rng.integers(0, n_clusters, N).astype(np.int32)
+    order = np.argsort(labels, kind="stable")
+    starts = np.searchsorted(labels[order], np.arange(n_clusters + 1))
+    half = K // 2
+    offs = np.concatenate([np.arange(-half, 0), np.arange(1, half + 1)]).astype(np.int64)
+    col = np.empty((N, 2 * half), np.uint32)
+    val = np.empty((N, 2 * half), np.float32)
+    for c in range(n_clusters):
+        members = order[starts[c]:starts[c + 1]]
+        members = members[rng.permutation(len(members))]              # random cyclic order
+        n_c = len(members)
+        for lo in range(0, n_c, 1 << 16):                               # bounded temporaries
+            k = np.arange(lo, min(n_c, lo + (1 << 16)), dtype=np.int64)[:, None]
+            kk = (k + offs[None, :]) % n_c
+            a, b = np.minimum(k, kk), np.maximum(k, kk)
+            h = (a * 2654435761 + b * 40503 + c * 97) & 0xFFFFFFFF   # symmetric in the pair
+            col[members[k[:, 0]]] = members[kk]
+            val[members[k[:, 0]]] = 0.1 + h.astype(np.float32) / np.float32(4294967296.0)
+    val = val.reshape(-1).astype(np.float64)
+    val = (val / val.sum()).astype(np.float32).astype(np.float64)
+    row = (np.arange(N + 1, dtype=np.uint64) * (2 * half)).astype(np.uint32)
+    return row, col.reshape(-1), val, labels
 
 
 def clustered_embedding(labels, dims, span, seed=1, n_clusters=10, spread=0.03):

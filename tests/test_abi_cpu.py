@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(fitsne_b200.Config) == 40
     assert ctypes.sizeof(fitsne_b200.StepParams) == 40
     assert ctypes.sizeof(fitsne_b200.Schedule) == 72
-    assert ctypes.sizeof(fitsne_b200.Stats) == 32 + 16 + 16 + 16 * 8 + 16
+    assert ctypes.sizeof(fitsne_b200.Stats) == 32 + 16 + 16 + 16 * 8 + 8
 
 
 def _has_cuda():
