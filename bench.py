@@ -316,7 +316,10 @@ def main():
         with fb.FitSNE(row, col, val, Y0, df=args.df, device=L.local_rank, rank=L.rank, world=L.world, nccl_id=L.nccl_id(fb)) as tp:
             dC, Z = tp.gradient(sched["early_exag_coeff"])
             kl = tp.kl(sched["early_exag_coeff"])
-        dC = L.sum_array(dC)                   # sharded: every rank holds its own rows, zeros elsewhere
+        if world > 1:                          # sharded: every rank computed its own rows; the rest of the buffer is scratch
+            b_, e_ = fb.shard_range(N, L.rank, L.world)
+            dC[:b_] = 0; dC[e_:] = 0
+        dC = L.sum_array(dC)
         if rank == 0:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             try:

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -100,11 +101,7 @@ struct fitsne_ctx {
     int device = 0;
     bool df_is_one = true;
     int n_fwd = 0, n_kern = 0, n_inv = 0;
-    cudaStream_t stream = nullptr;    // repulsive pipeline + update (high priority)
-    cudaStream_t stream2 = nullptr;   // attractive SpMV, concurrent with the repulsive pipeline (low priority)
-    cudaStream_t stream3 = nullptr;   // sharded runs, FITSNE_AG_STREAM=1: the Y all-gather on its own high-priority stream
-    cudaStream_t stream_k = nullptr;  // 2-D: kernel-spectrum side of the convolution, concurrent with sort + spread
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ag = nullptr, ev_kfork = nullptr, ev_kjoin = nullptr;
+    cudaStream_t stream = nullptr;    // everything runs here
     ncclComm_t comm = nullptr;
     // sharded runs: per-rank reduction records (all-gathered, 128 B each) and whether c->Y currently holds every rank's slice
     ShardStats *shard_stats = nullptr;
@@ -172,6 +169,7 @@ struct fitsne_ctx {
     size_t staging_elems = 0;
 
     std::map<int, Plans> plans;
+    std::set<int> nccl_warm;          // sharded: FFT lengths whose iteration has run eagerly once (before its graph is captured)
     struct GraphEntry { cudaGraphExec_t exec; uint64_t launches; };
     std::map<GraphKey, GraphEntry> graphs;
     int cur_B = -1, cur_M = -1;
@@ -411,40 +409,17 @@ static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
 
 // Everything from "bounds are known" to either dC (update=false) or the centred new Y and its bounds
 // (update=true).  B is only passed to k_setup_grid (which verifies it against the device's own bounds); every
-// launch shape below depends on M, the shard size and nterms only.  Pure stream work: capturable.
-// The attractive SpMV needs only Y and P, so it is forked onto a second, lower-priority stream and joins before
-// the update kernel: it overlaps the whole sort/spread/FFT/gather chain.
+// launch shape below depends on M, the shard size and nterms only.  Pure work on ONE stream: capturable, sharded or not.
+// (Round 1 forked the SpMV onto a second stream and round 2 first did the same with the kernel spectra.  Measured on
+// B200: the SpMV saturates every SM's load/store pipe, so kernels running beside it crawl and the iteration takes the
+// SUM of the kernel times either way -- 0.4446 ms with three streams, 0.4518 ms with one at N = 1M -- while in sharded
+// runs the extra streams starved NCCL: 4.08 ms per iteration against 2.32 ms on one stream at N = 10M on two GPUs.)
 template <int D>
 static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool update) {
     const int p = c->cfg.nterms, nloc = c->nloc;
     cudaStream_t st = c->stream;
     Plans *pl;
     CKRC(get_plans(c, M, &pl));
-    static const bool serial_env = getenv("FITSNE_SERIAL") && atoi(getenv("FITSNE_SERIAL")) != 0;     // diagnostics: no second / third stream
-    const bool overlap = !c->timing_this_iter && !serial_env;    // timers mode serialises everything to time each phase
-
-    // Sharded: after an optimiser step every rank only holds ITS slice of the new Y.  The all-gather that completes Y is
-    // issued here, on the SpMV's stream: the SpMV is its only consumer inside the iteration (bin / sort / spread / gather /
-    // update read the local slice), so the transfer overlaps this iteration's sort and spread.  NCCL calls on one
-    // communicator must keep one order on every rank: Y all-gather -> grid all-reduce -> stats all-gather, enforced by ev_ag.
-    if (overlap) {
-        CK(cudaEventRecord(c->ev_fork, st));
-        CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-        if (c->world > 1) {
-            // (experiment for the 8-GPU profile: NCCL's CTAs on the low-priority SpMV stream may be scheduled late behind the
-            //  repulsive kernels; FITSNE_AG_STREAM=1 runs the transfer on a high-priority stream of its own instead)
-            cudaStream_t ag = c->stream3 ? c->stream3 : c->stream2;
-            if (c->stream3) CK(cudaStreamWaitEvent(c->stream3, c->ev_fork, 0));
-            CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, ag));
-            CK(cudaEventRecord(c->ev_ag, ag));
-            if (c->stream3) CK(cudaStreamWaitEvent(c->stream2, c->ev_ag, 0));
-        }
-        CKRC(launch_attract<D>(c, c->stream2));
-        CK(cudaEventRecord(c->ev_join, c->stream2));
-    } else if (c->world > 1) {      // timers mode: everything on one stream (this transfer is outside the phase timers)
-        CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, st));
-    }
-    c->y_whole = true;
 
     phase_mark(c, FITSNE_PHASE_BOUNDS);
     kt(c, "(start)");
@@ -452,8 +427,6 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
                                     c->mismatch, c->sort_totals, c->work, c->tickets + 5);
     c->stats.kernel_launches += 1;
     kt(c, "k_setup_grid");
-    // 2-D: the kernel spectra depend on the grid geometry only (not on the points): sample + transform them on their own
-    // stream while this one sorts and spreads; joined right before the fused column pass
     static const int col_threads = getenv("FITSNE_COL_THREADS") ? std::min(COL_THREADS, std::max(64, atoi(getenv("FITSNE_COL_THREADS")))) : 256;
     auto launch_kernel_side = [&](cudaStream_t ks) -> int {
         const int Gc = M / 2, H = M / 2 + 1;
@@ -463,13 +436,6 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         c->stats.kernel_launches += 2;
         return 0;
     };
-    if (D == 2 && overlap) {
-        CK(cudaEventRecord(c->ev_kfork, st));
-        CK(cudaStreamWaitEvent(c->stream_k, c->ev_kfork, 0));
-        CKRC(launch_kernel_side(c->stream_k));
-        CK(cudaEventRecord(c->ev_kjoin, c->stream_k));
-    }
-
     // ---- bin + stable two-pass LSD radix sort by box (three launches; see fitsne_kernels.cuh)
     phase_mark(c, FITSNE_PHASE_SORT);
     const int tiles = cdiv(nloc, SORT_TILE);
@@ -506,7 +472,6 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         // every rank spread its own points: sum the partial grids (fp32).  2-D: the dense (M/2)^2 float4 region that holds
         // the G x G grid; 1-D: the two packed charge lines.  The element count depends on M only, like every launch shape.
         phase_mark(c, FITSNE_PHASE_COLLECTIVES);
-        if (overlap) CK(cudaStreamWaitEvent(st, c->ev_ag, 0));       // collective order: Y all-gather first (see above)
         if (D == 2) CKNCCL(g_nccl.AllReduce(c->chg, c->chg, cplane * 4, ncclFloat, ncclSum, c->comm, st));
         else CKNCCL(g_nccl.AllReduce(c->planes, c->planes, (size_t) M * 4, ncclFloat, ncclSum, c->comm, st));
     }
@@ -516,12 +481,12 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     phase_mark(c, FITSNE_PHASE_KERNEL_SPECTRUM);
     const int *gok = &c->gp->ok;
     if (D == 2) {
-        if (!overlap) { CKRC(launch_kernel_side(st)); kt(c, "k_kspec_rows + k_kspec_cols"); }
+        CKRC(launch_kernel_side(st));
+        kt(c, "k_kspec_rows + k_kspec_cols");
         phase_mark(c, FITSNE_PHASE_FFT);
         const int H = M / 2 + 1;
         k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp);
         kt(c, "k_conv_rows_fwd");
-        if (overlap) CK(cudaStreamWaitEvent(st, c->ev_kjoin, 0));
         k_conv_cols<<<H, col_threads, pl->smem_col, st>>>(pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
                                                           c->sc, c->tickets + 0);
         kt(c, "k_conv_cols");
@@ -546,10 +511,16 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     CKRC(launch_spread_gather<D>(c, true, skeys, sperm));
     kt(c, "k_gather");
 
-    // ---- attractive term (joined here) + optimiser step
+    // ---- attractive term + optimiser step.  Sharded: after an optimiser step every rank only holds ITS slice of the new Y;
+    // the SpMV is the only consumer of foreign rows inside the iteration (bin / sort / spread / gather / update read the
+    // local slice), so the all-gather that completes Y sits right in front of it.
+    if (c->world > 1) {
+        phase_mark(c, FITSNE_PHASE_ALLGATHER);
+        CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, st));
+    }
+    c->y_whole = true;
     phase_mark(c, FITSNE_PHASE_ATTRACT_UPDATE);
-    if (overlap) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
-    else CKRC(launch_attract<D>(c, st));
+    CKRC(launch_attract<D>(c, st));
     kt(c, "k_attract");
     const int rows = c->row_end - c->row_begin;
     const int ublocks = std::min(RED_BLOCKS, cdiv(rows, 256));
@@ -625,7 +596,6 @@ static int push_step_params(fitsne_ctx *c, const StepParams &sp) {
 static int reorder_points(fitsne_ctx *c) {
     const int N = c->N, D = c->D;
     cudaStream_t st = c->stream;
-    CK(cudaStreamSynchronize(c->stream2));
     const size_t E = c->E;
     if (!c->orig_of) {
         CKRC(dev_alloc(c, &c->orig_of, (size_t) N)); CKRC(dev_alloc(c, &c->orig_tmp, (size_t) N));
@@ -814,18 +784,30 @@ static int run_batch(fitsne_ctx *c, int n, int *done) {
     volatile unsigned long long *host_iter = reinterpret_cast<volatile unsigned long long *>(c->host_bounds + 4);
     const unsigned long long before = *host_iter;
     int ran = 0;
-    if (c->world == 1) {
+    // Sharded contexts replay graphs too (one stream, NCCL collectives captured as graph nodes); the first iteration at a new
+    // FFT length runs eagerly so that NCCL has seen every collective shape before it is captured.  Every rank sees the same
+    // bounds (derived from the same all-gathered bytes), hence takes the same decisions: collectives stay matched.
+    static const bool sharded_no_graph = getenv("FITSNE_SHARDED_NO_GRAPH") && atoi(getenv("FITSNE_SHARDED_NO_GRAPH")) != 0;
+    if (c->world == 1 || !sharded_no_graph) {
+        int eager = 0;
+        if (c->world > 1 && !c->nccl_warm.count(M)) {
+            c->timing_this_iter = false;
+            const uint64_t l0 = c->stats.kernel_launches;
+            CKRC(enqueue_iteration_d(c, M, true));
+            CK(cudaStreamSynchronize(c->stream));
+            c->stats.kernel_launches = l0;          // counted below with the replayed ones
+            c->nccl_warm.insert(M);
+            eager = 1;
+        }
         fitsne_ctx::GraphEntry *ge;
         CKRC(get_graph(c, M, true, &ge));
-        for (int i = 0; i < n; i++) CK(cudaGraphLaunch(ge->exec, c->stream));
+        for (int i = eager; i < n; i++) CK(cudaGraphLaunch(ge->exec, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         ran = (int) (*host_iter - before);
-        c->stats.graph_launches += n;
+        c->stats.graph_launches += n - eager;
         c->stats.kernel_launches += ge->launches * (uint64_t) ran;   // no-op launches are not counted as work
     } else {
-        // sharded: plain stream launches (the NCCL calls stay ordinary stream operations on two streams); the host runs
-        // ahead of the device by up to the whole batch, so launch latency is hidden just the same.  Every rank sees the
-        // same bounds (derived from the same all-gathered bytes), hence takes the same decisions: collectives stay matched.
+        // diagnostics (FITSNE_SHARDED_NO_GRAPH=1): plain stream launches, the host running ahead of the device by the batch
         const uint64_t l0 = c->stats.kernel_launches;
         uint64_t per_iter = 0;
         c->timing_this_iter = false;
@@ -839,6 +821,7 @@ static int run_batch(fitsne_ctx *c, int n, int *done) {
     }
     c->stats.iterations += ran;
     c->steps_total += ran;
+    if (c->world > 1 && ran > 0) c->y_whole = false;      // graph replays do not pass through enqueue_iteration's bookkeeping
     c->have_grad = c->have_grad || ran > 0;
     c->bounds_valid = true;
     TRACE("batch of %d at M=%d: %d ran", n, M, ran);
@@ -866,7 +849,7 @@ static int run_iteration(fitsne_ctx *c, bool update) {
     CK(cudaMemcpyAsync(c->host_B_dev, c->host_B, sizeof(int), cudaMemcpyHostToDevice, c->stream));
 
     const bool timers = (c->cfg.flags & FITSNE_FLAG_TIMERS) != 0;
-    const bool use_graph = !(c->cfg.flags & FITSNE_FLAG_NO_GRAPH) && !timers && c->world == 1;   // sharded: plain launches
+    const bool use_graph = !(c->cfg.flags & FITSNE_FLAG_NO_GRAPH) && !timers && c->world == 1;   // single steps of sharded contexts: plain launches
     c->timing_this_iter = timers;
     if (!use_graph) {
         CKRC(enqueue_iteration_d(c, M, update));
@@ -880,11 +863,11 @@ static int run_iteration(fitsne_ctx *c, bool update) {
     if (timers) {
         CK(cudaStreamSynchronize(c->stream));
         int order[] = {FITSNE_PHASE_BOUNDS, FITSNE_PHASE_SORT, FITSNE_PHASE_SPREAD, FITSNE_PHASE_COLLECTIVES,
-                       FITSNE_PHASE_KERNEL_SPECTRUM, FITSNE_PHASE_FFT, FITSNE_PHASE_GATHER, FITSNE_PHASE_ATTRACT_UPDATE,
-                       FITSNE_PHASE_CENTER, FITSNE_PHASE_COUNT};
+                       FITSNE_PHASE_KERNEL_SPECTRUM, FITSNE_PHASE_FFT, FITSNE_PHASE_GATHER, FITSNE_PHASE_ALLGATHER,
+                       FITSNE_PHASE_ATTRACT_UPDATE, FITSNE_PHASE_CENTER, FITSNE_PHASE_COUNT};
         std::vector<int> seq;
         for (int ph : order) {
-            if (ph == FITSNE_PHASE_COLLECTIVES && c->world == 1) continue;
+            if ((ph == FITSNE_PHASE_COLLECTIVES || ph == FITSNE_PHASE_ALLGATHER) && c->world == 1) continue;
             seq.push_back(ph);
         }
         for (size_t i = 0; i + 1 < seq.size(); i++) {
@@ -977,15 +960,6 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
-    CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
-    if (world > 1 && getenv("FITSNE_AG_STREAM") && atoi(getenv("FITSNE_AG_STREAM")) != 0)
-        CK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));
-    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_ag, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithPriority(&c->stream_k, cudaStreamNonBlocking, prio_hi));
-    CK(cudaEventCreateWithFlags(&c->ev_kfork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_kjoin, cudaEventDisableTiming));
     c->ktimes_on = getenv("FITSNE_KTIMES") && atoi(getenv("FITSNE_KTIMES")) != 0;
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_attract<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1110,9 +1084,6 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->stream2) cudaStreamSynchronize(c->stream2);
-    if (c->stream3) cudaStreamSynchronize(c->stream3);
-    if (c->stream_k) cudaStreamSynchronize(c->stream_k);
     drop_graphs(c);
     for (auto &p : c->plans) if (p.second.W) cudaFree(p.second.W);
     if (c->comm) g_nccl.CommDestroy(c->comm);
@@ -1127,14 +1098,6 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (c->host_sc) cudaFreeHost(c->host_sc);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->kt_ev) cudaEventDestroy(e);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->ev_ag) cudaEventDestroy(c->ev_ag);
-    if (c->ev_kfork) cudaEventDestroy(c->ev_kfork);
-    if (c->ev_kjoin) cudaEventDestroy(c->ev_kjoin);
-    if (c->stream_k) cudaStreamDestroy(c->stream_k);
-    if (c->stream2) cudaStreamDestroy(c->stream2);
-    if (c->stream3) cudaStreamDestroy(c->stream3);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;

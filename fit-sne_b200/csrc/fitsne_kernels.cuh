@@ -350,7 +350,7 @@ static inline T fk_host_fetch_add(T *p, T v) { const T old = *p; *p = old + v; r
 constexpr int BIN_THREADS = 512;                        // k_bin: SORT_TILE / 512 = 8 points per thread; every tile's CTA is resident at once
 constexpr int SWEEP_THREADS = 512;                      // k_radix_sweep: 16 warps x 8 keys per lane
 constexpr int SWEEP_IPT = SORT_TILE / SWEEP_THREADS;
-constexpr uint32_t SWEEP_READY = 0x80000000u;
+constexpr uint32_t SWEEP_AGGREGATE = 0x40000000u, SWEEP_INCLUSIVE = 0x80000000u, SWEEP_COUNT_MASK = 0x3fffffffu;   // look-back word = status | count
 
 __device__ __forceinline__ void tile_hist_flush(const uint32_t *cnt, int nb, uint32_t *hist, int tiles, uint32_t *totals) {
     for (int i = threadIdx.x; i < nb; i += blockDim.x) {
@@ -500,7 +500,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_radix_sweep(const uint32_t *_
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive prefix over this tile's warps, publish the tile total ...
+    // per digit: exclusive prefix over this tile's warps, publish the tile total (AGGREGATE), then look back over the
+    // earlier tiles -- sixteen words in flight -- adding aggregates until a tile that already knows its INCLUSIVE prefix
+    // is met, and publish this tile's inclusive prefix in turn (decoupled look-back: the walk is bounded by the number of
+    // tiles in flight, not by the number of tiles).
     uint32_t *mystate = state + ((size_t) pass * tiles + tile) * NBMAX;
     const uint32_t *prev = state + (size_t) pass * tiles * NBMAX;
     for (int d = threadIdx.x; d < nb; d += SWEEP_THREADS) {
@@ -511,35 +514,29 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_radix_sweep(const uint32_t *_
             cnt[ww * nb + d] = (uint16_t) run;
             run += t;
         }
-        *reinterpret_cast<volatile uint32_t *>(mystate + d) = SWEEP_READY | run;
-        gbase[d] = bases[(size_t) pass * NBMAX + d];
-    }
-    __syncthreads();
-    // ... and add the totals of the earlier tiles as they appear.  All threads take part: `parts` threads per digit, each
-    // summing every parts-th predecessor with sixteen words in flight; integer adds into shared memory (order-independent).
-    {
-        const int parts = nb < SWEEP_THREADS ? SWEEP_THREADS / nb : 1;
-        for (int task = threadIdx.x; task < nb * parts; task += SWEEP_THREADS) {
-            const int d = task & (nb - 1), part = task / nb;
-            uint32_t excl = 0;
-            int t = part;
-            while (t < tile) {
-                uint32_t v[16];
+        if (tile > 0) *reinterpret_cast<volatile uint32_t *>(mystate + d) = SWEEP_AGGREGATE | run;
+        uint32_t excl = 0;
+        int t = tile - 1;
+        while (t >= 0) {
+            uint32_t v[16];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int tt = t + j * parts;
-                    v[j] = tt < tile ? *reinterpret_cast<const volatile uint32_t *>(prev + (size_t) tt * NBMAX + d) : SWEEP_READY;
+            for (int j = 0; j < 16; j++)           // tiles before the first count as "inclusive prefix 0"
+                v[j] = t - j >= 0 ? *reinterpret_cast<const volatile uint32_t *>(prev + (size_t) (t - j) * NBMAX + d) : SWEEP_INCLUSIVE;
+            bool finished = false, stopped = false;
+            int used = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {         // consume in order: stop at a word that is not published yet (re-read from there)
+                const uint32_t status = v[j] >> 30;
+                if (!finished && !stopped) {
+                    if (status == 0) stopped = true;
+                    else { excl += v[j] & SWEEP_COUNT_MASK; used++; finished = status == 2; }
                 }
-                bool all = true;
-#pragma unroll
-                for (int j = 0; j < 16; j++) all = all && (v[j] & SWEEP_READY);
-                if (!all) continue;                   // some predecessor has not published yet: read the batch again
-#pragma unroll
-                for (int j = 0; j < 16; j++) excl += v[j] & ~SWEEP_READY;
-                t += 16 * parts;
             }
-            if (excl) atomicAdd(&gbase[d], excl);
+            if (finished) break;
+            t -= used;
         }
+        *reinterpret_cast<volatile uint32_t *>(mystate + d) = SWEEP_INCLUSIVE | (excl + run);
+        gbase[d] = bases[(size_t) pass * NBMAX + d] + excl;
     }
     __syncthreads();
 #pragma unroll

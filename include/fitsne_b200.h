@@ -98,7 +98,7 @@ typedef struct fitsne_stats {
 enum {
     FITSNE_PHASE_BOUNDS = 0, FITSNE_PHASE_SORT, FITSNE_PHASE_SPREAD, FITSNE_PHASE_KERNEL_SPECTRUM,
     FITSNE_PHASE_FFT, FITSNE_PHASE_GATHER, FITSNE_PHASE_ATTRACT_UPDATE, FITSNE_PHASE_CENTER, FITSNE_PHASE_KL,
-    FITSNE_PHASE_COLLECTIVES, FITSNE_PHASE_COUNT
+    FITSNE_PHASE_COLLECTIVES /* grid all-reduce */, FITSNE_PHASE_ALLGATHER /* Y all-gather */, FITSNE_PHASE_COUNT
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------------- */

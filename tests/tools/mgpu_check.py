@@ -1,4 +1,5 @@
-"""Run under torchrun (one rank per GPU): sharded context vs a single-GPU context on identical inputs.
+"""Run under torchrun (one rank per GPU): sharded context vs the ORACLE (gradient rel-L2 <= 1e-4, sum_Q <= 1e-5: the
+north-star tolerances) and vs a single-GPU context on identical inputs (gradient, KL, a 60-step run).
 Prints 'MGPU_OK' from rank 0 when every check passes."""
 import ctypes
 import os
@@ -68,6 +69,12 @@ def main():
             full = np.zeros_like(dC)
             for bb, ee, part in parts:
                 full[bb:ee] = part
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            from pyoracle import Oracle
+            ref_o, Z_o = Oracle().gradient(Y0, row, col, 4.0 * val, df=df)
+            r_o = np.linalg.norm(full - ref_o) / np.linalg.norm(ref_o)
+            print("dims=%d df=%g: sharded gradient vs ORACLE rel-L2 %.2e, sum_Q rel %.2e" % (dims, df, r_o, abs(Z - Z_o) / Z_o), flush=True)
+            ok = ok and r_o < 1e-4 and abs(Z - Z_o) / Z_o < 1e-5
             mark("single-GPU reference")
             with fb.FitSNE(row, col, val, Y0, df=df, device=local) as s:
                 dC1, Z1 = s.gradient(4.0)
