@@ -103,6 +103,15 @@ struct fitsne_ctx {
     int n_fwd = 0, n_kern = 0, n_inv = 0;
     cudaStream_t stream = nullptr;    // everything runs here
     ncclComm_t comm = nullptr;
+    // peer-memory fabric (sharded contexts; see fitsne_kernels.cuh): the iteration's exchanges run over mapped peer memory
+    bool p2p = false;
+    PeerComm pc{};
+    uint32_t *peer_flags = nullptr;
+    unsigned int *comm_seq = nullptr;
+    float2 *grid1d = nullptr;         // 1-D: this rank's partial charge lines (peers read them; the sum goes to planes)
+    std::vector<void *> ipc_opened;
+    cudaStream_t stream_c = nullptr;  // copy-engine pushes of the Y slice to the peers (DMA only)
+    cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;
     // sharded runs: per-rank reduction records (all-gathered, 128 B each) and whether c->Y currently holds every rank's slice
     ShardStats *shard_stats = nullptr;
     double *shard_sum_partial = nullptr;
@@ -333,7 +342,7 @@ static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int 
 
 template <int D, int P>
 static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, const uint32_t *skeys, const uint32_t *sperm) {
-    void *grid = D == 2 ? (void *) c->chg : (void *) c->planes;
+    void *grid = D == 2 ? (void *) c->chg : (c->p2p ? (void *) c->grid1d : (void *) c->planes);      // spread target
     if (!gather) {
         const int nchunks = cdiv(c->nloc, CHUNK);
         k_spread_chunks<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, spread_smem_bytes<D, P>(), c->stream>>>(
@@ -424,9 +433,25 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     phase_mark(c, FITSNE_PHASE_BOUNDS);
     kt(c, "(start)");
     k_setup_grid<<<1, 256, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
-                                    c->mismatch, c->sort_totals, c->work, c->tickets + 5);
+                                    c->mismatch, c->sort_totals, c->work, c->tickets + 5, c->p2p ? c->comm_seq : nullptr);
     c->stats.kernel_launches += 1;
     kt(c, "k_setup_grid");
+    // Sharded, peer fabric: push my slice of Y (centred by the previous step) into every peer's Y with the copy engines on
+    // a side stream -- DMA over NVLink, no SM involved -- while this stream sorts, spreads and convolves; the SpMV is the
+    // only consumer of foreign rows and waits for the peers' flags.  (Timers mode: same operations, in line.)
+    const bool push_Y = c->world > 1 && c->p2p;
+    if (push_Y) {
+        cudaStream_t cs = c->timing_this_iter ? st : c->stream_c;
+        if (cs != st) { CK(cudaEventRecord(c->ev_cfork, st)); CK(cudaStreamWaitEvent(cs, c->ev_cfork, 0)); }
+        const size_t off = (size_t) c->row_begin * D, bytes = (size_t) c->nloc * D * sizeof(float);
+        for (int k = 1; k < c->world; k++) {
+            const int r = (c->rank + k) % c->world;            // staggered targets: no two ranks hit the same peer first
+            CK(cudaMemcpyAsync(c->pc.Y[r] + off, c->Y + off, bytes, cudaMemcpyDeviceToDevice, cs));
+        }
+        k_peer_signal<<<1, 32, 0, cs>>>(c->pc, FLAG_Y);
+        if (cs != st) CK(cudaEventRecord(c->ev_cjoin, cs));
+        c->stats.kernel_launches += 1;
+    }
     static const int col_threads = getenv("FITSNE_COL_THREADS") ? std::min(COL_THREADS, std::max(64, atoi(getenv("FITSNE_COL_THREADS")))) : 256;
     auto launch_kernel_side = [&](cudaStream_t ks) -> int {
         const int Gc = M / 2, H = M / 2 + 1;
@@ -462,17 +487,24 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     phase_mark(c, FITSNE_PHASE_SPREAD);
     const int Gc = M / 2;
     const size_t cplane = D == 2 ? (size_t) Gc * Gc : (size_t) M;            // grid elements a length-M FFT can hold
+    void *spread_grid = D == 2 ? (void *) c->chg : (c->p2p ? (void *) c->grid1d : (void *) c->planes);
     if (D == 2) CK(cudaMemsetAsync(c->chg, 0, cplane * sizeof(float4), st));
-    else CK(cudaMemsetAsync(c->planes, 0, (size_t) 2 * M * sizeof(float2), st));
+    else CK(cudaMemsetAsync(spread_grid, 0, (size_t) 2 * M * sizeof(float2), st));
     CKRC(launch_spread_gather<D>(c, false, skeys, sperm));
     kt(c, "k_spread_chunks");
-    k_spread_combine<D><<<148 * 8, 256, 0, st>>>(c->slots, c->box_range, c->gp, c->work, D == 2 ? (void *) c->chg : (void *) c->planes);
+    k_spread_combine<D><<<148 * 8, 256, 0, st>>>(c->slots, c->box_range, c->gp, c->work, spread_grid);
     c->stats.kernel_launches += 1;
     if (c->world > 1) {
         // every rank spread its own points: sum the partial grids (fp32).  2-D: the dense (M/2)^2 float4 region that holds
         // the G x G grid; 1-D: the two packed charge lines.  The element count depends on M only, like every launch shape.
         phase_mark(c, FITSNE_PHASE_COLLECTIVES);
-        if (D == 2) CKNCCL(g_nccl.AllReduce(c->chg, c->chg, cplane * 4, ncclFloat, ncclSum, c->comm, st));
+        if (c->p2p) {
+            // peer fabric: announce "my partial grid is complete"; the sum over ranks happens inside k_conv_rows_fwd's loads
+            // (2-D) or in one small kernel (1-D)
+            k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_GRID);
+            if (D == 1) k_grid_sum_1d<<<cdiv(2 * M, 256), 256, 0, st>>>(c->pc, c->planes, 2 * M, &c->gp->ok);
+            c->stats.kernel_launches += D == 1 ? 2 : 1;
+        } else if (D == 2) CKNCCL(g_nccl.AllReduce(c->chg, c->chg, cplane * 4, ncclFloat, ncclSum, c->comm, st));
         else CKNCCL(g_nccl.AllReduce(c->planes, c->planes, (size_t) M * 4, ncclFloat, ncclSum, c->comm, st));
     }
     kt(c, "k_spread_combine(+collective)");
@@ -485,7 +517,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         kt(c, "k_kspec_rows + k_kspec_cols");
         phase_mark(c, FITSNE_PHASE_FFT);
         const int H = M / 2 + 1;
-        k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp);
+        k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp, c->pc, c->p2p ? 1 : 0);
         kt(c, "k_conv_rows_fwd");
         k_conv_cols<<<H, col_threads, pl->smem_col, st>>>(pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
                                                           c->sc, c->tickets + 0);
@@ -516,7 +548,11 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     // local slice), so the all-gather that completes Y sits right in front of it.
     if (c->world > 1) {
         phase_mark(c, FITSNE_PHASE_ALLGATHER);
-        CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, st));
+        if (push_Y) {
+            if (!c->timing_this_iter) CK(cudaStreamWaitEvent(st, c->ev_cjoin, 0));     // my own pushes are out ...
+            k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_Y);                               // ... and everybody's have landed here
+            c->stats.kernel_launches += 1;
+        } else CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, st));
     }
     c->y_whole = true;
     phase_mark(c, FITSNE_PHASE_ATTRACT_UPDATE);
@@ -529,6 +565,13 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
                                                    c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         c->stats.kernel_launches += 1;
         phase_mark(c, FITSNE_PHASE_CENTER);
+        if (c->p2p) {
+            // no statistics exchange closes a gradient-only pass: meet the peers explicitly, so that nobody clears its
+            // partial grid for the next pass while a slower rank still reads it
+            k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_STATS);
+            k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_STATS);
+            c->stats.kernel_launches += 2;
+        }
     } else if (c->world == 1) {
         // single GPU: k_update also produces the column means of the new positions (per-CTA register sums, last-block
         // reduction), the centring kernel subtracts them, finds the bounds and publishes them -- two launches for the tail
@@ -544,10 +587,10 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
                                                   c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         phase_mark(c, FITSNE_PHASE_CENTER);
         k_shard_stats<D><<<SHARD_BLOCKS, 256, 0, st>>>(c->Yb, c->row_begin, c->row_end, c->rank, c->gp, c->shard_sum_partial,
-                                                      c->shard_mm_partial, c->shard_stats + c->rank, c->tickets + 3);
-        CKNCCL(g_nccl.AllGather(c->shard_stats + c->rank, c->shard_stats, sizeof(ShardStats), ncclChar, c->comm, st));
+                                                      c->shard_mm_partial, c->shard_stats + c->rank, c->tickets + 3, c->pc, c->p2p ? 1 : 0);
+        if (!c->p2p) CKNCCL(g_nccl.AllGather(c->shard_stats + c->rank, c->shard_stats, sizeof(ShardStats), ncclChar, c->comm, st));
         k_center_shard<D><<<cdiv(rows, 256), 256, 0, st>>>(c->Yb, c->Y, c->row_begin, c->row_end, c->N, c->shard_stats, c->world,
-                                                          c->gp, c->sc, c->host_bounds_dev);
+                                                          c->gp, c->sc, c->host_bounds_dev, c->pc, c->p2p ? 1 : 0);
         c->stats.kernel_launches += 3;
         c->y_whole = false;
     }
@@ -925,6 +968,85 @@ static int read_scalars(fitsne_ctx *c) {
 }
 
 // ------------------------------------------------------------------------------------------- lifetime --
+// Sharded contexts: map every peer's exchange buffers (CUDA IPC; same node, NVLink / NVSwitch) so that the iteration's three
+// exchanges are plain loads / stores / DMA on peer memory (PeerComm, fitsne_kernels.cuh).  The handles travel through
+// one NCCL all-gather at creation; NCCL stays in use for the rare scalar reductions (KL, automatic exaggeration) and
+// for completing Y outside the loop.  Any failure leaves the context on the NCCL collectives (FITSNE_NO_P2P=1 forces that).
+struct IpcHandles { cudaIpcMemHandle_t Y, grid, stats, flags; };
+static int setup_peer_fabric(fitsne_ctx *c) {
+    static const bool no_p2p = getenv("FITSNE_NO_P2P") && atoi(getenv("FITSNE_NO_P2P")) != 0;
+    const int world = c->world;
+    if (no_p2p || world > MAX_RANKS) return 0;
+    // fixed-size grids for the lifetime of the context: the peers hold mappings of them
+    CKRC(ensure_grid_capacity(c, max_fft_len(c->D)));
+    CKRC(dev_alloc(c, &c->peer_flags, (size_t) 3 * world));
+    CKRC(dev_alloc(c, &c->comm_seq, (size_t) 1));
+    CK(cudaMemsetAsync(c->peer_flags, 0, sizeof(uint32_t) * 3 * world, c->stream));
+    CK(cudaMemsetAsync(c->comm_seq, 0, sizeof(unsigned int), c->stream));
+    if (c->D == 1) {
+        CKRC(dev_alloc(c, &c->grid1d, (size_t) 2 * max_fft_len(1)));
+        CK(cudaMemsetAsync(c->grid1d, 0, sizeof(float2) * 2 * max_fft_len(1), c->stream));
+    }
+    IpcHandles mine;
+    void *grid = c->D == 2 ? (void *) c->chg : (void *) c->grid1d;
+    int okl = cudaIpcGetMemHandle(&mine.Y, c->Y) == cudaSuccess && cudaIpcGetMemHandle(&mine.grid, grid) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.stats, c->shard_stats) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, c->peer_flags) == cudaSuccess;
+    cudaGetLastError();
+    // all-gather the handles (+ a per-rank "ok" word in front) through NCCL
+    const size_t rec = sizeof(int) * 4 + sizeof(IpcHandles);
+    unsigned char *dbuf = nullptr;
+    CKRC(dev_alloc(c, &dbuf, rec * world));
+    std::vector<unsigned char> host(rec * world, 0);
+    memcpy(host.data() + rec * c->rank, &okl, sizeof(int));
+    memcpy(host.data() + rec * c->rank + sizeof(int) * 4, &mine, sizeof mine);
+    CK(cudaMemcpyAsync(dbuf + rec * c->rank, host.data() + rec * c->rank, rec, cudaMemcpyHostToDevice, c->stream));
+    CKNCCL(g_nccl.AllGather(dbuf + rec * c->rank, dbuf, rec, ncclChar, c->comm, c->stream));
+    CK(cudaMemcpyAsync(host.data(), dbuf, rec * world, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(dbuf);
+    bool all_ok = true;
+    for (int r = 0; r < world; r++) { int o; memcpy(&o, host.data() + rec * r, sizeof(int)); all_ok = all_ok && o; }
+    PeerComm pc;
+    memset(&pc, 0, sizeof pc);
+    pc.rank = c->rank; pc.world = world; pc.seq = c->comm_seq;
+    int opened_ok = all_ok ? 1 : 0;
+    for (int r = 0; r < world && opened_ok; r++) {
+        if (r == c->rank) { pc.Y[r] = c->Y; pc.grid[r] = grid; pc.stats[r] = c->shard_stats; pc.flags[r] = c->peer_flags; continue; }
+        IpcHandles h;
+        memcpy(&h, host.data() + rec * r + sizeof(int) * 4, sizeof h);
+        void *p[4] = {nullptr, nullptr, nullptr, nullptr};
+        const cudaIpcMemHandle_t *hs[4] = {&h.Y, &h.grid, &h.stats, &h.flags};
+        for (int k = 0; k < 4; k++) {
+            if (cudaIpcOpenMemHandle(&p[k], *hs[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened_ok = 0; break; }
+            c->ipc_opened.push_back(p[k]);
+        }
+        pc.Y[r] = (float *) p[0]; pc.grid[r] = p[1]; pc.stats[r] = p[2]; pc.flags[r] = (uint32_t *) p[3];
+    }
+    // everybody must agree (a rank that failed to map a peer cannot be waited for)
+    int *agree = nullptr;
+    CKRC(dev_alloc(c, &agree, (size_t) 1));
+    CK(cudaMemcpyAsync(agree, &opened_ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CKNCCL(g_nccl.AllReduce(agree, agree, 1, ncclInt, ncclMin, c->comm, c->stream));
+    CK(cudaMemcpyAsync(&opened_ok, agree, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(agree);
+    if (!opened_ok) {
+        TRACE("peer fabric unavailable: staying on NCCL collectives");
+        for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+        c->ipc_opened.clear();
+        return 0;
+    }
+    c->pc = pc;
+    c->p2p = true;
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->stream_c, cudaStreamNonBlocking, prio_hi));
+    CK(cudaEventCreateWithFlags(&c->ev_cfork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_cjoin, cudaEventDisableTiming));
+    TRACE("peer fabric up: %d ranks", world);
+    return 0;
+}
+
 static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_dims, const unsigned int *row_P,
                        const unsigned int *col_P, const double *val_P, const double *Y0, int rank, int world,
                        int row_begin, int row_end, const void *nccl_id) {
@@ -1062,6 +1184,7 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
         ncclUniqueId id;
         memcpy(&id, nccl_id, sizeof id);
         CKNCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
+        CKRC(setup_peer_fabric(c));
     }
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -1086,13 +1209,25 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     drop_graphs(c);
     for (auto &p : c->plans) if (p.second.W) cudaFree(p.second.W);
+    if (c->p2p) {
+        // nobody frees a buffer a peer may still have mapped: close my mappings, then meet the others
+        if (c->stream_c) cudaStreamSynchronize(c->stream_c);
+        for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+        if (c->comm && c->comm_seq) {
+            g_nccl.AllReduce(c->comm_seq, c->comm_seq, 1, ncclInt, ncclMax, c->comm, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+        if (c->ev_cfork) cudaEventDestroy(c->ev_cfork);
+        if (c->ev_cjoin) cudaEventDestroy(c->ev_cjoin);
+        if (c->stream_c) cudaStreamDestroy(c->stream_c);
+    }
     if (c->comm) g_nccl.CommDestroy(c->comm);
     void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->edges, c->keys[0], c->keys[1],
                     c->perm[0], c->perm[1], c->sorted_u, c->box_range, c->gpart, c->hist, c->sweep_state, c->sort_bases, c->work, c->sort_totals, c->slots, c->attr, c->planes,
                     c->chg, c->pot, c->S, c->KR, c->KS, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->host_B_dev, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->edges2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
-                    c->nonempty, c->gp_reorder, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial, c->srt_cnt, c->srt_start, c->srt_cur};
+                    c->nonempty, c->gp_reorder, c->peer_flags, c->comm_seq, c->grid1d, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial, c->srt_cnt, c->srt_start, c->srt_cur};
     for (void *b : bufs) if (b) cudaFree(b);
     if (c->host_bounds) cudaFreeHost(c->host_bounds);
     if (c->host_sc) cudaFreeHost(c->host_sc);

@@ -230,19 +230,35 @@ __device__ __forceinline__ void tma_store_commit_and_wait() {
 // One CTA per grid row r < G (the launch covers M/2 rows; the rest exit): both packed sequences of the row through the
 // Stockham FFT of fitsne_fft.cuh (natural order out), then the real/imaginary-part spectra are separated with the row's
 // own mirror bins.
+// Sharded (p2p != 0): the row is the SUM of every rank's partial spread grid, added in rank order while loading (peer
+// memory over NVLink; identical bits on every rank) -- the grid all-reduce costs no pass of its own.
 __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_fwd(const float4 *__restrict__ chg, float2 *__restrict__ S, FftPlan plan,
-                                                               const float2 *__restrict__ W, const GridParams *__restrict__ gpp) {
+                                                               const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
+                                                               PeerComm pc, int p2p) {
     extern __shared__ __align__(16) float2 row_sm[];
     __shared__ FftPlan plan_s;
     const int G = gpp->G;
     if (!gpp->ok || (int) blockIdx.x >= G) return;
+    if (p2p && threadIdx.x == 0) peer_wait(pc.flags[pc.rank], FLAG_GRID, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
     for (int i = threadIdx.x; i < (int) (sizeof(FftPlan) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&plan_s)[i] = reinterpret_cast<const int *>(&plan)[i];
     const int M = plan.n, NS = fft_buf_len(M, 2), r = blockIdx.x;
     float2 *bufa = row_sm, *bufb = row_sm + 2 * NS;
     const float4 *src = chg + (size_t) r * G;
+    if (p2p) __syncthreads();                         // thread 0 has seen every rank's "grid complete" flag
     for (int c = threadIdx.x; c < M; c += blockDim.x) {
-        const float4 v = c < G ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < G) {
+            if (!p2p) v = src[c];
+            else {
+                float4 t[MAX_RANKS];
+#pragma unroll
+                for (int q = 0; q < MAX_RANKS; q++)       // all ranks' loads in flight together, then added in rank order
+                    t[q] = q < pc.world ? __ldcg(reinterpret_cast<const float4 *>(pc.grid[q]) + (size_t) r * G + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < MAX_RANKS; q++) { v.x += t[q].x; v.y += t[q].y; v.z += t[q].z; v.w += t[q].w; }
+            }
+        }
         const int ph = fft_phys(c);
         bufa[ph] = make_float2(v.x, v.y);            // w1 + i delta_x
         bufa[NS + ph] = make_float2(v.z, v.w);       // delta_y + i wbb

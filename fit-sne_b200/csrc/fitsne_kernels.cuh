@@ -69,6 +69,70 @@ struct Scalars {          // small device-resident results
     unsigned long long iter_done;   // optimiser steps that really executed (speculative launches that found a grid mismatch do not count)
 };
 
+// ---------------------------------------------------------------------------- peer-memory fabric (sharded) --
+// One process per GPU; every rank maps the others' exchange buffers (CUDA IPC over NVLink / NVSwitch) and the three
+// per-iteration exchanges are done by the kernels themselves, with loads / stores on peer memory -- no library
+// collective inside the iteration:
+//   grid reduction   k_conv_rows_fwd (2-D) / k_grid_sum_1d add the ranks' partial spread grids WHILE LOADING them, in rank
+//                    order, so every rank gets the same bits;
+//   statistics       k_shard_stats writes its 128-byte record straight into every peer's table, k_center_shard reads them;
+//   positions        every rank's centred slice of Y is pushed into the peers' Y by the copy engines (a side stream:
+//                    DMA over NVLink, no SM involved) while the next iteration sorts and spreads; the SpMV waits for it.
+// Ordering: flags[kind * world + r] in MY memory is written by rank r with the iteration's sequence number after its data
+// for that exchange is in place (system-scope fence in between); consumers spin on their own flags.  A rank can never be
+// more than one exchange ahead of its peers (each exchange needs everybody's signal), which is what makes single
+// buffers safe: see DESIGN.md section 7 for the three hazard arguments.
+constexpr int MAX_RANKS = 8;
+constexpr int FLAG_Y = 0, FLAG_GRID = 1, FLAG_STATS = 2;
+struct PeerComm {
+    float *Y[MAX_RANKS];             // every rank's Y (full N x D floats); [rank] = my own
+    void *grid[MAX_RANKS];           // every rank's partial spread grid: chg (2-D, float4 per node) or planes (1-D)
+    void *stats[MAX_RANKS];          // every rank's ShardStats[world] table
+    uint32_t *flags[MAX_RANKS];      // every rank's flag words [3 * world]
+    unsigned int *seq;               // my sequence counter (bumped once per enqueued iteration by k_setup_grid)
+    int rank, world;
+};
+
+__device__ __forceinline__ void peer_wait(const uint32_t *flags, int kind, const PeerComm &pc, uint32_t seq) {
+    // one thread: until every peer's flag of this kind has reached the iteration's sequence number
+    for (int r = 0; r < pc.world; r++) {
+        if (r == pc.rank) continue;
+        const volatile uint32_t *f = flags + kind * pc.world + r;
+        while ((int) (*f - seq) < 0) { }
+    }
+    __threadfence_system();
+}
+
+// tell every peer that my data for exchange `kind` is in place (one thread; everything written before is fenced first)
+__global__ void k_peer_signal(PeerComm pc, int kind) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __threadfence_system();
+    const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
+    for (int r = 0; r < pc.world; r++)
+        if (r != pc.rank) *reinterpret_cast<volatile uint32_t *>(pc.flags[r] + kind * pc.world + pc.rank) = seq;
+}
+// stream-level wait: one thread spins until every peer has signalled `kind` for this iteration
+__global__ void k_peer_wait(PeerComm pc, int kind) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    peer_wait(pc.flags[pc.rank], kind, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
+}
+
+// 1-D sharded runs: planes 0, 1 (two packed complex lines of length M) <- sum over ranks of their partial lines, in rank
+// order.  Every rank keeps its partial in `partial` (peer-readable) and writes the sum into its own FFT input.
+__global__ void __launch_bounds__(256) k_grid_sum_1d(PeerComm pc, float2 *__restrict__ planes, int n /* 2 * M */, const int *__restrict__ ok) {
+    if (!*ok) return;
+    if (threadIdx.x == 0) peer_wait(pc.flags[pc.rank], FLAG_GRID, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int r = 0; r < pc.world; r++) {
+        const float2 v = __ldcg(reinterpret_cast<const float2 *>(pc.grid[r]) + i);
+        acc.x += v.x; acc.y += v.y;
+    }
+    planes[i] = acc;
+}
+
 // ------------------------------------------------------------------------------------------ helpers --
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -284,9 +348,10 @@ __host__ __device__ inline int sort_bits_for(int B, int dims) {
 // Fill GridParams for a grid of B boxes/dim (the host's choice; verified against the device's own bounds).
 __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restrict__ sc, const int *__restrict__ B_host, int M, int p, int dims,
                              double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals,
-                             uint32_t *__restrict__ work, unsigned int *__restrict__ sweep_tickets) {
+                             uint32_t *__restrict__ work, unsigned int *__restrict__ sweep_tickets, unsigned int *__restrict__ comm_seq) {
     for (int i = threadIdx.x; i < 2 * (1 << SORT_MAX_BITS); i += blockDim.x) sort_totals[i] = 0;   // both passes
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (comm_seq) *comm_seq += 1;                    // sharded: this iteration's sequence number (also for no-op iterations)
     work[0] = 0;                                     // spread work list (boxes that span several chunks) starts empty
     sweep_tickets[0] = 0; sweep_tickets[1] = 0;      // tile tickets of the two sort passes
     // B_host > 0: the host sized the grid after reading the bounds (single-step API); 0: speculative launch, the device
@@ -1371,7 +1436,7 @@ template <int D>
 __global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Ynext, int row_begin, int row_end, int rank,
                                                      const GridParams *__restrict__ gpp, double *__restrict__ sum_partial,
                                                      float4 *__restrict__ mm_partial, ShardStats *__restrict__ out,
-                                                     unsigned int *__restrict__ ticket) {
+                                                     unsigned int *__restrict__ ticket, PeerComm pc, int p2p) {
     if (!gpp->ok) return;
     __shared__ double smd[32];
     __shared__ float4 smm[8];
@@ -1423,6 +1488,21 @@ __global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Y
         out->mn[0] = a.x; out->mn[1] = a.y; out->mx[0] = a.z; out->mx[1] = a.w;
         out->nhead = nhead_pts * 2;
         for (int i = 0; i < 2 * SHARD_HEAD; i++) out->head[i] = i < nhead_pts * 2 ? Ynext[(size_t) row_begin * 2 + i] : 0.f;
+        if (p2p) {
+            // peer-memory exchange: my 128-byte record goes straight into slot [rank] of every peer's table (32 remote
+            // 4-byte stores each), then the flag -- k_center_shard on the other side spins on it
+            __threadfence();
+            const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(out);
+            for (int r = 0; r < pc.world; r++) {
+                if (r == pc.rank) continue;
+                volatile uint32_t *dst = reinterpret_cast<volatile uint32_t *>(reinterpret_cast<ShardStats *>(pc.stats[r]) + pc.rank);
+                for (int i = 0; i < (int) (sizeof(ShardStats) / 4); i++) dst[i] = src[i];
+            }
+            __threadfence_system();
+            for (int r = 0; r < pc.world; r++)
+                if (r != pc.rank) *reinterpret_cast<volatile uint32_t *>(pc.flags[r] + FLAG_STATS * pc.world + pc.rank) = seq;
+        }
     }
 }
 
@@ -1430,34 +1510,37 @@ __global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Y
 // ranks), centre the local slice Y[row] = Ynext[row] - mean (tsne.cpp:1851-1876), publish the bounds.
 template <int D>
 __global__ void __launch_bounds__(256) k_center_shard(const float *__restrict__ Ynext, float *__restrict__ Y, int row_begin, int row_end,
-                                                      int N, const ShardStats *__restrict__ all, int world,
+                                                      int N, const ShardStats *all, int world,
                                                       const GridParams *__restrict__ gpp, Scalars *__restrict__ sc,
-                                                      volatile float *host_bounds) {
+                                                      volatile float *host_bounds, PeerComm pc, int p2p) {
     if (!gpp->ok) return;
     __shared__ double mean_s[2];
     if (threadIdx.x == 0) {
+        if (p2p) peer_wait(pc.flags[pc.rank], FLAG_STATS, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
+        const volatile ShardStats *va = all;       // (peers may have written these records: no cached / read-only loads)
         double t0 = 0, t1 = 0;
-        for (int r = 0; r < world; r++) { t0 += all[r].sum[0]; t1 += all[r].sum[1]; }
+        for (int r = 0; r < world; r++) { t0 += va[r].sum[0]; t1 += va[r].sum[1]; }
         mean_s[0] = t0 / (double) N; mean_s[1] = t1 / (double) N;
     }
     __syncthreads();
     const double m0 = mean_s[0], m1 = mean_s[1];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const volatile ShardStats *va = all;
         // centring is monotonic per dimension ((float)((double) y - mean)), so the bounds of the centred values are the
         // centred per-dimension bounds
         float bmn = INFINITY, bmx = -INFINITY;
         for (int r = 0; r < world; r++) {
             for (int d = 0; d < D; d++) {
                 const double m = d ? m1 : m0;
-                bmn = fminf(bmn, (float) ((double) all[r].mn[d] - m));
-                bmx = fmaxf(bmx, (float) ((double) all[r].mx[d] - m));
+                bmn = fminf(bmn, (float) ((double) va[r].mn[d] - m));
+                bmx = fmaxf(bmx, (float) ((double) va[r].mx[d] - m));
             }
         }
-        const int nh = all[0].nhead;
+        const int nh = va[0].nhead;
         float run = -INFINITY;
         bool ascending = true;
         for (int i = 0; i < nh; i++) {            // replay of the `if (>max) .. else if (<min)` scan on the head
-            const float v = (float) ((double) all[0].head[i] - ((i & 1) ? m1 : m0));
+            const float v = (float) ((double) va[0].head[i] - ((i & 1) ? m1 : m0));
             if (ascending && v > run) run = v;   // still in the strictly ascending prefix: max only
             else { ascending = false; bmn = fminf(bmn, v); }
         }
