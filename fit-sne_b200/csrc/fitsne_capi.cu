@@ -105,8 +105,10 @@ struct fitsne_ctx {
     ncclComm_t comm = nullptr;
     // peer-memory fabric (sharded contexts; see fitsne_kernels.cuh): the iteration's exchanges run over mapped peer memory
     bool p2p = false;
+    bool dist_conv = false;           // 2-D: convolution distributed over the ranks (else replicated, with the grid sum fused into its loads)
     PeerComm pc{};
     uint32_t *peer_flags = nullptr;
+    double *peer_zs = nullptr;        // per-rank sum_Q partials (peers write their slot)
     unsigned int *comm_seq = nullptr;
     float2 *grid1d = nullptr;         // 1-D: this rank's partial charge lines (peers read them; the sum goes to planes)
     std::vector<void *> ipc_opened;
@@ -456,7 +458,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     auto launch_kernel_side = [&](cudaStream_t ks) -> int {
         const int Gc = M / 2, H = M / 2 + 1;
         k_kspec_rows<<<Gc, ROW_THREADS, pl->smem_row1, ks>>>(c->KR, pl->plan, pl->W, c->gp, c->cfg.df);
-        k_kspec_cols<<<(H + 1) / 2, col_threads, pl->smem_col, ks>>>(c->KR, c->KS, pl->cplan, pl->W, c->gp);
+        k_kspec_cols<<<(H + 1) / 2, col_threads, pl->smem_col, ks>>>(c->KR, c->KS, pl->cplan, pl->W, c->gp, c->rank, c->p2p && c->dist_conv ? c->world : 1);
         LAUNCH_CHECK();
         c->stats.kernel_launches += 2;
         return 0;
@@ -517,14 +519,20 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         kt(c, "k_kspec_rows + k_kspec_cols");
         phase_mark(c, FITSNE_PHASE_FFT);
         const int H = M / 2 + 1;
-        k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp, c->pc, c->p2p ? 1 : 0);
+        k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp, c->pc, c->p2p ? (c->dist_conv ? 2 : 1) : 0);
         kt(c, "k_conv_rows_fwd");
+        const int dist = c->p2p && c->dist_conv ? 1 : 0, p2p = dist ? 2 : 0;
+        // sharded, distributed convolution: like a 2-D FFT -- rows and spectrum columns dealt out in blocks; every
+        // "transpose" is the producing kernel's stores on peer memory, a flag per stage tells the consumers
+        if (dist) k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_S1);
         k_conv_cols<<<H, col_threads, pl->smem_col, st>>>(pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
-                                                          c->sc, c->tickets + 0);
+                                                          c->sc, c->tickets + 0, c->pc, p2p);
         kt(c, "k_conv_cols");
-        k_conv_rows_inv<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->S, c->pot, pl->plan, pl->W, c->gp);
+        if (dist) k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_S2);
+        k_conv_rows_inv<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->S, c->pot, pl->plan, pl->W, c->gp, c->pc, p2p, c->N, c->sc);
         kt(c, "k_conv_rows_inv");
-        c->stats.kernel_launches += 3;
+        if (dist) { k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_POT); k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_POT); }
+        c->stats.kernel_launches += 3 + 4 * dist;
     } else {
         k_gen_kernels_1d<<<cdiv(M, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->planes);
         kt(c, "k_gen_kernels_1d");
@@ -972,16 +980,18 @@ static int read_scalars(fitsne_ctx *c) {
 // exchanges are plain loads / stores / DMA on peer memory (PeerComm, fitsne_kernels.cuh).  The handles travel through
 // one NCCL all-gather at creation; NCCL stays in use for the rare scalar reductions (KL, automatic exaggeration) and
 // for completing Y outside the loop.  Any failure leaves the context on the NCCL collectives (FITSNE_NO_P2P=1 forces that).
-struct IpcHandles { cudaIpcMemHandle_t Y, grid, stats, flags; };
+struct IpcHandles { cudaIpcMemHandle_t Y, grid, stats, flags, S, pot, zs; };
 static int setup_peer_fabric(fitsne_ctx *c) {
     static const bool no_p2p = getenv("FITSNE_NO_P2P") && atoi(getenv("FITSNE_NO_P2P")) != 0;
     const int world = c->world;
     if (no_p2p || world > MAX_RANKS) return 0;
     // fixed-size grids for the lifetime of the context: the peers hold mappings of them
     CKRC(ensure_grid_capacity(c, max_fft_len(c->D)));
-    CKRC(dev_alloc(c, &c->peer_flags, (size_t) 3 * world));
+    CKRC(dev_alloc(c, &c->peer_flags, (size_t) FLAG_KINDS * world));
+    CKRC(dev_alloc(c, &c->peer_zs, (size_t) MAX_RANKS));
+    CK(cudaMemsetAsync(c->peer_zs, 0, sizeof(double) * MAX_RANKS, c->stream));
     CKRC(dev_alloc(c, &c->comm_seq, (size_t) 1));
-    CK(cudaMemsetAsync(c->peer_flags, 0, sizeof(uint32_t) * 3 * world, c->stream));
+    CK(cudaMemsetAsync(c->peer_flags, 0, sizeof(uint32_t) * FLAG_KINDS * world, c->stream));
     CK(cudaMemsetAsync(c->comm_seq, 0, sizeof(unsigned int), c->stream));
     if (c->D == 1) {
         CKRC(dev_alloc(c, &c->grid1d, (size_t) 2 * max_fft_len(1)));
@@ -989,8 +999,11 @@ static int setup_peer_fabric(fitsne_ctx *c) {
     }
     IpcHandles mine;
     void *grid = c->D == 2 ? (void *) c->chg : (void *) c->grid1d;
+    memset(&mine, 0, sizeof mine);
     int okl = cudaIpcGetMemHandle(&mine.Y, c->Y) == cudaSuccess && cudaIpcGetMemHandle(&mine.grid, grid) == cudaSuccess &&
-              cudaIpcGetMemHandle(&mine.stats, c->shard_stats) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, c->peer_flags) == cudaSuccess;
+              cudaIpcGetMemHandle(&mine.stats, c->shard_stats) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, c->peer_flags) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.zs, c->peer_zs) == cudaSuccess;
+    if (c->D == 2) okl = okl && cudaIpcGetMemHandle(&mine.S, c->S) == cudaSuccess && cudaIpcGetMemHandle(&mine.pot, c->pot) == cudaSuccess;
     cudaGetLastError();
     // all-gather the handles (+ a per-rank "ok" word in front) through NCCL
     const size_t rec = sizeof(int) * 4 + sizeof(IpcHandles);
@@ -1011,16 +1024,22 @@ static int setup_peer_fabric(fitsne_ctx *c) {
     pc.rank = c->rank; pc.world = world; pc.seq = c->comm_seq;
     int opened_ok = all_ok ? 1 : 0;
     for (int r = 0; r < world && opened_ok; r++) {
-        if (r == c->rank) { pc.Y[r] = c->Y; pc.grid[r] = grid; pc.stats[r] = c->shard_stats; pc.flags[r] = c->peer_flags; continue; }
+        if (r == c->rank) {
+            pc.Y[r] = c->Y; pc.grid[r] = grid; pc.stats[r] = c->shard_stats; pc.flags[r] = c->peer_flags;
+            pc.S[r] = c->S; pc.pot[r] = c->pot; pc.zs[r] = c->peer_zs;
+            continue;
+        }
         IpcHandles h;
         memcpy(&h, host.data() + rec * r + sizeof(int) * 4, sizeof h);
-        void *p[4] = {nullptr, nullptr, nullptr, nullptr};
-        const cudaIpcMemHandle_t *hs[4] = {&h.Y, &h.grid, &h.stats, &h.flags};
-        for (int k = 0; k < 4; k++) {
+        void *p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        const cudaIpcMemHandle_t *hs[7] = {&h.Y, &h.grid, &h.stats, &h.flags, &h.zs, &h.S, &h.pot};
+        const int nh = c->D == 2 ? 7 : 5;
+        for (int k = 0; k < nh; k++) {
             if (cudaIpcOpenMemHandle(&p[k], *hs[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened_ok = 0; break; }
             c->ipc_opened.push_back(p[k]);
         }
         pc.Y[r] = (float *) p[0]; pc.grid[r] = p[1]; pc.stats[r] = p[2]; pc.flags[r] = (uint32_t *) p[3];
+        pc.zs[r] = (double *) p[4]; pc.S[r] = (float2 *) p[5]; pc.pot[r] = (float4 *) p[6];
     }
     // everybody must agree (a rank that failed to map a peer cannot be waited for)
     int *agree = nullptr;
@@ -1038,6 +1057,9 @@ static int setup_peer_fabric(fitsne_ctx *c) {
     }
     c->pc = pc;
     c->p2p = true;
+    // distributing the convolution trades 7/8 of its work for three more flag stages: worth it from four ranks up
+    // (measured on 2 x B200: 0.147 ms distributed vs 0.125 ms replicated at M = 1152); FITSNE_DIST_CONV=0/1 overrides
+    c->dist_conv = c->D == 2 && (getenv("FITSNE_DIST_CONV") ? atoi(getenv("FITSNE_DIST_CONV")) != 0 : world >= 4);
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CK(cudaStreamCreateWithPriority(&c->stream_c, cudaStreamNonBlocking, prio_hi));
@@ -1227,7 +1249,7 @@ int fitsne_destroy(fitsne_ctx *c) {
                     c->chg, c->pot, c->S, c->KR, c->KS, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->host_B_dev, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->edges2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
-                    c->nonempty, c->gp_reorder, c->peer_flags, c->comm_seq, c->grid1d, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial, c->srt_cnt, c->srt_start, c->srt_cur};
+                    c->nonempty, c->gp_reorder, c->peer_flags, c->peer_zs, c->comm_seq, c->grid1d, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial, c->srt_cnt, c->srt_start, c->srt_cur};
     for (void *b : bufs) if (b) cudaFree(b);
     if (c->host_bounds) cudaFreeHost(c->host_bounds);
     if (c->host_sc) cudaFreeHost(c->host_sc);

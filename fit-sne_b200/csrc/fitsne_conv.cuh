@@ -231,7 +231,9 @@ __device__ __forceinline__ void tma_store_commit_and_wait() {
 // Stockham FFT of fitsne_fft.cuh (natural order out), then the real/imaginary-part spectra are separated with the row's
 // own mirror bins.
 // Sharded (p2p != 0): the row is the SUM of every rank's partial spread grid, added in rank order while loading (peer
-// memory over NVLink; identical bits on every rank) -- the grid all-reduce costs no pass of its own.
+// memory over NVLink; identical bits on every rank) -- the grid all-reduce costs no pass of its own.  p2p == 1: every rank
+// transforms every row (replicated convolution); p2p == 2: distributed convolution, my block of rows only, every bin
+// stored into the S of the rank that owns its column.
 __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_fwd(const float4 *__restrict__ chg, float2 *__restrict__ S, FftPlan plan,
                                                                const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
                                                                PeerComm pc, int p2p) {
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_fwd(const float4 *__r
     __shared__ FftPlan plan_s;
     const int G = gpp->G;
     if (!gpp->ok || (int) blockIdx.x >= G) return;
+    if (p2p == 2 && part_owner(blockIdx.x, part_block(G, pc.world, 1), pc.world) != pc.rank) return;      // distributed: not my row
     if (p2p && threadIdx.x == 0) peer_wait(pc.flags[pc.rank], FLAG_GRID, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
     for (int i = threadIdx.x; i < (int) (sizeof(FftPlan) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&plan_s)[i] = reinterpret_cast<const int *>(&plan)[i];
@@ -266,32 +269,56 @@ __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_fwd(const float4 *__r
     __syncthreads();
     const float2 *res = fft_smem(bufa, bufb, NS, 2, plan_s, W);
     const int H = M / 2 + 1;
-    float4 *dst = reinterpret_cast<float4 *>(S + (size_t) r * H * COL_SLOTS);
+    const int kblock = p2p == 2 ? part_block(H, pc.world, 2) : H;
     for (int kx = threadIdx.x; kx < H; kx += blockDim.x) {
         const int km = kx ? M - kx : 0;
         float2 w1, dx, dy, wb;
         unpack_pair(res[fft_phys(kx)], res[fft_phys(km)], w1, dx);
         unpack_pair(res[NS + fft_phys(kx)], res[NS + fft_phys(km)], dy, wb);
-        dst[2 * kx] = make_float4(w1.x, w1.y, dx.x, dx.y);
-        dst[2 * kx + 1] = make_float4(dy.x, dy.y, wb.x, wb.y);
+        // sharded: the bin goes to the S of the rank that owns column kx (a store on peer memory: the transpose of a
+        // distributed 2-D FFT, done by the producing kernel)
+        float2 *Sd = p2p == 2 ? pc.S[part_owner(kx, kblock, pc.world)] : S;
+        float4 *dst = reinterpret_cast<float4 *>(Sd + ((size_t) r * H + kx) * COL_SLOTS);
+        dst[0] = make_float4(w1.x, w1.y, dx.x, dx.y);
+        dst[1] = make_float4(dy.x, dy.y, wb.x, wb.y);
     }
 }
 
 // rows r < G: x-half-spectra (v1~, Bx~, By~) -> real rows.  Z1 = v1~ + i Bx~ extended by Hermitian symmetry gives
 // v1 + i Bx in one complex inverse transform; By takes the second.  Inverse = conj(FFT(conj .)).
-__global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_inv(const float2 *__restrict__ S, float4 *__restrict__ pot, FftPlan plan,
-                                                               const float2 *__restrict__ W, const GridParams *__restrict__ gpp) {
+// Sharded: my rows only (their bins were written into my S by the ranks that own the columns); the finished row of the
+// potential grid goes to EVERY rank's pot (each rank gathers for its own points anywhere in the plane), and the first CTA
+// adds the ranks' sum_Q partials in rank order.
+__global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_inv(const float2 *S, float4 *__restrict__ pot, FftPlan plan,
+                                                               const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
+                                                               PeerComm pc, int p2p, int N, Scalars *__restrict__ sc) {
     extern __shared__ __align__(16) float2 row_sm[];
     __shared__ FftPlan plan_s;
     const int G = gpp->G;
     if (!gpp->ok || (int) blockIdx.x >= G) return;
+    if (p2p == 2) {
+        const bool mine = part_owner(blockIdx.x, part_block(G, pc.world, 1), pc.world) == pc.rank;
+        if (!mine && blockIdx.x != 0) return;
+        if (threadIdx.x == 0) {
+            peer_wait(pc.flags[pc.rank], FLAG_S2, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
+            if (blockIdx.x == 0) {        // sum_Q = (sum over ranks of their columns' Parseval partials, in rank order) - N
+                double tot = 0;
+                for (int q = 0; q < pc.world; q++) tot += *reinterpret_cast<const volatile double *>(pc.zs[pc.rank] + q);
+                const double Z = tot - (double) N;
+                sc->Z = Z;
+                sc->inv_Z = (float) (1.0 / Z);
+            }
+        }
+        if (!mine) return;
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < (int) (sizeof(FftPlan) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&plan_s)[i] = reinterpret_cast<const int *>(&plan)[i];
     const int M = plan.n, NS = fft_buf_len(M, 2), r = blockIdx.x, H = M / 2 + 1;
     float2 *bufa = row_sm, *bufb = row_sm + 2 * NS;
     const float4 *src = reinterpret_cast<const float4 *>(S + (size_t) r * H * COL_SLOTS);
     for (int kx = threadIdx.x; kx < H; kx += blockDim.x) {
-        const float4 a = __ldg(src + 2 * kx), b = __ldg(src + 2 * kx + 1);      // (v1, Bx), (By, -)
+        const float4 a = __ldcg(src + 2 * kx), b = __ldcg(src + 2 * kx + 1);    // (v1, Bx), (By, -)
         const int km = kx ? M - kx : 0;
         // conj(Z1[kx]) with Z1[kx] = v1 + i Bx;  conj(Z1[-kx]) with Z1[-kx] = conj(v1) + i conj(Bx)
         bufa[fft_phys(kx)] = make_float2(a.x - a.w, -(a.y + a.z));
@@ -303,10 +330,14 @@ __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_inv(const float2 *__r
     }
     __syncthreads();
     const float2 *res = fft_smem(bufa, bufb, NS, 2, plan_s, W);
-    float4 *dst = pot + (size_t) r * G;
     for (int c = threadIdx.x; c < G; c += blockDim.x) {
         const float2 o1 = res[fft_phys(c)], o2 = res[NS + fft_phys(c)];
-        dst[c] = make_float4(o1.x, -o1.y, o2.x, 0.f);
+        const float4 v = make_float4(o1.x, -o1.y, o2.x, 0.f);
+        if (p2p != 2) pot[(size_t) r * G + c] = v;
+        else {
+#pragma unroll
+            for (int q = 0; q < MAX_RANKS; q++) if (q < pc.world) pc.pot[q][(size_t) r * G + c] = v;
+        }
     }
 }
 
@@ -355,10 +386,13 @@ __global__ void __launch_bounds__(ROW_THREADS) k_kspec_rows(float4 *__restrict__
 // Re ZB = gx with Kgrad_x^ = i gx,  Im ZB = -gy with Kgrad_y^ = i gy).   KS[kx][pos] = (Ksq^, Kb^, gx, gy), pos = the
 // forward transform's digit-reversed frequency slot -- the order k_conv_cols meets them in.
 __global__ void __launch_bounds__(COL_THREADS) k_kspec_cols(const float4 *__restrict__ KR, float4 *__restrict__ KS, ColPlan plan,
-                                                            const float2 *__restrict__ W, const GridParams *__restrict__ gpp) {
+                                                            const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
+                                                            int rank, int world) {
     extern __shared__ __align__(128) float2 col_sm[];
     __shared__ ColPlan plan_s;
     if (!gpp->ok) return;
+    // sharded: only the columns whose convolution this rank performs (blocks are even-sized: a tile never straddles two ranks)
+    if (world > 1 && part_owner(2 * blockIdx.x, part_block(plan.n / 2 + 1, world, 2), world) != rank) return;
     for (int i = threadIdx.x; i < (int) (sizeof(ColPlan) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&plan_s)[i] = reinterpret_cast<const int *>(&plan)[i];
     const int M = plan.n, G = gpp->G, H = M / 2 + 1;
@@ -402,28 +436,36 @@ __global__ void __launch_bounds__(COL_THREADS) k_kspec_cols(const float4 *__rest
 __global__ void __launch_bounds__(COL_THREADS) k_conv_cols(const __grid_constant__ CUtensorMap tmS, const float4 *__restrict__ KS,
                                                            ColPlan plan, const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
                                                            int df_is_one, double *__restrict__ zpartial, int N, Scalars *__restrict__ sc,
-                                                           unsigned int *__restrict__ ticket) {
+                                                           unsigned int *__restrict__ ticket, PeerComm pc, int p2p) {
     extern __shared__ __align__(128) float2 col_sm[];
     __shared__ ColPlan plan_s;
     __shared__ __align__(8) uint64_t mbar;
     __shared__ double red[32];
     if (!gpp->ok) return;
     const int M = plan.n, G = gpp->G, kx = blockIdx.x;
+    // sharded: my block of columns only (the other ranks' CTAs leave; their partial-sum slots must read as zero), and not
+    // before every rank's rows have landed in my S
+    const bool dist = p2p == 2;
+    const bool mine = !dist || part_owner(kx, part_block(M / 2 + 1, pc.world, 2), pc.world) == pc.rank;
     const int nbox = (G + COL_BOX_ROWS - 1) / COL_BOX_ROWS;
     float2 *x = col_sm;
     if (threadIdx.x == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
     for (int i = threadIdx.x; i < (int) (sizeof(ColPlan) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&plan_s)[i] = reinterpret_cast<const int *>(&plan)[i];
     __syncthreads();
+    double zacc = 0;
+    if (mine) {
     if (threadIdx.x == 0) {
+        if (dist) {
+            peer_wait(pc.flags[pc.rank], FLAG_S1, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
+            asm volatile("fence.proxy.async;" ::: "memory");      // the peers' (generic-proxy) stores, then my TMA (async-proxy) reads
+        }
         mbar_expect_tx(&mbar, (uint32_t) nbox * COL_BOX_ROWS * COL_SLOTS * (uint32_t) sizeof(float2));
         for (int i = 0; i < nbox; i++) tma_load_2d(x + (size_t) i * COL_BOX_ROWS * COL_SLOTS, &tmS, kx * 2 * COL_SLOTS, i * COL_BOX_ROWS, &mbar);
     }
     mbar_wait(&mbar, 0);
     col_fft_forward(x, plan_s, G, W);
-    const double wt = (kx == 0 || 2 * kx == M) ? 1.0 : 2.0;
     const double bw2 = gpp->bw * gpp->bw;
-    double zacc = 0;
     const float4 *ks = KS + (size_t) kx * M;
     for (int pos = threadIdx.x; pos < M; pos += blockDim.x) {
         float4 *s = reinterpret_cast<float4 *>(x + pos * COL_SLOTS);
@@ -445,22 +487,38 @@ __global__ void __launch_bounds__(COL_THREADS) k_conv_cols(const __grid_constant
     }
     __syncthreads();
     col_fft_inverse_conj(x, plan_s, W, 3);             // v1, Bx, By: the fourth slot is not transformed (nobody reads it)
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < nbox; i++) tma_store_2d(&tmS, kx * 2 * COL_SLOTS, i * COL_BOX_ROWS, x + (size_t) i * COL_BOX_ROWS * COL_SLOTS);
-        tma_store_commit_and_wait();
+    if (!dist) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < nbox; i++) tma_store_2d(&tmS, kx * 2 * COL_SLOTS, i * COL_BOX_ROWS, x + (size_t) i * COL_BOX_ROWS * COL_SLOTS);
+            tma_store_commit_and_wait();
+        }
+    } else {
+        // sharded: row r of the convolved column belongs to the rank that owns row r -- 32-byte stores on peer memory
+        const int H = M / 2 + 1, rblock = part_block(G, pc.world, 1);
+        for (int r = threadIdx.x; r < G; r += blockDim.x) {
+            const float4 *sv = reinterpret_cast<const float4 *>(x + r * COL_SLOTS);
+            float4 *d = reinterpret_cast<float4 *>(pc.S[part_owner(r, rblock, pc.world)] + ((size_t) r * H + kx) * COL_SLOTS);
+            d[0] = sv[0]; d[1] = sv[1];
+        }
     }
-    const double rsum = block_sum(zacc * wt, red);
+    }   // mine
+    const double rsum = block_sum(zacc * ((kx == 0 || 2 * kx == M) ? 1.0 : 2.0), red);
     if (threadIdx.x == 0) zpartial[kx] = rsum;
     if (last_block_done(ticket)) {           // sum_Q = (sum of the partials, in index order) - N   (tsne.cpp:1110)
         double s2 = 0;
         for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) s2 += ld_partial(zpartial + i);
         const double tot = block_sum(s2, red);
         if (threadIdx.x == 0) {
-            const double Z = tot - (double) N;
-            sc->Z = Z;
-            sc->inv_Z = (float) (1.0 / Z);
+            if (!dist) {
+                const double Z = tot - (double) N;
+                sc->Z = Z;
+                sc->inv_Z = (float) (1.0 / Z);
+            } else {
+                // my columns' share goes to slot [rank] of every rank's table; k_conv_rows_inv adds the slots in rank order
+                for (int q = 0; q < pc.world; q++) *reinterpret_cast<volatile double *>(pc.zs[q] + pc.rank) = tot;
+            }
         }
     }
 }

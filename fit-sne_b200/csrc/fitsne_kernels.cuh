@@ -82,16 +82,33 @@ struct Scalars {          // small device-resident results
 // for that exchange is in place (system-scope fence in between); consumers spin on their own flags.  A rank can never be
 // more than one exchange ahead of its peers (each exchange needs everybody's signal), which is what makes single
 // buffers safe: see DESIGN.md section 7 for the three hazard arguments.
+//   convolution      (2-D) distributed like a 2-D FFT: rows of the grid and columns of the spectrum are dealt out to the
+//                    ranks in contiguous blocks; k_conv_rows_fwd writes each x-spectrum bin into the S of the rank that
+//                    owns its column, k_conv_cols writes each convolved bin into the S of the rank that owns its row,
+//                    k_conv_rows_inv writes its rows of the potential grid into everybody's pot; sum_Q partials travel
+//                    the same way.  The "transposes" are the kernels' own stores on peer memory.
 constexpr int MAX_RANKS = 8;
-constexpr int FLAG_Y = 0, FLAG_GRID = 1, FLAG_STATS = 2;
+constexpr int FLAG_Y = 0, FLAG_GRID = 1, FLAG_STATS = 2, FLAG_S1 = 3, FLAG_S2 = 4, FLAG_POT = 5, FLAG_KINDS = 6;
 struct PeerComm {
     float *Y[MAX_RANKS];             // every rank's Y (full N x D floats); [rank] = my own
     void *grid[MAX_RANKS];           // every rank's partial spread grid: chg (2-D, float4 per node) or planes (1-D)
     void *stats[MAX_RANKS];          // every rank's ShardStats[world] table
-    uint32_t *flags[MAX_RANKS];      // every rank's flag words [3 * world]
+    uint32_t *flags[MAX_RANKS];      // every rank's flag words [FLAG_KINDS * world]
+    float2 *S[MAX_RANKS];            // 2-D: every rank's S (x-spectra / convolved half-spectra)
+    float4 *pot[MAX_RANKS];          // 2-D: every rank's potential grid
+    double *zs[MAX_RANKS];           // 2-D: every rank's table of per-rank sum_Q partials [world]
     unsigned int *seq;               // my sequence counter (bumped once per enqueued iteration by k_setup_grid)
     int rank, world;
 };
+// contiguous block partition of n items over the ranks (block size rounded up to a multiple of `align`)
+__host__ __device__ __forceinline__ int part_block(int n, int world, int align) {
+    const int b = (n + world - 1) / world;
+    return (b + align - 1) / align * align;
+}
+__host__ __device__ __forceinline__ int part_owner(int i, int block, int world) {
+    const int q = i / block;
+    return q < world ? q : world - 1;
+}
 
 __device__ __forceinline__ void peer_wait(const uint32_t *flags, int kind, const PeerComm &pc, uint32_t seq) {
     // one thread: until every peer's flag of this kind has reached the iteration's sequence number
