@@ -139,11 +139,6 @@ struct fitsne_ctx {
     TileGeom tg{};
     size_t ntiles = 0;
     bool reordered = false, use_tiles = false;
-    // column-sorted edge layout for k_attract_sorted (opt-in, FITSNE_FLAG_SORTED_SPMV)
-    SortedGeom sg{};
-    uint32_t *srt_cnt = nullptr, *srt_start = nullptr, *srt_cur = nullptr;
-    size_t srt_tiles = 0;
-    bool use_sorted = false;
     uint64_t steps_total = 0;         // optimiser steps since creation (fitsne_reset_stats does not touch it: re-order scheduling)
     uint64_t last_reorder_iter = 0, reorder_interval = 50, reorders = 0;
     uint32_t nonempty_tiles = 0;
@@ -380,31 +375,19 @@ template <int D>
 static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
     const int rows = c->row_end - c->row_begin;
     const float inv_df = (float) (1.0 / c->cfg.df);
-    if (c->use_sorted) {
-        k_attract_sorted<D><<<c->sg.nchunks, SRT_THREADS, sizeof(SrtSmem<D>), st>>>(c->Y, c->N, c->sg, c->srt_start, c->tile_pack, c->tile_val,
-                                                                                    inv_df, c->tile_fix32, c->attr);
-        LAUNCH_CHECK();
-        c->stats.kernel_launches += 1;
-        return 0;
-    }
     if (c->use_tiles) {
-        // accumulation: 32-bit fixed point scaled by the largest row sum of P (|attr_i| <= rowsum_i / 2) -- native
-        // shared-memory integer atomics, order-independent => bitwise repeatable.  FITSNE_TILE_ACC overrides (experiments).
-        static const int acc_mode = getenv("FITSNE_TILE_ACC") ? atoi(getenv("FITSNE_TILE_ACC")) : 2;
-        const float fix32 = c->tile_fix32;
-#define TILES(A) k_attract_tiles<D, A><<<c->tg.nchunks, 1024, tiles_smem_bytes(D), st>>>(c->Y, c->N, c->tg, c->tile_start, c->tile_pack, \
-                                                                           c->tile_val, inv_df, fix32, c->attr)
-        if (acc_mode == 1) TILES(1); else if (acc_mode == 2) TILES(2); else if (acc_mode == 3) TILES(3); else TILES(0);
-#undef TILES
+        // accumulation: 32-bit fixed point scaled by the largest row sum of P -- native shared-memory integer atomics,
+        // order-independent => bitwise repeatable
+        k_attract_tiles<D><<<c->tg.nchunks, 1024, tiles_smem_bytes(D), st>>>(c->Y, c->N, c->tg, c->tile_start, c->tile_pack, c->tile_val,
+                                                                              inv_df, c->tile_fix32, c->attr);
         LAUNCH_CHECK();
         c->stats.kernel_launches += 1;
         return 0;
     }
     // persistent grid: `per_sm` CTAs of 256 threads per SM (never more than the row groups there are)
-    static const int per_sm = getenv("FITSNE_SPMV_CTAS_PER_SM") ? atoi(getenv("FITSNE_SPMV_CTAS_PER_SM")) : 8;
+    constexpr int per_sm = 8;          // B200 sweep (2..100000 CTAs per SM): a flat optimum from 6 up
     static const int lpr_env = getenv("FITSNE_LPR") ? atoi(getenv("FITSNE_LPR")) : 0;
-    static const int dummy_smem = getenv("FITSNE_SPMV_SMEM_KB") ? atoi(getenv("FITSNE_SPMV_SMEM_KB")) * 1024 : 0;
-#define ATT(L) k_attract<D, L><<<std::min(cdiv((long long) rows * L, 256), 148 * per_sm), 256, dummy_smem, st>>>( \
+#define ATT(L) k_attract<D, L><<<std::min(cdiv((long long) rows * L, 256), 148 * per_sm), 256, 0, st>>>( \
         c->row_P, c->edges, c->edge_base, c->Y, c->row_begin, c->row_end, inv_df, c->attr)
     switch (lpr_env ? lpr_env : c->lpr) {
         case 4: ATT(4); break;
@@ -454,7 +437,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         if (cs != st) CK(cudaEventRecord(c->ev_cjoin, cs));
         c->stats.kernel_launches += 1;
     }
-    static const int col_threads = getenv("FITSNE_COL_THREADS") ? std::min(COL_THREADS, std::max(64, atoi(getenv("FITSNE_COL_THREADS")))) : 256;
+    constexpr int col_threads = COL_THREADS;
     auto launch_kernel_side = [&](cudaStream_t ks) -> int {
         const int Gc = M / 2, H = M / 2 + 1;
         k_kspec_rows<<<Gc, ROW_THREADS, pl->smem_row1, ks>>>(c->KR, pl->plan, pl->W, c->gp, c->cfg.df);
@@ -677,9 +660,8 @@ static int reorder_points(fitsne_ctx *c) {
             // |q dx| / p <= sqrt(df) / 2 for the kernel (1 + d^2/df)^-1, so a row sum stays below rowsum * max(1, sqrt(df)) / 2
             c->tile_fix32 = (float) (1073741824.0 / (std::max(mx, 1e-300) * std::max(1.0, std::sqrt(c->cfg.df))));
         }
-#define SETSM(DD, A) CK(cudaFuncSetAttribute(k_attract_tiles<DD, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tiles_smem_bytes(DD)))
-        if (D == 2) { SETSM(2, 0); SETSM(2, 1); SETSM(2, 2); SETSM(2, 3); } else { SETSM(1, 0); SETSM(1, 1); SETSM(1, 2); SETSM(1, 3); }
-#undef SETSM
+        if (D == 2) CK(cudaFuncSetAttribute(k_attract_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tiles_smem_bytes(2)));
+        else CK(cudaFuncSetAttribute(k_attract_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tiles_smem_bytes(1)));
     }
     CKRC(refresh_bounds(c));     // sc->bmin / bmax of the current Y
     // 1. locality keys, stable 2 x 11-bit LSD sort (same kernels as the per-iteration box sort)
@@ -735,32 +717,6 @@ static int reorder_points(fitsne_ctx *c) {
     if (c->cfg.flags & FITSNE_FLAG_NO_TILES) c->use_tiles = false;
     TRACE("reorder #%llu: %u of %zu tiles non-empty, est tiles %.0f us vs csr %.0f us -> %s", (unsigned long long) c->reorders,
           c->nonempty_tiles, c->ntiles, est_tiles_us, est_csr_us, c->use_tiles ? "tiles" : "csr");
-    // 6. opt-in: edges of every row chunk regrouped by column block for k_attract_sorted (edge word = 12-bit row | 20-bit column)
-    c->use_sorted = false;
-    if ((c->cfg.flags & FITSNE_FLAG_SORTED_SPMV) && N <= (1 << SRT_COL_BITS)) {
-        static const int shift_env = getenv("FITSNE_SRT_COL_SHIFT") ? atoi(getenv("FITSNE_SRT_COL_SHIFT")) : 6;
-        c->sg.col_shift = std::min(12, std::max(3, shift_env));
-        c->sg.nchunks = cdiv(N, SRT_ROWS);
-        c->sg.ncb = cdiv(N, 1 << c->sg.col_shift);
-        const size_t nt = (size_t) c->sg.nchunks * c->sg.ncb;
-        if (nt != c->srt_tiles) {
-            CKRC(dev_alloc(c, &c->srt_cnt, nt + 1)); CKRC(dev_alloc(c, &c->srt_start, nt + 1)); CKRC(dev_alloc(c, &c->srt_cur, nt + 1));
-            c->srt_tiles = nt;
-            if (D == 2) CK(cudaFuncSetAttribute(k_attract_sorted<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SrtSmem<2>)));
-            else CK(cudaFuncSetAttribute(k_attract_sorted<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SrtSmem<1>)));
-        }
-        CK(cudaMemsetAsync(c->srt_cnt, 0, (nt + 1) * 4, st));
-        CK(cudaMemsetAsync(c->srt_cur, 0, (nt + 1) * 4, st));
-        k_sorted_count<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(c->row_P, c->edges, N, c->sg, c->srt_cnt);
-        k_scan_excl<<<1, 1024, 0, st>>>(c->srt_cnt, c->srt_start, (int) nt);
-        k_sorted_fill<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(c->row_P, c->edges, N, c->sg, c->srt_start, c->srt_cur,
-                                                                    c->tile_pack, c->tile_val);
-        LAUNCH_CHECK();
-        CK(cudaStreamSynchronize(st));
-        c->use_sorted = true;
-        c->use_tiles = false;
-        c->kernel_launches_reorder += 3;
-    }
     drop_graphs(c);              // CSR pointers and the attractive kernel changed
     c->kernel_launches_reorder += 20;
     return 0;
@@ -1106,10 +1062,6 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     c->ktimes_on = getenv("FITSNE_KTIMES") && atoi(getenv("FITSNE_KTIMES")) != 0;
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
-    CK(cudaFuncSetAttribute(k_attract<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(k_attract<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(k_attract<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(k_attract<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_radix_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute((k_spread_chunks<2, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) spread_smem_bytes<2, 4>()));
@@ -1249,7 +1201,7 @@ int fitsne_destroy(fitsne_ctx *c) {
                     c->chg, c->pot, c->S, c->KR, c->KS, c->colsum_partial, c->zpartial, c->kl_partial, c->bounds_partial,
                     c->gp, c->sp, c->sc, c->mismatch, c->tickets, c->host_B_dev, c->staging, c->orig_of, c->orig_tmp, c->pos_of, c->rank_map,
                     c->row_P2, c->edges2, c->tile_cnt, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val,
-                    c->nonempty, c->gp_reorder, c->peer_flags, c->peer_zs, c->comm_seq, c->grid1d, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial, c->srt_cnt, c->srt_start, c->srt_cur};
+                    c->nonempty, c->gp_reorder, c->peer_flags, c->peer_zs, c->comm_seq, c->grid1d, c->shard_stats, c->shard_sum_partial, c->shard_mm_partial};
     for (void *b : bufs) if (b) cudaFree(b);
     if (c->host_bounds) cudaFreeHost(c->host_bounds);
     if (c->host_sc) cudaFreeHost(c->host_sc);
@@ -1417,9 +1369,8 @@ int fitsne_run(fitsne_ctx *c, const fitsne_schedule *s, double *costs, double *Y
     auto t0 = std::chrono::steady_clock::now();
     // Sharded runs batch too, but with plain launches instead of graphs (run_batch); FITSNE_SHARDED_SYNC=1 restores one
     // host round trip per iteration there (diagnostics).
-    static const bool sharded_sync = getenv("FITSNE_SHARDED_SYNC") && atoi(getenv("FITSNE_SHARDED_SYNC")) != 0;
     const bool batched = c->world == 1 ? !(c->cfg.flags & (FITSNE_FLAG_NO_GRAPH | FITSNE_FLAG_TIMERS | FITSNE_FLAG_NO_SPECULATION))
-                                       : !(c->cfg.flags & (FITSNE_FLAG_TIMERS | FITSNE_FLAG_NO_SPECULATION)) && !sharded_sync;
+                                       : !(c->cfg.flags & (FITSNE_FLAG_TIMERS | FITSNE_FLAG_NO_SPECULATION));
     int iter = 0;
     while (iter < s->max_iter) {
         int mode = FITSNE_STEP_MOMENTUM_CLIP;

@@ -1592,8 +1592,6 @@ __global__ void __launch_bounds__(256) k_center_shard(const float *__restrict__ 
 // associative, so the result does not depend on the order edges arrive in -- bitwise repeatable.
 constexpr int TILE_ROWS = 4096;    // max points per row chunk  (row-local index fits 16 bits)
 constexpr int TILE_COLS = 14336;   // points per column block    (112 KB of float2)
-constexpr float FIX_SCALE = 1152921504606846976.f;          // 2^60
-constexpr double FIX_INV = 1.0 / 1152921504606846976.0;
 
 struct TileGeom {
     int rows_per_chunk, nchunks, ncb;   // chunk c = rows [c*rows_per_chunk, ...), column block b = points [b*TILE_COLS, ...)
@@ -1758,8 +1756,8 @@ __global__ void __launch_bounds__(256) k_count_nonempty(const uint32_t *__restri
 }
 
 // One CTA per row chunk.  Shared memory: own positions [R] | fixed-point accumulators [R][D] | column block [TILE_COLS].
-// ACC: 0 = 64-bit fixed point, 1 = float atomics (experiment), 2 = 32-bit fixed point, 3 = no accumulation (experiment)
-template <int D, int ACC>
+// Accumulation: 32-bit fixed point scaled by fix32 = 2^30 / (max row sum of P * max(1, sqrt(df))) (|q dx| / p <= sqrt(df) / 2).
+template <int D>
 __global__ void __launch_bounds__(1024, 1) k_attract_tiles(const float *__restrict__ Y, int n, TileGeom tg,
                                                            const uint32_t *__restrict__ tile_start,
                                                            const uint32_t *__restrict__ tile_pack, const float *__restrict__ tile_val,
@@ -1801,24 +1799,12 @@ __global__ void __launch_bounds__(1024, 1) k_attract_tiles(const float *__restri
                     const float2 yi = reinterpret_cast<const float2 *>(yrow)[rl], yj = reinterpret_cast<const float2 *>(ycol)[cl];
                     const float dx = yi.x - yj.x, dy = yi.y - yj.y;
                     const float q = pv[u] / (1.f + (dx * dx + dy * dy) * inv_df);
-                    if (ACC == 0) {
-                        atomicAdd(reinterpret_cast<unsigned long long *>(&acc[2 * rl]), (unsigned long long) __float2ll_rn(q * dx * FIX_SCALE));
-                        atomicAdd(reinterpret_cast<unsigned long long *>(&acc[2 * rl + 1]), (unsigned long long) __float2ll_rn(q * dy * FIX_SCALE));
-                    } else if (ACC == 1) {
-                        atomicAdd(reinterpret_cast<float *>(&acc[2 * rl]), q * dx);
-                        atomicAdd(reinterpret_cast<float *>(&acc[2 * rl + 1]), q * dy);
-                    } else if (ACC == 2) {
-                        atomicAdd(reinterpret_cast<int *>(&acc[2 * rl]), __float2int_rn(q * dx * fix32));
-                        atomicAdd(reinterpret_cast<int *>(&acc[2 * rl + 1]), __float2int_rn(q * dy * fix32));
-                    } else {
-                        if (q * dx == 123.456f) acc[0] = 1;
-                    }
+                    atomicAdd(reinterpret_cast<int *>(&acc[2 * rl]), __float2int_rn(q * dx * fix32));
+                    atomicAdd(reinterpret_cast<int *>(&acc[2 * rl + 1]), __float2int_rn(q * dy * fix32));
                 } else {
                     const float dx = reinterpret_cast<const float *>(yrow)[rl] - reinterpret_cast<const float *>(ycol)[cl];
                     const float q = pv[u] / (1.f + dx * dx * inv_df);
-                    if (ACC == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&acc[rl]), (unsigned long long) __float2ll_rn(q * dx * FIX_SCALE));
-                    else if (ACC == 1) atomicAdd(reinterpret_cast<float *>(&acc[rl]), q * dx);
-                    else if (ACC == 2) atomicAdd(reinterpret_cast<int *>(&acc[rl]), __float2int_rn(q * dx * fix32));
+                    atomicAdd(reinterpret_cast<int *>(&acc[rl]), __float2int_rn(q * dx * fix32));
                 }
             }
         }
@@ -1826,148 +1812,11 @@ __global__ void __launch_bounds__(1024, 1) k_attract_tiles(const float *__restri
     __syncthreads();
     for (int i = threadIdx.x; i < rn; i += blockDim.x) {
         float a0, a1 = 0.f;
-        if (ACC == 0) { a0 = (float) ((double) acc[(D == 2 ? 2 : 1) * i] * FIX_INV); if (D == 2) a1 = (float) ((double) acc[2 * i + 1] * FIX_INV); }
-        else if (ACC == 2) { a0 = (float) ((double) *reinterpret_cast<int *>(&acc[(D == 2 ? 2 : 1) * i]) / (double) fix32); if (D == 2) a1 = (float) ((double) *reinterpret_cast<int *>(&acc[2 * i + 1]) / (double) fix32); }
-        else { a0 = *reinterpret_cast<float *>(&acc[(D == 2 ? 2 : 1) * i]); if (D == 2) a1 = *reinterpret_cast<float *>(&acc[2 * i + 1]); }
+        a0 = (float) ((double) *reinterpret_cast<int *>(&acc[(D == 2 ? 2 : 1) * i]) / (double) fix32);
+        if (D == 2) a1 = (float) ((double) *reinterpret_cast<int *>(&acc[2 * i + 1]) / (double) fix32);
         if (D == 2) reinterpret_cast<float2 *>(attr)[r0 + i] = make_float2(a0, a1);
         else attr[r0 + i] = a0;
     }
-}
-
-// ------------------------------------------------- attractive term over column-sorted edges (opt-in, experimental) --
-// k_attract is bound by the L1 tag stage: every one of the E random 8-byte neighbour gathers is its own 128-byte-line
-// lookup (ncu: L1/TEX 80 %, one wavefront per lane), the DRAM traffic is only the algorithmic 8 B/edge.  This layout
-// attacks the lookup count instead of the bytes: after a Morton re-ordering the edges of a row chunk (SRT_ROWS
-// consecutive points) are regrouped by COLUMN block (2^col_shift consecutive points, default 64 = four lines), so the
-// 32 edges a warp handles together touch a handful of lines instead of 32.  The price is that edges of one row are no
-// longer adjacent: row sums are accumulated with shared-memory integer atomics in 32-bit fixed point (the same scale
-// as k_attract_tiles; integer addition is associative, so the result is independent of the arrival order and bitwise
-// repeatable).  One CTA per row chunk; shared memory holds the chunk's own positions and accumulators only.
-// Edge word: (row within chunk) << 20 | column, hence N <= 2^20 and SRT_ROWS = 4096.  Built by k_sorted_count /
-// k_scan_excl / k_sorted_fill at re-ordering time.  Phase functions are host-callable for tests/tools/spmv_emul.cu.
-constexpr int SRT_ROWS = 4096;
-constexpr int SRT_COL_BITS = 20;
-constexpr int SRT_THREADS = 512;
-
-struct SortedGeom {
-    int nchunks, ncb, col_shift;     // chunk c = rows [c*SRT_ROWS, ...); column block b = points [b << col_shift, ...)
-};
-
-
-// one lane (sub of 8) of one CSR row: count / place the row's edges into (row chunk, column block) groups
-__host__ __device__ __forceinline__ void sorted_count_lane(int row, int sub, const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges,
-                                                           SortedGeom g, uint32_t *__restrict__ cnt) {
-    const uint32_t rc = (uint32_t) row / SRT_ROWS;
-    for (uint32_t e = row_P[row] + sub; e < row_P[row + 1]; e += 8)
-        FK_ATOMIC_ADD(&cnt[(size_t) rc * g.ncb + (edges[e].x >> g.col_shift)], 1u);
-}
-__host__ __device__ __forceinline__ void sorted_fill_lane(int row, int sub, const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges,
-                                                          SortedGeom g, const uint32_t *__restrict__ start,
-                                                          uint32_t *__restrict__ cur, uint32_t *__restrict__ pack, float *__restrict__ val_out) {
-    const uint32_t rc = (uint32_t) row / SRT_ROWS, rl = (uint32_t) row - rc * SRT_ROWS;
-    for (uint32_t e = row_P[row] + sub; e < row_P[row + 1]; e += 8) {
-        const uint2 ed = edges[e];
-        const uint32_t c = ed.x;
-        const size_t t = (size_t) rc * g.ncb + (c >> g.col_shift);
-        const uint32_t pos = start[t] + FK_ATOMIC_ADD(&cur[t], 1u);
-        pack[pos] = (rl << SRT_COL_BITS) | c;
-#ifdef __CUDA_ARCH__
-        val_out[pos] = __uint_as_float(ed.y);
-#else
-        { float f; memcpy(&f, &ed.y, 4); val_out[pos] = f; }
-#endif
-    }
-}
-__global__ void __launch_bounds__(256) k_sorted_count(const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges, int n,
-                                                      SortedGeom g, uint32_t *__restrict__ cnt) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((gid >> 3) < n) sorted_count_lane(gid >> 3, gid & 7, row_P, edges, g, cnt);
-}
-__global__ void __launch_bounds__(256) k_sorted_fill(const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges,
-                                                     int n, SortedGeom g, const uint32_t *__restrict__ start,
-                                                     uint32_t *__restrict__ cur, uint32_t *__restrict__ pack, float *__restrict__ val_out) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((gid >> 3) < n) sorted_fill_lane(gid >> 3, gid & 7, row_P, edges, g, start, cur, pack, val_out);
-}
-
-// shared memory of one CTA: positions of the chunk's rows, then their D fixed-point accumulators
-template <int D>
-struct alignas(16) SrtSmem {
-    float y[SRT_ROWS * D];
-    int acc[SRT_ROWS * D];
-};
-// phase 1 (thread tid of nthreads): stage the chunk's positions, clear the accumulators
-template <int D>
-__host__ __device__ __forceinline__ void attract_sorted_load(int tid, int nthreads, int rc, const float *__restrict__ Y, int n, SrtSmem<D> &sm) {
-    const int r0 = rc * SRT_ROWS, rn = (n - r0) < SRT_ROWS ? (n - r0) : SRT_ROWS;
-    for (int i = tid; i < rn * D; i += nthreads) { sm.y[i] = Y[(size_t) r0 * D + i]; sm.acc[i] = 0; }
-}
-// phase 2: this thread's share of the chunk's edge stream (4 independent edges per trip)
-template <int D>
-__host__ __device__ __forceinline__ void attract_sorted_edges(int tid, int nthreads, int rc, const float *__restrict__ Y, SortedGeom g,
-                                                              const uint32_t *__restrict__ start, const uint32_t *__restrict__ pack,
-                                                              const float *__restrict__ val, float inv_df, float fix32, SrtSmem<D> &sm) {
-    const uint32_t e0 = start[(size_t) rc * g.ncb], e1 = start[(size_t) (rc + 1) * g.ncb];
-    for (uint32_t eb = e0 + tid; eb < e1; eb += 4u * nthreads) {
-        uint32_t pk[4];
-        float pv[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t e = eb + (uint32_t) u * nthreads;
-            pk[u] = e < e1 ? pack[e] : 0u;
-            pv[u] = e < e1 ? val[e] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (eb + (uint32_t) u * nthreads >= e1) break;
-            const uint32_t rl = pk[u] >> SRT_COL_BITS, c = pk[u] & ((1u << SRT_COL_BITS) - 1u);
-            if (D == 2) {
-                const float2 yj = reinterpret_cast<const float2 *>(Y)[c];
-                const float2 yi = reinterpret_cast<const float2 *>(sm.y)[rl];
-                const float dx = yi.x - yj.x, dy = yi.y - yj.y;
-#ifdef __CUDA_ARCH__
-                const float q = __fdividef(pv[u], 1.f + (dx * dx + dy * dy) * inv_df);      // as k_attract
-                atomicAdd(&sm.acc[2 * rl], __float2int_rn(q * dx * fix32));
-                atomicAdd(&sm.acc[2 * rl + 1], __float2int_rn(q * dy * fix32));
-#else
-                const float q = pv[u] / (1.f + (dx * dx + dy * dy) * inv_df);
-                sm.acc[2 * rl] += (int) lrintf(q * dx * fix32);
-                sm.acc[2 * rl + 1] += (int) lrintf(q * dy * fix32);
-#endif
-            } else {
-                const float dx = sm.y[rl] - Y[c];
-#ifdef __CUDA_ARCH__
-                const float q = __fdividef(pv[u], 1.f + dx * dx * inv_df);
-                atomicAdd(&sm.acc[rl], __float2int_rn(q * dx * fix32));
-#else
-                const float q = pv[u] / (1.f + dx * dx * inv_df);
-                sm.acc[rl] += (int) lrintf(q * dx * fix32);
-#endif
-            }
-        }
-    }
-}
-// phase 3: fixed point -> float
-template <int D>
-__host__ __device__ __forceinline__ void attract_sorted_store(int tid, int nthreads, int rc, int n, float fix32, const SrtSmem<D> &sm,
-                                                               float *__restrict__ attr) {
-    const int r0 = rc * SRT_ROWS, rn = (n - r0) < SRT_ROWS ? (n - r0) : SRT_ROWS;
-    for (int i = tid; i < rn * D; i += nthreads) attr[(size_t) r0 * D + i] = (float) ((double) sm.acc[i] / (double) fix32);
-}
-
-template <int D>
-__global__ void __launch_bounds__(SRT_THREADS) k_attract_sorted(const float *__restrict__ Y, int n, SortedGeom g,
-                                                                const uint32_t *__restrict__ start, const uint32_t *__restrict__ pack,
-                                                                const float *__restrict__ val, float inv_df, float fix32,
-                                                                float *__restrict__ attr) {
-    extern __shared__ __align__(16) unsigned char srt_raw[];
-    SrtSmem<D> &sm = *reinterpret_cast<SrtSmem<D> *>(srt_raw);
-    const int rc = blockIdx.x;
-    attract_sorted_load<D>(threadIdx.x, blockDim.x, rc, Y, n, sm);
-    __syncthreads();
-    attract_sorted_edges<D>(threadIdx.x, blockDim.x, rc, Y, g, start, pack, val, inv_df, fix32, sm);
-    __syncthreads();
-    attract_sorted_store<D>(threadIdx.x, blockDim.x, rc, n, fix32, sm, attr);
 }
 
 // ------------------------------------------------------------------------------------------------ KL --

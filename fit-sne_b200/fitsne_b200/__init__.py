@@ -14,7 +14,6 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfitsne_b200.so")
 
 STEP_MOMENTUM_CLIP, STEP_MOMENTUM, STEP_PLAIN_GD = 0, 1, 2
 FLAG_NO_GRAPH, FLAG_TIMERS, FLAG_NO_REORDER, FLAG_FORCE_TILES, FLAG_NO_TILES, FLAG_NO_SPECULATION = 1, 2, 4, 8, 16, 32
-FLAG_SORTED_SPMV = 2048
 PHASES = ["bounds", "sort", "spread", "kernel_spectrum", "fft", "gather", "attract_update", "center", "kl",
           "collectives", "allgather"]
 

@@ -50,7 +50,6 @@ typedef struct fitsne_config {
 #define FITSNE_FLAG_FORCE_TILES 8 /* always use the tiled attractive kernel after a re-ordering            */
 #define FITSNE_FLAG_NO_TILES 16   /* re-order for locality but keep the CSR attractive kernel              */
 #define FITSNE_FLAG_NO_SPECULATION 32 /* fitsne_run: one host round trip per iteration instead of batches  */
-#define FITSNE_FLAG_SORTED_SPMV 2048 /* attractive term over column-sorted edges + shared-memory integer accumulators (after a re-ordering, N <= 2^20) */
 
 /* One optimiser step's parameters: the state TSNE::run carries across iterations (tsne.cpp:437-544). */
 typedef struct fitsne_step_params {
