@@ -22,6 +22,7 @@ EXPORTS = [
     "fitsne_set_Y", "fitsne_get_Y", "fitsne_set_optimizer_state", "fitsne_get_optimizer_state", "fitsne_gradient",
     "fitsne_step", "fitsne_kl", "fitsne_run", "fitsne_run_host", "fitsne_synchronize", "fitsne_get_stats",
     "fitsne_reset_stats", "fitsne_last_run_ms", "fitsne_debug_copy", "fitsne_version", "fitsne_prewarm",
+    "fitsne_knn", "fitsne_similarities", "fitsne_free", "fitsne_prep_last_error",
 ]
 
 
@@ -275,8 +276,65 @@ def _load_hostlib():
     return _hostlib
 
 
+def knn(X, K, device=-1):
+    """Exact Euclidean kNN on the device (fitsne_knn): (nbr u32[N,K], dist f64[N,K]), ascending, self excluded."""
+    lib = load_library()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    N, D = X.shape
+    nbr = np.empty((N, K), np.uint32)
+    dist = np.empty((N, K), np.float64)
+    rc = lib.fitsne_knn(_dp(X), N, D, int(K), int(device), _dp(nbr), _dp(dist))
+    if rc != 0:
+        lib.fitsne_prep_last_error.restype = ctypes.c_char_p
+        raise FitsneError(rc, lib.fitsne_prep_last_error().decode())
+    return nbr, dist
+
+
+def similarities(nbr, dist, perplexity=30.0, sigma=-1.0, perplexity_list=None, device=-1):
+    """Perplexity search + symmetrisation on the device (fitsne_similarities): CSR (row u32, col u32, val f64)."""
+    lib = load_library()
+    nbr = np.ascontiguousarray(nbr, dtype=np.uint32)
+    dist = np.ascontiguousarray(dist, dtype=np.float64)
+    N, K = nbr.shape
+    if perplexity_list is not None:
+        perplexity = 0.0
+    pl = np.ascontiguousarray(perplexity_list if perplexity_list is not None else [0.0], np.float64)
+    row, col, val = ctypes.POINTER(ctypes.c_uint)(), ctypes.POINTER(ctypes.c_uint)(), ctypes.POINTER(ctypes.c_double)()
+    rc = lib.fitsne_similarities(_dp(nbr), _dp(dist), N, K, ctypes.c_double(perplexity), ctypes.c_double(sigma),
+                                 len(pl) if perplexity_list is not None else 0, _dp(pl), int(device),
+                                 ctypes.byref(row), ctypes.byref(col), ctypes.byref(val))
+    if rc != 0:
+        lib.fitsne_prep_last_error.restype = ctypes.c_char_p
+        raise FitsneError(rc, lib.fitsne_prep_last_error().decode())
+    r = np.ctypeslib.as_array(row, shape=(N + 1,)).copy()
+    c = np.ctypeslib.as_array(col, shape=(int(r[-1]),)).copy()
+    v = np.ctypeslib.as_array(val, shape=(int(r[-1]),)).copy()
+    lib.fitsne_free.argtypes = [ctypes.c_void_p]
+    for ptr in (row, col, val):
+        lib.fitsne_free(ctypes.cast(ptr, ctypes.c_void_p))
+    return r, c, v
+
+
+def input_similarities_device(X, perplexity=30.0, K=-1, sigma=-1.0, perplexity_list=None, device=-1):
+    """The reference's prologue (centre, max-abs normalise when a perplexity is used, K = 3 * perplexity; tsne.cpp:153-161,
+    :287-304) followed by the device kNN + similarities: the CSR TSNE::run builds before the loop."""
+    X = np.array(X, dtype=np.float64, order="C")
+    X -= X.mean(0)
+    if perplexity_list is not None:
+        perplexity = 0.0
+    if perplexity >= 0:
+        X /= np.abs(X).max()
+        K_use = int(3 * (perplexity if perplexity > 0 else max(perplexity_list)))
+        sigma_use = -1.0
+    else:
+        K_use, sigma_use = int(K), float(sigma)
+    nbr, dist = knn(X, K_use, device)
+    return similarities(nbr, dist, perplexity, sigma_use, perplexity_list, device)
+
+
 def input_similarities(X, perplexity=30.0, K=-1, sigma=-1.0, perplexity_list=None, nthreads=0):
-    """CSR P (row u32, col u32, val f64) exactly as TSNE::run builds it before the loop (tsne.cpp:153-161,282-330)."""
+    """CPU statement of the same (libfitsne_host.so, exact multi-threaded kNN): used by the protocol tests and as the
+    checker of the device path."""
     lib = _load_hostlib()
     X = np.array(X, dtype=np.float64, order="C")
     X -= X.mean(0)
@@ -340,7 +398,7 @@ def fast_tsne(X, theta=0.5, perplexity=30, map_dims=2, max_iter=750, stop_early_
     if load_affinities == "load":
         row = np.fromfile("P_row.dat", np.uint32); col = np.fromfile("P_col.dat", np.uint32); val = np.fromfile("P_val.dat", np.float64)
     else:
-        row, col, val = input_similarities(X, float(perplexity), K, sigma, perplexity_list, 0 if nthreads == -1 else nthreads)
+        row, col, val = input_similarities_device(X, float(perplexity), K, sigma, perplexity_list, device)
         if load_affinities == "save":
             row.tofile("P_row.dat"); col.tofile("P_col.dat"); val.tofile("P_val.dat")
     Y, costs = run_host(row, col, val, Y0, nterms=nterms, intervals_per_integer=intervals_per_integer,

@@ -313,8 +313,26 @@ int TSNE::run(double *X, int N, int D, double *Y, int no_dims, double perplexity
             sigma_to_use = -1;
         }
         if (knn_algo == 1) printf("Note: Annoy's approximate search is replaced by an exact kNN search in this build.\n");
-        const int rc = input_similarities(X, N, D, perplexity, K_to_use, sigma_to_use, perplexity_list_length, perplexity_list,
-                                          nthreads, &row_P, &col_P, &val_P);
+        // kNN, perplexity search and symmetrisation run on the device (fitsne_knn / fitsne_similarities: the same arithmetic
+        // as input_similarities() above, which stays as the CPU statement of it -- FITSNE_HOST_PREP=1 selects it)
+        int rc;
+        if (getenv("FITSNE_HOST_PREP") && atoi(getenv("FITSNE_HOST_PREP")) != 0) {
+            rc = input_similarities(X, N, D, perplexity, K_to_use, sigma_to_use, perplexity_list_length, perplexity_list, nthreads,
+                                    &row_P, &col_P, &val_P);
+        } else {
+            if (K_to_use >= N) { printf("K (%d) must be smaller than the number of points (%d)\n", K_to_use, N); return -1; }
+            if (perplexity > K_to_use) printf("Perplexity should be lower than K!\n");
+            printf("Exact kNN search (K=%d) on the device...\n", K_to_use);
+            std::vector<unsigned int> nbr((size_t) N * K_to_use);
+            std::vector<double> dist((size_t) N * K_to_use);
+            rc = fitsne_knn(X, N, D, K_to_use, -1, nbr.data(), dist.data());
+            if (rc == 0) {
+                printf("Perplexity search and symmetrisation on the device...\n");
+                rc = fitsne_similarities(nbr.data(), dist.data(), N, K_to_use, perplexity, sigma_to_use, perplexity_list_length,
+                                         perplexity_list, -1, &row_P, &col_P, &val_P);
+            }
+            if (rc != 0) { printf("Error: device preprocessing failed (%d): %s\n", rc, fitsne_prep_last_error()); return rc - 100; }
+        }
         if (rc < 0) return rc;
     }
     if (load_affinities == 2) {
@@ -350,7 +368,7 @@ int TSNE::run(double *X, int N, int D, double *Y, int no_dims, double perplexity
         printf("Error: the CUDA gradient loop failed (%d): %s\n", rc, fitsne_last_error(nullptr));
         return rc < 0 ? rc - 100 : -100;   // distinct from the reference's -1 / -2
     }
-    printf("Preprocessing %.2f s (host), gradient loop %.2f s (B200, incl. transfers)\n", preprocessing_seconds, loop_seconds);
+    printf("Preprocessing %.2f s, gradient loop %.2f s (B200, incl. transfers)\n", preprocessing_seconds, loop_seconds);
     return 0;
 }
 #endif  // FITSNE_HOST_ONLY

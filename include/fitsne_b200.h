@@ -161,6 +161,23 @@ int fitsne_run_host(const fitsne_config *cfg, const fitsne_schedule *s, int N, i
  * are no library plans to create); lengths are otherwise prepared on first use. */
 int fitsne_prewarm(fitsne_ctx *ctx, int n_boxes_lo, int n_boxes_hi);
 
+/* ---- the step before the loop, on the device (optional; the host shell and the Python mirror use it) -- */
+
+/* Exact Euclidean kNN of every row of X (row-major double[N*D], host) on the device: nbr[N*K] neighbour indices and
+ * dist[N*K] distances (ascending, ties by index, the point itself excluded), both host arrays.  Replaces the reference's
+ * Annoy / VP-tree searches (tsne.cpp:1535-1639, :1643-1726): the same neighbours as its exact VP-tree option. */
+int fitsne_knn(const double *X, int N, int D, int K, int device, unsigned int *nbr, double *dist);
+
+/* Conditional similarities by perplexity search (perplexity > 0), their average over a perplexity list (perplexity == 0)
+ * or a fixed bandwidth (perplexity < 0, sigma), then symmetrisation and normalisation to sum 1 -- computeGaussianPerplexity
+ * (tsne.cpp:1394-1500) + symmetrizeMatrix (:1730-1828) -- on the device.  Returns the CSR the loop consumes (columns
+ * ascending) in malloc'ed host arrays; release them with fitsne_free. */
+int fitsne_similarities(const unsigned int *nbr, const double *dist, int N, int K, double perplexity, double sigma,
+                        int perplexity_list_length, const double *perplexity_list, int device, unsigned int **row_P,
+                        unsigned int **col_P, double **val_P);
+void fitsne_free(void *p);
+const char *fitsne_prep_last_error(void);
+
 /* ---- introspection -------------------------------------------------------------------------------- */
 int fitsne_synchronize(fitsne_ctx *ctx);
 int fitsne_get_stats(fitsne_ctx *ctx, fitsne_stats *out);
