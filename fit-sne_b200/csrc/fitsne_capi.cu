@@ -192,6 +192,7 @@ struct fitsne_ctx {
     size_t kt_n = 0;
     std::map<std::string, std::pair<double, uint64_t>> kt_acc;
     std::string kt_text;
+    FILE *src_col = nullptr, *src_val = nullptr;     // fitsne_create_from_files: the edges are streamed from P_col.dat / P_val.dat
     std::string err;
 };
 
@@ -1090,20 +1091,39 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaMemcpyAsync(c->row_P, row_P, ((size_t) N + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     CKRC(dev_alloc(c, &c->edges, c->E + 1));
     if (c->E) {
-        if (!col_P || !val_P) return fail(c, FITSNE_EINVAL, "col_P/val_P are NULL but the graph has edges");
-        // (col u32, val f64) -> one 8-byte edge word (col, fp32 weight), in bounded chunks through two staging buffers
+        const bool from_files = c->src_col && c->src_val;
+        if (!from_files && (!col_P || !val_P)) return fail(c, FITSNE_EINVAL, "col_P/val_P are NULL but the graph has edges");
+        // (col u32, val f64) -> one 8-byte edge word (col, fp32 weight), in bounded chunks through two staging buffers.
+        // From files: the chunks are read into pinned memory and go straight to the device -- no host copy of the edges.
         const size_t chunk = 1u << 24;
         CKRC(dev_alloc(c, &c->staging, chunk)); c->staging_elems = chunk;
-        uint32_t *col_stage = nullptr;
+        uint32_t *col_stage = nullptr, *hcol = nullptr;
+        double *hval = nullptr;
         CKRC(dev_alloc(c, &col_stage, chunk));
-        for (size_t off = 0; off < c->E; off += chunk) {
+        if (from_files) {
+            CK(cudaHostAlloc((void **) &hcol, chunk * 4, cudaHostAllocDefault));
+            CK(cudaHostAlloc((void **) &hval, chunk * 8, cudaHostAllocDefault));
+            if (fseeko(c->src_col, (off_t) c->edge_base * 4, SEEK_SET) != 0 || fseeko(c->src_val, (off_t) c->edge_base * 8, SEEK_SET) != 0)
+                return fail(c, FITSNE_EINVAL, "cannot seek in the affinity files");
+        }
+        int rc_files = 0;
+        for (size_t off = 0; off < c->E && rc_files == 0; off += chunk) {
             const size_t n = std::min(chunk, c->E - off);
-            CK(cudaMemcpyAsync(col_stage, col_P + off, n * 4, cudaMemcpyHostToDevice, c->stream));
-            CK(cudaMemcpyAsync(c->staging, val_P + off, n * 8, cudaMemcpyHostToDevice, c->stream));
+            const uint32_t *cs = col_P ? col_P + off : nullptr;
+            const double *vs = val_P ? val_P + off : nullptr;
+            if (from_files) {
+                if (fread(hcol, 4, n, c->src_col) != n || fread(hval, 8, n, c->src_val) != n) { rc_files = 1; break; }
+                cs = hcol; vs = hval;
+            }
+            CK(cudaMemcpyAsync(col_stage, cs, n * 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->staging, vs, n * 8, cudaMemcpyHostToDevice, c->stream));
             k_pack_edges<<<cdiv(n, 256), 256, 0, c->stream>>>(col_stage, c->staging, c->edges + off, n);
             CK(cudaStreamSynchronize(c->stream));
         }
         cudaFree(col_stage);
+        if (hcol) cudaFreeHost(hcol);
+        if (hval) cudaFreeHost(hval);
+        if (rc_files) return fail(c, FITSNE_EINVAL, "affinity files are shorter than P_row.dat says (%zu edges)", c->E);
     }
     const double avg = (double) c->E / (double) std::max(1, c->nloc);
     c->lpr = avg > 96 ? 32 : avg > 40 ? 16 : avg > 6 ? 8 : 4;   // lanes per CSR row (B200 sweep at 30 nnz/row: 8 lanes best)
@@ -1232,6 +1252,40 @@ int fitsne_create_sharded(const fitsne_config *cfg, int N, int no_dims, const un
 int fitsne_create(const fitsne_config *cfg, int N, int no_dims, const unsigned int *row_P, const unsigned int *col_P,
                   const double *val_P, const double *Y0, fitsne_ctx **out) {
     return fitsne_create_sharded(cfg, N, no_dims, row_P, col_P, val_P, Y0, 0, 1, 0, N, nullptr, out);
+}
+
+// P as files: the reference's load_affinities side files (tsne.cpp:236-281, :334-366) as a first-class input
+static std::string affinity_path(const char *dir, const char *name) {
+    const char *d = dir && *dir ? dir : getenv("FITSNE_AFFINITIES_DIR");
+    return (d && *d ? std::string(d) + "/" : std::string()) + name;
+}
+int fitsne_create_from_files_sharded(const fitsne_config *cfg, const char *dir, int N, int no_dims, const double *Y0, int rank,
+                                     int world_size, const void *nccl_unique_id, fitsne_ctx **out) {
+    if (!out || N < 2 || world_size < 1) return FITSNE_EINVAL;
+    *out = nullptr;
+    FILE *fr = fopen(affinity_path(dir, "P_row.dat").c_str(), "rb");
+    FILE *fc = fopen(affinity_path(dir, "P_col.dat").c_str(), "rb");
+    FILE *fv = fopen(affinity_path(dir, "P_val.dat").c_str(), "rb");
+    std::vector<unsigned int> row((size_t) N + 1);
+    int rc = 0;
+    if (!fr || !fc || !fv) { g_create_error = "cannot open P_row.dat / P_col.dat / P_val.dat in " + affinity_path(dir, ""); rc = FITSNE_EINVAL; }
+    else if (fread(row.data(), sizeof(unsigned int), (size_t) N + 1, fr) != (size_t) N + 1) { g_create_error = "P_row.dat is shorter than N + 1 entries"; rc = FITSNE_EINVAL; }
+    if (rc == 0) {
+        fitsne_ctx *c = new fitsne_ctx();
+        c->src_col = fc; c->src_val = fv;
+        const int per = cdiv(N, world_size);
+        rc = create_impl(c, cfg, N, no_dims, row.data(), nullptr, nullptr, Y0, rank, world_size, rank * per, std::min(N, (rank + 1) * per),
+                         nccl_unique_id);
+        c->src_col = c->src_val = nullptr;
+        if (rc != 0) { g_create_error = c->err; fitsne_destroy(c); } else *out = c;
+    }
+    if (fr) fclose(fr);
+    if (fc) fclose(fc);
+    if (fv) fclose(fv);
+    return rc;
+}
+int fitsne_create_from_files(const fitsne_config *cfg, const char *dir, int N, int no_dims, const double *Y0, fitsne_ctx **out) {
+    return fitsne_create_from_files_sharded(cfg, dir, N, no_dims, Y0, 0, 1, nullptr, out);
 }
 
 const char *fitsne_last_error(const fitsne_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
@@ -1435,6 +1489,16 @@ int fitsne_run_host(const fitsne_config *cfg, const fitsne_schedule *s, int N, i
     TRACE("run_host: run");
     rc = fitsne_run(c, s, costs, Y);
     TRACE("run_host: destroy");
+    if (rc != 0) g_create_error = c->err;
+    fitsne_destroy(c);
+    return rc;
+}
+
+int fitsne_run_files(const fitsne_config *cfg, const fitsne_schedule *s, const char *dir, int N, int no_dims, double *Y, double *costs) {
+    fitsne_ctx *c = nullptr;
+    int rc = fitsne_create_from_files(cfg, dir, N, no_dims, Y, &c);
+    if (rc != 0) return rc;
+    rc = fitsne_run(c, s, costs, Y);
     if (rc != 0) g_create_error = c->err;
     fitsne_destroy(c);
     return rc;

@@ -23,6 +23,7 @@ EXPORTS = [
     "fitsne_step", "fitsne_kl", "fitsne_run", "fitsne_run_host", "fitsne_synchronize", "fitsne_get_stats",
     "fitsne_reset_stats", "fitsne_last_run_ms", "fitsne_debug_copy", "fitsne_version", "fitsne_prewarm",
     "fitsne_knn", "fitsne_similarities", "fitsne_free", "fitsne_prep_last_error",
+    "fitsne_create_from_files", "fitsne_create_from_files_sharded", "fitsne_run_files",
 ]
 
 
@@ -225,6 +226,23 @@ class FitSNE:
         self._ck(self._lib.fitsne_debug_copy(self._h, what.encode(), _dp(out), ctypes.c_size_t(out.nbytes),
                                              ctypes.byref(need)))
         return out
+
+
+def run_files(directory, N, Y0, schedule=None, nterms=3, intervals_per_integer=1.0, min_num_intervals=50, df=1.0, device=-1,
+              flags=0, **kw):
+    """fitsne_run_files: P from <directory>/P_row.dat, P_col.dat, P_val.dat (the reference's load_affinities files), streamed
+    to the device; host Y in, host Y + costs out."""
+    lib = load_library()
+    s = schedule or make_schedule(**kw)
+    Y = np.array(Y0, dtype=np.float64, order="C")
+    if Y.ndim == 1:
+        Y = Y[:, None]
+    costs = np.zeros(s.max_iter)
+    cfg = Config(int(nterms), float(intervals_per_integer), int(min_num_intervals), float(df), int(device), int(flags))
+    rc = lib.fitsne_run_files(ctypes.byref(cfg), ctypes.byref(s), (directory or "").encode(), int(N), Y.shape[1], _dp(Y), _dp(costs))
+    if rc != 0:
+        raise FitsneError(rc, lib.fitsne_last_error(None).decode())
+    return Y, costs
 
 
 def _kernel_times(self):

@@ -243,13 +243,6 @@ void TSNE::save_data(const char *result_path, double *data, double *costs, int n
 }
 
 #ifndef FITSNE_HOST_ONLY
-static bool read_file(const char *name, void *dst, size_t size, size_t count) {
-    FILE *h = fopen(name, "rb");
-    if (!h) { printf("Error: could not open data file.\n"); return false; }
-    const bool ok = fread(dst, size, count, h) == count;
-    fclose(h);
-    return ok;
-}
 static bool write_file(const char *name, const void *src, size_t size, size_t count) {
     FILE *h = fopen(name, "wb");
     if (!h) { printf("Error: could not open data file.\n"); return false; }
@@ -286,17 +279,9 @@ int TSNE::run(double *X, int N, int D, double *Y, int no_dims, double perplexity
 
     unsigned int *row_P = nullptr, *col_P = nullptr;
     double *val_P = nullptr;
-    if (load_affinities == 1) {
+    const bool stream_files = load_affinities == 1;          // P_row/P_col/P_val.dat go from disk straight to the device
+    if (stream_files) {
         printf("Loading approximate input similarities from files...\n");
-        row_P = (unsigned int *) malloc(((size_t) N + 1) * sizeof(unsigned int));
-        if (!row_P) { printf("Memory allocation failed!\n"); exit(1); }
-        if (!read_file("P_row.dat", row_P, sizeof(unsigned int), (size_t) N + 1)) return -2;
-        const size_t numel = row_P[N];
-        col_P = (unsigned int *) calloc(numel, sizeof(unsigned int));
-        val_P = (double *) calloc(numel, sizeof(double));
-        if (!col_P || !val_P) { printf("Memory allocation failed!\n"); exit(1); }
-        if (!read_file("P_val.dat", val_P, sizeof(double), numel)) return -2;
-        if (!read_file("P_col.dat", col_P, sizeof(unsigned int), numel)) return -2;
     } else {
         int K_to_use;
         double sigma_to_use;
@@ -349,7 +334,8 @@ int TSNE::run(double *X, int N, int D, double *Y, int no_dims, double perplexity
         printf("Y[0] = %lf\n", Y[0]);
     } else printf("Using the given initialization.\n");
     preprocessing_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pre).count();
-    printf("Input similarities computed (sparsity = %f)!\nLearning embedding...\n", (double) row_P[N] / ((double) N * (double) N));
+    if (row_P) printf("Input similarities computed (sparsity = %f)!\n", (double) row_P[N] / ((double) N * (double) N));
+    printf("Learning embedding...\n");
     printf("Using FIt-SNE approximation (B200 build: %s).\n", fitsne_version());
 
     fitsne_config cfg;
@@ -361,7 +347,9 @@ int TSNE::run(double *X, int N, int D, double *Y, int no_dims, double perplexity
     s.learning_rate = learning_rate; s.early_exag_coeff = early_exag_coeff; s.late_exag_coeff = late_exag_coeff;
     s.max_step_norm = max_step_norm; s.no_momentum_during_exag = no_momentum_during_exag ? 1 : 0; s.verbose = 1;
     const auto t_loop = std::chrono::steady_clock::now();
-    const int rc = fitsne_run_host(&cfg, &s, N, no_dims, row_P, col_P, val_P, Y, costs);
+    const int rc = stream_files ? fitsne_run_files(&cfg, &s, nullptr, N, no_dims, Y, costs)
+                                : fitsne_run_host(&cfg, &s, N, no_dims, row_P, col_P, val_P, Y, costs);
+    if (stream_files && rc == FITSNE_EINVAL) { printf("Error: could not open data file.\n"); return -2; }      // like tsne.cpp:186
     loop_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
     free(row_P); free(col_P); free(val_P);
     if (rc != 0) {

@@ -118,6 +118,14 @@ int fitsne_create_sharded(const fitsne_config *cfg, int N, int no_dims, const un
                           const void *nccl_unique_id, fitsne_ctx **out);
 int fitsne_nccl_unique_id(void *out_128_bytes);
 
+/* P as files -- the reference's load_affinities side files (tsne.cpp:236-281 reads, :334-366 writes): <dir>/P_row.dat
+ * (u32 x N+1), P_col.dat (u32 x E), P_val.dat (f64 x E).  dir == NULL or "": $FITSNE_AFFINITIES_DIR, else the current
+ * directory (where the reference looks).  The edges are streamed to the device in bounded chunks through pinned
+ * memory: no host copy of col/val is ever made; a sharded rank reads only its own rows' slice of the files. */
+int fitsne_create_from_files(const fitsne_config *cfg, const char *dir, int N, int no_dims, const double *Y0, fitsne_ctx **out);
+int fitsne_create_from_files_sharded(const fitsne_config *cfg, const char *dir, int N, int no_dims, const double *Y0, int rank,
+                                     int world_size, const void *nccl_unique_id, fitsne_ctx **out);
+
 int fitsne_destroy(fitsne_ctx *ctx);
 const char *fitsne_last_error(const fitsne_ctx *ctx); /* ctx may be NULL: last create() failure */
 
@@ -155,6 +163,10 @@ int fitsne_run(fitsne_ctx *ctx, const fitsne_schedule *s, double *costs, double 
 int fitsne_run_host(const fitsne_config *cfg, const fitsne_schedule *s, int N, int no_dims,
                     const unsigned int *row_P, const unsigned int *col_P, const double *val_P, double *Y,
                     double *costs);
+
+/* The same with P taken from files (fitsne_create_from_files): what the host shell calls for load_affinities == 1. */
+int fitsne_run_files(const fitsne_config *cfg, const fitsne_schedule *s, const char *dir, int N, int no_dims, double *Y,
+                     double *costs);
 
 /* Prepare (twiddle tables, buffers) every FFT length a grid of n_boxes_lo..n_boxes_hi boxes per dimension can need,
  * so that no allocation happens inside the iteration loop.  Optional and cheap (the FFTs are our own kernels: there

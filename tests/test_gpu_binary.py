@@ -97,3 +97,39 @@ def test_in_process_fast_tsne_matches_binary(tmp_path):
     # PCA / random initialisations and the 1-D path at least run and separate the clusters
     Y1 = fb.fast_tsne(X, perplexity=15, max_iter=250, map_dims=1, seed=3)
     assert Y1.shape == (N, 1) and np.isfinite(Y1).all()
+
+
+def test_affinity_files_are_streamed_to_the_device(tmp_path):
+    """P_row/P_col/P_val.dat as a first-class input -- from an explicit directory (C ABI / Python mirror), from
+    $FITSNE_AFFINITIES_DIR, and through the binary's load_affinities=1 (current directory, like the reference): all three
+    give the run that the same P gives when handed over as host arrays."""
+    import fitsne_b200 as fb
+    N = 20000
+    row, col, val, labels = bench_util.knn_like_graph(N, 12, seed=4)
+    Y0 = bench_util.clustered_embedding(labels, 2, 40.0, seed=2)
+    pdir = tmp_path / "affinities"
+    pdir.mkdir()
+    row.tofile(pdir / "P_row.dat"); col.tofile(pdir / "P_col.dat"); val.tofile(pdir / "P_val.dat")
+    kw = dict(max_iter=100, stop_lying_iter=30, mom_switch_iter=30, learning_rate=800.0, early_exag_coeff=6.0)
+    Yh, ch = fb.run_host(row, col, val, Y0, **kw)
+    Yf, cf = fb.run_files(str(pdir), N, Y0, **kw)
+    assert np.array_equal(Yh, Yf) and np.array_equal(ch, cf)
+    os.environ["FITSNE_AFFINITIES_DIR"] = str(pdir)
+    try:
+        Ye, ce = fb.run_files(None, N, Y0, **kw)
+    finally:
+        del os.environ["FITSNE_AFFINITIES_DIR"]
+    assert np.array_equal(Yh, Ye) and np.array_equal(ch, ce)
+    with pytest.raises(fb.FitsneError):
+        fb.run_files(str(tmp_path / "nowhere"), N, Y0, **kw)
+    (pdir / "P_val.dat").write_bytes(val[:100].tobytes())                 # truncated: loud failure, not garbage
+    with pytest.raises(fb.FitsneError):
+        fb.run_files(str(pdir), N, Y0, **kw)
+    # the binary: load_affinities=1 reads ./P_*.dat like the reference (tsne.cpp:236-281)
+    row.tofile(tmp_path / "P_row.dat"); col.tofile(tmp_path / "P_col.dat"); val.tofile(tmp_path / "P_val.dat")
+    bench_util.write_data_dat(str(tmp_path / "data.dat"), np.zeros((N, 1)), perplexity=-1.0, K=1, sigma=1.0, max_iter=100, stop_lying_iter=30,
+                              mom_switch_iter=30, learning_rate=800.0, early_exag_coeff=6.0, load_affinities=1, initialization=Y0, seed=1)
+    out = run_bin(tmp_path)
+    assert out.returncode == 0, out.stdout[-600:]
+    Yb, cb = bench_util.read_result(str(tmp_path / "result.dat"))
+    assert np.array_equal(Yb, Yh) and np.array_equal(cb, ch)
