@@ -579,7 +579,8 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
                                                   c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         phase_mark(c, FITSNE_PHASE_CENTER);
         k_shard_stats<D><<<SHARD_BLOCKS, 256, 0, st>>>(c->Yb, c->row_begin, c->row_end, c->rank, c->gp, c->shard_sum_partial,
-                                                      c->shard_mm_partial, c->shard_stats + c->rank, c->tickets + 3, c->pc, c->p2p ? 1 : 0);
+                                                      c->shard_mm_partial, c->shard_stats + c->rank, c->tickets + 3, c->pc, c->p2p ? 1 : 0,
+                                                      c->reordered ? c->orig_of : nullptr, c->reordered ? c->pos_of : nullptr);
         if (!c->p2p) CKNCCL(g_nccl.AllGather(c->shard_stats + c->rank, c->shard_stats, sizeof(ShardStats), ncclChar, c->comm, st));
         k_center_shard<D><<<cdiv(rows, 256), 256, 0, st>>>(c->Yb, c->Y, c->row_begin, c->row_end, c->N, c->shard_stats, c->world,
                                                           c->gp, c->sc, c->host_bounds_dev, c->pc, c->p2p ? 1 : 0);
@@ -723,8 +724,85 @@ static int reorder_points(fitsne_ctx *c) {
     return 0;
 }
 
+static int ensure_whole_Y(fitsne_ctx *c);
+
+// Sharded contexts: every rank Morton-orders the points of ITS OWN slice (block-diagonal permutation: row ownership does not
+// change, so no CSR row moves between ranks), the maps are all-gathered, the local CSR rows are re-labelled through the
+// global map.  Gives the sort / spread / gather their locality back and turns the SpMV's neighbour gathers into `world`
+// Morton-ordered windows instead of uniformly random reads.  Collective: every rank calls it at the same step count.
+static int reorder_points_sharded(fitsne_ctx *c) {
+    const int N = c->N, D = c->D, nloc = c->nloc, b = c->row_begin;
+    cudaStream_t st = c->stream;
+    const size_t E = c->E, padded = (size_t) c->per * c->world;
+    if (!c->orig_of) {
+        CKRC(dev_alloc(c, &c->orig_of, padded)); CKRC(dev_alloc(c, &c->orig_tmp, padded));
+        CKRC(dev_alloc(c, &c->pos_of, padded)); CKRC(dev_alloc(c, &c->rank_map, padded));
+        CKRC(dev_alloc(c, &c->row_P2, (size_t) N + 1)); CKRC(dev_alloc(c, &c->edges2, E + 1));
+        CKRC(dev_alloc(c, &c->gp_reorder, (size_t) 1));
+        GridParams g;
+        memset(&g, 0, sizeof g);
+        g.ok = 1; g.sort_bits = 11; g.sort_passes = 2;
+        CK(cudaMemcpyAsync(c->gp_reorder, &g, sizeof g, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    CKRC(refresh_bounds(c));     // whole Y, identical bounds on every rank
+    const int tiles = cdiv(nloc, SORT_TILE);
+    const int max_bins = 1 << SORT_MAX_BITS;
+    const size_t scatter_smem = (size_t) max_bins * 4 + (size_t) (SORT_THREADS / 32) * max_bins * 2;
+    if (D == 2) k_morton_keys<2><<<cdiv(nloc, 256), 256, 0, st>>>(c->Y + (size_t) b * D, nloc, c->sc, c->keys[0]);
+    else k_morton_keys<1><<<cdiv(nloc, 256), 256, 0, st>>>(c->Y + (size_t) b * D, nloc, c->sc, c->keys[0]);
+    CK(cudaMemsetAsync(c->sort_totals, 0, sizeof(uint32_t) * 2 * max_bins, st));
+    k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[0], nloc, 0, c->hist, tiles, c->sort_totals, c->gp_reorder);
+    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals, 0, c->gp_reorder);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], nloc, 0, c->hist, tiles, 0u, c->gp_reorder);
+    k_radix_hist<<<tiles, SORT_THREADS, 0, st>>>(c->keys[1], nloc, 1, c->hist, tiles, c->sort_totals + max_bins, c->gp_reorder);
+    k_radix_offsets<<<max_bins, 256, 0, st>>>(c->hist, tiles, c->sort_totals + max_bins, 1, c->gp_reorder);
+    k_radix_scatter<<<tiles, SORT_THREADS, scatter_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], nloc, 1, c->hist, tiles, 0u, c->gp_reorder);
+    // maps of my slice, then everybody's
+    k_reorder_maps_local<<<cdiv(nloc, 256), 256, 0, st>>>(c->perm[0], nloc, (uint32_t) b, c->rank_map, c->reordered ? c->orig_of : nullptr,
+                                                          c->orig_tmp, c->pos_of);
+    LAUNCH_CHECK();
+    uint32_t *maps[3] = {c->rank_map, c->orig_tmp, c->pos_of};
+    for (uint32_t *m : maps) CKNCCL(g_nccl.AllGather(m + (size_t) c->rank * c->per, m, (size_t) c->per, ncclUint32, c->comm, st));
+    CK(cudaMemcpyAsync(c->orig_of, c->orig_tmp, padded * 4, cudaMemcpyDeviceToDevice, st));
+    // per-point state of my rows; Y is completed again below
+    const size_t bytes = (size_t) nloc * D * sizeof(float);
+    float *state[3] = {c->Y, c->uY, c->gains};
+    for (float *buf : state) {
+        if (D == 2) k_permute_rows<2><<<cdiv(nloc, 256), 256, 0, st>>>(buf + (size_t) b * D, c->Yb, c->perm[0], nloc);
+        else k_permute_rows<1><<<cdiv(nloc, 256), 256, 0, st>>>(buf + (size_t) b * D, c->Yb, c->perm[0], nloc);
+        CK(cudaMemcpyAsync(buf + (size_t) b * D, c->Yb, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    // my CSR rows
+    uint32_t *new_len = c->keys[1], *row_new = c->keys[0];          // [nloc] / [nloc + 1] (keys are allocated with head room)
+    k_relabel_csr_local<<<cdiv((long long) nloc * 8, 256), 256, 0, st>>>(0, c->row_P, c->edge_base, c->edges, c->rank_map, b, nloc, new_len, nullptr, nullptr);
+    k_scan_excl<<<1, 1024, 0, st>>>(new_len, row_new, nloc);
+    k_relabel_csr_local<<<cdiv((long long) nloc * 8, 256), 256, 0, st>>>(1, c->row_P, c->edge_base, c->edges, c->rank_map, b, nloc, new_len, row_new, c->edges2);
+    CK(cudaMemcpyAsync(c->row_P2, c->row_P, ((size_t) N + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    k_local_row_offsets<<<cdiv(nloc + 1, 256), 256, 0, st>>>(row_new, nloc, b, c->edge_base, c->row_P2);
+    LAUNCH_CHECK();
+    CK(cudaStreamSynchronize(st));
+    std::swap(c->row_P, c->row_P2); std::swap(c->edges, c->edges2);
+    c->reordered = true;
+    c->reorders++;
+    c->y_whole = false;          // the other ranks re-ordered their slices too
+    CKRC(ensure_whole_Y(c));
+    c->bounds_valid = true;      // a permutation does not move the bounds
+    drop_graphs(c);
+    c->kernel_launches_reorder += 16;
+    return 0;
+}
+
 static int maybe_reorder(fitsne_ctx *c) {
-    if (c->world > 1 || (c->cfg.flags & FITSNE_FLAG_NO_REORDER) || c->E == 0) return 0;
+    if ((c->cfg.flags & FITSNE_FLAG_NO_REORDER) || c->E == 0) return 0;
+    if (c->world > 1) {
+        static const bool no_shard_reorder = getenv("FITSNE_NO_SHARD_REORDER") && atoi(getenv("FITSNE_NO_SHARD_REORDER")) != 0;
+        if (no_shard_reorder) return 0;
+        if (c->reordered && c->steps_total - c->last_reorder_iter < c->reorder_interval) return 0;
+        if (c->reordered) c->reorder_interval = std::min<uint64_t>(c->reorder_interval * 2, 400);
+        c->last_reorder_iter = c->steps_total;
+        return reorder_points_sharded(c);
+    }
     if (c->reordered && c->steps_total - c->last_reorder_iter < c->reorder_interval) return 0;
     if (c->reordered) c->reorder_interval = std::min<uint64_t>(c->reorder_interval * 2, 400);
     c->last_reorder_iter = c->steps_total;
@@ -1436,7 +1514,7 @@ int fitsne_run(fitsne_ctx *c, const fitsne_schedule *s, double *costs, double *Y
         auto clip = [&](long long ev) { if (ev >= iter && ev < end) end = (int) ev; };
         clip(s->stop_lying_iter); clip(s->start_late_exag_iter); clip(s->mom_switch_iter);
         clip((long long) (iter / 50 + 1) * 50 - 1);
-        if (c->world == 1 && !(c->cfg.flags & FITSNE_FLAG_NO_REORDER) && c->reordered)
+        if (!(c->cfg.flags & FITSNE_FLAG_NO_REORDER) && c->reordered)
             clip((long long) iter + (long long) (c->last_reorder_iter + c->reorder_interval - c->steps_total) - 1);
         int ran = 1;
         if (batched) CKRC(run_batch(c, end - iter + 1, &ran));

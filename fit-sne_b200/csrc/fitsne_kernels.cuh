@@ -1453,11 +1453,14 @@ template <int D>
 __global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Ynext, int row_begin, int row_end, int rank,
                                                      const GridParams *__restrict__ gpp, double *__restrict__ sum_partial,
                                                      float4 *__restrict__ mm_partial, ShardStats *__restrict__ out,
-                                                     unsigned int *__restrict__ ticket, PeerComm pc, int p2p) {
+                                                     unsigned int *__restrict__ ticket, PeerComm pc, int p2p,
+                                                     const uint32_t *__restrict__ orig_of, const uint32_t *__restrict__ pos_of) {
     if (!gpp->ok) return;
     __shared__ double smd[32];
     __shared__ float4 smm[8];
     const int n = row_end - row_begin;
+    // the head = the first SHARD_HEAD points in the caller's ORIGINAL order (rank 0 owns them; after a re-ordering of the
+    // slice they sit at pos_of[0..])
     const int nhead_pts = (rank == 0 && D == 2) ? min(SHARD_HEAD, n) : 0;
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int b = blockIdx.x * per, e = min(n, b + per);
@@ -1468,7 +1471,8 @@ __global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Y
             const float2 v = reinterpret_cast<const float2 *>(Ynext)[row_begin + i];
             s0 += v.x; s1 += v.y;
             mm.z = fmaxf(mm.z, v.x); mm.w = fmaxf(mm.w, v.y);
-            if (i >= nhead_pts) { mm.x = fminf(mm.x, v.x); mm.y = fminf(mm.y, v.y); }
+            const int o = orig_of ? (int) orig_of[row_begin + i] - row_begin : i;
+            if (o >= nhead_pts) { mm.x = fminf(mm.x, v.x); mm.y = fminf(mm.y, v.y); }
         } else {
             const float v = Ynext[row_begin + i];
             s0 += v;
@@ -1504,7 +1508,10 @@ __global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Y
         out->sum[0] = t0; out->sum[1] = t1;
         out->mn[0] = a.x; out->mn[1] = a.y; out->mx[0] = a.z; out->mx[1] = a.w;
         out->nhead = nhead_pts * 2;
-        for (int i = 0; i < 2 * SHARD_HEAD; i++) out->head[i] = i < nhead_pts * 2 ? Ynext[(size_t) row_begin * 2 + i] : 0.f;
+        for (int i = 0; i < 2 * SHARD_HEAD; i++) {
+            const size_t pt = pos_of ? (size_t) pos_of[row_begin + (i >> 1)] : (size_t) row_begin + (i >> 1);
+            out->head[i] = i < nhead_pts * 2 ? Ynext[pt * 2 + (i & 1)] : 0.f;
+        }
         if (p2p) {
             // peer-memory exchange: my 128-byte record goes straight into slot [rank] of every peer's table (32 remote
             // 4-byte stores each), then the flag -- k_center_shard on the other side spins on it
@@ -1637,6 +1644,48 @@ __global__ void __launch_bounds__(256) k_reorder_maps(const uint32_t *__restrict
     const uint32_t o = orig_old ? orig_old[prev] : prev;
     orig_new[k] = o;
     pos_of[o] = (uint32_t) k;
+}
+
+// Sharded contexts re-order WITHIN their slice (a block-diagonal permutation: ownership of the rows does not change, so no
+// CSR row ever has to move between ranks).  perm[k] = previous LOCAL position of the point that moves to local position k;
+// the maps are global (slice offset `base`), every rank fills its own slice and the slices are all-gathered afterwards.
+__global__ void __launch_bounds__(256) k_reorder_maps_local(const uint32_t *__restrict__ perm, int nloc, uint32_t base,
+                                                            uint32_t *__restrict__ rank, const uint32_t *__restrict__ orig_old,
+                                                            uint32_t *__restrict__ orig_new, uint32_t *__restrict__ pos_of) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nloc) return;
+    const uint32_t prev = base + perm[k];
+    rank[prev] = base + (uint32_t) k;
+    const uint32_t o = orig_old ? orig_old[prev] : prev;     // stays inside [base, base + nloc)
+    orig_new[base + k] = o;
+    pos_of[o] = base + (uint32_t) k;
+}
+// Relabel this rank's CSR rows: 8 lanes per OLD local row; new local row = rank[row] - row_begin, columns through the
+// (all-gathered) global rank map.  PASS 0: row lengths; PASS 1: copy the edges to their new offsets.
+__global__ void __launch_bounds__(256) k_relabel_csr_local(int pass, const uint32_t *__restrict__ row_old, uint32_t edge_base,
+                                                           const uint2 *__restrict__ edges_old, const uint32_t *__restrict__ rank,
+                                                           int row_begin, int nloc, uint32_t *__restrict__ new_len,
+                                                           const uint32_t *__restrict__ row_new, uint2 *__restrict__ edges_new) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = gid & 7, il = gid >> 3;
+    if (il >= nloc) return;
+    const uint32_t r = rank[row_begin + il] - (uint32_t) row_begin;
+    const uint32_t e0 = row_old[row_begin + il] - edge_base, e1 = row_old[row_begin + il + 1] - edge_base;
+    if (pass == 0) {
+        if (sub == 0) new_len[r] = e1 - e0;
+    } else {
+        const uint32_t nb = row_new[r];
+        for (uint32_t e = e0 + sub; e < e1; e += 8) {
+            const uint2 ed = edges_old[e];
+            edges_new[nb + (e - e0)] = make_uint2(rank[ed.x], ed.y);
+        }
+    }
+}
+// row_P entries of the local rows from the scanned local lengths
+__global__ void __launch_bounds__(256) k_local_row_offsets(const uint32_t *__restrict__ row_new, int nloc, int row_begin, uint32_t edge_base,
+                                                           uint32_t *__restrict__ row_P) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= nloc) row_P[row_begin + r] = edge_base + row_new[r];
 }
 
 template <int D>
