@@ -231,6 +231,9 @@ def phase_times(L, fb, row, col, val, Y, uY, gains, sched, nsteps, dims, df):
     for _ in range(nsteps):
         tt.step(**kw)
     sst = tt.stats()
+    if os.environ.get("FITSNE_KTIMES"):      # diagnostics: every rank's own warm per-kernel times (us per launch)
+        kt = tt.kernel_times()
+        print("[ktimes rank %d] " % L.rank + "  ".join("%s %.1f" % (k, 1e3 * v[0] / max(v[1], 1)) for k, v in kt.items()), file=sys.stderr, flush=True)
     tt.close()
     return sst
 

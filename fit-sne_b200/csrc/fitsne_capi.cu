@@ -114,6 +114,9 @@ struct fitsne_ctx {
     std::vector<void *> ipc_opened;
     cudaStream_t stream_c = nullptr;  // copy-engine pushes of the Y slice to the peers (DMA only)
     cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;
+    int chunk = CHUNK;                // sorted points per spread thread (FITSNE_CHUNK overrides: tests/tools/chunk_sweep.py)
+    cudaStream_t stream_k = nullptr;  // sharded runs: the kernel spectra, beside the sort and the spread
+    cudaEvent_t ev_kfork = nullptr, ev_kjoin = nullptr;
     // sharded runs: per-rank reduction records (all-gathered, 128 B each) and whether c->Y currently holds every rank's slice
     ShardStats *shard_stats = nullptr;
     double *shard_sum_partial = nullptr;
@@ -165,7 +168,7 @@ struct fitsne_ctx {
     StepParams *sp = nullptr;
     Scalars *sc = nullptr;
     int *mismatch = nullptr;
-    unsigned int *tickets = nullptr;   // last-block-done counters: [0] hadamard, [1] centre/bounds, [2] update, [3] shard stats
+    unsigned int *tickets = nullptr;   // last-block-done counters: [0] conv columns, [1] centre/bounds, [2] update, [3] shard stats, [4..6] sort, [7] combine, [8] rows fwd, [9] rows inv
     float *host_bounds = nullptr, *host_bounds_dev = nullptr;   // mapped pinned
     int *host_B = nullptr, *host_B_dev = nullptr;               // pinned word + its device-memory copy: the host's n_boxes for this iteration (0 = the device decides)
     Scalars *host_sc = nullptr;                                 // pinned staging for scalar read-back
@@ -342,9 +345,9 @@ template <int D, int P>
 static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, const uint32_t *skeys, const uint32_t *sperm) {
     void *grid = D == 2 ? (void *) c->chg : (c->p2p ? (void *) c->grid1d : (void *) c->planes);      // spread target
     if (!gather) {
-        const int nchunks = cdiv(c->nloc, CHUNK);
+        const int nchunks = cdiv(c->nloc, c->chunk);
         k_spread_chunks<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, spread_smem_bytes<D, P>(), c->stream>>>(
-            c->sorted_u, skeys, c->nloc, c->gp, c->slots, c->gpart, grid, c->box_range, c->work);
+            c->sorted_u, skeys, c->nloc, c->gp, c->slots, c->gpart, grid, c->box_range, c->work, c->chunk);
     } else {
         k_gather<D, P><<<cdiv(c->nloc, 256), 256, 0, c->stream>>>(c->sorted_u, skeys, sperm, c->nloc, c->gp, c->sc,
                                                                    D == 2 ? (const void *) c->pot : (const void *) c->planes, c->frep);
@@ -447,6 +450,13 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         c->stats.kernel_launches += 2;
         return 0;
     };
+    const bool kside = D == 2 && c->world > 1 && c->p2p && !c->timing_this_iter && c->stream_k != nullptr;
+    if (kside) {
+        CK(cudaEventRecord(c->ev_kfork, st));
+        CK(cudaStreamWaitEvent(c->stream_k, c->ev_kfork, 0));
+        CKRC(launch_kernel_side(c->stream_k));
+        CK(cudaEventRecord(c->ev_kjoin, c->stream_k));
+    }
     // ---- bin + stable two-pass LSD radix sort by box (three launches; see fitsne_kernels.cuh)
     phase_mark(c, FITSNE_PHASE_SORT);
     const int tiles = cdiv(nloc, SORT_TILE);
@@ -478,18 +488,20 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     else CK(cudaMemsetAsync(spread_grid, 0, (size_t) 2 * M * sizeof(float2), st));
     CKRC(launch_spread_gather<D>(c, false, skeys, sperm));
     kt(c, "k_spread_chunks");
-    k_spread_combine<D><<<148 * 8, 256, 0, st>>>(c->slots, c->box_range, c->gp, c->work, spread_grid);
+    // (sharded, peer fabric: the CTA of the combine that finishes last announces "my partial grid is complete" to the peers)
+    k_spread_combine<D><<<148 * 8, 256, 0, st>>>(c->slots, c->box_range, c->gp, c->work, spread_grid, c->tickets + 7, c->pc,
+                                                 c->world > 1 && c->p2p ? 1 : 0, c->chunk);
     c->stats.kernel_launches += 1;
     if (c->world > 1) {
         // every rank spread its own points: sum the partial grids (fp32).  2-D: the dense (M/2)^2 float4 region that holds
         // the G x G grid; 1-D: the two packed charge lines.  The element count depends on M only, like every launch shape.
         phase_mark(c, FITSNE_PHASE_COLLECTIVES);
         if (c->p2p) {
-            // peer fabric: announce "my partial grid is complete"; the sum over ranks happens inside k_conv_rows_fwd's loads
-            // (2-D) or in one small kernel (1-D)
-            k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_GRID);
-            if (D == 1) k_grid_sum_1d<<<cdiv(2 * M, 256), 256, 0, st>>>(c->pc, c->planes, 2 * M, &c->gp->ok);
-            c->stats.kernel_launches += D == 1 ? 2 : 1;
+            // peer fabric: the sum over ranks happens inside k_conv_rows_fwd's loads (2-D) or in one small kernel (1-D)
+            if (D == 1) {
+                k_grid_sum_1d<<<cdiv(2 * M, 256), 256, 0, st>>>(c->pc, c->planes, 2 * M, &c->gp->ok);
+                c->stats.kernel_launches += 1;
+            }
         } else if (D == 2) CKNCCL(g_nccl.AllReduce(c->chg, c->chg, cplane * 4, ncclFloat, ncclSum, c->comm, st));
         else CKNCCL(g_nccl.AllReduce(c->planes, c->planes, (size_t) M * 4, ncclFloat, ncclSum, c->comm, st));
     }
@@ -499,24 +511,27 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     phase_mark(c, FITSNE_PHASE_KERNEL_SPECTRUM);
     const int *gok = &c->gp->ok;
     if (D == 2) {
-        CKRC(launch_kernel_side(st));
+        // the kernel spectra depend on the grid geometry only.  Single GPU: in line (beside the SpMV-saturated kernels a second
+        // stream buys nothing, see above).  Sharded runs leave most of every GPU idle between exchanges: there the two kernels
+        // run on a side stream beside the sort and the spread (forked right after k_setup_grid, joined here).
+        if (kside) CK(cudaStreamWaitEvent(st, c->ev_kjoin, 0));
+        else CKRC(launch_kernel_side(st));
         kt(c, "k_kspec_rows + k_kspec_cols");
         phase_mark(c, FITSNE_PHASE_FFT);
         const int H = M / 2 + 1;
-        k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp, c->pc, c->p2p ? (c->dist_conv ? 2 : 1) : 0);
+        k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp, c->pc, c->p2p ? (c->dist_conv ? 2 : 1) : 0,
+                                                                        c->tickets + 8);
         kt(c, "k_conv_rows_fwd");
         const int dist = c->p2p && c->dist_conv ? 1 : 0, p2p = dist ? 2 : 0;
         // sharded, distributed convolution: like a 2-D FFT -- rows and spectrum columns dealt out in blocks; every
-        // "transpose" is the producing kernel's stores on peer memory, a flag per stage tells the consumers
-        if (dist) k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_S1);
+        // "transpose" is the producing kernel's stores on peer memory; the CTA that finishes last raises the stage's flag at
+        // the peers, the consuming kernel's CTAs wait for it themselves -- no launch of its own for any exchange
         k_conv_cols<<<H, col_threads, pl->smem_col, st>>>(pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
                                                           c->sc, c->tickets + 0, c->pc, p2p);
         kt(c, "k_conv_cols");
-        if (dist) k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_S2);
-        k_conv_rows_inv<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->S, c->pot, pl->plan, pl->W, c->gp, c->pc, p2p, c->N, c->sc);
+        k_conv_rows_inv<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->S, c->pot, pl->plan, pl->W, c->gp, c->pc, p2p, c->N, c->sc, c->tickets + 9);
         kt(c, "k_conv_rows_inv");
-        if (dist) { k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_POT); k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_POT); }
-        c->stats.kernel_launches += 3 + 4 * dist;
+        c->stats.kernel_launches += 3;
     } else {
         k_gen_kernels_1d<<<cdiv(M, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->planes);
         kt(c, "k_gen_kernels_1d");
@@ -532,6 +547,14 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
 
     // ---- gather (+ 1/Z)
     phase_mark(c, FITSNE_PHASE_GATHER);
+    const bool dist_conv_on = D == 2 && c->p2p && c->dist_conv;
+    if (dist_conv_on) {
+        // distributed convolution: the potential rows come from every rank -- one wait covers them AND the Y slices the
+        // SpMV needs further down (pushed at the start of the iteration: long since there)
+        if (push_Y && !c->timing_this_iter) CK(cudaStreamWaitEvent(st, c->ev_cjoin, 0));
+        k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_POT, push_Y ? FLAG_Y : -1);
+        c->stats.kernel_launches += 1;
+    }
     CKRC(launch_spread_gather<D>(c, true, skeys, sperm));
     kt(c, "k_gather");
 
@@ -541,9 +564,11 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     if (c->world > 1) {
         phase_mark(c, FITSNE_PHASE_ALLGATHER);
         if (push_Y) {
-            if (!c->timing_this_iter) CK(cudaStreamWaitEvent(st, c->ev_cjoin, 0));     // my own pushes are out ...
-            k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_Y);                               // ... and everybody's have landed here
-            c->stats.kernel_launches += 1;
+            if (!dist_conv_on) {
+                if (!c->timing_this_iter) CK(cudaStreamWaitEvent(st, c->ev_cjoin, 0));     // my own pushes are out ...
+                k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_Y, -1);                           // ... and everybody's have landed here
+                c->stats.kernel_launches += 1;
+            }
         } else CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, st));
     }
     c->y_whole = true;
@@ -561,7 +586,7 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
             // no statistics exchange closes a gradient-only pass: meet the peers explicitly, so that nobody clears its
             // partial grid for the next pass while a slower rank still reads it
             k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_STATS);
-            k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_STATS);
+            k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_STATS, -1);
             c->stats.kernel_launches += 2;
         }
     } else if (c->world == 1) {
@@ -573,18 +598,17 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         phase_mark(c, FITSNE_PHASE_CENTER);
         CKRC(launch_bounds_only<D>(c, c->Yb, c->Y, 1));
     } else {
-        // sharded tail: local update -> local sums / bounds -> 128-byte records all-gathered -> every rank centres its own
-        // slice with the global mean and publishes the (identical) global bounds.  Y itself is gathered next iteration.
-        k_update<D, true><<<ublocks, 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
-                                                  c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
+        // sharded tail: local update with its sums / bounds riding along -> 128-byte records exchanged -> every rank centres
+        // its own slice with the global mean and publishes the (identical) global bounds.  Y itself is gathered next iteration.
+        k_update_shard<D><<<ublocks, 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->rank, c->sp, c->gp, c->dC, c->uY,
+                                                   c->gains, c->Yb, c->shard_sum_partial, c->shard_mm_partial, c->shard_stats + c->rank,
+                                                   c->tickets + 3, c->pc, c->p2p ? 1 : 0, c->reordered ? c->orig_of : nullptr,
+                                                   c->reordered ? c->pos_of : nullptr);
         phase_mark(c, FITSNE_PHASE_CENTER);
-        k_shard_stats<D><<<SHARD_BLOCKS, 256, 0, st>>>(c->Yb, c->row_begin, c->row_end, c->rank, c->gp, c->shard_sum_partial,
-                                                      c->shard_mm_partial, c->shard_stats + c->rank, c->tickets + 3, c->pc, c->p2p ? 1 : 0,
-                                                      c->reordered ? c->orig_of : nullptr, c->reordered ? c->pos_of : nullptr);
         if (!c->p2p) CKNCCL(g_nccl.AllGather(c->shard_stats + c->rank, c->shard_stats, sizeof(ShardStats), ncclChar, c->comm, st));
         k_center_shard<D><<<cdiv(rows, 256), 256, 0, st>>>(c->Yb, c->Y, c->row_begin, c->row_end, c->N, c->shard_stats, c->world,
                                                           c->gp, c->sc, c->host_bounds_dev, c->pc, c->p2p ? 1 : 0);
-        c->stats.kernel_launches += 3;
+        c->stats.kernel_launches += 2;
         c->y_whole = false;
     }
     phase_mark(c, FITSNE_PHASE_COUNT);
@@ -1100,6 +1124,11 @@ static int setup_peer_fabric(fitsne_ctx *c) {
     CK(cudaStreamCreateWithPriority(&c->stream_c, cudaStreamNonBlocking, prio_hi));
     CK(cudaEventCreateWithFlags(&c->ev_cfork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_cjoin, cudaEventDisableTiming));
+    if (!getenv("FITSNE_NO_KSIDE")) {
+        CK(cudaStreamCreateWithFlags(&c->stream_k, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_kfork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_kjoin, cudaEventDisableTiming));
+    }
     TRACE("peer fabric up: %d ranks", world);
     return 0;
 }
@@ -1212,13 +1241,16 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     c->hist_cap = (size_t) cdiv(c->nloc, SORT_TILE) * (1 << SORT_MAX_BITS);
     CKRC(dev_alloc(c, &c->hist, c->hist_cap)); CKRC(dev_alloc(c, &c->sweep_state, 2 * c->hist_cap));
     CKRC(dev_alloc(c, &c->sort_bases, (size_t) 2 * (1 << SORT_MAX_BITS)));
-    CKRC(dev_alloc(c, &c->work, (size_t) cdiv(c->nloc, CHUNK) + 2));
+    c->chunk = CHUNK;
+    if (getenv("FITSNE_CHUNK") && atoi(getenv("FITSNE_CHUNK")) > 0) c->chunk = std::min(64, atoi(getenv("FITSNE_CHUNK")));
+    const int sp_points = SP2_THREADS * c->chunk;            // sorted points per spread CTA
+    CKRC(dev_alloc(c, &c->work, (size_t) cdiv(c->nloc, c->chunk) + 2));
     CKRC(dev_alloc(c, &c->sort_totals, (size_t) 2 * (1 << SORT_MAX_BITS)));
     {
         const size_t nodes = no_dims == 2 ? (size_t) cfg->nterms * cfg->nterms : (size_t) cfg->nterms;
-        CKRC(dev_alloc(c, &c->slots, (size_t) cdiv(c->nloc, SP2_POINTS) * 2 * nodes));
+        CKRC(dev_alloc(c, &c->slots, (size_t) cdiv(c->nloc, sp_points) * 2 * nodes));
         const bool generic = cfg->nterms < 2 || cfg->nterms > (no_dims == 2 ? 4 : 5);      // launch_spread_gather's fallback
-        if (generic) CKRC(dev_alloc(c, &c->gpart, (size_t) cdiv(c->nloc, SP2_POINTS) * SP2_THREADS * 2 * nodes));
+        if (generic) CKRC(dev_alloc(c, &c->gpart, (size_t) cdiv(c->nloc, sp_points) * SP2_THREADS * 2 * nodes));
     }
     CKRC(dev_alloc(c, &c->colsum_partial, (size_t) RED_BLOCKS * 2));
     CKRC(dev_alloc(c, &c->bounds_partial, (size_t) RED_BLOCKS));
@@ -1226,14 +1258,14 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CKRC(dev_alloc(c, &c->kl_partial, (size_t) 4096));
     CKRC(dev_alloc(c, &c->gp, (size_t) 1)); CKRC(dev_alloc(c, &c->sp, (size_t) 1)); CKRC(dev_alloc(c, &c->sc, (size_t) 1));
     CKRC(dev_alloc(c, &c->mismatch, (size_t) 1));
-    CKRC(dev_alloc(c, &c->tickets, (size_t) 8));
+    CKRC(dev_alloc(c, &c->tickets, (size_t) 16));
     if (world > 1) {
         CKRC(dev_alloc(c, &c->shard_stats, (size_t) world));
-        CKRC(dev_alloc(c, &c->shard_sum_partial, (size_t) SHARD_BLOCKS * 2));
-        CKRC(dev_alloc(c, &c->shard_mm_partial, (size_t) SHARD_BLOCKS));
+        CKRC(dev_alloc(c, &c->shard_sum_partial, (size_t) RED_BLOCKS * 2));
+        CKRC(dev_alloc(c, &c->shard_mm_partial, (size_t) RED_BLOCKS));
         CK(cudaMemsetAsync(c->shard_stats, 0, sizeof(ShardStats) * world, c->stream));
     }
-    CK(cudaMemsetAsync(c->tickets, 0, 8 * sizeof(unsigned int), c->stream));
+    CK(cudaMemsetAsync(c->tickets, 0, 16 * sizeof(unsigned int), c->stream));
     CK(cudaMemsetAsync(c->gp, 0, sizeof(GridParams), c->stream));
     CK(cudaMemsetAsync(c->sc, 0, sizeof(Scalars), c->stream));
     CK(cudaMemsetAsync(c->mismatch, 0, sizeof(int), c->stream));
@@ -1284,6 +1316,7 @@ int fitsne_destroy(fitsne_ctx *c) {
     if (c->p2p) {
         // nobody frees a buffer a peer may still have mapped: close my mappings, then meet the others
         if (c->stream_c) cudaStreamSynchronize(c->stream_c);
+        if (c->stream_k) cudaStreamSynchronize(c->stream_k);
         for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
         if (c->comm && c->comm_seq) {
             g_nccl.AllReduce(c->comm_seq, c->comm_seq, 1, ncclInt, ncclMax, c->comm, c->stream);
@@ -1292,6 +1325,9 @@ int fitsne_destroy(fitsne_ctx *c) {
         if (c->ev_cfork) cudaEventDestroy(c->ev_cfork);
         if (c->ev_cjoin) cudaEventDestroy(c->ev_cjoin);
         if (c->stream_c) cudaStreamDestroy(c->stream_c);
+        if (c->ev_kfork) cudaEventDestroy(c->ev_kfork);
+        if (c->ev_kjoin) cudaEventDestroy(c->ev_kjoin);
+        if (c->stream_k) cudaStreamDestroy(c->stream_k);
     }
     if (c->comm) g_nccl.CommDestroy(c->comm);
     void *bufs[] = {c->Y, c->Yb, c->uY, c->gains, c->frep, c->dC, c->row_P, c->edges, c->keys[0], c->keys[1],

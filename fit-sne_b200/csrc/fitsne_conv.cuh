@@ -236,12 +236,13 @@ __device__ __forceinline__ void tma_store_commit_and_wait() {
 // stored into the S of the rank that owns its column.
 __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_fwd(const float4 *__restrict__ chg, float2 *__restrict__ S, FftPlan plan,
                                                                const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
-                                                               PeerComm pc, int p2p) {
+                                                               PeerComm pc, int p2p, unsigned int *__restrict__ ticket) {
     extern __shared__ __align__(16) float2 row_sm[];
     __shared__ FftPlan plan_s;
     const int G = gpp->G;
-    if (!gpp->ok || (int) blockIdx.x >= G) return;
-    if (p2p == 2 && part_owner(blockIdx.x, part_block(G, pc.world, 1), pc.world) != pc.rank) return;      // distributed: not my row
+    bool live = gpp->ok && (int) blockIdx.x < G;
+    if (p2p == 2 && live) live = part_owner(blockIdx.x, part_block(G, pc.world, 1), pc.world) == pc.rank;   // distributed: my rows only
+    if (live) {
     if (p2p && threadIdx.x == 0) peer_wait(pc.flags[pc.rank], FLAG_GRID, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
     for (int i = threadIdx.x; i < (int) (sizeof(FftPlan) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&plan_s)[i] = reinterpret_cast<const int *>(&plan)[i];
@@ -282,6 +283,8 @@ __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_fwd(const float4 *__r
         dst[0] = make_float4(w1.x, w1.y, dx.x, dx.y);
         dst[1] = make_float4(dy.x, dy.y, wb.x, wb.y);
     }
+    }   // live
+    if (p2p == 2) peer_signal_last(ticket, pc, FLAG_S1, live ? 2 : 0);     // last CTA: "my rows are in every column owner's S"
 }
 
 // rows r < G: x-half-spectra (v1~, Bx~, By~) -> real rows.  Z1 = v1~ + i Bx~ extended by Hermitian symmetry gives
@@ -291,15 +294,15 @@ __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_fwd(const float4 *__r
 // adds the ranks' sum_Q partials in rank order.
 __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_inv(const float2 *S, float4 *__restrict__ pot, FftPlan plan,
                                                                const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
-                                                               PeerComm pc, int p2p, int N, Scalars *__restrict__ sc) {
+                                                               PeerComm pc, int p2p, int N, Scalars *__restrict__ sc,
+                                                               unsigned int *__restrict__ ticket) {
     extern __shared__ __align__(16) float2 row_sm[];
     __shared__ FftPlan plan_s;
     const int G = gpp->G;
-    if (!gpp->ok || (int) blockIdx.x >= G) return;
-    if (p2p == 2) {
+    bool live = gpp->ok && (int) blockIdx.x < G;
+    if (p2p == 2 && live) {
         const bool mine = part_owner(blockIdx.x, part_block(G, pc.world, 1), pc.world) == pc.rank;
-        if (!mine && blockIdx.x != 0) return;
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && (mine || blockIdx.x == 0)) {
             peer_wait(pc.flags[pc.rank], FLAG_S2, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
             if (blockIdx.x == 0) {        // sum_Q = (sum over ranks of their columns' Parseval partials, in rank order) - N
                 double tot = 0;
@@ -309,9 +312,10 @@ __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_inv(const float2 *S, 
                 sc->inv_Z = (float) (1.0 / Z);
             }
         }
-        if (!mine) return;
+        live = mine;
         __syncthreads();
     }
+    if (live) {
     for (int i = threadIdx.x; i < (int) (sizeof(FftPlan) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&plan_s)[i] = reinterpret_cast<const int *>(&plan)[i];
     const int M = plan.n, NS = fft_buf_len(M, 2), r = blockIdx.x, H = M / 2 + 1;
@@ -339,6 +343,8 @@ __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_inv(const float2 *S, 
             for (int q = 0; q < MAX_RANKS; q++) if (q < pc.world) pc.pot[q][(size_t) r * G + c] = v;
         }
     }
+    }   // live
+    if (p2p == 2) peer_signal_last(ticket, pc, FLAG_POT, live ? 2 : 0);    // last CTA: "my rows of the potential grid are everywhere"
 }
 
 // ---------------------------------------------------------------------------------- kernel side: rows --
@@ -441,7 +447,10 @@ __global__ void __launch_bounds__(COL_THREADS) k_conv_cols(const __grid_constant
     __shared__ ColPlan plan_s;
     __shared__ __align__(8) uint64_t mbar;
     __shared__ double red[32];
-    if (!gpp->ok) return;
+    if (!gpp->ok) {                                      // (the flag still goes out: one per iteration keeps the ranks in step)
+        if (p2p == 2) peer_signal_last(ticket, pc, FLAG_S2, 0);
+        return;
+    }
     const int M = plan.n, G = gpp->G, kx = blockIdx.x;
     // sharded: my block of columns only (the other ranks' CTAs leave; their partial-sum slots must read as zero), and not
     // before every rank's rows have landed in my S
@@ -505,7 +514,10 @@ __global__ void __launch_bounds__(COL_THREADS) k_conv_cols(const __grid_constant
     }
     }   // mine
     const double rsum = block_sum(zacc * ((kx == 0 || 2 * kx == M) ? 1.0 : 2.0), red);
-    if (threadIdx.x == 0) zpartial[kx] = rsum;
+    if (threadIdx.x == 0) {
+        zpartial[kx] = rsum;
+        if (dist && mine) __threadfence_system();     // (after block_sum's barriers: the whole CTA's peer stores, before the ticket)
+    }
     if (last_block_done(ticket)) {           // sum_Q = (sum of the partials, in index order) - N   (tsne.cpp:1110)
         double s2 = 0;
         for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) s2 += ld_partial(zpartial + i);
@@ -518,6 +530,11 @@ __global__ void __launch_bounds__(COL_THREADS) k_conv_cols(const __grid_constant
             } else {
                 // my columns' share goes to slot [rank] of every rank's table; k_conv_rows_inv adds the slots in rank order
                 for (int q = 0; q < pc.world; q++) *reinterpret_cast<volatile double *>(pc.zs[q] + pc.rank) = tot;
+                // ... and "my columns are back in every row owner's S": the exchange flag, by the CTA that finished last
+                __threadfence_system();
+                const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
+                for (int q = 0; q < pc.world; q++)
+                    if (q != pc.rank) *reinterpret_cast<volatile uint32_t *>(pc.flags[q] + FLAG_S2 * pc.world + pc.rank) = seq;
             }
         }
     }

@@ -1,7 +1,7 @@
 // fitsne_kernels.cuh -- hand-written sm_100a kernels for FIt-SNE's per-iteration gradient loop.
 //
 // Everything the reference does per iteration (reference = /root/reference/src/...) in fp32 on the device:
-//   bounds + zero-mean        tsne.cpp:1039-1049, :1851-1876        k_colsum, k_center_bounds, k_setup_grid (sharded: k_shard_stats, k_center_shard)
+//   bounds + zero-mean        tsne.cpp:1039-1049, :1851-1876        k_colsum, k_center_bounds, k_setup_grid (sharded: k_update_shard, k_center_shard)
 //   point -> box, sort        nbodyfft.cpp:85-114                    k_bin, k_radix_offsets, k_radix_scatter
 //   Lagrange spread           nbodyfft.cpp:123-147, :310-336         k_spread_chunks, k_spread_combine
 //   kernel samples            nbodyfft.cpp:52-61, tsne.cpp:69-94     k_gen_kernels        (+ forward FFTs, fitsne_fft.cuh)
@@ -23,7 +23,9 @@
 namespace fk {
 
 constexpr int PMAX = 16;          // max interpolation points per box and axis
-constexpr int CHUNK = 8;          // points per spread work item (one thread walks a chunk; 8 keeps ~26 warps per SM busy at N = 1M)
+constexpr int CHUNK = 8;          // points per spread work item (one thread walks a chunk).  Measured on B200 (spread_chunks, us, chunk
+                                  // 1 / 2 / 4 / 8): N=1M 135 / 78 / 49 / 36, N=500k 76 / 47 / 34 / 25, N=125k 32 / 23 / 20 / 19 -- longer
+                                  // chunks win at every size (fewer partials to park and stitch), so slices of a sharded run keep 8 too
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
@@ -32,7 +34,6 @@ constexpr int SORT_ONE_PASS_BITS = 8; // keys this short sort in ONE pass.  (Mea
                                       // is slower than two 6-bit passes: 84 vs 70 us at N=1M; so only short 1-D keys qualify.)
 constexpr int RED_BLOCKS = 1184;  // 8 x 148 SMs: partial-reduction width for bounds / column sums
 constexpr int Z_BLOCKS_1D = 32;      // Parseval partials of the 1-D Hadamard kernel
-constexpr int SHARD_BLOCKS = 148;  // one CTA per SM: per-rank sums / bounds of the local slice (sharded runs)
 
 // Device-resident description of this iteration's interpolation grid.  Rewritten every iteration by
 // k_setup_grid from the bounds; all kernels read it from memory so that one captured CUDA graph serves every
@@ -75,7 +76,7 @@ struct Scalars {          // small device-resident results
 // collective inside the iteration:
 //   grid reduction   k_conv_rows_fwd (2-D) / k_grid_sum_1d add the ranks' partial spread grids WHILE LOADING them, in rank
 //                    order, so every rank gets the same bits;
-//   statistics       k_shard_stats writes its 128-byte record straight into every peer's table, k_center_shard reads them;
+//   statistics       k_update_shard writes its 128-byte record straight into every peer's table, k_center_shard reads them;
 //   positions        every rank's centred slice of Y is pushed into the peers' Y by the copy engines (a side stream:
 //                    DMA over NVLink, no SM involved) while the next iteration sorts and spreads; the SpMV waits for it.
 // Ordering: flags[kind * world + r] in MY memory is written by rank r with the iteration's sequence number after its data
@@ -128,10 +129,34 @@ __global__ void k_peer_signal(PeerComm pc, int kind) {
     for (int r = 0; r < pc.world; r++)
         if (r != pc.rank) *reinterpret_cast<volatile uint32_t *>(pc.flags[r] + kind * pc.world + pc.rank) = seq;
 }
-// stream-level wait: one thread spins until every peer has signalled `kind` for this iteration
-__global__ void k_peer_wait(PeerComm pc, int kind) {
+// stream-level wait: one thread spins until every peer has signalled `kind` (and `kind2`, if >= 0) for this iteration
+__global__ void k_peer_wait(PeerComm pc, int kind, int kind2) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    peer_wait(pc.flags[pc.rank], kind, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
+    const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
+    peer_wait(pc.flags[pc.rank], kind, pc, seq);
+    if (kind2 >= 0) peer_wait(pc.flags[pc.rank], kind2, pc, seq);
+}
+// Producer-side signal, folded into the kernel that finishes the data: EVERY CTA of the grid calls this (all threads, on
+// every exit path) after its last store; each CTA publishes its stores and takes a ticket, the CTA that arrives last
+// raises my flag of this kind at every peer.  One graph node less per exchange than a separate one-thread k_peer_signal,
+// and the flag leaves as soon as the last CTA is done instead of after the kernel has drained.
+//   wrote: 0 = this CTA stored nothing the peers will read (no fence: a system-scope fence per CTA of a wide grid costs
+//   more than the launch it replaces -- measured +12 us on k_spread_combine's 1184 CTAs), 1 = it stored into LOCAL memory
+//   the peers read over NVLink (device-scope fence: their loads are served by this GPU's L2), 2 = it stored into PEER
+//   memory (system-scope fence: the stores have to have landed before the ticket is taken).
+__device__ __forceinline__ void peer_signal_last(unsigned int *ticket, const PeerComm &pc, int kind, int wrote) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (wrote == 2) __threadfence_system();
+        else if (wrote == 1) __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            *ticket = 0;
+            __threadfence_system();
+            const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
+            for (int r = 0; r < pc.world; r++)
+                if (r != pc.rank) *reinterpret_cast<volatile uint32_t *>(pc.flags[r] + kind * pc.world + pc.rank) = seq;
+        }
+    }
 }
 
 // 1-D sharded runs: planes 0, 1 (two packed complex lines of length M) <- sum over ranks of their partial lines, in rank
@@ -878,16 +903,16 @@ struct Sp2Meta {
 template <int D, int P>
 __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys,
                                                        int n, const GridParams &gp, float4 *__restrict__ part, Sp2Meta &meta,
-                                                       void *__restrict__ grid, uint2 *__restrict__ box_range) {
+                                                       void *__restrict__ grid, uint2 *__restrict__ box_range, int chunk = CHUNK) {
     constexpr int PP = P > 0 ? P : PMAX;
     constexpr int MAXN = D == 2 ? PP * PP : PP;
     const int p = P > 0 ? P : gp.p;
     const int nodes = D == 2 ? p * p : p;
     const int c = blk * SP2_THREADS + t;
-    const int kb = c * CHUNK;
+    const int kb = c * chunk;
     meta.flags[t] = 0;
     if (kb >= n) return;
-    const int ke = kb + CHUNK < n ? kb + CHUNK : n;
+    const int ke = kb + chunk < n ? kb + chunk : n;
     const size_t stride = (size_t) gp.M;              // 1-D: plane 0 -> plane 1
     float4 *myH = part + (size_t) t * 2 * nodes, *myT = myH + nodes;
     const uint32_t *kp = skeys + kb;
@@ -982,12 +1007,12 @@ __host__ __device__ __forceinline__ void spread2_chunk(int t, int blk, const flo
 template <int D, int P>
 __host__ __device__ __forceinline__ void spread2_stitch(int t, int blk, int n, const GridParams &gp, const float4 *__restrict__ part,
                                                         const Sp2Meta &meta, void *__restrict__ grid, float4 *__restrict__ cslots,
-                                                        uint32_t *__restrict__ work) {
+                                                        uint32_t *__restrict__ work, int chunk = CHUNK) {
     constexpr int PP = P > 0 ? P : PMAX;
     constexpr int MAXN = D == 2 ? PP * PP : PP;
     const int p = P > 0 ? P : gp.p;
     const int nodes = D == 2 ? p * p : p;
-    const int nch = min(SP2_THREADS, (n - blk * SP2_POINTS + CHUNK - 1) / CHUNK);       // chunks of this CTA
+    const int nch = min(SP2_THREADS, (n - blk * SP2_THREADS * chunk + chunk - 1) / chunk);       // chunks of this CTA
     if (t >= nch) return;
     const size_t stride = (size_t) gp.M;
     float4 *myc = cslots + (size_t) blk * 2 * nodes;
@@ -1040,7 +1065,7 @@ template <int D, int P>
 __global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks(const float *__restrict__ sorted_u, const uint32_t *__restrict__ skeys, int n,
                                                                const GridParams *__restrict__ gpp, float4 *__restrict__ cslots,
                                                                float4 *__restrict__ gpart, void *__restrict__ grid,
-                                                               uint2 *__restrict__ box_range, uint32_t *__restrict__ work) {
+                                                               uint2 *__restrict__ box_range, uint32_t *__restrict__ work, int chunk) {
     extern __shared__ __align__(16) unsigned char sp_raw[];
     __shared__ GridParams gps;
     __shared__ Sp2Meta meta;
@@ -1051,9 +1076,9 @@ __global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks(const float *__re
     const int p = P > 0 ? P : gps.p;
     const int nodes = D == 2 ? p * p : p;
     float4 *part = P > 0 ? reinterpret_cast<float4 *>(sp_raw) : gpart + (size_t) blockIdx.x * SP2_THREADS * 2 * nodes;
-    spread2_chunk<D, P>(threadIdx.x, blockIdx.x, sorted_u, skeys, n, gps, part, meta, grid, box_range);
+    spread2_chunk<D, P>(threadIdx.x, blockIdx.x, sorted_u, skeys, n, gps, part, meta, grid, box_range, chunk);
     __syncthreads();                                  // (block-scope barrier also orders the global-memory partials of P == 0)
-    spread2_stitch<D, P>(threadIdx.x, blockIdx.x, n, gps, part, meta, grid, cslots, work);
+    spread2_stitch<D, P>(threadIdx.x, blockIdx.x, n, gps, part, meta, grid, cslots, work, chunk);
 }
 
 // Combine the boxes that cross CTA boundaries of k_spread_chunks: work[0] = number of listed boxes, work[1..] = the boxes
@@ -1078,12 +1103,12 @@ __host__ __device__ __forceinline__ float4 combine_node_lane(const float4 *__res
 template <int D>
 __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict__ cslots, const uint2 *__restrict__ box_range,
                                                         const GridParams *__restrict__ gpp, const uint32_t *__restrict__ work,
-                                                        void *__restrict__ grid) {
+                                                        void *__restrict__ grid, unsigned int *__restrict__ ticket, PeerComm pc, int p2p,
+                                                        int chunk) {
     const GridParams &gp = *gpp;
-    if (!gp.ok) return;
     const int p = gp.p, nodes = D == 2 ? p * p : p;
     const int lane = threadIdx.x & 31;
-    const int ntask = (int) work[0] * nodes;
+    const int ntask = gp.ok ? (int) work[0] * nodes : 0;
     const int stride = gridDim.x * blockDim.x;
     for (int t0 = blockIdx.x * blockDim.x + threadIdx.x - lane; t0 < ntask; t0 += stride) {
         const int task = t0 + lane;
@@ -1093,7 +1118,7 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
             node = task - e * nodes;
             box = (int) work[1 + e];
             const uint2 r = box_range[box];
-            b0 = (int) r.x / SP2_POINTS; b1 = ((int) r.y - 1) / SP2_POINTS;
+            b0 = (int) r.x / (SP2_THREADS * chunk); b1 = ((int) r.y - 1) / (SP2_THREADS * chunk);
         }
         const bool coop = b1 - b0 + 1 >= COMBINE_COOP;
         if (task < ntask && !coop)
@@ -1116,6 +1141,9 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
             if (lane == 0) store_node<D>(grid, (size_t) gp.M, node_offset<D>(bbox, bnode, gp, p), acc);
         }
     }
+    // sharded, peer fabric: my partial grid is complete -- tell the peers (they add the partials inside k_conv_rows_fwd's
+    // loads / k_grid_sum_1d).  Sent whether or not the grid is valid: a flag per iteration keeps the ranks in step.
+    if (p2p) peer_signal_last(ticket, pc, FLAG_GRID, (int) (blockIdx.x * blockDim.x) < ntask ? 1 : 0);
 }
 #endif
 
@@ -1429,7 +1457,7 @@ __global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, con
 // ------------------------------------------------------------------------- sharded zero-mean + bounds --
 // Multi-GPU tail of an optimiser step.  Each rank has just written the new, un-centred positions of ITS points
 // (Ynext[row_begin..row_end)).  Instead of all-gathering Y first and then reducing over all N points on every GPU, each
-// rank reduces its own slice (k_shard_stats), the per-rank records (128 bytes) are all-gathered, and every rank derives
+// rank reduces its own slice (inside k_update_shard), the per-rank records (128 bytes) are all-gathered, and every rank derives
 // the same global column means and bounds from the same bytes (k_center_shard) while centring only its own slice.  The
 // big Y all-gather then runs on the second stream at the start of the NEXT iteration, overlapped with that iteration's
 // sort / spread (which only read the local slice).
@@ -1449,15 +1477,25 @@ struct ShardStats {              // one per rank, 128 bytes
 };
 static_assert(sizeof(ShardStats) == 128, "ShardStats is exchanged as 128 raw bytes");
 
+// Optimiser step of my slice + its statistics in ONE pass: the new positions are still in registers when their column sums
+// and bounds are taken (persistent grid like k_update: contiguous slice per CTA, thread-strided, fixed trees).  The CTA
+// that finishes last reduces the per-CTA partials, builds the 128-byte record and ships it -- every step of that tail
+// spread over the block's threads: a single thread walking a few hundred partials, the head and 32 remote words one
+// dependent L2 / NVLink latency at a time cost 40 us per iteration on 2 x B200.
 template <int D>
-__global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Ynext, int row_begin, int row_end, int rank,
-                                                     const GridParams *__restrict__ gpp, double *__restrict__ sum_partial,
-                                                     float4 *__restrict__ mm_partial, ShardStats *__restrict__ out,
-                                                     unsigned int *__restrict__ ticket, PeerComm pc, int p2p,
-                                                     const uint32_t *__restrict__ orig_of, const uint32_t *__restrict__ pos_of) {
+__global__ void __launch_bounds__(256) k_update_shard(const float *__restrict__ Y, const float *__restrict__ attr,
+                                                      const float *__restrict__ frep, int row_begin, int row_end, int rank,
+                                                      const StepParams *__restrict__ spp, const GridParams *__restrict__ gpp,
+                                                      float *__restrict__ dC_out, float *__restrict__ uY, float *__restrict__ gains,
+                                                      float *__restrict__ Ynext, double *__restrict__ sum_partial,
+                                                      float4 *__restrict__ mm_partial, ShardStats *__restrict__ out,
+                                                      unsigned int *__restrict__ ticket, PeerComm pc, int p2p,
+                                                      const uint32_t *__restrict__ orig_of, const uint32_t *__restrict__ pos_of) {
     if (!gpp->ok) return;
     __shared__ double smd[32];
     __shared__ float4 smm[8];
+    __shared__ ShardStats rec;
+    const StepParams sp = *spp;
     const int n = row_end - row_begin;
     // the head = the first SHARD_HEAD points in the caller's ORIGINAL order (rank 0 owns them; after a re-ordering of the
     // slice they sit at pos_of[0..])
@@ -1467,63 +1505,85 @@ __global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Y
     double s0 = 0, s1 = 0;
     float4 mm = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);      // (min0, min1, max0, max1)
     for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+        float v0 = 0.f, v1 = 0.f;               // this row's new (un-centred) position
+        update_row<D, true>(row_begin + i, Y, attr, frep, sp, dC_out, uY, gains, Ynext, v0, v1);
+        s0 += v0;
         if (D == 2) {
-            const float2 v = reinterpret_cast<const float2 *>(Ynext)[row_begin + i];
-            s0 += v.x; s1 += v.y;
-            mm.z = fmaxf(mm.z, v.x); mm.w = fmaxf(mm.w, v.y);
+            s1 += v1;
+            mm.z = fmaxf(mm.z, v0); mm.w = fmaxf(mm.w, v1);
             const int o = orig_of ? (int) orig_of[row_begin + i] - row_begin : i;
-            if (o >= nhead_pts) { mm.x = fminf(mm.x, v.x); mm.y = fminf(mm.y, v.y); }
+            if (o >= nhead_pts) { mm.x = fminf(mm.x, v0); mm.y = fminf(mm.y, v1); }
         } else {
-            const float v = Ynext[row_begin + i];
-            s0 += v;
-            mm.x = fminf(mm.x, v); mm.z = fmaxf(mm.z, v);
+            mm.x = fminf(mm.x, v0); mm.z = fmaxf(mm.z, v0);
         }
-    }
-    const double r0 = block_sum(s0, smd);
-    const double r1 = D == 2 ? block_sum(s1, smd) : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mm.x = fminf(mm.x, __shfl_xor_sync(0xffffffffu, mm.x, o)); mm.y = fminf(mm.y, __shfl_xor_sync(0xffffffffu, mm.y, o));
-        mm.z = fmaxf(mm.z, __shfl_xor_sync(0xffffffffu, mm.z, o)); mm.w = fmaxf(mm.w, __shfl_xor_sync(0xffffffffu, mm.w, o));
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) smm[w] = mm;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < (int) (blockDim.x >> 5); i++) {
-            mm.x = fminf(mm.x, smm[i].x); mm.y = fminf(mm.y, smm[i].y); mm.z = fmaxf(mm.z, smm[i].z); mm.w = fmaxf(mm.w, smm[i].w);
+    auto reduce_mm = [&](float4 v) -> float4 {           // result in thread 0
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v.x = fminf(v.x, __shfl_xor_sync(0xffffffffu, v.x, o)); v.y = fminf(v.y, __shfl_xor_sync(0xffffffffu, v.y, o));
+            v.z = fmaxf(v.z, __shfl_xor_sync(0xffffffffu, v.z, o)); v.w = fmaxf(v.w, __shfl_xor_sync(0xffffffffu, v.w, o));
         }
+        __syncthreads();
+        if (lane == 0) smm[w] = v;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int i = 1; i < (int) (blockDim.x >> 5); i++) {
+                v.x = fminf(v.x, smm[i].x); v.y = fminf(v.y, smm[i].y); v.z = fmaxf(v.z, smm[i].z); v.w = fmaxf(v.w, smm[i].w);
+            }
+        return v;
+    };
+    const double r0 = block_sum(s0, smd);
+    const double r1 = D == 2 ? block_sum(s1, smd) : 0.0;
+    mm = reduce_mm(mm);
+    if (threadIdx.x == 0) {
         sum_partial[blockIdx.x * 2] = r0; sum_partial[blockIdx.x * 2 + 1] = r1;
         mm_partial[blockIdx.x] = mm;
     }
-    if (last_block_done(ticket) && threadIdx.x == 0) {       // a few hundred partials: one thread, fixed order
-        double t0 = 0, t1 = 0;
-        float4 a = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
-        for (int i = 0; i < (int) gridDim.x; i++) {
-            t0 += __ldcg(sum_partial + 2 * i); t1 += __ldcg(sum_partial + 2 * i + 1);
-            const float4 v = __ldcg(mm_partial + i);
-            a.x = fminf(a.x, v.x); a.y = fminf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w);
-        }
-        out->sum[0] = t0; out->sum[1] = t1;
-        out->mn[0] = a.x; out->mn[1] = a.y; out->mx[0] = a.z; out->mx[1] = a.w;
-        out->nhead = nhead_pts * 2;
-        for (int i = 0; i < 2 * SHARD_HEAD; i++) {
+    // (last_block_done's device-scope fence in thread 0 follows block-wide barriers: it also covers the Ynext rows the other
+    // threads of this CTA stored, which the head below reads back)
+    if (!last_block_done(ticket)) return;
+    double t0 = 0, t1 = 0;
+    float4 a = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+    for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) {
+        t0 += __ldcg(sum_partial + 2 * i); t1 += __ldcg(sum_partial + 2 * i + 1);
+        const float4 v = __ldcg(mm_partial + i);
+        a.x = fminf(a.x, v.x); a.y = fminf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w);
+    }
+    t0 = block_sum(t0, smd);
+    t1 = block_sum(t1, smd);
+    a = reduce_mm(a);
+    if (threadIdx.x == 0) {
+        rec.sum[0] = t0; rec.sum[1] = t1;
+        rec.mn[0] = a.x; rec.mn[1] = a.y; rec.mx[0] = a.z; rec.mx[1] = a.w;
+        rec.nhead = nhead_pts * 2;
+        for (int i = 0; i < 7; i++) rec.pad_[i] = 0;
+    }
+    if ((int) threadIdx.x >= 32 && (int) threadIdx.x < 32 + 2 * SHARD_HEAD) {
+        const int i = threadIdx.x - 32;
+        float v = 0.f;
+        if (i < nhead_pts * 2) {
             const size_t pt = pos_of ? (size_t) pos_of[row_begin + (i >> 1)] : (size_t) row_begin + (i >> 1);
-            out->head[i] = i < nhead_pts * 2 ? Ynext[pt * 2 + (i & 1)] : 0.f;
+            v = __ldcg(Ynext + pt * 2 + (i & 1));
         }
-        if (p2p) {
-            // peer-memory exchange: my 128-byte record goes straight into slot [rank] of every peer's table (32 remote
-            // 4-byte stores each), then the flag -- k_center_shard on the other side spins on it
-            __threadfence();
-            const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(out);
-            for (int r = 0; r < pc.world; r++) {
-                if (r == pc.rank) continue;
-                volatile uint32_t *dst = reinterpret_cast<volatile uint32_t *>(reinterpret_cast<ShardStats *>(pc.stats[r]) + pc.rank);
-                for (int i = 0; i < (int) (sizeof(ShardStats) / 4); i++) dst[i] = src[i];
-            }
+        rec.head[i] = v;
+    }
+    __syncthreads();
+    // the record: slot [rank] of my own table and -- peer fabric -- of every peer's (one 4-byte remote store per lane and
+    // peer), then the flag; k_center_shard on the other side spins on it
+    if (threadIdx.x < sizeof(ShardStats) / 4) {
+        const uint32_t wv = reinterpret_cast<const uint32_t *>(&rec)[threadIdx.x];
+        reinterpret_cast<uint32_t *>(out)[threadIdx.x] = wv;
+        if (p2p)
+            for (int r = 0; r < pc.world; r++)
+                if (r != pc.rank)
+                    reinterpret_cast<volatile uint32_t *>(reinterpret_cast<ShardStats *>(pc.stats[r]) + pc.rank)[threadIdx.x] = wv;
+    }
+    if (p2p) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
             __threadfence_system();
+            const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
             for (int r = 0; r < pc.world; r++)
                 if (r != pc.rank) *reinterpret_cast<volatile uint32_t *>(pc.flags[r] + FLAG_STATS * pc.world + pc.rank) = seq;
         }
@@ -1531,7 +1591,8 @@ __global__ void __launch_bounds__(256) k_shard_stats(const float *__restrict__ Y
 }
 
 // Every rank: global means and bounds from the all-gathered records (identical bytes => identical results on all
-// ranks), centre the local slice Y[row] = Ynext[row] - mean (tsne.cpp:1851-1876), publish the bounds.
+// ranks), centre the local slice Y[row] = Ynext[row] - mean (tsne.cpp:1851-1876), publish the bounds.  Thread r of every
+// CTA waits for rank r's record and fetches it (the waits and the loads of all ranks overlap), thread 0 adds in rank order.
 template <int D>
 __global__ void __launch_bounds__(256) k_center_shard(const float *__restrict__ Ynext, float *__restrict__ Y, int row_begin, int row_end,
                                                       int N, const ShardStats *all, int world,
@@ -1539,32 +1600,48 @@ __global__ void __launch_bounds__(256) k_center_shard(const float *__restrict__ 
                                                       volatile float *host_bounds, PeerComm pc, int p2p) {
     if (!gpp->ok) return;
     __shared__ double mean_s[2];
+    __shared__ double sum_s[2 * MAX_RANKS];
+    __shared__ float mm_s[4 * MAX_RANKS];
+    __shared__ float head_s[2 * SHARD_HEAD];
+    const volatile ShardStats *va = all;           // (peers may have written these records: no cached / read-only loads)
+    if ((int) threadIdx.x < world) {
+        const int r = threadIdx.x;
+        if (p2p && r != pc.rank) {
+            const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
+            const volatile uint32_t *f = pc.flags[pc.rank] + FLAG_STATS * pc.world + r;
+            while ((int) (*f - seq) < 0) { }
+            __threadfence_system();
+        }
+        sum_s[2 * r] = va[r].sum[0]; sum_s[2 * r + 1] = va[r].sum[1];
+        if (blockIdx.x == 0) {
+            mm_s[4 * r] = va[r].mn[0]; mm_s[4 * r + 1] = va[r].mn[1]; mm_s[4 * r + 2] = va[r].mx[0]; mm_s[4 * r + 3] = va[r].mx[1];
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && (int) threadIdx.x < 2 * SHARD_HEAD) head_s[threadIdx.x] = va[0].head[threadIdx.x];   // (record 0 is in: barrier above)
     if (threadIdx.x == 0) {
-        if (p2p) peer_wait(pc.flags[pc.rank], FLAG_STATS, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
-        const volatile ShardStats *va = all;       // (peers may have written these records: no cached / read-only loads)
         double t0 = 0, t1 = 0;
-        for (int r = 0; r < world; r++) { t0 += va[r].sum[0]; t1 += va[r].sum[1]; }
+        for (int r = 0; r < world; r++) { t0 += sum_s[2 * r]; t1 += sum_s[2 * r + 1]; }
         mean_s[0] = t0 / (double) N; mean_s[1] = t1 / (double) N;
     }
     __syncthreads();
     const double m0 = mean_s[0], m1 = mean_s[1];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const volatile ShardStats *va = all;
         // centring is monotonic per dimension ((float)((double) y - mean)), so the bounds of the centred values are the
         // centred per-dimension bounds
         float bmn = INFINITY, bmx = -INFINITY;
         for (int r = 0; r < world; r++) {
             for (int d = 0; d < D; d++) {
                 const double m = d ? m1 : m0;
-                bmn = fminf(bmn, (float) ((double) va[r].mn[d] - m));
-                bmx = fmaxf(bmx, (float) ((double) va[r].mx[d] - m));
+                bmn = fminf(bmn, (float) ((double) mm_s[4 * r + d] - m));
+                bmx = fmaxf(bmx, (float) ((double) mm_s[4 * r + 2 + d] - m));
             }
         }
         const int nh = va[0].nhead;
         float run = -INFINITY;
         bool ascending = true;
         for (int i = 0; i < nh; i++) {            // replay of the `if (>max) .. else if (<min)` scan on the head
-            const float v = (float) ((double) va[0].head[i] - ((i & 1) ? m1 : m0));
+            const float v = (float) ((double) head_s[i] - ((i & 1) ? m1 : m0));
             if (ascending && v > run) run = v;   // still in the strictly ascending prefix: max only
             else { ascending = false; bmn = fminf(bmn, v); }
         }

@@ -31,11 +31,13 @@ static GridParams make_gp(int D, int B, int p, int M) {
 }
 
 
+static int g_chunk = CHUNK;      // chunk length under test (the device uses CHUNK; FITSNE_CHUNK overrides it for sweeps)
+
 template <int D, int P>
 static void run_spread(int n, const GridParams &gp, const std::vector<uint32_t> &skeys, const std::vector<float> &su,
                        std::vector<float> &grid, std::vector<uint2> &box_range, std::vector<uint32_t> &work, size_t gsize) {
     const int p = gp.p, nodes = D == 2 ? p * p : p;
-    const int nchunks = (n + CHUNK - 1) / CHUNK;
+    const int nchunks = (n + g_chunk - 1) / g_chunk;
     const int nblocks = (nchunks + SP2_THREADS - 1) / SP2_THREADS;
     std::vector<float4> cslots((size_t) nblocks * 2 * nodes, make_float4(NAN, NAN, NAN, NAN));
     std::vector<float4> part((size_t) SP2_THREADS * 2 * nodes);
@@ -45,14 +47,14 @@ static void run_spread(int n, const GridParams &gp, const std::vector<uint32_t> 
     static Sp2Meta meta;
     for (int blk = 0; blk < nblocks; blk++) {
         std::fill(part.begin(), part.end(), make_float4(NAN, NAN, NAN, NAN));   // poison: only parked partials may be read
-        for (int t = 0; t < SP2_THREADS; t++) spread2_chunk<D, P>(t, blk, su.data(), skeys.data(), n, gp, part.data(), meta, grid.data(), box_range.data());
-        for (int t = 0; t < SP2_THREADS; t++) spread2_stitch<D, P>(t, blk, n, gp, part.data(), meta, grid.data(), cslots.data(), work.data());
+        for (int t = 0; t < SP2_THREADS; t++) spread2_chunk<D, P>(t, blk, su.data(), skeys.data(), n, gp, part.data(), meta, grid.data(), box_range.data(), g_chunk);
+        for (int t = 0; t < SP2_THREADS; t++) spread2_stitch<D, P>(t, blk, n, gp, part.data(), meta, grid.data(), cslots.data(), work.data(), g_chunk);
     }
     // k_spread_combine: one lane per (box, node) in plain CTA order; COMBINE_COOP CTAs or more: 32 lanes + xor-shuffle tree
     for (uint32_t e = 0; e < work[0]; e++) {
         const int box = (int) work[1 + e];
         const int s = (int) box_range[box].x, en = (int) box_range[box].y;
-        const int c0 = s / SP2_POINTS, c1 = (en - 1) / SP2_POINTS;
+        const int c0 = s / (SP2_THREADS * g_chunk), c1 = (en - 1) / (SP2_THREADS * g_chunk);
         for (int node = 0; node < nodes; node++) {
             if (c1 - c0 + 1 < 32) {
                 store_node<D>(grid.data(), (size_t) gp.M, node_offset<D>(box, node, gp, p), combine_node_lane<D>(cslots.data(), c0, c1, nodes, node, 0, 1));
@@ -105,9 +107,9 @@ static bool run_case(const char *name, int n, int B, int M, double heavy_frac, u
     bool ok = true;
     for (int b = 0; b < gp.nb; b++) if (bs_ref[b + 1] > bs_ref[b] && (box_range[b].x != bs_ref[b] || box_range[b].y != bs_ref[b + 1])) {
         printf("%s: box_range[%d] = [%u, %u), expected [%u, %u)\n", name, b, box_range[b].x, box_range[b].y, bs_ref[b], bs_ref[b + 1]); ok = false; break; }
-    {   // work list == boxes crossing a CTA boundary (one CTA = SP2_POINTS sorted points)
+    {   // work list == boxes crossing a CTA boundary (one CTA = SP2_THREADS chunks of sorted points)
         std::vector<uint32_t> want, got(work.begin() + 1, work.begin() + 1 + work[0]);
-        for (int b = 0; b < gp.nb; b++) if (bs_ref[b + 1] > bs_ref[b] && bs_ref[b] / SP2_POINTS != (bs_ref[b + 1] - 1) / SP2_POINTS) want.push_back(b);
+        for (int b = 0; b < gp.nb; b++) if (bs_ref[b + 1] > bs_ref[b] && bs_ref[b] / (SP2_THREADS * g_chunk) != (bs_ref[b + 1] - 1) / (SP2_THREADS * g_chunk)) want.push_back(b);
         std::sort(got.begin(), got.end());
         if (got != want) { printf("%s: work list has %zu boxes, expected %zu\n", name, got.size(), want.size()); ok = false; }
     }
@@ -147,6 +149,8 @@ static bool run_case(const char *name, int n, int B, int M, double heavy_frac, u
 
 int main() {
     bool ok = true;
+    for (int chunk : {8, 4, 2, 1}) {      // the kernel takes the chunk length at run time
+    g_chunk = chunk;
     ok &= run_case<2, 3>("2-D p=3 late (small boxes)", 50000, 50, 320, 0.0, 1);
     ok &= run_case<2, 3>("2-D p=3 ragged tail", 50000 + 17, 36, 224, 0.0, 2);
     ok &= run_case<2, 3>("2-D p=3 heavy box", 40000, 25, 160, 0.6, 3);
@@ -160,7 +164,8 @@ int main() {
     ok &= run_case<1, 5>("1-D p=5 heavy", 33333, 50, 512, 0.5, 9);
     ok &= run_case<1, 0>("1-D p=7 (run-time p)", 20000, 60, 864, 0.0, 10, 7);
     ok &= run_case<2, 3>("2-D p=3 tiny n", 7, 25, 160, 0.0, 11);
-    ok &= run_case<2, 3>("2-D p=3 n = 1 block + 1", SP2_POINTS + 1, 50, 320, 0.0, 12);
+    ok &= run_case<2, 3>("2-D p=3 n = 1 block + 1", SP2_THREADS * g_chunk + 1, 50, 320, 0.0, 12);
+    }
     if (ok) printf("SPREAD_EMUL_OK\n");
     return ok ? 0 : 1;
 }
