@@ -287,7 +287,8 @@ def main():
                           "symmetrised, ~30 nnz/row) injected as load_affinities=1; %s phase" % (args.points, args.phase),
               "points": args.points, "phase": args.phase, "dims": args.dims, "df": args.df, "nterms": 3, "intervals_per_integer": 1, "min_num_intervals": 50,
               "l2": "inputs larger than L2: the CSR P (8 B/edge, ~240 MB at 1M points) is streamed from HBM every step",
-              "sharding": "points/rows sharded across %d rank(s); NCCL grid all-reduce + Y all-gather" % max(world, 1)}
+              "sharding": ("single GPU" if world <= 1 else "points/rows sharded across %d ranks; exchanges (partial grids, convolution transposes from 4 ranks up, "
+                           "statistics, Y slices) go over peer memory on NVLink inside the kernels / by the copy engines, NCCL only at set-up" % world)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -398,7 +399,9 @@ def main():
             Yout, costs2 = fb.run_host(prow, pcol, pval, pY, max_iter=args.steps, device=L.local_rank, df=args.df, **sched)
         else:
             with fb.FitSNE(prow, pcol, pval, pY, df=args.df, device=L.local_rank, rank=L.rank, world=L.world, nccl_id=nid) as te:
+                t_created = time.perf_counter()
                 Yout, costs2 = te.run(max_iter=args.steps, **sched)
+                t_ran = time.perf_counter()
         L.barrier()
         dt = L.max(time.perf_counter() - t0)
         h2d = prow.nbytes + pcol.nbytes + pval.nbytes + pY.nbytes
@@ -406,6 +409,9 @@ def main():
         e2e = {"value": args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                "call": ("fitsne_run_host" if world == 1 else "fitsne_create_sharded + fitsne_run + download, per rank") +
                        " (create + %d iterations + download), host wall clock, max over ranks" % args.steps}
+        if world > 1:     # where a sharded call's time goes: the one-off set-up (NCCL communicator, peer-memory handles, CSR upload) vs the iterations
+            e2e["breakdown_s"] = {"create_sharded (NCCL init + IPC fabric + upload)": round(L.max(t_created - t0), 3),
+                                  "run + download": round(L.max(t_ran - t_created), 3)}
         del prow, pcol, pval, pY, pinned       # release the pinned buffers while the CUDA context is still alive
 
     # ---- the other BASELINE configs, short runs (every rank takes part: the contexts are sharded like the headline)

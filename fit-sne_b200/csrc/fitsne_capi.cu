@@ -114,6 +114,7 @@ struct fitsne_ctx {
     std::vector<void *> ipc_opened;
     cudaStream_t stream_c = nullptr;  // copy-engine pushes of the Y slice to the peers (DMA only)
     cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;
+    bool use_pdl = true, in_chain = false, prev_is_kernel = false;     // programmatic dependent launch bookkeeping (launch_k)
     int chunk = CHUNK;                // sorted points per spread thread (FITSNE_CHUNK overrides: tests/tools/chunk_sweep.py)
     cudaStream_t stream_k = nullptr;  // sharded runs: the kernel spectra, beside the sort and the spread
     cudaEvent_t ev_kfork = nullptr, ev_kjoin = nullptr;
@@ -328,12 +329,34 @@ static inline void kt(fitsne_ctx *c, const char *name) {
     c->kt_n++;
 }
 
+// Every kernel of the iteration chain goes through launch_k: a plain launch, or -- when the operation before it on the same
+// stream was a kernel of the chain too (FITSNE_PDL=0 turns it off) -- one with programmatic stream serialisation (captured as a
+// programmatic graph edge): the kernel is set up while its predecessor drains and waits for it in its first instruction
+// (pdl_prologue): +1.2 % at N = 1M, +1.4 % at N = 10k on B200.  Anything else enqueued on the main stream
+// (memset, event wait, collective) calls pdl_break().
+template <typename... KArgs, typename... Args>
+static inline void launch_k(fitsne_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at;
+    memset(&at, 0, sizeof at);
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    const bool on = c->use_pdl && c->in_chain && c->prev_is_kernel && st == c->stream && !c->timing_this_iter;
+    cfg.attrs = &at; cfg.numAttrs = on ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    if (st == c->stream) c->prev_is_kernel = true;
+}
+#define LK(c, kern, grid, block, smem, st, ...) launch_k((c), kern, dim3(grid), dim3(block), (size_t) (smem), (st), __VA_ARGS__)
+static inline void pdl_break(fitsne_ctx *c) { c->prev_is_kernel = false; }
+
 template <int D>
 static int launch_bounds_only(fitsne_ctx *c, const float *Yin, float *Yout, int do_center) {
     // do_center == 1: closing kernel of an optimiser step (skipped, like the rest, when the grid check failed); the means
     // are in Scalars::mean (k_update).  The last block to finish combines the per-block bounds and publishes them.
     const GridParams *gate = do_center ? c->gp : nullptr;
-    k_center_bounds<D><<<RED_BLOCKS, 256, 0, c->stream>>>(Yin, Yout, c->N, do_center, c->bounds_partial, c->sc,
+    LK(c, k_center_bounds<D>, RED_BLOCKS, 256, 0, c->stream, Yin, Yout, c->N, do_center, c->bounds_partial, c->sc,
                                                           c->reordered ? c->orig_of : nullptr, c->reordered ? c->pos_of : nullptr, gate,
                                                           c->host_bounds_dev, c->tickets + 1);
     LAUNCH_CHECK();
@@ -346,10 +369,10 @@ static int launch_spread_gather_variant(fitsne_ctx *c, bool gather, const uint32
     void *grid = D == 2 ? (void *) c->chg : (c->p2p ? (void *) c->grid1d : (void *) c->planes);      // spread target
     if (!gather) {
         const int nchunks = cdiv(c->nloc, c->chunk);
-        k_spread_chunks<D, P><<<cdiv(nchunks, SP2_THREADS), SP2_THREADS, spread_smem_bytes<D, P>(), c->stream>>>(
+        LK(c, (k_spread_chunks<D, P>), cdiv(nchunks, SP2_THREADS), SP2_THREADS, (spread_smem_bytes<D, P>()), c->stream,
             c->sorted_u, skeys, c->nloc, c->gp, c->slots, c->gpart, grid, c->box_range, c->work, c->chunk);
     } else {
-        k_gather<D, P><<<cdiv(c->nloc, 256), 256, 0, c->stream>>>(c->sorted_u, skeys, sperm, c->nloc, c->gp, c->sc,
+        LK(c, (k_gather<D, P>), cdiv(c->nloc, 256), 256, 0, c->stream, c->sorted_u, skeys, sperm, c->nloc, c->gp, c->sc,
                                                                    D == 2 ? (const void *) c->pot : (const void *) c->planes, c->frep);
     }
     LAUNCH_CHECK();
@@ -382,7 +405,7 @@ static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
     if (c->use_tiles) {
         // accumulation: 32-bit fixed point scaled by the largest row sum of P -- native shared-memory integer atomics,
         // order-independent => bitwise repeatable
-        k_attract_tiles<D><<<c->tg.nchunks, 1024, tiles_smem_bytes(D), st>>>(c->Y, c->N, c->tg, c->tile_start, c->tile_pack, c->tile_val,
+        LK(c, k_attract_tiles<D>, c->tg.nchunks, 1024, tiles_smem_bytes(D), st, c->Y, c->N, c->tg, c->tile_start, c->tile_pack, c->tile_val,
                                                                               inv_df, c->tile_fix32, c->attr);
         LAUNCH_CHECK();
         c->stats.kernel_launches += 1;
@@ -391,7 +414,7 @@ static int launch_attract(fitsne_ctx *c, cudaStream_t st) {
     // persistent grid: `per_sm` CTAs of 256 threads per SM (never more than the row groups there are)
     constexpr int per_sm = 8;          // B200 sweep (2..100000 CTAs per SM): a flat optimum from 6 up
     static const int lpr_env = getenv("FITSNE_LPR") ? atoi(getenv("FITSNE_LPR")) : 0;
-#define ATT(L) k_attract<D, L><<<std::min(cdiv((long long) rows * L, 256), 148 * per_sm), 256, 0, st>>>( \
+#define ATT(L) LK(c, (k_attract<D, L>), std::min(cdiv((long long) rows * L, 256), 148 * per_sm), 256, 0, st,  \
         c->row_P, c->edges, c->edge_base, c->Y, c->row_begin, c->row_end, inv_df, c->attr)
     switch (lpr_env ? lpr_env : c->lpr) {
         case 4: ATT(4); break;
@@ -419,9 +442,11 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     Plans *pl;
     CKRC(get_plans(c, M, &pl));
 
+    c->in_chain = true;
+    pdl_break(c);
     phase_mark(c, FITSNE_PHASE_BOUNDS);
     kt(c, "(start)");
-    k_setup_grid<<<1, 256, 0, st>>>(c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
+    LK(c, k_setup_grid, 1, 256, 0, st, c->gp, c->sc, B_dev_arg, M, p, D, c->cfg.intervals_per_integer, c->cfg.min_num_intervals,
                                     c->mismatch, c->sort_totals, c->work, c->tickets + 5, c->p2p ? c->comm_seq : nullptr);
     c->stats.kernel_launches += 1;
     kt(c, "k_setup_grid");
@@ -437,15 +462,23 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
             const int r = (c->rank + k) % c->world;            // staggered targets: no two ranks hit the same peer first
             CK(cudaMemcpyAsync(c->pc.Y[r] + off, c->Y + off, bytes, cudaMemcpyDeviceToDevice, cs));
         }
-        k_peer_signal<<<1, 32, 0, cs>>>(c->pc, FLAG_Y);
+        LK(c, k_peer_signal, 1, 32, 0, cs, c->pc, FLAG_Y);
         if (cs != st) CK(cudaEventRecord(c->ev_cjoin, cs));
         c->stats.kernel_launches += 1;
     }
-    constexpr int col_threads = COL_THREADS;
+    // column CTAs: 256 threads (~4 CTAs share an SM on one GPU).  FITSNE_COL_THREADS=512 selects the wide instantiation for
+    // experiments with the distributed convolution, where a rank's few columns have an SM each: on 2 x B200 (289 columns
+    // per rank) it shortened the serialised convolution phase 0.160 -> 0.141 ms but not the graph-replayed iteration
+    // (0.348 -> 0.356 ms), so 256 stays the default.
+    static const int col_env = getenv("FITSNE_COL_THREADS") ? atoi(getenv("FITSNE_COL_THREADS")) : 0;
+    const int col_threads = col_env >= 64 && col_env <= COL_THREADS_MAX ? col_env / 32 * 32 : COL_THREADS;
     auto launch_kernel_side = [&](cudaStream_t ks) -> int {
         const int Gc = M / 2, H = M / 2 + 1;
-        k_kspec_rows<<<Gc, ROW_THREADS, pl->smem_row1, ks>>>(c->KR, pl->plan, pl->W, c->gp, c->cfg.df);
-        k_kspec_cols<<<(H + 1) / 2, col_threads, pl->smem_col, ks>>>(c->KR, c->KS, pl->cplan, pl->W, c->gp, c->rank, c->p2p && c->dist_conv ? c->world : 1);
+        LK(c, k_kspec_rows, Gc, ROW_THREADS, pl->smem_row1, ks, c->KR, pl->plan, pl->W, c->gp, c->cfg.df);
+        if (col_threads <= COL_THREADS)
+            LK(c, k_kspec_cols<COL_THREADS>, (H + 1) / 2, col_threads, pl->smem_col, ks, c->KR, c->KS, pl->cplan, pl->W, c->gp, c->rank, c->p2p && c->dist_conv ? c->world : 1);
+        else
+            LK(c, k_kspec_cols<COL_THREADS_MAX>, (H + 1) / 2, col_threads, pl->smem_col, ks, c->KR, c->KS, pl->cplan, pl->W, c->gp, c->rank, c->p2p && c->dist_conv ? c->world : 1);
         LAUNCH_CHECK();
         c->stats.kernel_launches += 2;
         return 0;
@@ -466,13 +499,13 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     // update) -> sweep#1 -> sorted_u.  One-pass layout: k_bin writes keys[1] and the coordinates straight to dC, sweep#0
     // returns at once.
     float *u0 = c->frep, *u1 = c->dC;
-    k_bin<D><<<tiles, BIN_THREADS, 0, st>>>(c->Y, c->row_begin, nloc, c->gp, c->keys[0], c->keys[1], u0, u1, c->sort_totals, c->sort_bases,
+    LK(c, k_bin<D>, tiles, BIN_THREADS, 0, st, c->Y, c->row_begin, nloc, c->gp, c->keys[0], c->keys[1], u0, u1, c->sort_totals, c->sort_bases,
                                            c->sweep_state, tiles, c->tickets + 4);
     kt(c, "k_bin");
-    k_radix_sweep<<<tiles, SWEEP_THREADS, sweep_smem, st>>>(c->keys[0], nullptr, c->keys[1], c->perm[1], nloc, 0, c->sort_bases, c->sweep_state,
+    LK(c, k_radix_sweep, tiles, SWEEP_THREADS, sweep_smem, st, c->keys[0], nullptr, c->keys[1], c->perm[1], nloc, 0, c->sort_bases, c->sweep_state,
                                                            tiles, c->tickets + 5, (uint32_t) c->row_begin, c->gp, u0, u1, D);
     kt(c, "k_radix_sweep#0");
-    k_radix_sweep<<<tiles, SWEEP_THREADS, sweep_smem, st>>>(c->keys[1], c->perm[1], c->keys[0], c->perm[0], nloc, 1, c->sort_bases, c->sweep_state,
+    LK(c, k_radix_sweep, tiles, SWEEP_THREADS, sweep_smem, st, c->keys[1], c->perm[1], c->keys[0], c->perm[0], nloc, 1, c->sort_bases, c->sweep_state,
                                                            tiles, c->tickets + 6, (uint32_t) c->row_begin, c->gp, u1, c->sorted_u, D);
     const uint32_t *skeys = c->keys[0], *sperm = c->perm[0];
     kt(c, "k_radix_sweep#1");
@@ -486,10 +519,11 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     void *spread_grid = D == 2 ? (void *) c->chg : (c->p2p ? (void *) c->grid1d : (void *) c->planes);
     if (D == 2) CK(cudaMemsetAsync(c->chg, 0, cplane * sizeof(float4), st));
     else CK(cudaMemsetAsync(spread_grid, 0, (size_t) 2 * M * sizeof(float2), st));
+    pdl_break(c);
     CKRC(launch_spread_gather<D>(c, false, skeys, sperm));
     kt(c, "k_spread_chunks");
     // (sharded, peer fabric: the CTA of the combine that finishes last announces "my partial grid is complete" to the peers)
-    k_spread_combine<D><<<148 * 8, 256, 0, st>>>(c->slots, c->box_range, c->gp, c->work, spread_grid, c->tickets + 7, c->pc,
+    LK(c, k_spread_combine<D>, 148 * 8, 256, 0, st, c->slots, c->box_range, c->gp, c->work, spread_grid, c->tickets + 7, c->pc,
                                                  c->world > 1 && c->p2p ? 1 : 0, c->chunk);
     c->stats.kernel_launches += 1;
     if (c->world > 1) {
@@ -499,11 +533,11 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         if (c->p2p) {
             // peer fabric: the sum over ranks happens inside k_conv_rows_fwd's loads (2-D) or in one small kernel (1-D)
             if (D == 1) {
-                k_grid_sum_1d<<<cdiv(2 * M, 256), 256, 0, st>>>(c->pc, c->planes, 2 * M, &c->gp->ok);
+                LK(c, k_grid_sum_1d, cdiv(2 * M, 256), 256, 0, st, c->pc, c->planes, 2 * M, &c->gp->ok);
                 c->stats.kernel_launches += 1;
             }
-        } else if (D == 2) CKNCCL(g_nccl.AllReduce(c->chg, c->chg, cplane * 4, ncclFloat, ncclSum, c->comm, st));
-        else CKNCCL(g_nccl.AllReduce(c->planes, c->planes, (size_t) M * 4, ncclFloat, ncclSum, c->comm, st));
+        } else if (D == 2) { CKNCCL(g_nccl.AllReduce(c->chg, c->chg, cplane * 4, ncclFloat, ncclSum, c->comm, st)); pdl_break(c); }
+        else { CKNCCL(g_nccl.AllReduce(c->planes, c->planes, (size_t) M * 4, ncclFloat, ncclSum, c->comm, st)); pdl_break(c); }
     }
     kt(c, "k_spread_combine(+collective)");
 
@@ -514,32 +548,37 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         // the kernel spectra depend on the grid geometry only.  Single GPU: in line (beside the SpMV-saturated kernels a second
         // stream buys nothing, see above).  Sharded runs leave most of every GPU idle between exchanges: there the two kernels
         // run on a side stream beside the sort and the spread (forked right after k_setup_grid, joined here).
-        if (kside) CK(cudaStreamWaitEvent(st, c->ev_kjoin, 0));
+        if (kside) { CK(cudaStreamWaitEvent(st, c->ev_kjoin, 0)); pdl_break(c); }
         else CKRC(launch_kernel_side(st));
         kt(c, "k_kspec_rows + k_kspec_cols");
         phase_mark(c, FITSNE_PHASE_FFT);
         const int H = M / 2 + 1;
-        k_conv_rows_fwd<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->chg, c->S, pl->plan, pl->W, c->gp, c->pc, c->p2p ? (c->dist_conv ? 2 : 1) : 0,
+        LK(c, k_conv_rows_fwd, Gc, ROW_THREADS, pl->smem_row2, st, c->chg, c->S, pl->plan, pl->W, c->gp, c->pc, c->p2p ? (c->dist_conv ? 2 : 1) : 0,
                                                                         c->tickets + 8);
         kt(c, "k_conv_rows_fwd");
         const int dist = c->p2p && c->dist_conv ? 1 : 0, p2p = dist ? 2 : 0;
         // sharded, distributed convolution: like a 2-D FFT -- rows and spectrum columns dealt out in blocks; every
         // "transpose" is the producing kernel's stores on peer memory; the CTA that finishes last raises the stage's flag at
         // the peers, the consuming kernel's CTAs wait for it themselves -- no launch of its own for any exchange
-        k_conv_cols<<<H, col_threads, pl->smem_col, st>>>(pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
-                                                          c->sc, c->tickets + 0, c->pc, p2p);
+        if (col_threads <= COL_THREADS) {
+            LK(c, k_conv_cols<COL_THREADS>, H, col_threads, pl->smem_col, st, pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
+                                                              c->sc, c->tickets + 0, c->pc, p2p);
+        } else {
+            LK(c, k_conv_cols<COL_THREADS_MAX>, H, col_threads, pl->smem_col, st, pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
+                                                              c->sc, c->tickets + 0, c->pc, p2p);
+        }
         kt(c, "k_conv_cols");
-        k_conv_rows_inv<<<Gc, ROW_THREADS, pl->smem_row2, st>>>(c->S, c->pot, pl->plan, pl->W, c->gp, c->pc, p2p, c->N, c->sc, c->tickets + 9);
+        LK(c, k_conv_rows_inv, Gc, ROW_THREADS, pl->smem_row2, st, c->S, c->pot, pl->plan, pl->W, c->gp, c->pc, p2p, c->N, c->sc, c->tickets + 9);
         kt(c, "k_conv_rows_inv");
         c->stats.kernel_launches += 3;
     } else {
-        k_gen_kernels_1d<<<cdiv(M, 256), 256, 0, st>>>(c->gp, c->cfg.df, c->planes);
+        LK(c, k_gen_kernels_1d, cdiv(M, 256), 256, 0, st, c->gp, c->cfg.df, c->planes);
         kt(c, "k_gen_kernels_1d");
         phase_mark(c, FITSNE_PHASE_FFT);
         // lines 0,1 = charges (zero beyond G: substituted while loading), lines 2,3 = kernels
-        k_fft_line<<<4, FFT_THREADS, pl->smem_line, st>>>(c->planes, pl->plan, pl->W, 0, 0x0u, &c->gp->G, gok);
-        k_hadamard_1d<<<Z_BLOCKS_1D, 256, 0, st>>>(c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0);
-        k_fft_line<<<1, FFT_THREADS, pl->smem_line, st>>>(c->planes, pl->plan, pl->W, 1, 0u, &c->gp->G, gok);
+        LK(c, k_fft_line, 4, FFT_THREADS, pl->smem_line, st, c->planes, pl->plan, pl->W, 0, 0x0u, &c->gp->G, gok);
+        LK(c, k_hadamard_1d, Z_BLOCKS_1D, 256, 0, st, c->planes, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0);
+        LK(c, k_fft_line, 1, FFT_THREADS, pl->smem_line, st, c->planes, pl->plan, pl->W, 1, 0u, &c->gp->G, gok);
         kt(c, "1-D convolution");
         c->stats.kernel_launches += 4;
     }
@@ -551,8 +590,8 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     if (dist_conv_on) {
         // distributed convolution: the potential rows come from every rank -- one wait covers them AND the Y slices the
         // SpMV needs further down (pushed at the start of the iteration: long since there)
-        if (push_Y && !c->timing_this_iter) CK(cudaStreamWaitEvent(st, c->ev_cjoin, 0));
-        k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_POT, push_Y ? FLAG_Y : -1);
+        if (push_Y && !c->timing_this_iter) { CK(cudaStreamWaitEvent(st, c->ev_cjoin, 0)); pdl_break(c); }
+        LK(c, k_peer_wait, 1, 32, 0, st, c->pc, FLAG_POT, push_Y ? FLAG_Y : -1);
         c->stats.kernel_launches += 1;
     }
     CKRC(launch_spread_gather<D>(c, true, skeys, sperm));
@@ -565,11 +604,11 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         phase_mark(c, FITSNE_PHASE_ALLGATHER);
         if (push_Y) {
             if (!dist_conv_on) {
-                if (!c->timing_this_iter) CK(cudaStreamWaitEvent(st, c->ev_cjoin, 0));     // my own pushes are out ...
-                k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_Y, -1);                           // ... and everybody's have landed here
+                if (!c->timing_this_iter) { CK(cudaStreamWaitEvent(st, c->ev_cjoin, 0)); pdl_break(c); }     // my own pushes are out ...
+                LK(c, k_peer_wait, 1, 32, 0, st, c->pc, FLAG_Y, -1);                           // ... and everybody's have landed here
                 c->stats.kernel_launches += 1;
             }
-        } else CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, st));
+        } else { CKNCCL(g_nccl.AllGather(c->Y + (size_t) c->rank * c->per * D, c->Y, (size_t) c->per * D, ncclFloat, c->comm, st)); pdl_break(c); }
     }
     c->y_whole = true;
     phase_mark(c, FITSNE_PHASE_ATTRACT_UPDATE);
@@ -578,21 +617,21 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     const int rows = c->row_end - c->row_begin;
     const int ublocks = std::min(RED_BLOCKS, cdiv(rows, 256));
     if (!update) {
-        k_update<D, false><<<ublocks, 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
+        LK(c, (k_update<D, false>), ublocks, 256, 0, st, c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
                                                    c->uY, c->gains, c->Yb, nullptr, c->N, c->sc, c->tickets + 2);
         c->stats.kernel_launches += 1;
         phase_mark(c, FITSNE_PHASE_CENTER);
         if (c->p2p) {
             // no statistics exchange closes a gradient-only pass: meet the peers explicitly, so that nobody clears its
             // partial grid for the next pass while a slower rank still reads it
-            k_peer_signal<<<1, 32, 0, st>>>(c->pc, FLAG_STATS);
-            k_peer_wait<<<1, 32, 0, st>>>(c->pc, FLAG_STATS, -1);
+            LK(c, k_peer_signal, 1, 32, 0, st, c->pc, FLAG_STATS);
+            LK(c, k_peer_wait, 1, 32, 0, st, c->pc, FLAG_STATS, -1);
             c->stats.kernel_launches += 2;
         }
     } else if (c->world == 1) {
         // single GPU: k_update also produces the column means of the new positions (per-CTA register sums, last-block
         // reduction), the centring kernel subtracts them, finds the bounds and publishes them -- two launches for the tail
-        k_update<D, true><<<ublocks, 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
+        LK(c, (k_update<D, true>), ublocks, 256, 0, st, c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->sp, c->gp, c->dC,
                                                   c->uY, c->gains, c->Yb, c->colsum_partial, c->N, c->sc, c->tickets + 2);
         c->stats.kernel_launches += 1;
         phase_mark(c, FITSNE_PHASE_CENTER);
@@ -600,18 +639,19 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     } else {
         // sharded tail: local update with its sums / bounds riding along -> 128-byte records exchanged -> every rank centres
         // its own slice with the global mean and publishes the (identical) global bounds.  Y itself is gathered next iteration.
-        k_update_shard<D><<<ublocks, 256, 0, st>>>(c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->rank, c->sp, c->gp, c->dC, c->uY,
+        LK(c, k_update_shard<D>, ublocks, 256, 0, st, c->Y, c->attr, c->frep, c->row_begin, c->row_end, c->rank, c->sp, c->gp, c->dC, c->uY,
                                                    c->gains, c->Yb, c->shard_sum_partial, c->shard_mm_partial, c->shard_stats + c->rank,
                                                    c->tickets + 3, c->pc, c->p2p ? 1 : 0, c->reordered ? c->orig_of : nullptr,
                                                    c->reordered ? c->pos_of : nullptr);
         phase_mark(c, FITSNE_PHASE_CENTER);
-        if (!c->p2p) CKNCCL(g_nccl.AllGather(c->shard_stats + c->rank, c->shard_stats, sizeof(ShardStats), ncclChar, c->comm, st));
-        k_center_shard<D><<<cdiv(rows, 256), 256, 0, st>>>(c->Yb, c->Y, c->row_begin, c->row_end, c->N, c->shard_stats, c->world,
+        if (!c->p2p) { CKNCCL(g_nccl.AllGather(c->shard_stats + c->rank, c->shard_stats, sizeof(ShardStats), ncclChar, c->comm, st)); pdl_break(c); }
+        LK(c, k_center_shard<D>, cdiv(rows, 256), 256, 0, st, c->Yb, c->Y, c->row_begin, c->row_end, c->N, c->shard_stats, c->world,
                                                           c->gp, c->sc, c->host_bounds_dev, c->pc, c->p2p ? 1 : 0);
         c->stats.kernel_launches += 2;
         c->y_whole = false;
     }
     phase_mark(c, FITSNE_PHASE_COUNT);
+    c->in_chain = false;
     LAUNCH_CHECK();
     kt(c, "k_update + zero-mean/bounds tail");
     return 0;
@@ -1168,6 +1208,7 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+    c->use_pdl = !(getenv("FITSNE_PDL") && atoi(getenv("FITSNE_PDL")) == 0);
     c->ktimes_on = getenv("FITSNE_KTIMES") && atoi(getenv("FITSNE_KTIMES")) != 0;
     for (auto &e : c->ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1177,8 +1218,10 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     CK(cudaFuncSetAttribute(k_conv_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(k_conv_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(k_kspec_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CK(cudaFuncSetAttribute(k_kspec_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CK(cudaFuncSetAttribute(k_conv_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_kspec_cols<COL_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_kspec_cols<COL_THREADS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_conv_cols<COL_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(cudaFuncSetAttribute(k_conv_cols<COL_THREADS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 
     const size_t yel = (size_t) c->per * world * no_dims;
     c->y_elems = yel;

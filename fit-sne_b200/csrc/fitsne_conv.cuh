@@ -40,7 +40,8 @@
 namespace fk {
 
 constexpr int COL_SLOTS = 4;          // sequences per column tile
-constexpr int COL_THREADS = 256;      // upper bound (launch bounds); the launch picks 128..256
+constexpr int COL_THREADS = 256;      // threads per column CTA (single GPU, replicated convolution: ~4 CTAs share an SM)
+constexpr int COL_THREADS_MAX = 512;  // second instantiation's launch bound: distributed convolution (a rank's few columns, one CTA per SM) launches wider CTAs
 constexpr int COL_BOX_ROWS = 128;     // rows per TMA box (box = 128 rows x 32 bytes)
 constexpr int ROW_THREADS = 256;
 
@@ -237,6 +238,7 @@ __device__ __forceinline__ void tma_store_commit_and_wait() {
 __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_fwd(const float4 *__restrict__ chg, float2 *__restrict__ S, FftPlan plan,
                                                                const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
                                                                PeerComm pc, int p2p, unsigned int *__restrict__ ticket) {
+    pdl_prologue();
     extern __shared__ __align__(16) float2 row_sm[];
     __shared__ FftPlan plan_s;
     const int G = gpp->G;
@@ -296,6 +298,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_inv(const float2 *S, 
                                                                const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
                                                                PeerComm pc, int p2p, int N, Scalars *__restrict__ sc,
                                                                unsigned int *__restrict__ ticket) {
+    pdl_prologue();
     extern __shared__ __align__(16) float2 row_sm[];
     __shared__ FftPlan plan_s;
     const int G = gpp->G;
@@ -354,6 +357,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_conv_rows_inv(const float2 *S, 
 //   Re Z = Ksq~,  Im Z = a~ + Kb~  with a~ odd:   KR[dr][kx] = (Ksq~, Kb~, a~, 0)  for kx <= M/2   (Kgrad_x~ = i a~).
 __global__ void __launch_bounds__(ROW_THREADS) k_kspec_rows(float4 *__restrict__ KR, FftPlan plan, const float2 *__restrict__ W,
                                                             const GridParams *__restrict__ gpp, double df) {
+    pdl_prologue();
     extern __shared__ __align__(16) float2 row_sm[];
     __shared__ FftPlan plan_s;
     const int G = gpp->G;
@@ -391,9 +395,11 @@ __global__ void __launch_bounds__(ROW_THREADS) k_kspec_rows(float4 *__restrict__
 // gap) of   zA = Ksq~ + i Kb~   (both even in dr -> real spectra Ksq^, Kb^)   and   zB = a~ - (dr/p) Ksq~   (even - odd:
 // Re ZB = gx with Kgrad_x^ = i gx,  Im ZB = -gy with Kgrad_y^ = i gy).   KS[kx][pos] = (Ksq^, Kb^, gx, gy), pos = the
 // forward transform's digit-reversed frequency slot -- the order k_conv_cols meets them in.
-__global__ void __launch_bounds__(COL_THREADS) k_kspec_cols(const float4 *__restrict__ KR, float4 *__restrict__ KS, ColPlan plan,
+template <int BOUND>
+__global__ void __launch_bounds__(BOUND) k_kspec_cols(const float4 *__restrict__ KR, float4 *__restrict__ KS, ColPlan plan,
                                                             const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
                                                             int rank, int world) {
+    pdl_prologue();
     extern __shared__ __align__(128) float2 col_sm[];
     __shared__ ColPlan plan_s;
     if (!gpp->ok) return;
@@ -439,10 +445,12 @@ __global__ void __launch_bounds__(COL_THREADS) k_kspec_cols(const float4 *__rest
 //   df!=1: <w1,Kb*w1>                                                                          (tsne.cpp:950-955)
 // (delta, wbb, Kgrad, B are in box units: the bracketed terms carry bw^2).  Three inverse FFTs in place, TMA stores the
 // tile back over its input.  The last CTA to finish adds the per-column partials in index order: sum_Q, 1/sum_Q.
-__global__ void __launch_bounds__(COL_THREADS) k_conv_cols(const __grid_constant__ CUtensorMap tmS, const float4 *__restrict__ KS,
+template <int BOUND>
+__global__ void __launch_bounds__(BOUND) k_conv_cols(const __grid_constant__ CUtensorMap tmS, const float4 *__restrict__ KS,
                                                            ColPlan plan, const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
                                                            int df_is_one, double *__restrict__ zpartial, int N, Scalars *__restrict__ sc,
                                                            unsigned int *__restrict__ ticket, PeerComm pc, int p2p) {
+    pdl_prologue();
     extern __shared__ __align__(128) float2 col_sm[];
     __shared__ ColPlan plan_s;
     __shared__ __align__(8) uint64_t mbar;

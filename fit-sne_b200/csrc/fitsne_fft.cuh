@@ -222,6 +222,7 @@ __device__ __forceinline__ float2 *fft_smem(float2 *a, float2 *b, int NS, int ba
 constexpr int FFT_THREADS = 512;
 __global__ void __launch_bounds__(FFT_THREADS) k_fft_line(float2 *__restrict__ data, FftPlan plan, const float2 *__restrict__ W, int inverse,
                                                           unsigned zero_mask, const int *__restrict__ zero_from, const int *__restrict__ ok) {
+    pdl_prologue();
     if (ok && !*ok) return;
     extern __shared__ float2 fft_sm[];
     __shared__ FftPlan plan_s;

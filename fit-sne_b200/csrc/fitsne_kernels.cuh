@@ -101,6 +101,17 @@ struct PeerComm {
     unsigned int *seq;               // my sequence counter (bumped once per enqueued iteration by k_setup_grid)
     int rank, world;
 };
+// First statement of every kernel of the iteration chain (see launch_k in fitsne_capi.cu).  Launched with programmatic
+// stream serialisation, a kernel may be set up while its predecessor drains; "wait" blocks until the
+// predecessor grid has completed and its memory is visible -- nothing before it may touch global memory.  A no-op in a
+// plain launch.  (No early "launch_dependents": measured on B200 with the trigger at the top of every kernel, the
+// dependents' CTAs became resident beside multi-wave predecessors and took their SM slots -- 1M points 2518 -> 2073 it/s,
+// 10M 349 -> 175 it/s.  The implicit trigger at grid exit keeps the order of the waves intact.)
+__device__ __forceinline__ void pdl_prologue() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 // contiguous block partition of n items over the ranks (block size rounded up to a multiple of `align`)
 __host__ __device__ __forceinline__ int part_block(int n, int world, int align) {
     const int b = (n + world - 1) / world;
@@ -123,6 +134,7 @@ __device__ __forceinline__ void peer_wait(const uint32_t *flags, int kind, const
 
 // tell every peer that my data for exchange `kind` is in place (one thread; everything written before is fenced first)
 __global__ void k_peer_signal(PeerComm pc, int kind) {
+    pdl_prologue();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     __threadfence_system();
     const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
@@ -131,6 +143,7 @@ __global__ void k_peer_signal(PeerComm pc, int kind) {
 }
 // stream-level wait: one thread spins until every peer has signalled `kind` (and `kind2`, if >= 0) for this iteration
 __global__ void k_peer_wait(PeerComm pc, int kind, int kind2) {
+    pdl_prologue();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const uint32_t seq = *reinterpret_cast<volatile unsigned int *>(pc.seq);
     peer_wait(pc.flags[pc.rank], kind, pc, seq);
@@ -162,6 +175,7 @@ __device__ __forceinline__ void peer_signal_last(unsigned int *ticket, const Pee
 // 1-D sharded runs: planes 0, 1 (two packed complex lines of length M) <- sum over ranks of their partial lines, in rank
 // order.  Every rank keeps its partial in `partial` (peer-readable) and writes the sum into its own FFT input.
 __global__ void __launch_bounds__(256) k_grid_sum_1d(PeerComm pc, float2 *__restrict__ planes, int n /* 2 * M */, const int *__restrict__ ok) {
+    pdl_prologue();
     if (!*ok) return;
     if (threadIdx.x == 0) peer_wait(pc.flags[pc.rank], FLAG_GRID, pc, *reinterpret_cast<volatile unsigned int *>(pc.seq));
     __syncthreads();
@@ -255,6 +269,7 @@ __global__ void __launch_bounds__(256) k_center_bounds(const float *__restrict__
                                                        Scalars *__restrict__ sc, const uint32_t *__restrict__ orig_of,
                                                        const uint32_t *__restrict__ pos_of, const GridParams *__restrict__ gpp,
                                                        volatile float *host_bounds, unsigned int *__restrict__ ticket) {
+    pdl_prologue();
     if (gpp && !gpp->ok) return;
     __shared__ float smf[64];
     double mean[2] = {0, 0};
@@ -391,6 +406,7 @@ __host__ __device__ inline int sort_bits_for(int B, int dims) {
 __global__ void k_setup_grid(GridParams *__restrict__ gp, const Scalars *__restrict__ sc, const int *__restrict__ B_host, int M, int p, int dims,
                              double ipi, int min_int, int *__restrict__ mismatch, uint32_t *__restrict__ sort_totals,
                              uint32_t *__restrict__ work, unsigned int *__restrict__ sweep_tickets, unsigned int *__restrict__ comm_seq) {
+    pdl_prologue();
     for (int i = threadIdx.x; i < 2 * (1 << SORT_MAX_BITS); i += blockDim.x) sort_totals[i] = 0;   // both passes
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (comm_seq) *comm_seq += 1;                    // sharded: this iteration's sequence number (also for no-op iterations)
@@ -496,6 +512,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const float *__restrict__ Y
                                                      float *__restrict__ ubuf_one_pass, uint32_t *__restrict__ totals,
                                                      uint32_t *__restrict__ bases, uint32_t *__restrict__ state, int tiles,
                                                      unsigned int *__restrict__ ticket) {
+    pdl_prologue();
     __shared__ uint32_t cnt[2 << SORT_MAX_BITS];       // digit 0 | digit 1
     __shared__ GridParams gps;
     __shared__ uint32_t scan_sm[33];
@@ -564,6 +581,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_radix_sweep(const uint32_t *_
                                                                unsigned int *__restrict__ ticket, uint32_t val_base,
                                                                const GridParams *__restrict__ gpp, const float *__restrict__ u_in,
                                                                float *__restrict__ u_out, int dims) {
+    pdl_prologue();
     if (!gpp->ok) return;
     const bool one = gpp->sort_passes == 1;
     if (one && pass == 0) return;
@@ -1066,6 +1084,7 @@ __global__ void __launch_bounds__(SP2_THREADS) k_spread_chunks(const float *__re
                                                                const GridParams *__restrict__ gpp, float4 *__restrict__ cslots,
                                                                float4 *__restrict__ gpart, void *__restrict__ grid,
                                                                uint2 *__restrict__ box_range, uint32_t *__restrict__ work, int chunk) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char sp_raw[];
     __shared__ GridParams gps;
     __shared__ Sp2Meta meta;
@@ -1105,6 +1124,7 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
                                                         const GridParams *__restrict__ gpp, const uint32_t *__restrict__ work,
                                                         void *__restrict__ grid, unsigned int *__restrict__ ticket, PeerComm pc, int p2p,
                                                         int chunk) {
+    pdl_prologue();
     const GridParams &gp = *gpp;
     const int p = gp.p, nodes = D == 2 ? p * p : p;
     const int lane = threadIdx.x & 31;
@@ -1155,6 +1175,7 @@ __global__ void __launch_bounds__(256) k_spread_combine(const float4 *__restrict
 //   Ksq=(1+r2/df)^-(df+1)   Kgrad = (R/bw)*Ksq  (box units)   Kb=(1+r2/df)^-df      (tsne.cpp:69-94)
 // Values carry the 1/M inverse-FFT normalisation (nbodyfft.cpp:427-430).
 __global__ void __launch_bounds__(256) k_gen_kernels_1d(const GridParams *__restrict__ gpp, double df, float2 *__restrict__ planes) {
+    pdl_prologue();
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
     const int M = gp.M, G = gp.G;
@@ -1196,6 +1217,7 @@ __device__ __forceinline__ void unpack_pair(float2 zk, float2 zm, float2 &A, flo
 __global__ void __launch_bounds__(256) k_hadamard_1d(float2 *__restrict__ planes, const GridParams *__restrict__ gpp,
                                                      int df_is_one, double *__restrict__ zpartial, int N, Scalars *__restrict__ sc,
                                                      unsigned int *__restrict__ ticket) {
+    pdl_prologue();
     __shared__ double sm[32];
     const GridParams &gp = *gpp;
     if (!gp.ok) return;
@@ -1248,6 +1270,7 @@ __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted
                                                 const uint32_t *__restrict__ perm, int n,
                                                 const GridParams *__restrict__ gpp, const Scalars *__restrict__ sc,
                                                 const void *__restrict__ field, float *__restrict__ frep) {
+    pdl_prologue();
     __shared__ GridParams gps;
     for (int i = threadIdx.x; i < (int) (sizeof(GridParams) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&gps)[i] = reinterpret_cast<const int *>(gpp)[i];
@@ -1314,6 +1337,7 @@ template <int D, int LPR>
 __global__ void __launch_bounds__(256) k_attract(const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges, uint32_t edge_base,
                                                  const float *__restrict__ Y, int row_begin, int row_end, float inv_df,
                                                  float *__restrict__ attr) {
+    pdl_prologue();
     constexpr int RPB = 256 / LPR;                       // rows per CTA per trip
     const int sub = threadIdx.x % LPR;
     const int nrows = row_end - row_begin;
@@ -1425,6 +1449,7 @@ __global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, con
                                                 float *__restrict__ dC_out, float *__restrict__ uY, float *__restrict__ gains,
                                                 float *__restrict__ Ynext, double *__restrict__ colsum_partial, int N_total,
                                                 Scalars *__restrict__ sc, unsigned int *__restrict__ ticket) {
+    pdl_prologue();
     if (!gpp->ok) return;
     const StepParams sp = *spp;
     const int per = (row_end - row_begin + gridDim.x - 1) / gridDim.x;
@@ -1491,6 +1516,7 @@ __global__ void __launch_bounds__(256) k_update_shard(const float *__restrict__ 
                                                       float4 *__restrict__ mm_partial, ShardStats *__restrict__ out,
                                                       unsigned int *__restrict__ ticket, PeerComm pc, int p2p,
                                                       const uint32_t *__restrict__ orig_of, const uint32_t *__restrict__ pos_of) {
+    pdl_prologue();
     if (!gpp->ok) return;
     __shared__ double smd[32];
     __shared__ float4 smm[8];
@@ -1598,6 +1624,7 @@ __global__ void __launch_bounds__(256) k_center_shard(const float *__restrict__ 
                                                       int N, const ShardStats *all, int world,
                                                       const GridParams *__restrict__ gpp, Scalars *__restrict__ sc,
                                                       volatile float *host_bounds, PeerComm pc, int p2p) {
+    pdl_prologue();
     if (!gpp->ok) return;
     __shared__ double mean_s[2];
     __shared__ double sum_s[2 * MAX_RANKS];
@@ -1888,6 +1915,7 @@ __global__ void __launch_bounds__(1024, 1) k_attract_tiles(const float *__restri
                                                            const uint32_t *__restrict__ tile_start,
                                                            const uint32_t *__restrict__ tile_pack, const float *__restrict__ tile_val,
                                                            float inv_df, float fix32, float *__restrict__ attr) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = tg.rows_per_chunk;
     using YT = typename std::conditional<D == 2, float2, float>::type;
