@@ -1182,6 +1182,8 @@ static int create_impl(fitsne_ctx *c, const fitsne_config *cfg, int N, int no_di
     if (cfg->nterms < 1 || cfg->nterms > PMAX) return fail(c, FITSNE_EINVAL, "nterms must be in 1..%d", PMAX);
     if (!(cfg->df > 0) || !(cfg->intervals_per_integer > 0) || cfg->min_num_intervals < 1)
         return fail(c, FITSNE_EINVAL, "df, intervals_per_integer and min_num_intervals must be positive");
+    if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world)
+        return fail(c, FITSNE_EINVAL, "world size must be in 1..%d (the GPUs of one node) and 0 <= rank < world, got rank %d of %d", MAX_RANKS, rank, world);
     c->cfg = *cfg;
     c->N = N; c->D = no_dims;
     c->rank = rank; c->world = world;

@@ -104,14 +104,17 @@ enum {
 
 /* Create a context holding P (converted to fp32 CSR) and the optimiser state (Y, uY=0, gains=1) on the
  * device.  Replaces the allocations at tsne.cpp:143-150.  Y0 may be NULL (zeros; set it later).
- * For a sharded run (fitsne_comm_init) every rank passes the FULL row_P / Y0 but may pass only its own
+ * For a sharded run every rank passes the FULL row_P / Y0 but may pass only its own
  * rows' col_P/val_P slice -- see fitsne_create_sharded. */
 int fitsne_create(const fitsne_config *cfg, int N, int no_dims, const unsigned int *row_P,
                   const unsigned int *col_P, const double *val_P, const double *Y0, fitsne_ctx **out);
 
 /* Sharded variant: this rank owns points/rows [row_begin, row_end); col_P/val_P hold only the edges of
  * those rows (row_P is still the full N+1 offsets array).  nccl_unique_id is the 128-byte ncclUniqueId
- * produced by fitsne_nccl_unique_id on rank 0 and shipped by the launcher (torch.distributed, MPI, ...). */
+ * produced by fitsne_nccl_unique_id on rank 0 and shipped by the launcher (torch.distributed, MPI, ...).
+ * Rows are dealt out in contiguous blocks of ceil(N / world_size): rank r owns [r * per, min(N, (r + 1) * per)), which
+ * must not be empty (FITSNE_EINVAL otherwise -- e.g. N = 9 on 4 ranks leaves rank 3 without rows: use fewer ranks);
+ * 1 <= world_size <= 8, all ranks on one node (peer-memory exchanges over NVLink; NCCL collectives without peer access). */
 int fitsne_create_sharded(const fitsne_config *cfg, int N, int no_dims, const unsigned int *row_P,
                           const unsigned int *col_P_local, const double *val_P_local, const double *Y0,
                           int rank, int world_size, int row_begin, int row_end,
