@@ -54,12 +54,12 @@ struct ColPlan {
     FastDiv div_m[FFT_MAX_STAGES];
 };
 
-__host__ inline bool col_make_plan(int n, ColPlan *p) {
-    p->n = n; p->nstages = 0;
-    int mm = n;
-    auto take = [&](int r) { while (mm % r == 0 && p->nstages < FFT_MAX_STAGES) { p->radix[p->nstages++] = r; mm /= r; } };
-    take(8); take(4); take(2); take(3); take(5);       // odd radices last: see the layout note above
-    if (mm != 1) return false;
+// Radices: fft_pick_radices (fitsne_fft.cuh) -- narrow (8, 4, 2, 3, 5) or wide (up to 16: as few passes over the tile as
+// possible).  Either way the even radices come first and an odd one last: see the layout note above.
+__host__ inline bool col_make_plan(int n, ColPlan *p, bool wide = false) {
+    p->n = n;
+    p->nstages = fft_pick_radices(n, wide, p->radix);
+    if (p->nstages == 0) return false;
     int n_cur = n;
     for (int st = 0; st < p->nstages; st++) {
         p->m[st] = n_cur / p->radix[st];
@@ -67,7 +67,7 @@ __host__ inline bool col_make_plan(int n, ColPlan *p) {
         p->div_m[st] = make_fastdiv((uint32_t) p->m[st]);
         n_cur = p->m[st];
     }
-    return true;
+    return n_cur == 1;
 }
 
 __host__ __device__ __forceinline__ float2 ld_tw(const float2 *__restrict__ W, int i) {
@@ -147,6 +147,8 @@ __host__ __device__ __forceinline__ void col_run_fwd_stage(float2 *x, const ColP
     const int M = pl.n, m = pl.m[st], tws = pl.tws[st];
     const FastDiv dm = pl.div_m[st];
     switch (pl.radix[st]) {
+        case 16: col_fwd_stage<16, FIRST>(x, M, m, tws, dm, nz, W, tid, nthreads); break;
+        case 9: col_fwd_stage<9, FIRST>(x, M, m, tws, dm, nz, W, tid, nthreads); break;
         case 8: col_fwd_stage<8, FIRST>(x, M, m, tws, dm, nz, W, tid, nthreads); break;
         case 4: col_fwd_stage<4, FIRST>(x, M, m, tws, dm, nz, W, tid, nthreads); break;
         case 2: col_fwd_stage<2, FIRST>(x, M, m, tws, dm, nz, W, tid, nthreads); break;
@@ -160,6 +162,8 @@ __host__ __device__ __forceinline__ void col_run_inv_stage(float2 *x, const ColP
     const int M = pl.n, m = pl.m[st], tws = pl.tws[st];
     const FastDiv dm = pl.div_m[st];
     switch (pl.radix[st]) {
+        case 16: col_inv_stage<16, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
+        case 9: col_inv_stage<9, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
         case 8: col_inv_stage<8, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
         case 4: col_inv_stage<4, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
         case 2: col_inv_stage<2, CONJ_OUT>(x, M, m, tws, dm, W, tid, nthreads, nslots); break;
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(BOUND) k_kspec_cols(const float4 *__restrict__
 // (delta, wbb, Kgrad, B are in box units: the bracketed terms carry bw^2).  Three inverse FFTs in place, TMA stores the
 // tile back over its input.  The last CTA to finish adds the per-column partials in index order: sum_Q, 1/sum_Q.
 template <int BOUND>
-__global__ void __launch_bounds__(BOUND) k_conv_cols(const __grid_constant__ CUtensorMap tmS, const float4 *__restrict__ KS,
+__global__ void __launch_bounds__(BOUND, BOUND == COL_THREADS ? 4 : 1) k_conv_cols(const __grid_constant__ CUtensorMap tmS, const float4 *__restrict__ KS,
                                                            ColPlan plan, const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
                                                            int df_is_one, double *__restrict__ zpartial, int N, Scalars *__restrict__ sc,
                                                            unsigned int *__restrict__ ticket, PeerComm pc, int p2p) {

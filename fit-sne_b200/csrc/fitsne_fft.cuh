@@ -57,12 +57,34 @@ struct FftPlan {
     int tpl_log2[FFT_MAX_STAGES];      // per stage: log2(butterfly slots per line group), see fft_stage
 };
 
+// radices of a length-n transform.  wide == false: 8, 4, 2, 3, 5.  wide == true: as few stages as radices up to 16 allow --
+// 2^a as 16s plus one of (8 | 4 | 2 | 8 4), 3^b as 9s plus a 3, then the 5s (1152 = 16 8 9, 1280 = 16 16 5).  Even radices
+// first, odd ones last.  Returns the stage count, 0 if n is not of the form 2^a 3^b 5^c.
+__host__ inline int fft_pick_radices(int n, bool wide, int *radix) {
+    int ns = 0, m = n;
+    auto push = [&](int r) { if (ns < FFT_MAX_STAGES) radix[ns++] = r; };
+    auto take = [&](int r) { while (m % r == 0 && ns < FFT_MAX_STAGES) { radix[ns++] = r; m /= r; } };
+    if (wide) {
+        int a = 0;
+        while (m % 2 == 0) { m /= 2; a++; }
+        const int k = a / 4, r = a % 4;
+        if (r == 1 && k >= 1) { for (int i = 0; i < k - 1; i++) push(16); push(8); push(4); }
+        else { for (int i = 0; i < k; i++) push(16); if (r == 1) push(2); else if (r == 2) push(4); else if (r == 3) push(8); }
+        take(9); take(3); take(5);
+    } else {
+        take(8); take(4); take(2); take(3); take(5);
+    }
+    return m == 1 ? ns : 0;
+}
+
+// The Stockham transforms (rows, 1-D lines) keep the narrow radices.  Measured on B200 with radix-16 / radix-9 stages in
+// fft_stage (1152 = 16 8 9): the row kernels grew from 64-80 to 127 registers, the convolution phase went 0.0925 -> 0.0908 ms
+// and the iteration did not move (2 597 -> 2 589 it/s), while every length that keeps narrow radices paid for the lower
+// occupancy (2 597 -> 2 510 it/s) -- unlike the in-place column transform, where a stage is a pass over the whole tile.
 __host__ inline bool fft_make_plan(int n, FftPlan *p) {
-    p->n = n; p->nstages = 0;
-    int m = n;
-    auto take = [&](int r) { while (m % r == 0 && p->nstages < FFT_MAX_STAGES) { p->radix[p->nstages++] = r; m /= r; } };
-    take(8); take(4); take(2); take(3); take(5);
-    if (m != 1) return false;
+    p->n = n;
+    p->nstages = fft_pick_radices(n, false, p->radix);
+    if (p->nstages == 0) return false;
     int sacc = 1;
     for (int st = 0; st < p->nstages; st++) {
         p->div_s[st] = make_fastdiv((uint32_t) sacc);
@@ -137,6 +159,67 @@ __host__ __device__ __forceinline__ void dft_small<5>(float2 (&a)[5]) {
     const float2 q2 = mul_mi(make_float2(s2 * v1.x - s1 * v2.x, s2 * v1.y - s1 * v2.y));   // -i * q2
     a[0] = make_float2(a[0].x + u1.x + u2.x, a[0].y + u1.y + u2.y);
     a[1] = cadd(p1, q1); a[4] = csub(p1, q1); a[2] = cadd(p2, q2); a[3] = csub(p2, q2);
+}
+
+// a * (c - i s): multiplication by the constant twiddle exp(-i phi), c = cos phi, s = sin phi
+__host__ __device__ __forceinline__ float2 cmul_cs(float2 a, float c, float s) { return make_float2(a.x * c + a.y * s, a.y * c - a.x * s); }
+
+// Radix 16 = 4 x 4 and radix 9 = 3 x 3 (Cooley-Tukey inside the registers: sub-DFTs over n1 with stride R2, constant
+// twiddles w_R^(n2 k1), sub-DFTs over n2; X[k1 + R1 k2]).  Used by the in-place column transform of fitsne_conv.cuh, where
+// a stage is a full pass over the shared-memory tile: 1152 = 16 * 8 * 9 takes three passes instead of five (8 8 2 3 3).
+template <>
+__host__ __device__ __forceinline__ void dft_small<16>(float2 (&a)[16]) {
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    float2 y[4][4];                          // y[n2][k1]
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) {
+        float2 t[4] = {a[n2], a[4 + n2], a[8 + n2], a[12 + n2]};
+        dft_small<4>(t);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) y[n2][k1] = t[k1];
+    }
+    // w16^(n2 k1)
+    y[1][1] = cmul_cs(y[1][1], c1, s1);                                          // w^1
+    y[1][2] = make_float2(h * (y[1][2].x + y[1][2].y), h * (y[1][2].y - y[1][2].x));   // w^2 = (1 - i)/sqrt2
+    y[1][3] = cmul_cs(y[1][3], s1, c1);                                          // w^3
+    y[2][1] = make_float2(h * (y[2][1].x + y[2][1].y), h * (y[2][1].y - y[2][1].x));   // w^2
+    y[2][2] = mul_mi(y[2][2]);                                                   // w^4 = -i
+    y[2][3] = make_float2(h * (y[2][3].y - y[2][3].x), -h * (y[2][3].x + y[2][3].y));  // w^6 = (-1 - i)/sqrt2
+    y[3][1] = cmul_cs(y[3][1], s1, c1);                                          // w^3
+    y[3][2] = make_float2(h * (y[3][2].y - y[3][2].x), -h * (y[3][2].x + y[3][2].y));  // w^6
+    y[3][3] = cmul_cs(y[3][3], -c1, -s1);                                        // w^9 = -cos(pi/8) + i sin(pi/8)
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) {
+        float2 t[4] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1]};
+        dft_small<4>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) a[k1 + 4 * k2] = t[k2];
+    }
+}
+template <>
+__host__ __device__ __forceinline__ void dft_small<9>(float2 (&a)[9]) {
+    const float c1 = 0.76604444311897803520f, s1 = 0.64278760968653932632f;     // 40 degrees
+    const float c2 = 0.17364817766693034885f, s2 = 0.98480775301220805937f;     // 80 degrees
+    const float c4 = -0.93969262078590838405f, s4 = 0.34202014332566873304f;    // 160 degrees
+    float2 y[3][3];                          // y[n2][k1]
+#pragma unroll
+    for (int n2 = 0; n2 < 3; n2++) {
+        float2 t[3] = {a[n2], a[3 + n2], a[6 + n2]};
+        dft_small<3>(t);
+#pragma unroll
+        for (int k1 = 0; k1 < 3; k1++) y[n2][k1] = t[k1];
+    }
+    y[1][1] = cmul_cs(y[1][1], c1, s1);      // w9^1
+    y[1][2] = cmul_cs(y[1][2], c2, s2);      // w9^2
+    y[2][1] = cmul_cs(y[2][1], c2, s2);      // w9^2
+    y[2][2] = cmul_cs(y[2][2], c4, s4);      // w9^4
+#pragma unroll
+    for (int k1 = 0; k1 < 3; k1++) {
+        float2 t[3] = {y[0][k1], y[1][k1], y[2][k1]};
+        dft_small<3>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < 3; k2++) a[k1 + 3 * k2] = t[k2];
+    }
 }
 
 // One Stockham stage of radix R for `batch` independent length-N sequences stored at x + b*NS, written to y + b*NS.

@@ -60,9 +60,9 @@ static double run_len(int M, int lines, bool *plan_ok, int *nstages) {
 }
 
 // in-place column transform: returns the worse of (forward vs DFT, round trip vs M * input), relative
-static double run_col(int M, int nz, bool *plan_ok, int inv_slots = COL_SLOTS) {
+static double run_col(int M, int nz, bool *plan_ok, int inv_slots = COL_SLOTS, bool wide = false) {
     ColPlan pl;
-    *plan_ok = col_make_plan(M, &pl);
+    *plan_ok = col_make_plan(M, &pl, wide);
     if (!*plan_ok) return 0;
     std::vector<float2> W(M), x((size_t) M * COL_SLOTS, make_float2(NAN, NAN));
     for (int k = 0; k < M; k++) { const double a = -2.0 * M_PI * (double) k / (double) M; W[k] = make_float2((float) cos(a), (float) sin(a)); }
@@ -129,7 +129,10 @@ int main() {
         if (M <= 4096) {
             for (int nz : {M / 2, M / 2 - M / 7, M}) {
                 bool pc;
-                const double ec = std::max(run_col(M, nz, &pc), run_col(M, nz, &pc, 3));
+                bool pw1, pw2;
+                const double ec = std::max(std::max(run_col(M, nz, &pc), run_col(M, nz, &pc, 3)),
+                                           std::max(run_col(M, nz, &pw1, COL_SLOTS, true), run_col(M, nz, &pw2, 3, true)));   // both plan families
+                pc = pc && pw1 && pw2;
                 if (!pc || !(ec < 4e-6)) { printf("M=%d nz=%d: in-place column transform err %.2e  FAILED\n", M, nz, ec); ok = false; }
                 worst_col = std::max(worst_col, ec);
             }
