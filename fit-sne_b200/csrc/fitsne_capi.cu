@@ -772,26 +772,40 @@ static int reorder_points(fitsne_ctx *c) {
                                                                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     k_scan_excl<<<1, 1024, 0, st>>>(new_len, c->row_P2, N);
     k_scan_excl<<<1, 1024, 0, st>>>(c->tile_cnt, c->tile_start, (int) c->ntiles);
-    k_relabel_csr<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(1, c->row_P, c->edges, c->rank_map, N, c->tg, new_len, c->tile_cnt,
-                                                                 c->row_P2, c->edges2, c->tile_start, c->tile_cur, c->tile_pack, c->tile_val);
     k_count_nonempty<<<cdiv(c->ntiles, 256), 256, 0, st>>>(c->tile_cnt, c->ntiles, c->nonempty);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(&c->nonempty_tiles, c->nonempty, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    std::swap(c->row_P, c->row_P2); std::swap(c->edges, c->edges2);
-    c->reordered = true;
-    c->reorders++;
     // 5. which attractive kernel: modelled cost of the tiled path (column-block fills from L2 + the edge stream) vs
     //    the CSR gather path (~2 cycles per divergent gather per SM; measured 6.9 ps/edge chip-wide on B200)
     // (calibrated on B200, N=1M/E=30M: 4393 non-empty tiles -> 340 us without accumulation => ~78 ns per column-block fill)
     const double est_tiles_us = (double) c->nonempty_tiles * 0.078 + (double) E * 8.0 / 5.0e6 + 5.0;
     const double est_csr_us = (double) E * 6.9e-6 + 5.0;
+    const bool was_reordered = c->reordered, old_tiles = c->use_tiles;
     c->use_tiles = est_tiles_us < est_csr_us;
     if (c->cfg.flags & FITSNE_FLAG_FORCE_TILES) c->use_tiles = true;
     if (c->cfg.flags & FITSNE_FLAG_NO_TILES) c->use_tiles = false;
+    c->reorders++;
     TRACE("reorder #%llu: %u of %zu tiles non-empty, est tiles %.0f us vs csr %.0f us -> %s", (unsigned long long) c->reorders,
           c->nonempty_tiles, c->ntiles, est_tiles_us, est_csr_us, c->use_tiles ? "tiles" : "csr");
-    drop_graphs(c);              // CSR pointers and the attractive kernel changed
+    // second pass: the relabelled CSR, and -- only if the tiled kernel will run -- the edges scattered into their tiles
+    // (an atomic and 8 scattered bytes per edge that the CSR path never reads)
+    k_relabel_csr<<<cdiv((long long) N * 8, 256), 256, 0, st>>>(1, c->row_P, c->edges, c->rank_map, N, c->tg, new_len, c->tile_cnt,
+                                                                 c->row_P2, c->edges2, c->tile_start, c->tile_cur,
+                                                                 c->use_tiles ? c->tile_pack : nullptr, c->tile_val);
+    LAUNCH_CHECK();
+    if (was_reordered && c->use_tiles == old_tiles) {
+        // a later re-ordering: the new CSR goes back into the buffers the captured graphs point at -- a 250 MB device copy
+        // (~80 us at N = 1M) instead of capturing and instantiating every graph again
+        CK(cudaMemcpyAsync(c->row_P, c->row_P2, ((size_t) N + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(c->edges, c->edges2, E * sizeof(uint2), cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    } else {
+        CK(cudaStreamSynchronize(st));
+        std::swap(c->row_P, c->row_P2); std::swap(c->edges, c->edges2);
+        drop_graphs(c);          // CSR pointers (first re-ordering: also the order maps) or the attractive kernel changed
+    }
+    c->reordered = true;
     c->kernel_launches_reorder += 20;
     return 0;
 }
@@ -853,14 +867,20 @@ static int reorder_points_sharded(fitsne_ctx *c) {
     CK(cudaMemcpyAsync(c->row_P2, c->row_P, ((size_t) N + 1) * 4, cudaMemcpyDeviceToDevice, st));
     k_local_row_offsets<<<cdiv(nloc + 1, 256), 256, 0, st>>>(row_new, nloc, b, c->edge_base, c->row_P2);
     LAUNCH_CHECK();
-    CK(cudaStreamSynchronize(st));
-    std::swap(c->row_P, c->row_P2); std::swap(c->edges, c->edges2);
+    if (c->reordered) {          // a later re-ordering: back into the buffers the captured graphs point at (see reorder_points)
+        CK(cudaMemcpyAsync(c->row_P, c->row_P2, ((size_t) N + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(c->edges, c->edges2, c->E * sizeof(uint2), cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    } else {
+        CK(cudaStreamSynchronize(st));
+        std::swap(c->row_P, c->row_P2); std::swap(c->edges, c->edges2);
+        drop_graphs(c);
+    }
     c->reordered = true;
     c->reorders++;
     c->y_whole = false;          // the other ranks re-ordered their slices too
     CKRC(ensure_whole_Y(c));
     c->bounds_valid = true;      // a permutation does not move the bounds
-    drop_graphs(c);
     c->kernel_launches_reorder += 16;
     return 0;
 }

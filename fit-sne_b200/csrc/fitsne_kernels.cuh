@@ -1865,7 +1865,7 @@ __global__ void __launch_bounds__(1024) k_scan_excl(const uint32_t *__restrict__
 
 // Relabel the CSR into the new point order.  One 8-lane group per OLD row i (new row r = rank[i]).
 //   PASS 0: new_len[r] = len(i); tile_cnt[tile(r, rank[col])]++
-//   PASS 1: copy the row's edges to new_row_P[r] (relabelled columns) and scatter them into their tiles
+//   PASS 1: copy the row's edges to new_row_P[r] (relabelled columns) and -- tile_pack != nullptr -- scatter them into their tiles
 __global__ void __launch_bounds__(256) k_relabel_csr(int pass, const uint32_t *__restrict__ row_old, const uint2 *__restrict__ edges_old,
                                                      const uint32_t *__restrict__ rank, int n,
                                                      TileGeom tg, uint32_t *__restrict__ new_len, uint32_t *__restrict__ tile_cnt,
@@ -1892,6 +1892,7 @@ __global__ void __launch_bounds__(256) k_relabel_csr(int pass, const uint32_t *_
             const uint32_t c = rank[ed.x];
             const float v = __uint_as_float(ed.y);
             edges_new[nb + (e - e0)] = make_uint2(c, ed.y);
+            if (tile_pack == nullptr) continue;              // the CSR path was chosen: nobody reads the tiles
             const uint32_t cb = c / TILE_COLS;
             const size_t t = (size_t) rc * tg.ncb + cb;
             const uint32_t pos = tile_start[t] + atomicAdd(&tile_cur[t], 1u);
