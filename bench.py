@@ -375,9 +375,17 @@ def main():
         if world > 1 and sst["phase_ms"].get("collectives", 0) > 0:
             kern["collectives"] = {"ms": round(sst["phase_ms"]["collectives"] / nsteps_t, 5), "what": "NCCL all-reduce of the spread grid (the Y all-gather overlaps the sort)"}
         dom = max((k for k in kern if k in algo), key=lambda k: kern[k]["ms"])
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this very workload
+        # (profiles/r2_ncu_full_iteration.txt: k_attract 252.07 + 9.35 MB, k_update 40.02 + 0.02 MB; the 126 MB L2 absorbs most
+        # writes of the 8 MB per-point arrays).  Only quoted for the configuration the capture was taken on.
+        traffic, traffic_note = None, "not measured for this configuration; ncu dram__bytes of the 1M-point single-GPU workload are in profiles/"
+        if dom == "attract_update" and world == 1 and N == 1000000 and d == 2 and args.phase == "late" and args.df == 1.0:
+            traffic = int(round((252.067584 + 9.353728 + 40.021760 + 0.019712) * 1e6))
+            traffic_note = ("ncu --set full capture of the same workload, committed as profiles/r2_ncu_full_iteration.txt (k_attract + k_update, "
+                            "DRAM read + write per launch); not re-measured in this run")
         roofline = {"kernel": names[dom], "phase": dom, "dominant_by": "time (live CUDA events, serialised phases)", "bound": "hbm",
-                    "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": None,
-                    "traffic_note": "not measured in this run; ncu dram__bytes of the same kernels are in profiles/",
+                    "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic,
+                    "traffic_note": traffic_note,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"], "avg_launch_ms": kern[dom]["ms"]}
         total_bytes = 8 * El + 140 * Nl + 32 * G ** d + 124 * M ** d          # whole iteration
         roofline_total = {"algorithmic_bytes_per_step": int(total_bytes), "ms_per_step": round(ms / args.steps, 5),
