@@ -483,10 +483,10 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
     auto launch_kernel_side = [&](cudaStream_t ks) -> int {
         const int Gc = M / 2, H = M / 2 + 1;
         LK(c, k_kspec_rows, Gc, ROW_THREADS, pl->smem_row1, ks, c->KR, pl->plan, pl->W, c->gp, c->cfg.df);
-        if (col_threads <= COL_THREADS)
-            LK(c, k_kspec_cols<COL_THREADS>, (H + 1) / 2, col_threads, pl->smem_col, ks, c->KR, c->KS, pl->cplan, pl->W, c->gp, c->rank, c->p2p && c->dist_conv ? c->world : 1);
-        else
-            LK(c, k_kspec_cols<COL_THREADS_MAX>, (H + 1) / 2, col_threads, pl->smem_col, ks, c->KR, c->KS, pl->cplan, pl->W, c->gp, c->rank, c->p2p && c->dist_conv ? c->world : 1);
+#define COL_LAUNCH(KERN, GRID, STREAM, ...) do { \
+        if (col_threads <= COL_THREADS) LK(c, KERN<COL_THREADS>, GRID, col_threads, pl->smem_col, STREAM, __VA_ARGS__); \
+        else LK(c, KERN<COL_THREADS_MAX>, GRID, col_threads, pl->smem_col, STREAM, __VA_ARGS__); } while (0)
+        COL_LAUNCH(k_kspec_cols, (H + 1) / 2, ks, c->KR, c->KS, pl->cplan, pl->W, c->gp, c->rank, c->p2p && c->dist_conv ? c->world : 1);
         LAUNCH_CHECK();
         c->stats.kernel_launches += 2;
         return 0;
@@ -568,13 +568,8 @@ static int enqueue_iteration(fitsne_ctx *c, const int *B_dev_arg, int M, bool up
         // sharded, distributed convolution: like a 2-D FFT -- rows and spectrum columns dealt out in blocks; every
         // "transpose" is the producing kernel's stores on peer memory; the CTA that finishes last raises the stage's flag at
         // the peers, the consuming kernel's CTAs wait for it themselves -- no launch of its own for any exchange
-        if (col_threads <= COL_THREADS) {
-            LK(c, k_conv_cols<COL_THREADS>, H, col_threads, pl->smem_col, st, pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
-                                                              c->sc, c->tickets + 0, c->pc, p2p);
-        } else {
-            LK(c, k_conv_cols<COL_THREADS_MAX>, H, col_threads, pl->smem_col, st, pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N,
-                                                              c->sc, c->tickets + 0, c->pc, p2p);
-        }
+        COL_LAUNCH(k_conv_cols, H, st, pl->tmS, c->KS, pl->cplan, pl->W, c->gp, c->df_is_one ? 1 : 0, c->zpartial, c->N, c->sc, c->tickets + 0,
+                   c->pc, p2p);
         kt(c, "k_conv_cols");
         LK(c, k_conv_rows_inv, Gc, ROW_THREADS, pl->smem_row2, st, c->S, c->pot, pl->plan, pl->W, c->gp, c->pc, p2p, c->N, c->sc, c->tickets + 9);
         kt(c, "k_conv_rows_inv");

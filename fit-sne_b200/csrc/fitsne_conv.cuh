@@ -40,7 +40,8 @@
 namespace fk {
 
 constexpr int COL_SLOTS = 4;          // sequences per column tile
-constexpr int COL_THREADS = 256;      // threads per column CTA (single GPU, replicated convolution: ~4 CTAs share an SM)
+constexpr int COL_THREADS = 256;      // threads per column CTA (4 CTAs share an SM).  Measured at M = 1152 (stage tasks 288 | 576 | 512):
+                                      // 192, 224 and 256 threads give the same iteration time, 288 (3 CTAs per SM) is 1.6 % slower
 constexpr int COL_THREADS_MAX = 512;  // second instantiation's launch bound: distributed convolution (a rank's few columns, one CTA per SM) launches wider CTAs
 constexpr int COL_BOX_ROWS = 128;     // rows per TMA box (box = 128 rows x 32 bytes)
 constexpr int ROW_THREADS = 256;
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_kspec_rows(float4 *__restrict__
 // Re ZB = gx with Kgrad_x^ = i gx,  Im ZB = -gy with Kgrad_y^ = i gy).   KS[kx][pos] = (Ksq^, Kb^, gx, gy), pos = the
 // forward transform's digit-reversed frequency slot -- the order k_conv_cols meets them in.
 template <int BOUND>
-__global__ void __launch_bounds__(BOUND) k_kspec_cols(const float4 *__restrict__ KR, float4 *__restrict__ KS, ColPlan plan,
+__global__ void __launch_bounds__(BOUND, BOUND == COL_THREADS ? 4 : 1) k_kspec_cols(const float4 *__restrict__ KR, float4 *__restrict__ KS, ColPlan plan,
                                                             const float2 *__restrict__ W, const GridParams *__restrict__ gpp,
                                                             int rank, int world) {
     pdl_prologue();
