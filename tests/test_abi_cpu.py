@@ -69,6 +69,33 @@ def test_no_cpu_fallback_without_device():
     assert "no CPU fallback" in str(ei.value)
 
 
+def test_argument_errors_come_before_any_device_work():
+    """Bad shard layouts are refused with FITSNE_EINVAL and a message, on any box (the checks precede device selection):
+    more ranks than the peer tables hold, a rank outside the world, a rank whose ceil(N / world) block is empty."""
+    import fitsne_b200
+    lib = fitsne_b200.load_library()
+    row = np.arange(0, 10, dtype=np.uint32)          # N = 9, one edge per row
+    col = np.arange(9, dtype=np.uint32)[::-1].copy()
+    val = np.full(9, 1.0 / 9)
+    Y = np.random.default_rng(0).standard_normal((9, 2))
+    cfg = fitsne_b200.Config(3, 1.0, 50, 1.0, 0, 0)
+    ident = (ctypes.c_ubyte * 128)()
+
+    def create(rank, world, b, e):
+        ctx = ctypes.c_void_p()
+        rc = lib.fitsne_create_sharded(ctypes.byref(cfg), 9, 2, row.ctypes.data_as(ctypes.c_void_p), col.ctypes.data_as(ctypes.c_void_p),
+                                       val.ctypes.data_as(ctypes.c_void_p), Y.ctypes.data_as(ctypes.c_void_p), rank, world, b, e,
+                                       ident, ctypes.byref(ctx))
+        return rc, lib.fitsne_last_error(None).decode()
+
+    rc, msg = create(0, 9, 0, 1)
+    assert rc == -1 and "world size" in msg, (rc, msg)          # FITSNE_EINVAL
+    rc, msg = create(4, 4, 0, 3)
+    assert rc == -1 and "rank" in msg, (rc, msg)
+    rc, msg = create(3, 4, 9, 9)                                 # ceil(9 / 4) = 3 rows per rank: rank 3 would own [9, 9)
+    assert rc == -1 and "must own rows" in msg, (rc, msg)
+
+
 def test_product_never_imports_the_oracle():
     """The product path must not route through oracle/ (it is test infrastructure)."""
     pkg = os.path.join(ROOT, "fit-sne_b200")
