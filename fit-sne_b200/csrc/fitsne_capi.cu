@@ -227,10 +227,11 @@ static inline int cdiv(long long a, long long b) { return (int) ((a + b - 1) / b
 
 static inline int max_fft_len(int D) { return D == 2 ? 4096 : 8192; }   // 1-D: two buffers + twiddles must fit in shared memory
 
-// (Tried: the stream-ordered pool -- cudaMallocAsync / cudaFreeAsync with the release threshold raised -- for single-GPU
-// contexts, to take the ~50 cudaMalloc / cudaFree round trips out of every fitsne_run_host call: create 19 ms + destroy 16 ms of
-// a 120 ms call at N = 1M.  Measured on B200: the first call of a process took 790 ms instead of 146 ms (the pool's first
-// growth), later calls 127-139 ms, no better than before.  A process that makes ONE call is the common case: plain cudaMalloc.)
+// (Tried, to shorten fitsne_run_host's create (19 ms) and destroy (16 ms) at N = 1M, both measured on B200 with
+// tests/tools/e2e_trace.py: (1) the stream-ordered pool, cudaMallocAsync / cudaFreeAsync with the release threshold raised --
+// the first call of a process took 790 ms instead of 146 ms (the pool's first growth), later calls were no faster;
+// (2) carving all ~60 buffers out of two or three slabs -- 115-137 ms per call against 118-156 ms, inside the box's noise: the
+// cudaMalloc / cudaFree round trips are not where the time goes.  Neither is kept.)
 template <typename T>
 static int dev_alloc(fitsne_ctx *c, T **p, size_t count) {
     if (*p) { cudaFree(*p); *p = nullptr; }
