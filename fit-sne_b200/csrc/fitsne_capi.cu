@@ -671,7 +671,7 @@ static int enqueue_iteration_d(fitsne_ctx *c, int M, bool update) {
 }
 
 // Sharded: make c->Y hold every rank's slice again (after a step only the local slice is current; the next iteration's
-// own all-gather does this on the second stream, anything else that reads foreign rows -- KL, downloads, a bounds scan --
+// own exchange (peer pushes / all-gather) does this, anything else that reads foreign rows -- KL, downloads, a bounds scan --
 // calls this first).  Collective: every rank reaches it at the same point of the call sequence.
 static int ensure_whole_Y(fitsne_ctx *c) {
     if (c->world == 1 || c->y_whole) return 0;

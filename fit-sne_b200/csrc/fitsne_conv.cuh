@@ -1,7 +1,7 @@
 // fitsne_conv.cuh -- the 2-D circulant kernel convolution (nbodyfft.cpp:150-217 + the kernel spectrum of
 // precompute_2d, nbodyfft.cpp:52-68) as five kernels around ONE fused column pass.
 //
-//   charge side (critical path)                                   kernel side (own stream, overlaps sort + spread)
+//   charge side (critical path)                                   kernel side (in line; sharded runs: a side stream beside sort + spread)
 //   k_conv_rows_fwd   rows r < G of the spread grid               k_kspec_rows   rows dr in [0, G) of the kernel lattice,
 //                     (w1 + i dx), (dy + i wbb) -> x-spectra,                    sampled in fp64 IN the kernel (no sample pass
 //                     separated into 4 half-spectra  S[r][kx][4]                 over HBM), x-transform  -> KR[dr][kx]
@@ -17,7 +17,8 @@
 //     Columns: one kx owns all four spectra at (ky, kx), so the Hadamard product and the Parseval terms are local to
 //     the tile and the forward-columns -> Hadamard -> inverse-columns chain never leaves shared memory.
 //   * The column FFT is IN PLACE (decimation in frequency forward, decimation in time back), so a tile is M x 32 bytes
-//     (41 KB at M = 1280: five CTAs per SM, 641 tiles = one wave) instead of a ping-pong pair.  The forward transform
+//     (37 KB at M = 1152: four CTAs per SM, 577 tiles = one wave) instead of a ping-pong pair, and it uses radices up to 16
+//     where that saves passes over the tile (1152 = 16 x 8 x 9: three stages each way instead of five).  The forward transform
 //     leaves the frequencies in digit-reversed order; the Hadamard product is pointwise, the kernel spectra are produced
 //     by the very same transform (k_kspec_cols) in the very same order, and the inverse consumes that order -- nobody
 //     ever needs the permutation.

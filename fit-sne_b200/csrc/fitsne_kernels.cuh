@@ -1,13 +1,13 @@
 // fitsne_kernels.cuh -- hand-written sm_100a kernels for FIt-SNE's per-iteration gradient loop.
 //
 // Everything the reference does per iteration (reference = /root/reference/src/...) in fp32 on the device:
-//   bounds + zero-mean        tsne.cpp:1039-1049, :1851-1876        k_colsum, k_center_bounds, k_setup_grid (sharded: k_update_shard, k_center_shard)
-//   point -> box, sort        nbodyfft.cpp:85-114                    k_bin, k_radix_offsets, k_radix_scatter
+//   bounds + zero-mean        tsne.cpp:1039-1049, :1851-1876        k_center_bounds, k_setup_grid (sharded: k_update_shard, k_center_shard)
+//   point -> box, sort        nbodyfft.cpp:85-114                    k_bin, k_radix_sweep x 2 (look-back)
 //   Lagrange spread           nbodyfft.cpp:123-147, :310-336         k_spread_chunks, k_spread_combine
-//   kernel samples            nbodyfft.cpp:52-61, tsne.cpp:69-94     k_gen_kernels        (+ forward FFTs, fitsne_fft.cuh)
-//   Hadamard + sum_Q          nbodyfft.cpp:184-191, tsne.cpp:1101-1110  k_hadamard           (+ inverse FFTs)
+//   kernel samples + spectra  nbodyfft.cpp:52-68, tsne.cpp:69-94     2-D: k_kspec_rows / k_kspec_cols (fitsne_conv.cuh); 1-D: k_gen_kernels_1d + k_fft_line
+//   convolution + sum_Q       nbodyfft.cpp:150-217, tsne.cpp:1101-1110  2-D: k_conv_rows_fwd / k_conv_cols / k_conv_rows_inv; 1-D: k_hadamard_1d
 //   gather + normalise        nbodyfft.cpp:222-239, tsne.cpp:1149-1151  k_gather
-//   attractive + optimiser    tsne.cpp:1121-1137, :479-513           k_attract (2nd stream), k_update
+//   attractive + optimiser    tsne.cpp:1121-1137, :479-513           k_attract (or k_attract_tiles), k_update
 //   KL                        tsne.cpp:1329-1355                      k_kl
 //
 // The repulsive part uses the "local offset" formulation documented in tests/device_model.py (identical
@@ -1328,11 +1328,10 @@ __global__ void __launch_bounds__(256) k_gather(const float *__restrict__ sorted
 
 // ------------------------------------------------------------------- attractive term + optimiser step --
 // k_attract: LPR lanes cooperate on one CSR row: attr_i = sum_j p_ij q_ij (y_i - y_j), q = 1/(1+d2/df)
-// (tsne.cpp:1121-1137; exaggeration is applied later as a scalar).  It depends on Y and P only, so it runs on a
-// second stream concurrently with the whole repulsive pipeline (sort/spread/FFT/gather).
+// (tsne.cpp:1121-1137; exaggeration is applied later as a scalar).  It depends on Y and P only; it runs in line after the
+// gather (beside other kernels it saturates every SM's load/store pipe and nothing is gained: see enqueue_iteration).
 // Row offsets are local to this rank's edge slice: edges of row i are [row_P[i]-edge_base, row_P[i+1]-edge_base).
-// Persistent form: a fixed grid (a few CTAs per SM, set by the host) strides over the row groups, so the kernel
-// never occupies more than its share of each SM and the repulsive pipeline's kernels co-run beside it.
+// Persistent form: a fixed grid (8 CTAs per SM, set by the host) strides over the row groups.
 template <int D, int LPR>
 __global__ void __launch_bounds__(256) k_attract(const uint32_t *__restrict__ row_P, const uint2 *__restrict__ edges, uint32_t edge_base,
                                                  const float *__restrict__ Y, int row_begin, int row_end, float inv_df,
@@ -1484,8 +1483,8 @@ __global__ void __launch_bounds__(256) k_update(const float *__restrict__ Y, con
 // (Ynext[row_begin..row_end)).  Instead of all-gathering Y first and then reducing over all N points on every GPU, each
 // rank reduces its own slice (inside k_update_shard), the per-rank records (128 bytes) are all-gathered, and every rank derives
 // the same global column means and bounds from the same bytes (k_center_shard) while centring only its own slice.  The
-// big Y all-gather then runs on the second stream at the start of the NEXT iteration, overlapped with that iteration's
-// sort / spread (which only read the local slice).
+// positions themselves travel at the start of the NEXT iteration (copy-engine pushes into the peers' Y on a side stream, or
+// an NCCL all-gather without peer access), overlapped with that iteration's sort / spread, which only read the local slice.
 //
 // The 2-D scan quirk (tsne.cpp:1045-1048, see k_center_bounds) acts on the centred, interleaved sequence from flat
 // index 0, i.e. on the head of rank 0's slice -- but the means are only known after the exchange.  Rank 0 therefore
