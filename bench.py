@@ -8,7 +8,8 @@ A "step" is one full iteration of TSNE::run's loop (gradient + gains/momentum up
 evaluation runs every 50th step inside the timed region, as in the reference).  The headline (`value`) is
 BASELINE.json's config 3: synthetic N=1M points, 2-D, learning_rate=N/12, fixed kNN-style graph injected like
 load_affinities=1 (E ~ 30 N), late phase.  `value` times device-resident state with CUDA events on the library's
-stream (fitsne_run); `e2e` times create + run + download through the C ABI with host buffers and a host clock.
+stream (fitsne_run); `e2e` times create + run + download through the C ABI with host buffers and a host clock
+(single GPU: the median of three whole calls after one untimed call; all three are listed in `e2e.calls_ms`).
 The same line also carries: `roofline` (the phase that takes longest, live CUDA-event times), `roofline_total`,
 `kernels` (every phase), `parity` (our gradient vs the oracle on this very workload, outside the timed region),
 `cpu_baseline` (the unmodified reference on the host cores) and `other_configs` (BASELINE configs 1, 2, 4, 5 and
@@ -401,22 +402,34 @@ def main():
         pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (row, lc, lv, Y0)]   # keep the owners alive
         prow, pcol, pval, pY = [p_.numpy() for p_ in pinned]
         nid = L.nccl_id(fb)
-        L.barrier()
-        t0 = time.perf_counter()
+        calls_ms = []
         if world == 1:
-            Yout, costs2 = fb.run_host(prow, pcol, pval, pY, max_iter=args.steps, device=L.local_rank, df=args.df, **sched)
+            # the whole call, repeated: one untimed call, then three timed ones; the MEDIAN is reported (a call is ~0.1 s of
+            # host-side work -- allocation, a 364 MB upload over PCIe -- and single calls on a shared box scatter by 2x)
+            for rep in range(4):
+                L.barrier()
+                t0 = time.perf_counter()
+                Yout, costs2 = fb.run_host(prow, pcol, pval, pY, max_iter=args.steps, device=L.local_rank, df=args.df, **sched)
+                if rep > 0:
+                    calls_ms.append((time.perf_counter() - t0) * 1e3)
+            dt = sorted(calls_ms)[len(calls_ms) // 2] * 1e-3
         else:
+            L.barrier()
+            t0 = time.perf_counter()
             with fb.FitSNE(prow, pcol, pval, pY, df=args.df, device=L.local_rank, rank=L.rank, world=L.world, nccl_id=nid) as te:
                 t_created = time.perf_counter()
                 Yout, costs2 = te.run(max_iter=args.steps, **sched)
                 t_ran = time.perf_counter()
-        L.barrier()
-        dt = L.max(time.perf_counter() - t0)
+            L.barrier()
+            dt = L.max(time.perf_counter() - t0)
         h2d = prow.nbytes + pcol.nbytes + pval.nbytes + pY.nbytes
         d2h = Yout.nbytes + costs2.nbytes
         e2e = {"value": args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                "call": ("fitsne_run_host" if world == 1 else "fitsne_create_sharded + fitsne_run + download, per rank") +
                        " (create + %d iterations + download), host wall clock, max over ranks" % args.steps}
+        if calls_ms:
+            e2e["calls_ms"] = [round(x, 1) for x in calls_ms]
+            e2e["aggregate"] = "median of 3 timed calls after 1 untimed call"
         if world > 1:     # where a sharded call's time goes: the one-off set-up (NCCL communicator, peer-memory handles, CSR upload) vs the iterations
             e2e["breakdown_s"] = {"create_sharded (NCCL init + IPC fabric + upload)": round(L.max(t_created - t0), 3),
                                   "run + download": round(L.max(t_ran - t_created), 3)}
