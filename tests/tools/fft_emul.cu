@@ -118,6 +118,18 @@ int main() {
     int count = 0, ccount = 0;
     double worst = 0, worst_col = 0;
     for (int M : lens) {
+        {   // plan families: both factor M exactly, the wide one never needs more stages, and an odd radix comes last when there is one
+            int rn[FFT_MAX_STAGES], rw[FFT_MAX_STAGES];
+            const int sn = fft_pick_radices(M, false, rn), sw = fft_pick_radices(M, true, rw);
+            long long pn = 1, pw = 1;
+            for (int i = 0; i < sn; i++) pn *= rn[i];
+            for (int i = 0; i < sw; i++) pw *= rw[i];
+            bool odd_in = false;
+            for (int i = 0; i < sw; i++) odd_in = odd_in || (rw[i] & 1);
+            if (sn == 0 || sw == 0 || pn != M || pw != M || sw > sn || (odd_in && !(rw[sw - 1] & 1))) {
+                printf("M=%d: radix plans inconsistent (narrow %d stages, wide %d stages)\n", M, sn, sw); ok = false;
+            }
+        }
         for (int lines : {1, 2}) {
             if (lines > 1 && M > 4096) continue;
             bool pn; int sn = 0;
